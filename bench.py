@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Benchmark of the PoET deformable encoder/decoder hot path on B200 (driver contract).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # reference arm: CPU oracle port on host cores
+
+Workload (config.workload): BASELINE.json configs[1] — YCB-V shape: 5 enc / 5 dec layers, 16 heads,
+d=256, 10 queries, 22 class slots, batch 16 per GPU, 640x480 REF pyramid (S=1600), forward+backward
+through the fixed-cotangent loss of SURVEY.md §8d, fp32.  A "step" = one forward+backward over one
+batch (N>1: plus the flat-buffer gradient all-reduce).  Metric: images/s.
+
+Timing: per-step CUDA events on the launching stream, an L2 flush (256 MiB write) between timed
+steps outside the events, barrier + synchronize on both sides, MAX over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = "cfg2"
+METRIC = "images/sec, PoET deformable enc/dec fwd+bwd (5enc/5dec/16h, 640x480 REF pyramid, batch 16/GPU)"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]), tf_sust=float(p["bf16_tflops_sustained"]),
+                    source="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback")
+
+
+def config_dict(cfg, extra=None):
+    from poet_b200 import synthetic as S
+    d = {"workload": f"{WORKLOAD}: YCB-V 5enc/5dec/16h d256 Q10 22 class slots, fwd+bwd, synthetic cotangent loss",
+         "batch_per_gpu": cfg["batch"], "pyramid": S.pyramid_of(cfg), "tokens": S.n_tokens(cfg),
+         "dropout": 0.0, "l2": "flushed between timed steps (256 MiB write, outside the events)"}
+    if extra:
+        d.update(extra)
+    return d
+
+
+# ------------------------------------------------------------------------------------------
+# CPU legs (the only places bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------
+def cpu_step_fn(cfg, batch):
+    from oracle import poet_oracle as O
+    from poet_b200 import synthetic as S
+    P = {k: v.requires_grad_(True) for k, v in S.make_params(cfg).items()}
+    inp = S.make_inputs(cfg, batch=batch)
+    g_t, g_R = S.make_cotangents(cfg, batch=batch)
+
+    def step():
+        for v in P.values():
+            v.grad = None
+        cap = {}
+        O.poet_path_forward(P, cfg, inp["srcs"], inp["masks"], inp["boxes"], inp["labels"], capture=cap)
+        loss = O.synthetic_loss((cap["translation_all"], cap["rotation_all"]), g_t, g_R)
+        loss.backward()
+        return float(loss.detach())
+    return step
+
+
+def cpu_baseline(cfg, batch=4, reps=2):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_step_fn(cfg, batch)
+    step()                                             # warm-up
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        step()
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": batch / dt, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} fwd+bwd steps of {batch} images of the same workload (oracle/poet_oracle.py, torch CPU fp32, "
+                      f"{cores} threads) after 1 warm-up"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores.  The reference is pure Python and
+    /root/reference does not exist on the GPU box, so this is the oracle port (kind 'port')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from poet_b200 import synthetic as S
+    cfg = S.CONFIGS[WORKLOAD]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = 2                                           # bounded sample per step
+    step = cpu_step_fn(cfg, batch)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    times = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = batch * args.steps / total
+    sample = f"each step = fwd+bwd of {batch} images of {WORKLOAD} (bounded sample), oracle port, {cores} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": config_dict(cfg, {"batch_per_step": batch}),
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc = gpu_index, None
+        self.path = tempfile.mktemp(prefix="poet_clocks_", suffix=".csv")
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons, power = [], [], set(), []
+        try:
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            busy = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(power))
+        return out
+
+
+def build_gpu_model(cfg, dev):
+    from poet_b200 import synthetic as S
+    from poet_b200.deformable_transformer import DeformableTransformer
+    from poet_b200.pose_estimation_transformer import PoET
+    tr = DeformableTransformer(cfg["d_model"], cfg["nheads"], cfg["enc_layers"], cfg["dec_layers"], cfg["dim_ff"], 0.0,
+                               "relu", True, cfg["n_levels"], cfg["n_points"], cfg["n_points"])
+    model = PoET(None, tr, cfg["num_queries"], cfg["n_levels"], cfg["n_classes"], class_mode=cfg["class_mode"])
+    model.load_state_dict(S.make_params(cfg), strict=True)
+    return model.to(dev).train()
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+    from poet_b200 import ops, synthetic as S
+    from poet_b200.data_parallel import FlatGradReducer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    ops.set_gemm_precision(args.precision)
+
+    cfg = S.CONFIGS[WORKLOAD]
+    B = cfg["batch"]
+    model = build_gpu_model(cfg, dev)
+    reducer = FlatGradReducer(model.parameters())
+    inp = S.make_inputs(cfg, seed=1234 + rank)           # each rank owns a different image shard (weak scaling)
+    g_t, g_R = (t.to(dev) for t in S.make_cotangents(cfg))
+    d_srcs = [s.to(dev) for s in inp["srcs"]]
+    d_masks = [m.to(dev) for m in inp["masks"]]
+    d_boxes = [b.to(dev) for b in inp["boxes"]]
+    d_labels = [l.to(dev) for l in inp["labels"]]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(srcs, masks, boxes, labels):
+        reducer.zero()
+        out, _ = model.forward_pyramid(srcs, masks, boxes, labels)
+        t = torch.stack([a["pred_translation"] for a in out["aux_outputs"]] + [out["pred_translation"]])
+        R = torch.stack([a["pred_rotation"] for a in out["aux_outputs"]] + [out["pred_rotation"]])
+        loss = (t * g_t).sum() + (R * g_R).sum()
+        loss.backward()
+        reducer.all_reduce()
+        return loss, out
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(d_srcs, d_masks, d_boxes, d_labels)
+    sync_all()
+
+    # ---- device-resident timed region -------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.launch_count()
+    ops.kernel_timing(args.kernel_table)
+    evs = []
+    sync_all()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        step(d_srcs, d_masks, d_boxes, d_labels)
+        e.record()
+        evs.append((s, e))
+    sync_all()
+    launches = ops.launch_count() - launches0
+    ktimes = ops.kernel_times_ms() if args.kernel_table else {}
+    ops.kernel_timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(s.elapsed_time(e) for s, e in evs)
+    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms = float(tt.item())
+
+    # ---- end-to-end: host buffers in, host result out, through the public module API ---------
+    h_srcs = [s.pin_memory() for s in inp["srcs"]]
+    h_masks = [m.pin_memory() for m in inp["masks"]]
+    h2d = sum(t.numel() * t.element_size() for t in h_srcs + h_masks) + sum(b.numel() * 4 + l.numel() * 8 for b, l in zip(inp["boxes"], inp["labels"]))
+    d2h = 0
+    e2e_ms = 0.0
+    sync_all()
+    for it in range(args.steps + 1):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        srcs = [s.to(dev, non_blocking=True) for s in h_srcs]
+        masks = [m.to(dev, non_blocking=True) for m in h_masks]
+        loss, out = step(srcs, masks, inp["boxes"], inp["labels"])          # host box lists: padded on host, one H2D
+        host = [loss.detach().cpu(), out["pred_translation"].detach().cpu(), out["pred_rotation"].detach().cpu()]
+        torch.cuda.synchronize()
+        if it > 0:                                                         # first pass warms the pinned path
+            e2e_ms += 1e3 * (time.perf_counter() - t0)
+        d2h = sum(t.numel() * t.element_size() for t in host)
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+
+    if rank == 0:
+        peaks = load_peaks()
+        ms_per_step = total_ms / args.steps
+        value = B * world * args.steps / (total_ms / 1e3)
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "fp32" if args.precision == "fp32" else f"fp32 ({args.precision} tensor-core GEMMs)",
+                "data": "synthetic",
+                "config": config_dict(cfg, {"global_batch": B * world, "parallelism": f"dp{world}",
+                                            "grad_allreduce_bytes": reducer.nbytes() if world > 1 else 0,
+                                            "gemm_precision": args.precision}),
+                "e2e": {"value": B * world * args.steps / (e2e_ms / 1e3), "unit": "images/s",
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches, "clocks": clocks}
+        if ktimes:
+            line["roofline"], line["kernels"] = roofline_from(ktimes, peaks, args.steps, ms_per_step)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(cfg)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline_from(ktimes, peaks, steps, ms_per_step):
+    """Per-kernel table from the CUDA-event brackets; `roofline` = the kernel with the largest time share.
+    GEMMs are judged against the tensor pipe (sustained bf16 peak: the kernel is timed inside a long step),
+    everything else against HBM.  Algorithmic bytes/flops per launch are the figures of DESIGN.md."""
+    rows = []
+    for name, (ms, n, nbytes, flops) in ktimes.items():
+        if ms <= 0:
+            continue
+        is_gemm = name.startswith("poet_gemm")
+        if is_gemm:
+            ach, peak, unit, bound = flops / (ms * 1e-3) / 1e12, peaks["tf_sust"], "TFLOP/s", "tensor"
+        else:
+            ach, peak, unit, bound = nbytes / (ms * 1e-3) / 1e9, peaks["hbm"], "GB/s", "hbm"
+        rows.append({"kernel": name, "launches_per_step": n / steps, "ms_per_step": ms / steps,
+                     "share": ms / steps / ms_per_step, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
+                     "frac": ach / peak if nbytes or flops else None,
+                     "hbm_gbs": nbytes / (ms * 1e-3) / 1e9 if nbytes else None})
+    rows.sort(key=lambda r: -r["ms_per_step"])
+    # group GEMM shapes into one dominant-kernel line as well
+    gemm = [r for r in rows if r["kernel"].startswith("poet_gemm")]
+    top = rows[0]
+    roof = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
+            "unit": top["unit"], "frac": top["frac"], "traffic": None, "peak_source": peaks["source"],
+            "share_of_step": top["share"]}
+    if gemm:
+        roof["all_gemm_share_of_step"] = sum(r["share"] for r in gemm)
+    return roof, rows[:24]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("POET_GEMM_PRECISION", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--no-kernel-table", dest="kernel_table", action="store_false")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the poet_b200 path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,161 @@
+/* poet_b200.h — C ABI of libpoet_b200.so: the B200 (sm_100a) kernels of PoET's deformable
+ * encoder/decoder hot path.
+ *
+ * Boundary contract (SURVEY.md §8 B-c):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in
+ *     `_host`.  The caller (PyTorch, or any other host) allocates all inputs, outputs and
+ *     workspaces; the library never allocates, frees or retains device memory, never
+ *     synchronises the device and launches only on `stream`.
+ *   - re-entrant, no global mutable state: the reference runs backward on the autograd worker
+ *     thread and fires NCCL from hooks (reference main.py:282), so calls may come from any thread.
+ *   - return value: 0 = ok, <0 = poet_status argument error, >0 = cudaError_t of the launch.
+ *   - layouts are row-major contiguous, channels-last ([B,S,C]); float tensors are fp32 and
+ *     16-byte aligned (vector loads / TMA).
+ *
+ * What each entry point replaces in the reference (file:line in aau-cns/poet):
+ *   poet_posenc_sine            models/position_encoding.py:40-60   PositionEmbeddingSine.forward
+ *   poet_bbox_embed_pad         models/position_encoding.py:71-84 + pose_estimation_transformer.py:203-239
+ *   poet_nchw_to_tokens(_bwd)   models/deformable_transformer.py:124-140 (flatten/transpose/cat, + level_embed)
+ *   poet_enc_reference_points   models/deformable_transformer.py:217-230 get_reference_points
+ *   poet_msda_fwd / _bwd        deformable_attention.MSDeformAttn core (third-party ms_deform_attn_forward/backward,
+ *                               called at deformable_transformer.py:201,283-285), optionally fused with the
+ *                               softmax and loc = ref + off/(W,H) of the module
+ *   poet_gemm                   every nn.Linear on the path (deformable_transformer.py:182-185,258-261,
+ *                               pose_estimation_transformer.py:684) and their dgrad/wgrad
+ *   poet_add_layernorm_fwd/bwd  residual + nn.LayerNorm (deformable_transformer.py:196-197,202-203,270-271,279-280,286-287)
+ *   poet_mha_smallq_fwd/bwd     nn.MultiheadAttention core on Q<=32 rows (deformable_transformer.py:277-278)
+ *   poet_heads_select_rot6d_*   class-specific select + rotation_6d_to_matrix (pose_estimation_transformer.py:354,365-374,434-451)
+ */
+#ifndef POET_B200_H_
+#define POET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* poet_stream_t; /* cudaStream_t */
+
+enum poet_status {
+  POET_OK = 0,
+  POET_ERR_BAD_SHAPE = -1,
+  POET_ERR_BAD_ALIGNMENT = -2,
+  POET_ERR_UNSUPPORTED = -3,
+  POET_ERR_NULL_POINTER = -4,
+  POET_ERR_WORKSPACE = -5,
+  POET_ERR_WRONG_DEVICE = -6
+};
+
+/* ---- library ------------------------------------------------------------------------- */
+int poet_version(void);                      /* 100*major + minor */
+int poet_sm(void);                           /* 100: the only target this library is built for */
+int poet_check_device(int device);           /* POET_OK iff `device` has compute capability 10.0 */
+const char* poet_error_string(int code);     /* static string for any return value */
+
+/* ---- A0: sinusoidal image position encoding ------------------------------------------- */
+/* mask [B,H,W] uint8 (1 = padded).  dim_t [F] = temperature^(2*floor(i/2)/F).
+ * layout 0: out is [B,2F,H,W] (reference layout).
+ * layout 1: out is token-major: row (b*S_total + row_offset + y*W + x), 2F channels, plus
+ *           level_embed[2F] if non-NULL (== lvl_pos_embed_flatten, deformable_transformer.py:133-135). */
+int poet_posenc_sine(const uint8_t* mask, const float* dim_t, const float* level_embed, float* out,
+                     int B, int H, int W, int F, float scale, int normalize, int layout,
+                     int S_total, int row_offset, poet_stream_t stream);
+
+/* ---- A1: bounding-box embedding with dummy padding -------------------------------------- */
+/* boxes [B,Q,4] already padded with -1; n_boxes [B] int32.  query_embeds [B,Q,2C], C = 8*F:
+ * real rows = [emb|emb], emb = per coord [sin(c*2^k) k<F | cos(c*2^k) k<F]; dummy rows = -10. */
+int poet_bbox_embed_pad(const float* boxes, const int32_t* n_boxes, float* query_embeds,
+                        int B, int Q, int F, poet_stream_t stream);
+
+/* ---- A6: flatten one NCHW level into the token matrix (and back) ------------------------ */
+/* tokens[(b*S_total + row_offset + hw), c] = src[b,c,hw] (+ add_vec[c] if non-NULL). */
+int poet_nchw_to_tokens(const float* src, const float* add_vec, float* tokens, int B, int C, int HW,
+                        int S_total, int row_offset, poet_stream_t stream);
+/* grad_src[b,c,hw] = grad_tokens[(b*S_total+row_offset+hw), c]; if grad_vec != NULL also
+ * grad_vec[c] += sum_{b,hw} grad_tokens[...] (grad_vec must be pre-initialised). */
+int poet_tokens_to_nchw(const float* grad_tokens, float* grad_src, float* grad_vec, int B, int C, int HW,
+                        int S_total, int row_offset, poet_stream_t stream);
+
+/* ---- A5: encoder reference points -------------------------------------------------------- */
+/* valid_ratios [B,L,2] (w,h).  out [B,S,L,2].  shapes_host [L*2] = (H_l, W_l). */
+int poet_enc_reference_points(const float* valid_ratios, float* out, const int32_t* shapes_host,
+                              int B, int L, poet_stream_t stream);
+
+/* ---- A2/A3: multi-scale deformable attention -------------------------------------------- */
+/* value [B,S,M,D] fp32.  shapes_host [L*2] = (H_l,W_l) on the HOST (no device sync).
+ * mode 0 ("core", == upstream ms_deform_attn_forward): a = sampling locations [B,Lq,M,L,P,2] in [0,1],
+ *         w = attention weights [B,Lq,M,L,P] (already soft-maxed), ref ignored.
+ * mode 1 ("block"): a = raw sampling offsets, w = raw attention logits, ref [B,Lq,L,2]; the kernel
+ *         applies softmax over L*P and loc = ref + off/(W_l,H_l) itself.
+ * lda / ldw: row strides (floats) between consecutive (b,q) rows of a / w, so both may live
+ *         inside one fused projection output row.  out [B,Lq,M*D]. */
+int poet_msda_fwd(const float* value, const float* a, int64_t lda, const float* w, int64_t ldw,
+                  const float* ref, float* out, const int32_t* shapes_host,
+                  int B, int S, int Lq, int M, int D, int L, int P, int mode, poet_stream_t stream);
+/* grad_value [B,S,M,D] is ACCUMULATED into (caller zero-fills); grad_a / grad_w are overwritten
+ * (same strides as a / w).  mode 1 returns gradients w.r.t. the raw offsets / logits. */
+int poet_msda_bwd(const float* value, const float* a, int64_t lda, const float* w, int64_t ldw,
+                  const float* ref, const float* grad_out, float* grad_value, float* grad_a, float* grad_w,
+                  const int32_t* shapes_host, int B, int S, int Lq, int M, int D, int L, int P, int mode,
+                  poet_stream_t stream);
+
+/* ---- dense contractions ----------------------------------------------------------------- */
+/* C[M,N] = epilogue( alpha * op(A)[M,K] . op(B)[K,N] ).
+ *   a_kcontig = 1: A stored [M,K] (lda = row stride), 0: A stored [K,M].
+ *   b_kcontig = 1: B stored [N,K] (ldb = row stride) i.e. an nn.Linear weight, 0: B stored [K,N].
+ * epilogue, in order: + bias[N] (nullable); relu if flags&POET_GEMM_RELU;
+ *   *(gate>0) if gate != NULL (gate [M,N], ldc stride: relu backward); rows with row_mask[m]!=0 set to 0
+ *   (MSDeformAttn value masked_fill); + C_old if flags&POET_GEMM_ACCUMULATE.
+ * precision: POET_GEMM_FP32 (SIMT fp32 FFMA), POET_GEMM_BF16X3 / POET_GEMM_BF16 (tcgen05).
+ * workspace: poet_gemm_workspace_bytes(); may be NULL when that is 0. */
+enum { POET_GEMM_RELU = 1, POET_GEMM_ACCUMULATE = 2 };
+enum { POET_GEMM_FP32 = 0, POET_GEMM_BF16X3 = 1, POET_GEMM_BF16 = 2 };
+size_t poet_gemm_workspace_bytes(int M, int N, int K, int a_kcontig, int b_kcontig, int precision);
+int poet_gemm(const float* A, int64_t lda, int a_kcontig, const float* Bm, int64_t ldb, int b_kcontig,
+              float* C, int64_t ldc, int M, int N, int K, float alpha, const float* bias, const float* gate,
+              const uint8_t* row_mask, int flags, int precision, void* workspace, size_t workspace_bytes,
+              poet_stream_t stream);
+/* out[N] (+)= sum_m X[m,n]  (bias gradients).  accumulate=0 overwrites. */
+int poet_colsum(const float* X, int64_t ldx, float* out, int M, int N, int accumulate, poet_stream_t stream);
+
+/* ---- residual + LayerNorm ---------------------------------------------------------------- */
+/* z = x + r (r nullable); y = LN(z)*gamma + beta; y2 = y + pos (if y2 != NULL);
+ * xhat [R,C] and rstd [R] are saved for backward when non-NULL. C % 128 == 0, C <= 1024. */
+int poet_add_layernorm_fwd(const float* x, const float* r, const float* gamma, const float* beta,
+                           const float* pos, float* y, float* y2, float* xhat, float* rstd,
+                           int R, int C, float eps, poet_stream_t stream);
+/* dz = LN backward of (dy [+ dy2]); dgamma/dbeta [C] are ACCUMULATED into (caller zero-fills). */
+int poet_layernorm_bwd(const float* dy, const float* dy2, const float* xhat, const float* rstd,
+                       const float* gamma, float* dz, float* dgamma, float* dbeta,
+                       int R, int C, poet_stream_t stream);
+/* x[r,:] = 0 where mask[r] != 0 (in place; MSDeformAttn value masked_fill and its backward). */
+int poet_mask_rows(float* x, const uint8_t* mask, int R, int C, poet_stream_t stream);
+/* out = a + b (nullable b -> copy); elementwise over n floats, n % 4 == 0. */
+int poet_add(const float* a, const float* b, float* out, int64_t n, poet_stream_t stream);
+
+/* ---- decoder self-attention core (Q <= 32) ---------------------------------------------- */
+/* q,k,v: [B,Q,*] with row strides ldq/ldk/ldv (so they may be slices of one projection output);
+ * head m uses channels [m*D,(m+1)*D).  probs [B,M,Q,Q] saved.  out [B,Q,M*D]. */
+int poet_mha_smallq_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                        float* out, float* probs, int B, int Q, int M, int D, float scale, poet_stream_t stream);
+int poet_mha_smallq_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                        const float* probs, const float* grad_out, float* gq, int64_t ldgq, float* gk, int64_t ldgk,
+                        float* gv, int64_t ldgv, int B, int Q, int M, int D, float scale, poet_stream_t stream);
+
+/* ---- heads: class-specific select + 6D -> SO(3) ------------------------------------------ */
+/* rot_all [R, n_slots*6], trans_all [R, n_slots*3], classes [R] int64 (slot = max(cls,0); n_slots = 1 => slot 0).
+ * out: trans [R,3], rot6d [R,6] (selected, saved for backward), rotmat [R,9] row-major 3x3 with columns (x,y,z). */
+int poet_heads_select_rot6d_fwd(const float* rot_all, const float* trans_all, const int64_t* classes,
+                                float* trans, float* rot6d, float* rotmat, int R, int n_slots,
+                                poet_stream_t stream);
+/* grad_rot_all / grad_trans_all are fully overwritten (zeros outside the selected slot). */
+int poet_heads_select_rot6d_bwd(const float* rot6d, const int64_t* classes, const float* grad_trans,
+                                const float* grad_rotmat, float* grad_rot_all, float* grad_trans_all,
+                                int R, int n_slots, poet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POET_B200_H_ */

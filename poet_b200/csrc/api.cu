@@ -1,0 +1,66 @@
+// Library-level entry points of the C ABI (include/poet_b200.h) and the poet_gemm dispatcher.
+#include "common.cuh"
+
+int poet_gemm_simt(const float* A, int64_t lda, int a_kcontig, const float* Bm, int64_t ldb, int b_kcontig, float* C,
+                   int64_t ldc, int M, int N, int K, float alpha, const float* bias, const float* gate,
+                   const uint8_t* row_mask, int flags, cudaStream_t s);
+#ifdef POET_HAVE_TC_GEMM
+size_t poet_gemm_tc_workspace_bytes(int M, int N, int K, int a_kcontig, int b_kcontig, int precision);
+int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, int64_t ldb, int b_kcontig, float* C,
+                 int64_t ldc, int M, int N, int K, float alpha, const float* bias, const float* gate,
+                 const uint8_t* row_mask, int flags, int precision, void* workspace, size_t workspace_bytes,
+                 cudaStream_t s);
+bool poet_gemm_tc_supported(int M, int N, int K, int a_kcontig, int b_kcontig, int64_t lda, int64_t ldb, int64_t ldc);
+#endif
+
+extern "C" int poet_version(void) { return 1; }
+extern "C" int poet_sm(void) { return 100; }
+
+extern "C" int poet_check_device(int device) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return (int)e;
+  return (prop.major == 10 && prop.minor == 0) ? POET_OK : POET_ERR_WRONG_DEVICE;
+}
+
+extern "C" const char* poet_error_string(int code) {
+  switch (code) {
+    case POET_OK: return "ok";
+    case POET_ERR_BAD_SHAPE: return "poet_b200: bad shape";
+    case POET_ERR_BAD_ALIGNMENT: return "poet_b200: pointer or stride not 16-byte aligned";
+    case POET_ERR_UNSUPPORTED: return "poet_b200: unsupported configuration";
+    case POET_ERR_NULL_POINTER: return "poet_b200: required pointer is NULL";
+    case POET_ERR_WORKSPACE: return "poet_b200: workspace missing or too small";
+    case POET_ERR_WRONG_DEVICE: return "poet_b200: device is not compute capability 10.0 (B200)";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "poet_b200: unknown error";
+}
+
+extern "C" size_t poet_gemm_workspace_bytes(int M, int N, int K, int a_kcontig, int b_kcontig, int precision) {
+#ifdef POET_HAVE_TC_GEMM
+  if (precision != POET_GEMM_FP32) return poet_gemm_tc_workspace_bytes(M, N, K, a_kcontig, b_kcontig, precision);
+#endif
+  (void)M; (void)N; (void)K; (void)a_kcontig; (void)b_kcontig; (void)precision;
+  return 0;
+}
+
+extern "C" int poet_gemm(const float* A, int64_t lda, int a_kcontig, const float* Bm, int64_t ldb, int b_kcontig,
+                         float* C, int64_t ldc, int M, int N, int K, float alpha, const float* bias, const float* gate,
+                         const uint8_t* row_mask, int flags, int precision, void* workspace, size_t workspace_bytes,
+                         poet_stream_t stream) {
+  POET_REQUIRE(A && Bm && C, POET_ERR_NULL_POINTER);
+  POET_REQUIRE(M > 0 && N > 0 && K > 0, POET_ERR_BAD_SHAPE);
+  POET_REQUIRE(lda >= (a_kcontig ? K : M) && ldb >= (b_kcontig ? K : N) && ldc >= N, POET_ERR_BAD_SHAPE);
+  POET_REQUIRE(precision >= POET_GEMM_FP32 && precision <= POET_GEMM_BF16, POET_ERR_UNSUPPORTED);
+  cudaStream_t s = (cudaStream_t)stream;
+#ifdef POET_HAVE_TC_GEMM
+  if (precision != POET_GEMM_FP32 && poet_gemm_tc_supported(M, N, K, a_kcontig, b_kcontig, lda, ldb, ldc))
+    return poet_gemm_tc(A, lda, a_kcontig, Bm, ldb, b_kcontig, C, ldc, M, N, K, alpha, bias, gate, row_mask, flags,
+                        precision, workspace, workspace_bytes, s);
+#endif
+  (void)workspace; (void)workspace_bytes;
+  // small / ragged shapes (decoder rows, head outputs) always take the exact fp32 SIMT path
+  return poet_gemm_simt(A, lda, a_kcontig, Bm, ldb, b_kcontig, C, ldc, M, N, K, alpha, bias, gate, row_mask, flags, s);
+}

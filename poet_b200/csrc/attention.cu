@@ -1,0 +1,173 @@
+// Decoder self-attention core for Q <= 32 object queries.
+// Replaces the softmax(q k^T / sqrt(D)) v inside nn.MultiheadAttention as called at reference
+// models/deformable_transformer.py:277-278 (q = k = tgt + query_pos, v = tgt, no masks: dummy
+// queries attend and are attended, SURVEY.md §7 "exact semantics").  The in/out projections are
+// poet_gemm calls.  One warp per (image, head); lane i owns query row i.  Launch-latency-bound by
+// construction (B*M warps of ~Q*Q*D flops), so the kernel just keeps everything in registers/smem.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarps = 4;
+
+template <int D>
+__global__ void __launch_bounds__(kWarps * 32) mha_fwd_kernel(const float* __restrict__ q, int64_t ldq,
+                                                              const float* __restrict__ k, int64_t ldk,
+                                                              const float* __restrict__ v, int64_t ldv,
+                                                              float* __restrict__ out, float* __restrict__ probs,
+                                                              int B, int Q, int M, float scale) {
+  const int warp = blockIdx.x * kWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (warp >= B * M) return;
+  const int b = warp / M, m = warp % M;
+  const bool row = lane < Q;
+  float qi[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) qi[d] = row ? __ldg(q + ((int64_t)b * Q + lane) * ldq + m * D + d) * scale : 0.f;
+  float sc[32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    sc[j] = -INFINITY;
+    if (j < Q) {
+      const float* kj = k + ((int64_t)b * Q + j) * ldk + m * D;
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) s = fmaf(qi[d], __ldg(kj + d), s);
+      sc[j] = s;
+      mx = fmaxf(mx, s);
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (j < Q) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
+  const float inv = 1.f / sum;
+  float o[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) o[d] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (j < Q) {
+      const float pj = sc[j] * inv;
+      if (row && probs) probs[(((int64_t)b * M + m) * Q + lane) * Q + j] = pj;
+      const float* vj = v + ((int64_t)b * Q + j) * ldv + m * D;
+#pragma unroll
+      for (int d = 0; d < D; ++d) o[d] = fmaf(pj, __ldg(vj + d), o[d]);
+    }
+  if (row) {
+    float* op = out + ((int64_t)b * Q + lane) * (M * D) + m * D;
+#pragma unroll
+    for (int d = 0; d < D; d += 4) st4(op + d, make_float4(o[d], o[d + 1], o[d + 2], o[d + 3]));
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kWarps * 32) mha_bwd_kernel(const float* __restrict__ q, int64_t ldq,
+                                                              const float* __restrict__ k, int64_t ldk,
+                                                              const float* __restrict__ v, int64_t ldv,
+                                                              const float* __restrict__ probs, const float* __restrict__ go,
+                                                              float* __restrict__ gq, int64_t ldgq, float* __restrict__ gk,
+                                                              int64_t ldgk, float* __restrict__ gv, int64_t ldgv,
+                                                              int B, int Q, int M, float scale) {
+  __shared__ float s_p[kWarps][32][33];
+  __shared__ float s_ds[kWarps][32][33];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * kWarps + w;
+  if (warp >= B * M) return;
+  const int b = warp / M, m = warp % M;
+  const bool row = lane < Q;
+  float gi[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) gi[d] = row ? __ldg(go + ((int64_t)b * Q + lane) * (M * D) + m * D + d) : 0.f;
+  // dp_ij = <go_i, v_j>;  ds_ij = p_ij (dp_ij - sum_j p_ij dp_ij)
+  float dp[32], pr[32];
+  float dsum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    dp[j] = 0.f; pr[j] = 0.f;
+    if (j < Q) {
+      const float* vj = v + ((int64_t)b * Q + j) * ldv + m * D;
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) s = fmaf(gi[d], __ldg(vj + d), s);
+      dp[j] = s;
+      pr[j] = row ? __ldg(probs + (((int64_t)b * M + m) * Q + lane) * Q + j) : 0.f;
+      dsum = fmaf(pr[j], s, dsum);
+    }
+  }
+  float dq[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) dq[d] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (j < Q) {
+      const float ds = pr[j] * (dp[j] - dsum);
+      s_p[w][lane][j] = pr[j];
+      s_ds[w][lane][j] = ds;
+      const float* kj = k + ((int64_t)b * Q + j) * ldk + m * D;
+#pragma unroll
+      for (int d = 0; d < D; ++d) dq[d] = fmaf(ds, __ldg(kj + d), dq[d]);
+    }
+  if (row) {
+    float* p = gq + ((int64_t)b * Q + lane) * ldgq + m * D;
+#pragma unroll
+    for (int d = 0; d < D; ++d) p[d] = dq[d] * scale;
+  }
+  __syncwarp();
+  // lane j: dk_j = scale * sum_i ds_ij q_i ; dv_j = sum_i p_ij go_i
+  float dk[D], dv[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
+  for (int i = 0; i < Q; ++i) {
+    const float ds = row ? s_ds[w][i][lane] : 0.f, pp = row ? s_p[w][i][lane] : 0.f;
+    const float* qi = q + ((int64_t)b * Q + i) * ldq + m * D;
+    const float* gp = go + ((int64_t)b * Q + i) * (M * D) + m * D;
+#pragma unroll
+    for (int d = 0; d < D; ++d) { dk[d] = fmaf(ds, __ldg(qi + d), dk[d]); dv[d] = fmaf(pp, __ldg(gp + d), dv[d]); }
+  }
+  if (row) {
+    float* pk = gk + ((int64_t)b * Q + lane) * ldgk + m * D;
+    float* pv = gv + ((int64_t)b * Q + lane) * ldgv + m * D;
+#pragma unroll
+    for (int d = 0; d < D; ++d) { pk[d] = dk[d] * scale; pv[d] = dv[d]; }
+  }
+}
+
+}  // namespace
+
+extern "C" int poet_mha_smallq_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                                   float* out, float* probs, int B, int Q, int M, int D, float scale, poet_stream_t stream) {
+  POET_REQUIRE(q && k && v && out, POET_ERR_NULL_POINTER);
+  POET_REQUIRE(B > 0 && M > 0 && Q >= 1 && Q <= 32, POET_ERR_BAD_SHAPE);
+  POET_REQUIRE(poet_aligned16(out), POET_ERR_BAD_ALIGNMENT);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = poet_ceil_div(B * M, kWarps);
+  switch (D) {
+    case 8: mha_fwd_kernel<8><<<grid, kWarps * 32, 0, s>>>(q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale); break;
+    case 16: mha_fwd_kernel<16><<<grid, kWarps * 32, 0, s>>>(q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale); break;
+    case 32: mha_fwd_kernel<32><<<grid, kWarps * 32, 0, s>>>(q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale); break;
+    case 64: mha_fwd_kernel<64><<<grid, kWarps * 32, 0, s>>>(q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale); break;
+    default: return POET_ERR_UNSUPPORTED;
+  }
+  return poet_launch_status();
+}
+
+extern "C" int poet_mha_smallq_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                                   const float* probs, const float* grad_out, float* gq, int64_t ldgq, float* gk,
+                                   int64_t ldgk, float* gv, int64_t ldgv, int B, int Q, int M, int D, float scale,
+                                   poet_stream_t stream) {
+  POET_REQUIRE(q && k && v && probs && grad_out && gq && gk && gv, POET_ERR_NULL_POINTER);
+  POET_REQUIRE(B > 0 && M > 0 && Q >= 1 && Q <= 32, POET_ERR_BAD_SHAPE);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = poet_ceil_div(B * M, kWarps);
+#define POET_MHA_BWD(DD) mha_bwd_kernel<DD><<<grid, kWarps * 32, 0, s>>>(q, ldq, k, ldk, v, ldv, probs, grad_out, gq, ldgq, gk, ldgk, gv, ldgv, B, Q, M, scale)
+  switch (D) {
+    case 8: POET_MHA_BWD(8); break;
+    case 16: POET_MHA_BWD(16); break;
+    case 32: POET_MHA_BWD(32); break;
+    case 64: POET_MHA_BWD(64); break;
+    default: return POET_ERR_UNSUPPORTED;
+  }
+#undef POET_MHA_BWD
+  return poet_launch_status();
+}

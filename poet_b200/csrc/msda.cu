@@ -1,0 +1,320 @@
+// Multi-scale deformable attention: gather (forward) and scatter (backward) kernels.
+//
+// Replaces the third-party op behind `from deformable_attention import MSDeformAttn`
+// (reference models/deformable_transformer.py:24; upstream ms_deform_attn_forward/backward).
+// Sampling convention (pinned by oracle.msda_core_direct): pixel x = loc_x*W - 0.5,
+// y = loc_y*H - 0.5, bilinear with zero padding, a sample contributes iff -1 < x < W, -1 < y < H.
+//
+// Work decomposition (general path, any S / Lq): one thread per (b, q, m, 4-channel group).
+// The D/4 lanes that share a (b,q,m) sit next to each other in a warp, so every bilinear corner
+// is one contiguous D*4-byte segment per group (64 B at D=16, 128 B at D=32) fetched with
+// 128-bit loads, and the output row [B,Lq,M*D] is written as one fully coalesced float4 stream.
+// mode 1 fuses the module's softmax over L*P and loc = ref + off/(W_l,H_l), so the [B,Lq,M,L,P,2]
+// location and [B,Lq,M,L,P] attention tensors are never materialised (SURVEY.md §8d msda_block).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxLevels = 4;
+constexpr int kMaxLP = 32;   // L*P register budget
+
+struct Levels {
+  int H[kMaxLevels];
+  int W[kMaxLevels];
+  int start[kMaxLevels];
+};
+
+struct MsdaArgs {
+  const float* value; const float* a; int64_t lda; const float* w; int64_t ldw; const float* ref;
+  float* out;
+  const float* grad_out; float* grad_value; float* grad_a; float* grad_w;
+  int B, S, Lq, M, D, L, P;
+  Levels lv;
+};
+
+template <int LP>
+__device__ __forceinline__ void load_row(const float* __restrict__ p, float (&dst)[LP]) {
+#pragma unroll
+  for (int i = 0; i < LP; i += 4) {
+    float4 v = ldg4(p + i);
+    dst[i] = v.x; dst[i + 1] = v.y; dst[i + 2] = v.z; dst[i + 3] = v.w;
+  }
+}
+
+template <int LP>
+__device__ __forceinline__ void softmax_inplace(float (&x)[LP]) {
+  float mx = x[0];
+#pragma unroll
+  for (int i = 1; i < LP; ++i) mx = fmaxf(mx, x[i]);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < LP; ++i) { x[i] = expf(x[i] - mx); sum += x[i]; }
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int i = 0; i < LP; ++i) x[i] *= inv;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+template <int L, int P, bool FUSED>
+__global__ void __launch_bounds__(256) msda_fwd_kernel(const MsdaArgs p) {
+  constexpr int LP = L * P;
+  const int G = p.D >> 2;                                    // lanes per (b,q,m)
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)p.B * p.Lq * p.M * G;
+  if (t >= total) return;
+  const int c4 = (int)(t % G);
+  const int64_t bqm = t / G;
+  const int m = (int)(bqm % p.M);
+  const int64_t bq = bqm / p.M;
+  const int b = (int)(bq / p.Lq);
+
+  float aw[LP];
+  load_row<LP>(p.w + bq * p.ldw + m * LP, aw);
+  if (FUSED) softmax_inplace<LP>(aw);
+
+  const float* arow = p.a + bq * p.lda + m * LP * 2;
+  const float* vbase = p.value + ((int64_t)b * p.S * p.M + m) * p.D + c4 * 4;
+  const int64_t vstride = (int64_t)p.M * p.D;
+
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const int H = p.lv.H[l], W = p.lv.W[l];
+    const float* vl = vbase + (int64_t)p.lv.start[l] * vstride;
+    float rx = 0.f, ry = 0.f;
+    if (FUSED) { float2 r = __ldg(reinterpret_cast<const float2*>(p.ref + (bq * L + l) * 2)); rx = r.x; ry = r.y; }
+    float xy[2 * P];
+#pragma unroll
+    for (int i = 0; i < 2 * P; i += 4) {
+      float4 v = ldg4(arow + l * 2 * P + i);
+      xy[i] = v.x; xy[i + 1] = v.y; xy[i + 2] = v.z; xy[i + 3] = v.w;
+    }
+#pragma unroll
+    for (int s = 0; s < P; ++s) {
+      float lx = xy[2 * s], ly = xy[2 * s + 1];
+      if (FUSED) { lx = rx + lx / (float)W; ly = ry + ly / (float)H; }
+      const float x = lx * (float)W - 0.5f, y = ly * (float)H - 0.5f;
+      if (x > -1.f && y > -1.f && x < (float)W && y < (float)H) {
+        const float xf = floorf(x), yf = floorf(y);
+        const int x0 = (int)xf, y0 = (int)yf;
+        const float fx = x - xf, fy = y - yf;
+        const float a = aw[l * P + s];
+        const float w00 = (1.f - fy) * (1.f - fx) * a, w01 = (1.f - fy) * fx * a;
+        const float w10 = fy * (1.f - fx) * a, w11 = fy * fx * a;
+        const bool xl = x0 >= 0, xh = x0 + 1 < W, yl = y0 >= 0, yh = y0 + 1 < H;
+        const float* p00 = vl + ((int64_t)y0 * W + x0) * vstride;
+        float4 v00 = make_float4(0.f, 0.f, 0.f, 0.f), v01 = v00, v10 = v00, v11 = v00;
+        if (yl && xl) v00 = ldg4(p00);
+        if (yl && xh) v01 = ldg4(p00 + vstride);
+        if (yh && xl) v10 = ldg4(p00 + (int64_t)W * vstride);
+        if (yh && xh) v11 = ldg4(p00 + (int64_t)(W + 1) * vstride);
+        acc.x += w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x;
+        acc.y += w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y;
+        acc.z += w00 * v00.z + w01 * v01.z + w10 * v10.z + w11 * v11.z;
+        acc.w += w00 * v00.w + w01 * v01.w + w10 * v10.w + w11 * v11.w;
+      }
+    }
+  }
+  st4(p.out + t * 4, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float group_sum(float v, int G) {
+  for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void red_add4(float* p, float4 v) {
+  // one 128-bit reduction per corner (sm_90+): red.global.add.v4.f32
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+
+template <int L, int P, bool FUSED>
+__global__ void __launch_bounds__(256) msda_bwd_kernel(const MsdaArgs p) {
+  constexpr int LP = L * P;
+  const int G = p.D >> 2;
+  const int64_t total = (int64_t)p.B * p.Lq * p.M * G;       // host guarantees total % 32 == 0 handling below
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = t < total;
+  if (!live) t = total - 1;                                  // keep the warp converged for the shuffles
+  const int c4 = (int)(t % G);
+  const int64_t bqm = t / G;
+  const int m = (int)(bqm % p.M);
+  const int64_t bq = bqm / p.M;
+  const int b = (int)(bq / p.Lq);
+
+  float aw[LP];
+  load_row<LP>(p.w + bq * p.ldw + m * LP, aw);
+  if (FUSED) softmax_inplace<LP>(aw);
+
+  const float* arow = p.a + bq * p.lda + m * LP * 2;
+  const int64_t vstride = (int64_t)p.M * p.D;
+  const int64_t voff = ((int64_t)b * p.S * p.M + m) * p.D + c4 * 4;
+  const float4 go = ldg4(p.grad_out + t * 4);
+
+  float g_attn[LP], g_x[LP], g_y[LP];
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const int H = p.lv.H[l], W = p.lv.W[l];
+    const int64_t lbase = voff + (int64_t)p.lv.start[l] * vstride;
+    float rx = 0.f, ry = 0.f;
+    if (FUSED) { float2 r = __ldg(reinterpret_cast<const float2*>(p.ref + (bq * L + l) * 2)); rx = r.x; ry = r.y; }
+    float xy[2 * P];
+#pragma unroll
+    for (int i = 0; i < 2 * P; i += 4) {
+      float4 v = ldg4(arow + l * 2 * P + i);
+      xy[i] = v.x; xy[i + 1] = v.y; xy[i + 2] = v.z; xy[i + 3] = v.w;
+    }
+#pragma unroll
+    for (int s = 0; s < P; ++s) {
+      float lx = xy[2 * s], ly = xy[2 * s + 1];
+      if (FUSED) { lx = rx + lx / (float)W; ly = ry + ly / (float)H; }
+      const float x = lx * (float)W - 0.5f, y = ly * (float)H - 0.5f;
+      float ga = 0.f, gx = 0.f, gy = 0.f;
+      if (x > -1.f && y > -1.f && x < (float)W && y < (float)H) {
+        const float xf = floorf(x), yf = floorf(y);
+        const int x0 = (int)xf, y0 = (int)yf;
+        const float fx = x - xf, fy = y - yf;
+        const float a = aw[l * P + s];
+        const bool xl = x0 >= 0, xh = x0 + 1 < W, yl = y0 >= 0, yh = y0 + 1 < H;
+        const int64_t i00 = lbase + ((int64_t)y0 * W + x0) * vstride;
+        float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;      // <grad_out, corner value>
+        const float4 ga4 = make_float4(go.x * a, go.y * a, go.z * a, go.w * a);
+        if (yl && xl) {
+          d00 = dot4(go, ldg4(p.value + i00));
+          const float w = (1.f - fy) * (1.f - fx);
+          if (live) red_add4(p.grad_value + i00, make_float4(ga4.x * w, ga4.y * w, ga4.z * w, ga4.w * w));
+        }
+        if (yl && xh) {
+          d01 = dot4(go, ldg4(p.value + i00 + vstride));
+          const float w = (1.f - fy) * fx;
+          if (live) red_add4(p.grad_value + i00 + vstride, make_float4(ga4.x * w, ga4.y * w, ga4.z * w, ga4.w * w));
+        }
+        if (yh && xl) {
+          d10 = dot4(go, ldg4(p.value + i00 + (int64_t)W * vstride));
+          const float w = fy * (1.f - fx);
+          if (live) red_add4(p.grad_value + i00 + (int64_t)W * vstride,
+                             make_float4(ga4.x * w, ga4.y * w, ga4.z * w, ga4.w * w));
+        }
+        if (yh && xh) {
+          d11 = dot4(go, ldg4(p.value + i00 + (int64_t)(W + 1) * vstride));
+          const float w = fy * fx;
+          if (live) red_add4(p.grad_value + i00 + (int64_t)(W + 1) * vstride,
+                             make_float4(ga4.x * w, ga4.y * w, ga4.z * w, ga4.w * w));
+        }
+        ga = (1.f - fy) * (1.f - fx) * d00 + (1.f - fy) * fx * d01 + fy * (1.f - fx) * d10 + fy * fx * d11;
+        // d sampled / d x (pixels) and / d y, times attention weight; pixels = loc * size
+        gx = a * ((1.f - fy) * (d01 - d00) + fy * (d11 - d10)) * (float)W;
+        gy = a * ((1.f - fx) * (d10 - d00) + fx * (d11 - d01)) * (float)H;
+      }
+      g_attn[l * P + s] = group_sum(ga, G);
+      g_x[l * P + s] = group_sum(gx, G);
+      g_y[l * P + s] = group_sum(gy, G);
+    }
+  }
+
+  if (FUSED) {
+    // softmax backward: g_logit_i = a_i (g_attn_i - sum_j a_j g_attn_j); offsets: loc = ref + off/(W,H)
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < LP; ++i) dot += aw[i] * g_attn[i];
+#pragma unroll
+    for (int i = 0; i < LP; ++i) g_attn[i] = aw[i] * (g_attn[i] - dot);
+#pragma unroll
+    for (int l = 0; l < L; ++l)
+#pragma unroll
+      for (int s = 0; s < P; ++s) {
+        g_x[l * P + s] /= (float)p.lv.W[l];
+        g_y[l * P + s] /= (float)p.lv.H[l];
+      }
+  }
+  if (!live) return;
+  // the G lanes of a group split the stores: float4 chunk j is written by lane (j % G)
+  float* gw = p.grad_w + bq * p.ldw + m * LP;
+  float* ga = p.grad_a + bq * p.lda + m * LP * 2;
+#pragma unroll
+  for (int j = 0; j < LP / 4; ++j)
+    if (j % G == c4) st4(gw + j * 4, make_float4(g_attn[j * 4], g_attn[j * 4 + 1], g_attn[j * 4 + 2], g_attn[j * 4 + 3]));
+#pragma unroll
+  for (int j = 0; j < LP / 2; ++j)
+    if (j % G == c4) st4(ga + j * 4, make_float4(g_x[2 * j], g_y[2 * j], g_x[2 * j + 1], g_y[2 * j + 1]));
+}
+
+int fill_args(MsdaArgs& a, const int32_t* shapes_host, int B, int S, int Lq, int M, int D, int L, int P,
+              const float* value, const float* aa, int64_t lda, const float* w, int64_t ldw, const float* ref, int mode) {
+  POET_REQUIRE(value && aa && w && shapes_host, POET_ERR_NULL_POINTER);
+  POET_REQUIRE(mode == 0 || (mode == 1 && ref != nullptr), POET_ERR_NULL_POINTER);
+  POET_REQUIRE(B > 0 && S > 0 && Lq > 0 && M > 0, POET_ERR_BAD_SHAPE);
+  POET_REQUIRE(L >= 1 && L <= kMaxLevels && (L * P) % 4 == 0 && L * P <= kMaxLP, POET_ERR_UNSUPPORTED);
+  POET_REQUIRE(D == 8 || D == 16 || D == 32 || D == 64, POET_ERR_UNSUPPORTED);   // D/4 lanes must divide a warp
+  POET_REQUIRE(lda % 4 == 0 && ldw % 4 == 0 && lda >= (int64_t)M * L * P * 2 && ldw >= (int64_t)M * L * P,
+               POET_ERR_BAD_ALIGNMENT);
+  POET_REQUIRE(poet_aligned16(value) && poet_aligned16(aa) && poet_aligned16(w), POET_ERR_BAD_ALIGNMENT);
+  int start = 0;
+  for (int l = 0; l < L; ++l) {
+    a.lv.H[l] = shapes_host[2 * l]; a.lv.W[l] = shapes_host[2 * l + 1]; a.lv.start[l] = start;
+    POET_REQUIRE(a.lv.H[l] > 0 && a.lv.W[l] > 0, POET_ERR_BAD_SHAPE);
+    start += a.lv.H[l] * a.lv.W[l];
+  }
+  POET_REQUIRE(start == S, POET_ERR_BAD_SHAPE);
+  a.value = value; a.a = aa; a.lda = lda; a.w = w; a.ldw = ldw; a.ref = ref;
+  a.B = B; a.S = S; a.Lq = Lq; a.M = M; a.D = D; a.L = L; a.P = P;
+  return POET_OK;
+}
+
+template <bool BWD>
+int dispatch(const MsdaArgs& a, int mode, cudaStream_t s) {
+  const int64_t total = (int64_t)a.B * a.Lq * a.M * (a.D / 4);
+  const int grid = poet_ceil_div(total, 256);
+#define POET_MSDA_CASE(LL, PP)                                                                         \
+  if (a.L == LL && a.P == PP) {                                                                        \
+    if (BWD) { if (mode) msda_bwd_kernel<LL, PP, true><<<grid, 256, 0, s>>>(a);                         \
+               else msda_bwd_kernel<LL, PP, false><<<grid, 256, 0, s>>>(a); }                           \
+    else     { if (mode) msda_fwd_kernel<LL, PP, true><<<grid, 256, 0, s>>>(a);                         \
+               else msda_fwd_kernel<LL, PP, false><<<grid, 256, 0, s>>>(a); }                           \
+    return poet_launch_status();                                                                       \
+  }
+  POET_MSDA_CASE(4, 4)
+  POET_MSDA_CASE(4, 2)
+  POET_MSDA_CASE(3, 4)
+  POET_MSDA_CASE(2, 2)
+  POET_MSDA_CASE(2, 4)
+  POET_MSDA_CASE(1, 4)
+#undef POET_MSDA_CASE
+  return POET_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+extern "C" int poet_msda_fwd(const float* value, const float* a, int64_t lda, const float* w, int64_t ldw,
+                             const float* ref, float* out, const int32_t* shapes_host, int B, int S, int Lq,
+                             int M, int D, int L, int P, int mode, poet_stream_t stream) {
+  MsdaArgs args{};
+  int rc = fill_args(args, shapes_host, B, S, Lq, M, D, L, P, value, a, lda, w, ldw, ref, mode);
+  if (rc) return rc;
+  POET_REQUIRE(out != nullptr, POET_ERR_NULL_POINTER);
+  POET_REQUIRE(poet_aligned16(out), POET_ERR_BAD_ALIGNMENT);
+  args.out = out;
+  return dispatch<false>(args, mode, (cudaStream_t)stream);
+}
+
+extern "C" int poet_msda_bwd(const float* value, const float* a, int64_t lda, const float* w, int64_t ldw,
+                             const float* ref, const float* grad_out, float* grad_value, float* grad_a,
+                             float* grad_w, const int32_t* shapes_host, int B, int S, int Lq, int M, int D,
+                             int L, int P, int mode, poet_stream_t stream) {
+  MsdaArgs args{};
+  int rc = fill_args(args, shapes_host, B, S, Lq, M, D, L, P, value, a, lda, w, ldw, ref, mode);
+  if (rc) return rc;
+  POET_REQUIRE(grad_out && grad_value && grad_a && grad_w, POET_ERR_NULL_POINTER);
+  POET_REQUIRE(poet_aligned16(grad_out) && poet_aligned16(grad_value) && poet_aligned16(grad_a) &&
+               poet_aligned16(grad_w), POET_ERR_BAD_ALIGNMENT);
+  args.grad_out = grad_out; args.grad_value = grad_value; args.grad_a = grad_a; args.grad_w = grad_w;
+  return dispatch<true>(args, mode, (cudaStream_t)stream);
+}

@@ -1,0 +1,245 @@
+"""B200-native DeformableTransformer behind the reference's nn.Module surface.
+
+Mirror of reference models/deformable_transformer.py (class names, constructor signatures,
+attribute / state_dict names, forward signatures and return tuple) so it can replace
+``models.deformable_transformer`` (seam B-py2); every numeric step is a
+libpoet_b200 kernel via ``poet_b200.ops``:
+
+  flatten + level_embed        :124-140  -> ops.flatten_levels           (poet_nchw_to_tokens)
+  encoder reference points     :217-230  -> ops.enc_reference_points
+  encoder layer                :199-208  -> MSDeformAttn + ops.add_layernorm + ops.mlp
+  decoder layer                :275-292  -> in_proj GEMMs + ops.mha_smallq + MSDeformAttn + LN + FFN
+  next-layer query (x + pos)             -> second output of the LayerNorm kernel (fused)
+
+Dropout is the identity on the parity path (eval() or dropout=0); training with
+dropout > 0 uses the counter-based dropout of ops when available and raises otherwise.
+"""
+from __future__ import annotations
+
+import copy
+from typing import List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from . import ops
+from .deformable_attention import MSDeformAttn
+
+
+def _clones(module: nn.Module, n: int) -> nn.ModuleList:
+    return nn.ModuleList(copy.deepcopy(module) for _ in range(n))
+
+
+def _check_dropout(mod: nn.Module, p: float) -> None:
+    if mod.training and p > 0.0:
+        raise NotImplementedError("poet_b200: dropout > 0 in train mode is not implemented yet; build the model "
+                                  "with dropout=0 (the parity / benchmark configuration) or call eval()")
+
+
+class _SelfAttentionParams(nn.Module):
+    """Parameter container with nn.MultiheadAttention's state_dict layout
+    (in_proj_weight, in_proj_bias, out_proj.{weight,bias})."""
+
+    def __init__(self, embed_dim: int, num_heads: int, dropout: float = 0.0):
+        super().__init__()
+        self.embed_dim, self.num_heads, self.dropout = embed_dim, num_heads, dropout
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * embed_dim, embed_dim))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * embed_dim))
+        self.out_proj = nn.Linear(embed_dim, embed_dim)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.zeros_(self.out_proj.bias)
+
+    def forward(self, qk_in: torch.Tensor, v_in: torch.Tensor) -> torch.Tensor:
+        """qk_in = tgt + query_pos, v_in = tgt, both [B,Q,C] (batch-first) -> attention output [B,Q,C]."""
+        C = self.embed_dim
+        qk = ops.linear(qk_in, self.in_proj_weight[: 2 * C], self.in_proj_bias[: 2 * C])
+        v = ops.linear(v_in, self.in_proj_weight[2 * C:], self.in_proj_bias[2 * C:])
+        o = ops.mha_smallq(qk, v, self.num_heads)
+        return ops.linear(o, self.out_proj.weight, self.out_proj.bias)
+
+
+class DeformableTransformerEncoderLayer(nn.Module):
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4):
+        super().__init__()
+        if activation != "relu":
+            raise NotImplementedError("poet_b200 implements the 'relu' FFN used by every PoET config")
+        self.p_drop = dropout
+        self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.dropout2 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout3 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+
+    def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None,
+                query=None, emit_next_query=False):
+        """Reference signature plus two optional arguments used by our encoder stack: `query`
+        (= src + pos, produced by the previous layer's LayerNorm kernel) and `emit_next_query`."""
+        _check_dropout(self, self.p_drop)
+        if query is None:
+            query = src if pos is None else ops.add_tensors(src, pos)
+        attn = self.self_attn(query, reference_points, src, spatial_shapes, level_start_index, padding_mask)
+        src = ops.add_layernorm(src, attn, self.norm1.weight, self.norm1.bias, eps=self.norm1.eps)
+        ffn = ops.mlp(src, ((self.linear1.weight, self.linear1.bias), (self.linear2.weight, self.linear2.bias)))
+        if emit_next_query and pos is not None:
+            return ops.add_layernorm(src, ffn, self.norm2.weight, self.norm2.bias, pos=pos, eps=self.norm2.eps)
+        return ops.add_layernorm(src, ffn, self.norm2.weight, self.norm2.bias, eps=self.norm2.eps)
+
+
+class DeformableTransformerEncoder(nn.Module):
+    def __init__(self, encoder_layer, num_layers):
+        super().__init__()
+        self.layers = _clones(encoder_layer, num_layers)
+        self.num_layers = num_layers
+
+    @staticmethod
+    def get_reference_points(spatial_shapes, valid_ratios, device=None):
+        from .deformable_attention import host_shapes
+        return ops.enc_reference_points(valid_ratios.float().contiguous(), host_shapes(spatial_shapes))
+
+    def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None):
+        ref = self.get_reference_points(spatial_shapes, valid_ratios, device=src.device)
+        out, query = src, None
+        for i, layer in enumerate(self.layers):
+            last = i == self.num_layers - 1
+            res = layer(out, pos, ref, spatial_shapes, level_start_index, padding_mask, query=query,
+                        emit_next_query=not last)
+            out, query = res if isinstance(res, tuple) else (res, None)
+        return out
+
+
+class DeformableTransformerDecoderLayer(nn.Module):
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4):
+        super().__init__()
+        if activation != "relu":
+            raise NotImplementedError("poet_b200 implements the 'relu' FFN used by every PoET config")
+        self.p_drop = dropout
+        self.cross_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.self_attn = _SelfAttentionParams(d_model, n_heads, dropout=dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.dropout3 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout4 = nn.Dropout(dropout)
+        self.norm3 = nn.LayerNorm(d_model)
+
+    def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index,
+                src_padding_mask=None):
+        _check_dropout(self, self.p_drop)
+        if tgt.shape[1] > 32:
+            raise NotImplementedError("decoder self-attention kernel supports at most 32 object queries")
+        q = tgt if query_pos is None else ops.add_tensors(tgt, query_pos)
+        sa = self.self_attn(q, tgt)
+        if query_pos is not None:
+            tgt, q2 = ops.add_layernorm(tgt, sa, self.norm2.weight, self.norm2.bias, pos=query_pos, eps=self.norm2.eps)
+        else:
+            tgt = ops.add_layernorm(tgt, sa, self.norm2.weight, self.norm2.bias, eps=self.norm2.eps)
+            q2 = tgt
+        ca = self.cross_attn(q2, reference_points, src, src_spatial_shapes, level_start_index, src_padding_mask)
+        tgt = ops.add_layernorm(tgt, ca, self.norm1.weight, self.norm1.bias, eps=self.norm1.eps)
+        ffn = ops.mlp(tgt, ((self.linear1.weight, self.linear1.bias), (self.linear2.weight, self.linear2.bias)))
+        return ops.add_layernorm(tgt, ffn, self.norm3.weight, self.norm3.bias, eps=self.norm3.eps)
+
+
+class DeformableTransformerDecoder(nn.Module):
+    def __init__(self, decoder_layer, num_layers, return_intermediate=False):
+        super().__init__()
+        self.layers = _clones(decoder_layer, num_layers)
+        self.num_layers = num_layers
+        self.return_intermediate = return_intermediate
+        self.bbox_embed = None      # PoET never refines boxes (reference :302,:321)
+        self.class_embed = None
+
+    def forward(self, tgt, reference_points, src, src_spatial_shapes, src_level_start_index, src_valid_ratios,
+                query_pos=None, src_padding_mask=None):
+        if self.bbox_embed is not None:
+            raise NotImplementedError("iterative box refinement is not part of PoET")
+        if reference_points.shape[-1] != 2:
+            raise NotImplementedError("only 2-d reference points (PoET 'bbox' mode) are implemented")
+        ref_in = (reference_points[:, :, None] * src_valid_ratios[:, None]).contiguous()     # [B,Q,L,2]
+        out, inter, inter_ref = tgt, [], []
+        for layer in self.layers:
+            out = layer(out, query_pos, ref_in, src, src_spatial_shapes, src_level_start_index, src_padding_mask)
+            if self.return_intermediate:
+                inter.append(out)
+                inter_ref.append(reference_points)
+        if self.return_intermediate:
+            return torch.stack(inter), torch.stack(inter_ref)
+        return out, reference_points
+
+
+class DeformableTransformer(nn.Module):
+    def __init__(self, d_model=256, nhead=8, num_encoder_layers=6, num_decoder_layers=6, dim_feedforward=1024,
+                 dropout=0.1, activation="relu", return_intermediate_dec=False, num_feature_levels=4,
+                 dec_n_points=4, enc_n_points=4):
+        super().__init__()
+        self.d_model, self.nhead = d_model, nhead
+        self.encoder = DeformableTransformerEncoder(
+            DeformableTransformerEncoderLayer(d_model, dim_feedforward, dropout, activation, num_feature_levels,
+                                              nhead, enc_n_points), num_encoder_layers)
+        self.decoder = DeformableTransformerDecoder(
+            DeformableTransformerDecoderLayer(d_model, dim_feedforward, dropout, activation, num_feature_levels,
+                                              nhead, dec_n_points), num_decoder_layers, return_intermediate_dec)
+        self.level_embed = nn.Parameter(torch.empty(num_feature_levels, d_model))
+        # unused when reference points come from boxes (reference :157-158) but part of the checkpoint format
+        self.reference_points = nn.Linear(d_model, 2)
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        for m in self.modules():
+            if isinstance(m, MSDeformAttn):
+                m._reset_parameters()
+        nn.init.xavier_uniform_(self.reference_points.weight, gain=1.0)
+        nn.init.zeros_(self.reference_points.bias)
+        nn.init.normal_(self.level_embed)
+
+    @staticmethod
+    def get_valid_ratio(mask: torch.Tensor) -> torch.Tensor:
+        _, H, W = mask.shape
+        vh = (~mask[:, :, 0]).sum(1).float() / H
+        vw = (~mask[:, 0, :]).sum(1).float() / W
+        return torch.stack((vw, vh), -1)
+
+    def forward(self, srcs, masks, pos_embeds, query_embed=None, reference_points=None, pos_tokens=None):
+        """Reference signature (deformable_transformer.py:120).  `pos_tokens` (optional, ours):
+        lvl_pos_embed_flatten [B,S,C] already in token layout with level_embed added."""
+        if query_embed is None:
+            raise ValueError("query_embed is required")
+        if reference_points is None:
+            raise NotImplementedError("learned reference points are not used by PoET ('bbox' mode only)")
+        shapes = tuple((int(s.shape[2]), int(s.shape[3])) for s in srcs)
+        src = ops.flatten_levels(list(srcs))
+        pos = pos_tokens if pos_tokens is not None else ops.flatten_levels(list(pos_embeds), self.level_embed)
+        mask = torch.cat([m.flatten(1) for m in masks], 1)
+        spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=src.device)
+        spatial_shapes._poet_host = shapes
+        level_start = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
+        valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
+        pad = mask.to(torch.uint8)              # converted once; every MSDeformAttn layer reuses it
+
+        memory = self.encoder(src, spatial_shapes, level_start, valid_ratios, pos, pad)
+
+        C = memory.shape[2]
+        if query_embed.dim() == 2:
+            query_embed = query_embed.unsqueeze(0).expand(memory.shape[0], -1, -1)
+        query_pos = query_embed[..., :C].contiguous()
+        tgt = query_embed[..., C:].contiguous()
+        hs, inter_refs = self.decoder(tgt, reference_points, memory, spatial_shapes, level_start, valid_ratios,
+                                      query_pos, pad)
+        return hs, reference_points, inter_refs, None, None
+
+
+def build_deforamble_transformer(args):      # (sic) the reference spells it this way, :358
+    return DeformableTransformer(
+        d_model=args.hidden_dim, nhead=args.nheads, num_encoder_layers=args.enc_layers,
+        num_decoder_layers=args.dec_layers, dim_feedforward=args.dim_feedforward, dropout=args.dropout,
+        activation="relu", return_intermediate_dec=True, num_feature_levels=args.num_feature_levels,
+        dec_n_points=args.dec_n_points, enc_n_points=args.enc_n_points)

@@ -1,0 +1,530 @@
+"""Raw wrappers over the C ABI and the torch.autograd.Function bindings built on them.
+
+PyTorch is plumbing here: it owns device memory, the CUDA stream and the autograd tape; every
+numeric operation below is a call into libpoet_b200.so.  Nothing in this file has a CPU or
+eager-PyTorch fallback: a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+GEMM_FP32, GEMM_BF16X3, GEMM_BF16 = 0, 1, 2
+_PRECISION = {"fp32": GEMM_FP32, "bf16x3": GEMM_BF16X3, "bf16": GEMM_BF16}
+_state = {"precision": GEMM_FP32, "launches": 0}
+
+
+def set_gemm_precision(name: str) -> None:
+    """'fp32' (SIMT FFMA), 'bf16x3' (tcgen05 split-bf16, fp32-grade) or 'bf16' (tcgen05 single pass)."""
+    _state["precision"] = _PRECISION[name]
+
+
+def get_gemm_precision() -> str:
+    return {v: k for k, v in _PRECISION.items()}[_state["precision"]]
+
+
+def launch_count() -> int:
+    """Number of libpoet_b200 kernel-launching calls issued so far (bench.py's gpu_launches)."""
+    return _state["launches"]
+
+
+# ------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.PoetLibraryError("poet_b200 ops run on CUDA tensors only (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _stream(t: torch.Tensor):
+    _lib.require_b200(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+_timing = {"on": False, "events": {}}
+
+
+def kernel_timing(enable: bool) -> None:
+    """bench.py: bracket every library call with CUDA events on the launching stream."""
+    _timing["on"] = enable
+    if enable:
+        _timing["events"] = {}
+        _timing["work"] = {}
+
+
+def kernel_times_ms() -> dict:
+    """name -> (total ms, launches, algorithmic bytes, flops); call after a device synchronize."""
+    work = _timing.get("work", {})
+    return {k: (sum(s.elapsed_time(e) for s, e in v), len(v), *work.get(k, (0, 0))) for k, v in _timing["events"].items()}
+
+
+def _call(name: str, *args, tag: Optional[str] = None, work=None) -> None:
+    """`tag` / `work` = (algorithmic bytes, flops) only feed bench.py's per-kernel roofline table."""
+    _state["launches"] += 1
+    if _timing["on"]:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = getattr(_lib.lib(), name)(*args)
+        e.record()
+        key = name if tag is None else f"{name}[{tag}]"
+        _timing["events"].setdefault(key, []).append((s, e))
+        if work is not None:
+            acc = _timing.setdefault("work", {}).setdefault(key, [0, 0])
+            acc[0] += work[0]
+            acc[1] += work[1]
+    else:
+        rc = getattr(_lib.lib(), name)(*args)
+    if rc != 0:
+        _lib.check(rc, name)
+
+
+def shapes_array(shapes: Sequence[Tuple[int, int]]):
+    flat = [int(v) for hw in shapes for v in hw]
+    return (C.c_int32 * len(flat))(*flat)
+
+
+# ------------------------------------------------------------------------------------------
+# raw ops (no autograd)
+# ------------------------------------------------------------------------------------------
+def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_kcontig: bool = True, b_kcontig: bool = True,
+         lda: Optional[int] = None, ldb: Optional[int] = None, bias=None, relu=False, gate=None, row_mask=None,
+         out: Optional[torch.Tensor] = None, accumulate=False, alpha: float = 1.0,
+         precision: Optional[int] = None) -> torch.Tensor:
+    """out[M,N] = epi(alpha * op(A) @ op(B)); see include/poet_b200.h poet_gemm."""
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    lda = (K if a_kcontig else M) if lda is None else lda
+    ldb = (K if b_kcontig else N) if ldb is None else ldb
+    prec = _state["precision"] if precision is None else precision
+    ws, ws_bytes = None, 0
+    if prec != GEMM_FP32:
+        ws_bytes = _lib.lib().poet_gemm_workspace_bytes(M, N, K, int(a_kcontig), int(b_kcontig), prec)
+        if ws_bytes:
+            ws = torch.empty(ws_bytes, device=A.device, dtype=torch.uint8)
+    flags = (1 if relu else 0) | (2 if accumulate else 0)
+    _call("poet_gemm", _p(A), lda, int(a_kcontig), _p(Bm), ldb, int(b_kcontig), _p(out), out.stride(0), M, N, K,
+          alpha, _p(bias), _p(gate), _p(row_mask), flags, prec, _p(ws), ws_bytes, _stream(A),
+          tag=f"{M}x{N}x{K}" if _timing["on"] else None, work=(4 * (M * K + N * K + M * N), 2 * M * N * K))
+    return out
+
+
+def colsum(X: torch.Tensor, M: int, N: int, out: Optional[torch.Tensor] = None, accumulate=False) -> torch.Tensor:
+    if out is None:
+        out = torch.empty(N, device=X.device, dtype=torch.float32)
+    _call("poet_colsum", _p(X), N, _p(out), M, N, int(accumulate), _stream(X))
+    return out
+
+
+def mask_rows_(x2d: torch.Tensor, mask_u8: torch.Tensor) -> torch.Tensor:
+    _call("poet_mask_rows", _p(x2d), _p(mask_u8), x2d.shape[0], x2d.shape[1], _stream(x2d))
+    return x2d
+
+
+def add(a: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
+    out = torch.empty_like(a)
+    _call("poet_add", _p(a), _p(b), _p(out), a.numel(), _stream(a))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# autograd: Linear / FFN / MLP
+# ------------------------------------------------------------------------------------------
+def _linear_bwd(gy2: torch.Tensor, x2: torch.Tensor, W: torch.Tensor, need_x: bool, need_w: bool, need_b: bool,
+                gate: Optional[torch.Tensor] = None):
+    """gy2 [R,N], x2 [R,K], W [N,K] -> (dx [R,K] (gated by `gate`>0 if given), dW [N,K], db [N])."""
+    R, N = gy2.shape
+    K = x2.shape[1]
+    dx = gemm(gy2, W, R, K, N, a_kcontig=True, b_kcontig=False, gate=gate) if need_x else None
+    dW = gemm(gy2, x2, N, K, R, a_kcontig=False, b_kcontig=False) if need_w else None
+    db = colsum(gy2, R, N) if need_b else None
+    return dx, dW, db
+
+
+class _Linear(torch.autograd.Function):
+    """y = x W^T + b, rows with row_mask zeroed (MSDeformAttn value_proj + masked_fill)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, row_mask, mask_grad_inplace):
+        ctx.mask_grad_inplace = mask_grad_inplace
+        x2 = _chk(x).view(-1, x.shape[-1])
+        W = _chk(W)
+        R, K = x2.shape
+        N = W.shape[0]
+        y = gemm(x2, W, R, N, K, bias=b, row_mask=row_mask)
+        ctx.save_for_backward(x2, W)
+        ctx.row_mask = row_mask
+        ctx.has_bias = b is not None
+        ctx.xshape = x.shape
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, W = ctx.saved_tensors
+        gy2 = _chk(gy).view(-1, gy.shape[-1])
+        if ctx.row_mask is not None:
+            gy2 = mask_rows_(gy2 if ctx.mask_grad_inplace else gy2.clone(), ctx.row_mask)
+        dx, dW, db = _linear_bwd(gy2, x2, W, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                 ctx.has_bias and ctx.needs_input_grad[2])
+        return (dx.view(ctx.xshape) if dx is not None else None), dW, db, None, None
+
+
+def linear(x, W, b=None, row_mask=None, mask_grad_inplace=False):
+    return _Linear.apply(x, W, b, row_mask, mask_grad_inplace)
+
+
+class _MLP(torch.autograd.Function):
+    """Chain of Linear layers with ReLU between them (FFN blocks: deformable_transformer.py:193-197,
+    267-271; pose heads MLP: pose_estimation_transformer.py:677-689).  The ReLU lives in the
+    producing GEMM's epilogue; its backward is the `gate` epilogue of the dgrad GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, *wb):
+        n = len(wb) // 2
+        x2 = _chk(x).view(-1, x.shape[-1])
+        acts = [x2]
+        for i in range(n):
+            W, b = _chk(wb[2 * i]), wb[2 * i + 1]
+            h = acts[-1]
+            acts.append(gemm(h, W, h.shape[0], W.shape[0], W.shape[1], bias=b, relu=(i < n - 1)))
+        ctx.save_for_backward(*acts[:-1], *[wb[2 * i] for i in range(n)])
+        ctx.n = n
+        ctx.xshape = x.shape
+        return acts[-1].view(*x.shape[:-1], acts[-1].shape[1])
+
+    @staticmethod
+    def backward(ctx, gy):
+        n = ctx.n
+        acts, Ws = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
+        g = _chk(gy).view(-1, gy.shape[-1])
+        grads = [None] * (2 * n)
+        for i in range(n - 1, -1, -1):
+            need_x = i > 0 or ctx.needs_input_grad[0]
+            dx, dW, db = _linear_bwd(g, acts[i], Ws[i], need_x, ctx.needs_input_grad[1 + 2 * i],
+                                     ctx.needs_input_grad[2 + 2 * i], gate=acts[i] if i > 0 else None)
+            grads[2 * i], grads[2 * i + 1] = dW, db
+            g = dx
+        return (g.view(ctx.xshape) if g is not None else None, *grads)
+
+
+def mlp(x, layers: Sequence[Tuple[torch.Tensor, torch.Tensor]]):
+    flat = []
+    for W, b in layers:
+        flat += [W, b]
+    return _MLP.apply(x, *flat)
+
+
+# ------------------------------------------------------------------------------------------
+# autograd: residual + LayerNorm
+# ------------------------------------------------------------------------------------------
+class _AddLayerNorm(torch.autograd.Function):
+    """y = LN(x + r); optionally also y2 = y + pos (the next layer's query), one pass over HBM."""
+
+    @staticmethod
+    def forward(ctx, x, r, gamma, beta, pos, eps):
+        x2 = _chk(x).view(-1, x.shape[-1])
+        r2 = None if r is None else _chk(r).view(-1, x.shape[-1])
+        R, Cc = x2.shape
+        y = torch.empty_like(x2)
+        need_grad = any(ctx.needs_input_grad[:4])
+        xhat = torch.empty_like(x2) if need_grad else None
+        rstd = torch.empty(R, device=x.device, dtype=torch.float32) if need_grad else None
+        p2 = None if pos is None else _chk(pos).view(-1, Cc)
+        y2 = torch.empty_like(x2) if pos is not None else None
+        _call("poet_add_layernorm_fwd", _p(x2), _p(r2), _p(gamma), _p(beta), _p(p2), _p(y), _p(y2), _p(xhat), _p(rstd),
+              R, Cc, eps, _stream(x))
+        if need_grad:
+            ctx.save_for_backward(xhat, rstd, gamma)
+        ctx.has_r, ctx.has_pos, ctx.shape = r is not None, pos is not None, x.shape
+        if pos is not None:
+            return y.view(x.shape), y2.view(x.shape)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, gy, gy2=None):
+        xhat, rstd, gamma = ctx.saved_tensors
+        R, Cc = xhat.shape
+        gy = None if gy is None else _chk(gy).view(R, Cc)
+        gy2 = None if gy2 is None else _chk(gy2).view(R, Cc)
+        if gy is None:
+            gy, gy2 = gy2, None
+        dz = torch.empty_like(xhat)
+        dgb = torch.zeros(2, Cc, device=xhat.device, dtype=torch.float32)
+        _call("poet_layernorm_bwd", _p(gy), _p(gy2), _p(xhat), _p(rstd), _p(gamma), _p(dz), _p(dgb[0]), _p(dgb[1]),
+              R, Cc, _stream(xhat))
+        dz = dz.view(ctx.shape)
+        gpos = None
+        if ctx.has_pos and ctx.needs_input_grad[4]:
+            gpos = gy2.view(ctx.shape) if gy2 is not None else None
+        return dz, (dz if ctx.has_r else None), dgb[0], dgb[1], gpos, None
+
+
+def add_layernorm(x, r, gamma, beta, pos=None, eps: float = 1e-5):
+    return _AddLayerNorm.apply(x, r, gamma, beta, pos, eps)
+
+
+class _Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return add(_chk(a), _chk(b))
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add_tensors(a, b):
+    return _Add.apply(a, b)
+
+
+# ------------------------------------------------------------------------------------------
+# autograd: multi-scale deformable attention
+# ------------------------------------------------------------------------------------------
+def msda_fwd_raw(value, a, lda, w, ldw, ref, shapes, B, S, Lq, M, D, L, P, mode):
+    out = torch.empty((B, Lq, M * D), device=value.device, dtype=torch.float32)
+    _call("poet_msda_fwd", _p(value), _p(a), lda, _p(w), ldw, _p(ref), _p(out), shapes_array(shapes),
+          B, S, Lq, M, D, L, P, mode, _stream(value), tag=f"Lq={Lq}",
+          work=(4 * B * (S * M * D + 3 * Lq * M * L * P + Lq * M * D), 10 * B * Lq * M * D * L * P))
+    return out
+
+
+class _MsdaCore(torch.autograd.Function):
+    """mode 0: upstream MSDeformAttnFunction semantics (value, sampling_locations, attention_weights)."""
+
+    @staticmethod
+    def forward(ctx, value, shapes, loc, attn):
+        value, loc, attn = _chk(value), _chk(loc), _chk(attn)
+        B, S, M, D = value.shape
+        _, Lq, _, L, P, _ = loc.shape
+        ctx.dims = (B, S, Lq, M, D, L, P)
+        ctx.shapes = shapes
+        ctx.save_for_backward(value, loc, attn)
+        return msda_fwd_raw(value, loc, M * L * P * 2, attn, M * L * P, None, shapes, B, S, Lq, M, D, L, P, 0)
+
+    @staticmethod
+    def backward(ctx, go):
+        value, loc, attn = ctx.saved_tensors
+        B, S, Lq, M, D, L, P = ctx.dims
+        go = _chk(go)
+        gv = torch.zeros_like(value)
+        gl, ga = torch.empty_like(loc), torch.empty_like(attn)
+        _call("poet_msda_bwd", _p(value), _p(loc), M * L * P * 2, _p(attn), M * L * P, None, _p(go), _p(gv), _p(gl),
+              _p(ga), shapes_array(ctx.shapes), B, S, Lq, M, D, L, P, 0, _stream(value))
+        return gv, None, gl, ga
+
+
+def msda_core(value, shapes, loc, attn):
+    return _MsdaCore.apply(value, tuple(tuple(s) for s in shapes), loc, attn)
+
+
+class _MsdaBlock(torch.autograd.Function):
+    """mode 1: `oa` is the fused projection output [B,Lq, M*L*P*2 + M*L*P] = [offsets | logits];
+    softmax and loc = ref + off/(W,H) happen inside the gather kernel."""
+
+    @staticmethod
+    def forward(ctx, value, oa, ref, shapes, M, L, P):
+        value, oa, ref = _chk(value), _chk(oa), _chk(ref)
+        B, S, Cc = value.shape
+        Lq = oa.shape[1]
+        D = Cc // M
+        n_off = M * L * P * 2
+        ld = oa.shape[2]
+        ctx.dims = (B, S, Lq, M, D, L, P, n_off, ld)
+        ctx.shapes = shapes
+        ctx.save_for_backward(value, oa, ref)
+        logits = oa.view(-1)[n_off:]
+        return msda_fwd_raw(value, oa, ld, logits, ld, ref, shapes, B, S, Lq, M, D, L, P, 1)
+
+    @staticmethod
+    def backward(ctx, go):
+        value, oa, ref = ctx.saved_tensors
+        B, S, Lq, M, D, L, P, n_off, ld = ctx.dims
+        go = _chk(go)
+        gv = torch.zeros_like(value)
+        goa = torch.empty_like(oa)
+        _call("poet_msda_bwd", _p(value), _p(oa), ld, _p(oa.view(-1)[n_off:]), ld, _p(ref), _p(go), _p(gv), _p(goa),
+              _p(goa.view(-1)[n_off:]), shapes_array(ctx.shapes), B, S, Lq, M, D, L, P, 1, _stream(value),
+              tag=f"Lq={Lq}", work=(4 * B * (2 * S * M * D + 6 * Lq * M * L * P + Lq * M * D), 30 * B * Lq * M * D * L * P))
+        return gv, goa, None, None, None, None, None
+
+
+def msda_block(value, oa, ref, shapes, M, L, P):
+    return _MsdaBlock.apply(value, oa, ref, tuple(tuple(s) for s in shapes), M, L, P)
+
+
+# ------------------------------------------------------------------------------------------
+# autograd: decoder self-attention core
+# ------------------------------------------------------------------------------------------
+class _MhaSmallQ(torch.autograd.Function):
+    """qk [B,Q,2C] (q | k projections of tgt+pos), v [B,Q,C] -> softmax(q k^T / sqrt(D)) v  [B,Q,C]."""
+
+    @staticmethod
+    def forward(ctx, qk, v, M):
+        qk, v = _chk(qk), _chk(v)
+        B, Q, C2 = qk.shape
+        Cc = C2 // 2
+        D = Cc // M
+        out = torch.empty((B, Q, Cc), device=qk.device, dtype=torch.float32)
+        probs = torch.empty((B, M, Q, Q), device=qk.device, dtype=torch.float32)
+        scale = 1.0 / math.sqrt(D)
+        _call("poet_mha_smallq_fwd", _p(qk), C2, _p(qk.view(-1)[Cc:]), C2, _p(v), Cc, _p(out), _p(probs), B, Q, M, D,
+              scale, _stream(qk))
+        ctx.save_for_backward(qk, v, probs)
+        ctx.dims = (B, Q, M, D, Cc, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        qk, v, probs = ctx.saved_tensors
+        B, Q, M, D, Cc, scale = ctx.dims
+        go = _chk(go)
+        gqk, gv = torch.empty_like(qk), torch.empty_like(v)
+        _call("poet_mha_smallq_bwd", _p(qk), 2 * Cc, _p(qk.view(-1)[Cc:]), 2 * Cc, _p(v), Cc, _p(probs), _p(go),
+              _p(gqk), 2 * Cc, _p(gqk.view(-1)[Cc:]), 2 * Cc, _p(gv), Cc, B, Q, M, D, scale, _stream(qk))
+        return gqk, gv, None
+
+
+def mha_smallq(qk, v, M):
+    return _MhaSmallQ.apply(qk, v, M)
+
+
+# ------------------------------------------------------------------------------------------
+# autograd: heads tail
+# ------------------------------------------------------------------------------------------
+class _HeadsSelect(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rot_all, trans_all, classes, n_slots):
+        rot_all, trans_all = _chk(rot_all), _chk(trans_all)
+        lead = rot_all.shape[:-1]
+        R = rot_all.numel() // rot_all.shape[-1]
+        cls = None if classes is None else _chk(classes.reshape(-1), torch.int64)
+        dev = rot_all.device
+        trans = torch.empty((R, 3), device=dev, dtype=torch.float32)
+        rot6d = torch.empty((R, 6), device=dev, dtype=torch.float32)
+        rotmat = torch.empty((R, 9), device=dev, dtype=torch.float32)
+        _call("poet_heads_select_rot6d_fwd", _p(rot_all), _p(trans_all), _p(cls), _p(trans), _p(rot6d), _p(rotmat), R,
+              n_slots, _stream(rot_all))
+        ctx.save_for_backward(rot6d, cls) if cls is not None else ctx.save_for_backward(rot6d)
+        ctx.meta = (R, n_slots, cls is not None, rot_all.shape, trans_all.shape)
+        ctx.mark_non_differentiable(rot6d)
+        return trans.view(*lead, 3), rotmat.view(*lead, 3, 3), rot6d.view(*lead, 6)
+
+    @staticmethod
+    def backward(ctx, g_trans, g_rot, _g6):
+        R, n_slots, has_cls, rshape, tshape = ctx.meta
+        saved = ctx.saved_tensors
+        rot6d, cls = saved[0], (saved[1] if has_cls else None)
+        dev = rot6d.device
+        g_trans = torch.zeros((R, 3), device=dev) if g_trans is None else _chk(g_trans)
+        g_rot = torch.zeros((R, 9), device=dev) if g_rot is None else _chk(g_rot)
+        gr = torch.empty(rshape, device=dev, dtype=torch.float32)
+        gt = torch.empty(tshape, device=dev, dtype=torch.float32)
+        _call("poet_heads_select_rot6d_bwd", _p(rot6d), _p(cls), _p(g_trans), _p(g_rot), _p(gr), _p(gt), R, n_slots,
+              _stream(rot6d))
+        return gr, gt, None, None
+
+
+def heads_select_rot6d(rot_all, trans_all, classes, n_slots):
+    return _HeadsSelect.apply(rot_all, trans_all, classes, n_slots)
+
+
+# ------------------------------------------------------------------------------------------
+# position encodings / layout (no parameters except level_embed)
+# ------------------------------------------------------------------------------------------
+_dim_t_cache = {}
+
+
+def _dim_t(F: int, temperature: float, device) -> torch.Tensor:
+    key = (F, float(temperature), str(device))
+    if key not in _dim_t_cache:
+        k = torch.arange(F, dtype=torch.float32)
+        _dim_t_cache[key] = (temperature ** (2 * (k // 2) / F)).to(device)     # position_encoding.py:52-53
+    return _dim_t_cache[key]
+
+
+def posenc_sine_nchw(mask: torch.Tensor, F: int = 128, temperature: float = 10000.0, normalize: bool = True,
+                     scale: float = 2 * math.pi) -> torch.Tensor:
+    """mask [B,H,W] bool -> [B,2F,H,W] (reference layout, position_encoding.py:40-60)."""
+    B, H, W = mask.shape
+    m8 = _chk(mask.to(torch.uint8), torch.uint8)
+    out = torch.empty((B, 2 * F, H, W), device=mask.device, dtype=torch.float32)
+    _call("poet_posenc_sine", _p(m8), _p(_dim_t(F, temperature, mask.device)), None, _p(out), B, H, W, F, scale,
+          int(normalize), 0, 0, 0, _stream(out))
+    return out
+
+
+def posenc_sine_tokens_(out: torch.Tensor, mask: torch.Tensor, level_embed_row: Optional[torch.Tensor], row_offset: int,
+                        F: int = 128, temperature: float = 10000.0, normalize: bool = True,
+                        scale: float = 2 * math.pi) -> None:
+    """Writes pos (+level_embed) for one level straight into the token-major [B,S,2F] buffer."""
+    B, H, W = mask.shape
+    m8 = _chk(mask.to(torch.uint8), torch.uint8)
+    _call("poet_posenc_sine", _p(m8), _p(_dim_t(F, temperature, mask.device)), _p(level_embed_row), _p(out), B, H, W, F,
+          scale, int(normalize), 1, out.shape[1], row_offset, _stream(out))
+
+
+def bbox_embed_pad(boxes_padded: torch.Tensor, n_boxes: torch.Tensor, F: int) -> torch.Tensor:
+    """boxes [B,Q,4] (dummies -1), n_boxes [B] int32 -> query_embeds [B,Q,16F]."""
+    B, Q, _ = boxes_padded.shape
+    out = torch.empty((B, Q, 16 * F), device=boxes_padded.device, dtype=torch.float32)
+    _call("poet_bbox_embed_pad", _p(_chk(boxes_padded)), _p(_chk(n_boxes, torch.int32)), _p(out), B, Q, F, _stream(out))
+    return out
+
+
+def enc_reference_points(valid_ratios: torch.Tensor, shapes) -> torch.Tensor:
+    B, L, _ = valid_ratios.shape
+    S = sum(h * w for h, w in shapes)
+    out = torch.empty((B, S, L, 2), device=valid_ratios.device, dtype=torch.float32)
+    _call("poet_enc_reference_points", _p(_chk(valid_ratios)), _p(out), shapes_array(shapes), B, L, _stream(out))
+    return out
+
+
+class _FlattenLevels(torch.autograd.Function):
+    """L x [B,C,H,W] -> [B,S,C] tokens (deformable_transformer.py:124-140); optional per-level vector
+    add (level_embed) whose gradient is the per-level column sum."""
+
+    @staticmethod
+    def forward(ctx, level_embed, *maps):
+        B, Cc = maps[0].shape[:2]
+        hws = [m.shape[2] * m.shape[3] for m in maps]
+        S = sum(hws)
+        out = torch.empty((B, S, Cc), device=maps[0].device, dtype=torch.float32)
+        off = 0
+        for l, m in enumerate(maps):
+            vec = None if level_embed is None else level_embed[l]
+            _call("poet_nchw_to_tokens", _p(_chk(m)), _p(vec), _p(out), B, Cc, hws[l], S, off, _stream(out))
+            off += hws[l]
+        ctx.meta = (B, Cc, hws, S, [m.shape for m in maps], level_embed is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, Cc, hws, S, shapes, has_le = ctx.meta
+        g = _chk(g)
+        gle = torch.zeros((len(hws), Cc), device=g.device, dtype=torch.float32) if (has_le and ctx.needs_input_grad[0]) else None
+        outs = []
+        off = 0
+        for l, hw in enumerate(hws):
+            need = ctx.needs_input_grad[1 + l]
+            gm = torch.empty(shapes[l], device=g.device, dtype=torch.float32) if need else None
+            if need or gle is not None:
+                _call("poet_tokens_to_nchw", _p(g), _p(gm), _p(gle[l]) if gle is not None else None, B, Cc, hw, S, off,
+                      _stream(g))
+            outs.append(gm)
+            off += hw
+        return (gle, *outs)
+
+
+def flatten_levels(maps: Sequence[torch.Tensor], level_embed: Optional[torch.Tensor] = None) -> torch.Tensor:
+    return _FlattenLevels.apply(level_embed, *maps)

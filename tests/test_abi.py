@@ -1,0 +1,70 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds, loads and exports every symbol
+include/poet_b200.h declares, and the ctypes table covers exactly that set (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "poet_b200.h")
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(poet_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def library():
+    from poet_b200 import build
+    return ctypes.CDLL(build.build())
+
+
+def test_header_declares_entry_points():
+    names = declared_functions()
+    assert len(names) >= 20
+    for must in ("poet_msda_fwd", "poet_msda_bwd", "poet_gemm", "poet_add_layernorm_fwd", "poet_mha_smallq_fwd",
+                 "poet_heads_select_rot6d_fwd", "poet_posenc_sine", "poet_bbox_embed_pad", "poet_sm"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(library):
+    for name in declared_functions():
+        assert hasattr(library, name), f"{name} declared in include/poet_b200.h but not exported"
+
+
+def test_ctypes_table_matches_header():
+    from poet_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_functions()
+    header = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for name, (_, args) in _lib.SIGNATURES.items():
+        m = re.search(r"\b" + name + r"\s*\(([^;]*?)\)\s*;", header, flags=re.S)
+        assert m, name
+        params = [p for p in m.group(1).split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == len(args), f"{name}: header has {len(params)} parameters, ctypes table {len(args)}"
+
+
+def test_library_identity_without_gpu(library):
+    library.poet_sm.restype = ctypes.c_int
+    library.poet_error_string.restype = ctypes.c_char_p
+    assert library.poet_sm() == 100
+    assert library.poet_version() >= 1
+    assert b"NULL" in library.poet_error_string(-4)
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from poet_b200 import ops, _lib
+    with pytest.raises(_lib.PoetLibraryError):
+        ops.linear(torch.zeros(4, 8), torch.zeros(8, 8), torch.zeros(8))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "poet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f

@@ -1,0 +1,162 @@
+"""GPU parity tests, module level: our nn.Module mirrors (DeformableTransformer, PoET, MSDeformAttn)
+against the CPU oracle and against the golden fixtures produced by the unmodified reference.
+
+Tolerances (BASELINE.json north_star): |translation| <= 1e-4 abs, rot-6D / rotation matrix <= 1e-3."""
+import math
+
+import pytest
+import torch
+
+from oracle import poet_oracle as O
+from poet_b200 import synthetic as S
+from helpers import load_golden, sample_indices, oracle_poet_from_feats
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL_T, TOL_R = 1e-4, 1e-3
+
+
+def build_model(cfg, P):
+    from poet_b200.deformable_transformer import DeformableTransformer
+    from poet_b200.pose_estimation_transformer import PoET
+    tr = DeformableTransformer(cfg["d_model"], cfg["nheads"], cfg["enc_layers"], cfg["dec_layers"], cfg["dim_ff"], 0.0,
+                               "relu", True, cfg["n_levels"], cfg["n_points"], cfg["n_points"])
+    model = PoET(None, tr, cfg["num_queries"], cfg["n_levels"], cfg["n_classes"], class_mode=cfg["class_mode"])
+    model.load_state_dict({k: v for k, v in P.items() if not k.startswith("input_proj")}, strict=True)
+    return model.to(DEV).train()
+
+
+def stack_outputs(out):
+    t = torch.stack([a["pred_translation"] for a in out["aux_outputs"]] + [out["pred_translation"]])
+    R = torch.stack([a["pred_rotation"] for a in out["aux_outputs"]] + [out["pred_rotation"]])
+    return t, R
+
+
+@pytest.mark.parametrize("key", ["transformer/tiny/pad0", "transformer/tiny/pad1", "transformer/tiny16/pad1",
+                                 "transformer/cfg1/pad0"])
+def test_transformer_vs_reference_golden(key):
+    """DeformableTransformer.forward with the reference's call signature (NCHW srcs/pos) vs the fixture."""
+    from poet_b200 import ops
+    g = load_golden(key)
+    cfg = S.CONFIGS[g["cfg"]]
+    P = S.make_params(cfg)
+    model = build_model(cfg, P)
+    inp = S.make_inputs(cfg, pad_columns=g["pad"])
+    assert S.fingerprint(inp["srcs"]) == g["fp_inputs"]
+    masks = [m.to(DEV) for m in inp["masks"]]
+    pos = [ops.posenc_sine_nchw(m, cfg["d_model"] // 2) for m in masks]
+    qe, pb, pc, _ = model.build_queries(inp["boxes"], inp["labels"], DEV)
+    with torch.no_grad():
+        hs, init_ref, inter, _, _ = model.transformer([s.to(DEV) for s in inp["srcs"]], masks, pos, qe,
+                                                      pb[:, :, :2].contiguous())
+    assert float((hs.cpu() - g["hs"]).abs().max()) < 1e-4
+    assert torch.equal(init_ref.cpu(), g["init_ref"]) and torch.equal(inter.cpu(), g["inter_ref"])
+
+
+@pytest.mark.parametrize("key", ["poet/tiny/pad1", "poet/tiny16/pad0", "poet/cfg1/pad0", "poet/cfg2_b2/pad1"])
+def test_poet_path_vs_reference_golden(key):
+    """forward_pyramid + backward vs the fixture from the reference PoET (input_proj done by the oracle,
+    which is outside the CUDA path: SURVEY.md §8f N1)."""
+    g = load_golden(key)
+    cfg = S.CONFIGS[g["cfg"]]
+    P, feats, srcs, masks, inp, _, _, _ = oracle_poet_from_feats(cfg, g["pad"], need_grad=False)
+    model = build_model(cfg, {k: v.detach() for k, v in P.items()})
+    d_srcs = [s.detach().to(DEV).requires_grad_(True) for s in srcs]
+    out, n_boxes = model.forward_pyramid(d_srcs, [m.to(DEV) for m in masks], inp["boxes"], inp["labels"])
+    assert n_boxes == g["n_boxes"]
+    assert torch.equal(out["pred_boxes"].cpu(), g["pred_boxes"]) and torch.equal(out["pred_classes"].cpu(), g["pred_classes"])
+    t, R = stack_outputs(out)
+    assert float((t.detach().cpu() - g["translation"]).abs().max()) < TOL_T
+    assert float((R.detach().cpu() - g["rotation"]).abs().max()) < TOL_R
+    g_t, g_R = S.make_cotangents(cfg)
+    ((t * g_t.to(DEV)).sum() + (R * g_R.to(DEV)).sum()).backward()
+    checked = 0
+    for name, p in model.named_parameters():
+        rec = g["grads"].get(name)
+        if rec is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        flat = p.grad.detach().cpu().flatten()
+        scale = max(rec["norm"] / math.sqrt(flat.numel()), 1e-6)
+        assert float((flat[sample_indices(flat.numel())] - rec["samples"]).abs().max()) < 5e-3 * scale + 1e-5, name
+        assert abs(float(flat.double().norm()) - rec["norm"]) < 2e-3 * max(rec["norm"], 1e-3), name
+        checked += 1
+    assert checked > 20
+
+
+@pytest.mark.parametrize("name,pad", [("tiny16", True), ("cfg1", False), ("cfg2_b2", True)])
+def test_poet_path_vs_oracle_all_grads(name, pad):
+    """Every output of every decoder layer and the gradient of every parameter and of the input
+    pyramid vs the oracle (fp32 CPU) on identical seeded inputs."""
+    cfg = S.CONFIGS[name]
+    P = S.make_params(cfg)
+    inp = S.make_inputs(cfg, pad_columns=pad)
+    g_t, g_R = S.make_cotangents(cfg)
+    Pr = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    r_srcs = [s.clone().requires_grad_(True) for s in inp["srcs"]]
+    cap = {}
+    O.poet_path_forward(Pr, cfg, r_srcs, inp["masks"], inp["boxes"], inp["labels"], capture=cap)
+    O.synthetic_loss((cap["translation_all"], cap["rotation_all"]), g_t, g_R).backward()
+
+    model = build_model(cfg, P)
+    d_srcs = [s.to(DEV).requires_grad_(True) for s in inp["srcs"]]
+    out, _ = model.forward_pyramid(d_srcs, [m.to(DEV) for m in inp["masks"]], inp["boxes"], inp["labels"])
+    t, R = stack_outputs(out)
+    ((t * g_t.to(DEV)).sum() + (R * g_R.to(DEV)).sum()).backward()
+    assert float((t.detach().cpu() - cap["translation_all"]).abs().max()) < TOL_T
+    assert float((R.detach().cpu() - cap["rotation_all"]).abs().max()) < TOL_R
+    for k, p in model.named_parameters():
+        ref = Pr[k].grad
+        if ref is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        err = float((p.grad.cpu() - ref).abs().max())
+        assert err < 2e-3 * float(ref.abs().max()) + 1e-6, (k, err, float(ref.abs().max()))
+    for s_d, s_r in zip(d_srcs, r_srcs):
+        err = float((s_d.grad.cpu() - s_r.grad).abs().max())
+        assert err < 2e-3 * float(s_r.grad.abs().max()) + 1e-7
+
+
+def test_msdeformattn_seam_matches_oracle_module():
+    """Seam B-py1: MSDeformAttn.forward with the reference's argument list (tensor spatial shapes,
+    bool padding mask) vs oracle.msda_module, including gradients."""
+    from poet_b200.deformable_attention import MSDeformAttn
+    g = torch.Generator().manual_seed(8)
+    shapes = S.PYRAMIDS["REF640"]
+    S_ = sum(h * w for h, w in shapes)
+    B, Lq, C, M = 2, 12, 256, 8
+    mod = MSDeformAttn(C, 4, M, 4)
+    with torch.no_grad():
+        for p in mod.parameters():
+            p.add_(torch.randn(p.shape, generator=g) * 0.02)
+    query, src = torch.randn(B, Lq, C, generator=g), torch.randn(B, S_, C, generator=g)
+    ref_pts = torch.rand(B, Lq, 4, 2, generator=g)
+    mask = torch.rand(B, S_, generator=g) < 0.1
+    cot = torch.randn(B, Lq, C, generator=g)
+    P = {k: v.detach().clone().requires_grad_(True) for k, v in mod.state_dict().items()}
+    q_r, s_r = query.clone().requires_grad_(True), src.clone().requires_grad_(True)
+    ref = O.msda_module(P, "", q_r, ref_pts, s_r, shapes, mask, M, 4)
+    (ref * cot).sum().backward()
+    mod = mod.to(DEV)
+    q_d, s_d = query.to(DEV).requires_grad_(True), src.to(DEV).requires_grad_(True)
+    ss = torch.as_tensor(shapes, dtype=torch.long, device=DEV)
+    lsi = torch.cat((ss.new_zeros(1), ss.prod(1).cumsum(0)[:-1]))
+    out = mod(q_d, ref_pts.to(DEV), s_d, ss, lsi, mask.to(DEV))
+    (out * cot.to(DEV)).sum().backward()
+    assert float((out.detach().cpu() - ref.detach()).abs().max()) < 1e-4
+    assert float((q_d.grad.cpu() - q_r.grad).abs().max()) < 1e-3 * float(q_r.grad.abs().max()) + 1e-6
+    assert float((s_d.grad.cpu() - s_r.grad).abs().max()) < 1e-3 * float(s_r.grad.abs().max()) + 1e-6
+    for k, p in mod.named_parameters():
+        assert float((p.grad.cpu() - P[k].grad).abs().max()) < 2e-3 * float(P[k].grad.abs().max()) + 1e-6, k
+
+
+def test_native_library_is_loaded():
+    """The CUDA path must be libpoet_b200.so, not a silent fallback."""
+    from poet_b200 import _lib, ops
+    x = torch.randn(8, 256, device=DEV)
+    before = ops.launch_count()
+    ops.linear(x, torch.randn(256, 256, device=DEV), torch.zeros(256, device=DEV))
+    assert ops.launch_count() > before
+    maps = open("/proc/self/maps").read()
+    assert "libpoet_b200.so" in maps
+    assert _lib.lib().poet_check_device(0) == 0

@@ -1,0 +1,321 @@
+"""GPU parity tests, op level: every C-ABI kernel against the CPU oracle / fp64 torch math on the
+same seeded inputs.  Tolerances are written next to each check (fp32 kernels vs fp64 truth)."""
+import math
+
+import pytest
+import torch
+
+from oracle import poet_oracle as O
+from poet_b200 import synthetic as S
+from helpers import load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def ops():
+    from poet_b200 import ops as _ops
+    return _ops
+
+
+def rel_err(got, ref):
+    ref = ref.double()
+    return float((got.double().cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+
+
+def bad_fraction(got, ref, tol):
+    """Fraction of elements off by more than tol*max|ref|.  Bilinear-location gradients jump at integer
+    pixel coordinates, so an fp32 kernel and the fp64 oracle may legitimately disagree on the handful of
+    samples that sit within fp32 rounding of a pixel edge."""
+    ref = ref.double()
+    err = (got.double().cpu() - ref).abs() / ref.abs().max().clamp_min(1e-30)
+    return float((err > tol).double().mean())
+
+
+# ------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(160, 256, 256), (160, 66, 256), (160, 256, 66), (1600, 768, 256),
+                                   (3200, 1024, 256), (37, 50, 19), (25600, 256, 256)])
+@pytest.mark.parametrize("a_k,b_k", [(True, True), (True, False), (False, False), (False, True)])
+def test_gemm_fp32_layouts(M, N, K, a_k, b_k):
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn((M, K) if a_k else (K, M), generator=g)
+    Bm = torch.randn((N, K) if b_k else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    ref = (A.double() if a_k else A.double().t()) @ (Bm.double().t() if b_k else Bm.double()) + bias.double()
+    out = ops().gemm(A.to(DEV), Bm.to(DEV), M, N, K, a_kcontig=a_k, b_kcontig=b_k, bias=bias.to(DEV),
+                     precision=ops().GEMM_FP32)
+    assert rel_err(out, ref) < 2e-6 * math.sqrt(K)
+
+
+def test_gemm_epilogues_and_splitk():
+    o = ops()
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 512, 256, 4096
+    A, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g)
+    gate = torch.randn(M, N, generator=g)
+    mask = (torch.rand(M, generator=g) < 0.2).to(torch.uint8)
+    ref = A.double() @ W.double().t() + b.double()
+    relu = o.gemm(A.to(DEV), W.to(DEV), M, N, K, bias=b.to(DEV), relu=True, precision=o.GEMM_FP32)
+    assert rel_err(relu, ref.clamp_min(0)) < 1e-4
+    gated = o.gemm(A.to(DEV), W.to(DEV), M, N, K, bias=b.to(DEV), gate=gate.to(DEV), precision=o.GEMM_FP32)
+    assert rel_err(gated, ref * (gate > 0)) < 1e-4
+    masked = o.gemm(A.to(DEV), W.to(DEV), M, N, K, bias=b.to(DEV), row_mask=mask.to(DEV), precision=o.GEMM_FP32)
+    assert rel_err(masked, ref * (mask == 0)[:, None]) < 1e-4
+    # wgrad shape: tiny output, long K -> split-K path; with and without accumulate
+    X, dY = torch.randn(25600, 64, generator=g), torch.randn(25600, 96, generator=g)
+    ref_w = dY.double().t() @ X.double()
+    dW = o.gemm(dY.to(DEV), X.to(DEV), 96, 64, 25600, a_kcontig=False, b_kcontig=False, precision=o.GEMM_FP32)
+    assert rel_err(dW, ref_w) < 1e-4
+    base = torch.randn(96, 64, generator=g)
+    acc = o.gemm(dY.to(DEV), X.to(DEV), 96, 64, 25600, a_kcontig=False, b_kcontig=False, out=base.to(DEV).clone(),
+                 accumulate=True, precision=o.GEMM_FP32)
+    assert rel_err(acc, ref_w + base.double()) < 1e-4
+    cs = o.colsum(dY.to(DEV), 25600, 96)
+    assert rel_err(cs, dY.double().sum(0)) < 1e-5
+
+
+def test_linear_and_mlp_autograd():
+    o = ops()
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 50, 256, generator=g)
+    Ws = [torch.randn(256, 256, generator=g) * 0.06, torch.randn(256, 256, generator=g) * 0.06,
+          torch.randn(66, 256, generator=g) * 0.06]
+    bs = [torch.randn(256, generator=g) * 0.1, torch.randn(256, generator=g) * 0.1, torch.randn(66, generator=g) * 0.1]
+    cot = torch.randn(3, 50, 66, generator=g)
+
+    def run(dev, dt):
+        xs = x.to(dev, dt).requires_grad_(True)
+        ps = [(W.to(dev, dt).requires_grad_(True), b.to(dev, dt).requires_grad_(True)) for W, b in zip(Ws, bs)]
+        if dev == "cpu":
+            h = xs
+            for i, (W, b) in enumerate(ps):
+                h = torch.nn.functional.linear(h, W, b)
+                if i < 2:
+                    h = h.relu()
+        else:
+            h = o.mlp(xs, ps)
+        (h * cot.to(dev, dt)).sum().backward()
+        return [h.detach(), xs.grad] + [t.grad for pr in ps for t in pr]
+
+    ref, got = run("cpu", torch.float64), run(DEV, torch.float32)
+    for r, t in zip(ref, got):
+        assert rel_err(t, r) < 2e-5
+
+
+# ------------------------------------------------------------------------------- MSDA
+def _msda_inputs(B, M, D, Lq, P, shapes, seed):
+    g = torch.Generator().manual_seed(seed)
+    S_ = sum(h * w for h, w in shapes)
+    L = len(shapes)
+    value = torch.randn(B, S_, M, D, generator=g)
+    loc = torch.rand(B, Lq, M, L, P, 2, generator=g) * 1.6 - 0.3
+    loc[0, 0] = -1.0
+    attn = torch.softmax(torch.randn(B, Lq, M, L * P, generator=g), -1).view(B, Lq, M, L, P)
+    cot = torch.randn(B, Lq, M * D, generator=g)
+    return value, loc, attn, cot
+
+
+@pytest.mark.parametrize("B,M,D,Lq,P,shapes", [
+    (1, 2, 8, 2, 2, [(6, 4), (3, 2)]),                                   # upstream test.py shapes (D rounded to 8)
+    (2, 16, 16, 37, 4, [(30, 40), (15, 20), (8, 10), (4, 5)]),           # YCB-V head geometry on the REF pyramid
+    (2, 8, 32, 50, 4, [(30, 40), (15, 20), (8, 10), (4, 5)]),            # cfg1 head geometry
+    (1, 4, 64, 9, 4, [(6, 8), (3, 4), (2, 2), (1, 1)]),
+])
+def test_msda_core_fwd_bwd(B, M, D, Lq, P, shapes):
+    o = ops()
+    value, loc, attn, cot = _msda_inputs(B, M, D, Lq, P, shapes, seed=B + M + D)
+    v64, l64, a64 = (t.double().requires_grad_(True) for t in (value, loc, attn))
+    ref = O.msda_core(v64, shapes, l64, a64)
+    (ref * cot.double()).sum().backward()
+    v, l, a = (t.to(DEV).requires_grad_(True) for t in (value, loc, attn))
+    out = o.msda_core(v, shapes, l, a)
+    (out * cot.to(DEV)).sum().backward()
+    assert float(out[0, 0].abs().max()) == 0.0                            # dummy reference point -> exact zero
+    assert rel_err(out, ref) < 5e-6
+    assert rel_err(v.grad, v64.grad) < 5e-6
+    assert rel_err(a.grad, a64.grad) < 5e-6
+    assert bad_fraction(l.grad, l64.grad, 5e-5) < 1e-3
+
+
+def test_msda_block_matches_module_math():
+    """mode 1 (fused softmax + ref + off/(W,H)) == oracle module math, forward and all gradients."""
+    o = ops()
+    shapes = [(30, 40), (15, 20), (8, 10), (4, 5)]
+    B, M, D, Lq, L, P = 2, 16, 16, 64, 4, 4
+    g = torch.Generator().manual_seed(21)
+    S_ = sum(h * w for h, w in shapes)
+    value = torch.randn(B, S_, M * D, generator=g)
+    off = torch.randn(B, Lq, M * L * P * 2, generator=g) * 3
+    logit = torch.randn(B, Lq, M * L * P, generator=g)
+    ref_pts = torch.rand(B, Lq, L, 2, generator=g)
+    ref_pts[1, 3] = -1.0
+    cot = torch.randn(B, Lq, M * D, generator=g)
+    v64, o64, g64 = (t.double().requires_grad_(True) for t in (value, off, logit))
+    wh = torch.tensor([[w, h] for h, w in shapes], dtype=torch.float64)
+    loc = ref_pts.double()[:, :, None, :, None, :] + o64.view(B, Lq, M, L, P, 2) / wh[None, None, None, :, None, :]
+    a = torch.softmax(g64.view(B, Lq, M, L * P), -1).view(B, Lq, M, L, P)
+    ref = O.msda_core(v64.view(B, S_, M, D), shapes, loc, a)
+    (ref * cot.double()).sum().backward()
+    v = value.to(DEV).requires_grad_(True)
+    oa = torch.cat((off, logit), -1).to(DEV).requires_grad_(True)
+    out = o.msda_block(v, oa, ref_pts.to(DEV), shapes, M, L, P)
+    (out * cot.to(DEV)).sum().backward()
+    assert rel_err(out, ref) < 5e-6
+    assert rel_err(v.grad, v64.grad) < 5e-6
+    assert bad_fraction(oa.grad[..., : M * L * P * 2], o64.grad, 5e-5) < 1e-3
+    assert rel_err(oa.grad[..., M * L * P * 2:], g64.grad) < 5e-5
+
+
+def test_msda_full_size_properties():
+    """BASELINE cfg2 size (B=16, S=Lq=1600, M=16, D=16): linearity in value and a per-head checksum
+    against uniform attention on a constant map, which no CPU oracle run is needed for."""
+    o = ops()
+    shapes = [(30, 40), (15, 20), (8, 10), (4, 5)]
+    B, M, D, L, P = 16, 16, 16, 4, 4
+    S_ = Lq = 1600
+    g = torch.Generator().manual_seed(77)
+    v1 = torch.randn(B, S_, M, D, generator=g).to(DEV)
+    v2 = torch.randn(B, S_, M, D, generator=g).to(DEV)
+    loc = (torch.rand(B, Lq, M, L, P, 2, generator=g) * 0.8 + 0.1).to(DEV)
+    attn = torch.softmax(torch.randn(B, Lq, M, L * P, generator=g), -1).view(B, Lq, M, L, P).to(DEV)
+    a, b_, c = (o.msda_core(v, shapes, loc, attn) for v in (v1, v2, 2.0 * v1 - 3.0 * v2))
+    assert float((c - (2.0 * a - 3.0 * b_)).abs().max()) < 5e-5
+    const = torch.ones(B, S_, M, D, device=DEV) * torch.arange(1, M + 1, device=DEV).view(1, 1, M, 1)
+    out = o.msda_core(const, shapes, loc, attn).view(B, Lq, M, D)         # interior samples of a constant map
+    assert float((out - torch.arange(1, M + 1, device=DEV).view(1, 1, M, 1)).abs().max()) < 1e-4
+
+
+# ------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("R,C,with_r,with_pos", [(160, 256, True, True), (3200, 256, True, False), (77, 128, False, False),
+                                                 (50, 1024, True, True)])
+def test_add_layernorm_fwd_bwd(R, C, with_r, with_pos):
+    o = ops()
+    g = torch.Generator().manual_seed(R + C)
+    x, r, pos = (torch.randn(R, C, generator=g) for _ in range(3))
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    c1, c2 = torch.randn(R, C, generator=g), torch.randn(R, C, generator=g)
+
+    def run(dev, dt):
+        xs, rs, ga, be = (t.to(dev, dt).requires_grad_(True) for t in (x, r, gamma, beta))
+        ps = pos.to(dev, dt).requires_grad_(True)
+        if dev == "cpu":
+            y = torch.nn.functional.layer_norm(xs + rs if with_r else xs, (C,), ga, be, 1e-5)
+            y2 = y + ps
+        else:
+            res = o.add_layernorm(xs, rs if with_r else None, ga, be, pos=ps if with_pos else None)
+            y, y2 = res if with_pos else (res, None)
+        loss = (y * c1.to(dev, dt)).sum()
+        if with_pos:
+            loss = loss + (y2 * c2.to(dev, dt)).sum()
+        loss.backward()
+        outs = [y.detach(), xs.grad, ga.grad, be.grad]
+        if with_r:
+            outs.append(rs.grad)
+        if with_pos:
+            outs += [y2.detach(), ps.grad]
+        return outs
+
+    for r_, t_ in zip(run("cpu", torch.float64), run(DEV, torch.float32)):
+        assert rel_err(t_, r_) < 2e-5
+
+
+# ------------------------------------------------------------------------------- decoder self-attention
+@pytest.mark.parametrize("B,Q,M,D", [(16, 10, 16, 16), (3, 5, 8, 32), (2, 25, 8, 32), (1, 32, 4, 64)])
+def test_mha_smallq_fwd_bwd(B, Q, M, D):
+    o = ops()
+    C = M * D
+    g = torch.Generator().manual_seed(B * Q)
+    qk, v, cot = torch.randn(B, Q, 2 * C, generator=g), torch.randn(B, Q, C, generator=g), torch.randn(B, Q, C, generator=g)
+    qk64, v64 = qk.double().requires_grad_(True), v.double().requires_grad_(True)
+    q_, k_ = qk64[..., :C].view(B, Q, M, D).transpose(1, 2), qk64[..., C:].view(B, Q, M, D).transpose(1, 2)
+    p = torch.softmax(q_ @ k_.transpose(-1, -2) / math.sqrt(D), -1)
+    ref = (p @ v64.view(B, Q, M, D).transpose(1, 2)).transpose(1, 2).reshape(B, Q, C)
+    (ref * cot.double()).sum().backward()
+    qkd, vd = qk.to(DEV).requires_grad_(True), v.to(DEV).requires_grad_(True)
+    out = o.mha_smallq(qkd, vd, M)
+    (out * cot.to(DEV)).sum().backward()
+    assert rel_err(out, ref) < 1e-5
+    assert rel_err(qkd.grad, qk64.grad) < 2e-5
+    assert rel_err(vd.grad, v64.grad) < 1e-5
+
+
+# ------------------------------------------------------------------------------- heads tail
+@pytest.mark.parametrize("n_slots", [1, 9, 22])
+def test_heads_select_rot6d(n_slots):
+    o = ops()
+    g = torch.Generator().manual_seed(n_slots)
+    R = 160
+    rot, tr = torch.randn(R, n_slots * 6, generator=g), torch.randn(R, n_slots * 3, generator=g)
+    cls = torch.randint(-1, n_slots, (R,), generator=g)
+    ct, cR = torch.randn(R, 3, generator=g), torch.randn(R, 3, 3, generator=g)
+    slot = cls.clamp_min(0) if n_slots > 1 else torch.zeros(R, dtype=torch.long)
+    r64, t64 = rot.double().requires_grad_(True), tr.double().requires_grad_(True)
+    rows = torch.arange(R)
+    Rm = O.rotation_6d_to_matrix(r64.view(R, n_slots, 6)[rows, slot])
+    ts = t64.view(R, n_slots, 3)[rows, slot]
+    ((Rm * cR.double()).sum() + (ts * ct.double()).sum()).backward()
+    rd, td = rot.to(DEV).requires_grad_(True), tr.to(DEV).requires_grad_(True)
+    t, Rg, r6 = o.heads_select_rot6d(rd, td, cls.to(DEV) if n_slots > 1 else None, n_slots)
+    ((Rg * cR.to(DEV)).sum() + (t * ct.to(DEV)).sum()).backward()
+    assert rel_err(t, ts) == 0.0
+    assert rel_err(Rg, Rm) < 2e-6
+    assert rel_err(rd.grad, r64.grad) < 2e-5
+    assert rel_err(td.grad, t64.grad) == 0.0
+    # orthonormality of the produced rotations
+    eye = (Rg.transpose(1, 2) @ Rg - torch.eye(3, device=DEV)).abs().max()
+    assert float(eye) < 1e-5
+
+
+# ------------------------------------------------------------------------------- position encodings / layout
+def test_posenc_matches_reference_golden():
+    o = ops()
+    for key, rec in load_golden("posenc").items():
+        if not key.startswith("pos_"):
+            continue
+        got = o.posenc_sine_nchw(rec["mask"].to(DEV), 128)
+        # same fp32 argument; CUDA sinf/cosf vs CPU libm differ by <= 2 ulp at |arg| <= 2*pi
+        assert float((got.cpu() - rec["pos"]).abs().max()) < 1e-6, key
+        B, H, W = rec["mask"].shape
+        le = torch.randn(256)
+        tok = torch.zeros(B, H * W + 5, 256, device=DEV)
+        o.posenc_sine_tokens_(tok, rec["mask"].to(DEV), le.to(DEV), 3, F=128)
+        ref_tok = rec["pos"].flatten(2).transpose(1, 2) + le
+        assert float((tok[:, 3:3 + H * W].cpu() - ref_tok).abs().max()) < 1e-6
+        assert float(tok[:, :3].abs().max()) == 0.0 and float(tok[:, 3 + H * W:].abs().max()) == 0.0
+
+
+def test_bbox_embedding_matches_reference_golden():
+    from poet_b200.position_encoding import BoundingBoxEmbeddingSine
+    rec = load_golden("posenc")["bbox"]
+    got = BoundingBoxEmbeddingSine(32)(rec["boxes"].to(DEV)).cpu()
+    # arguments reach c * 2^31: needs the accurate (Payne-Hanek) sinf/cosf slow path
+    assert float((got - rec["embed"]).abs().max()) < 5e-7
+    qe = ops().bbox_embed_pad(torch.cat((rec["boxes"], -torch.ones(3, 4))).view(1, -1, 4).to(DEV),
+                              torch.tensor([rec["boxes"].shape[0]], dtype=torch.int32, device=DEV), 32)
+    assert torch.equal(qe[0, :, :256], qe[0, :, 256:])
+    assert float((qe[0, -3:] + 10).abs().max()) == 0.0
+
+
+def test_flatten_levels_and_reference_points():
+    o = ops()
+    cfg = S.CONFIGS["tiny16"]
+    inp = S.make_inputs(cfg, pad_columns=True)
+    le = torch.randn(4, 256)
+    srcs = [s.to(DEV).requires_grad_(True) for s in inp["srcs"]]
+    led = le.to(DEV).requires_grad_(True)
+    tok = o.flatten_levels(srcs, led)
+    ref = torch.cat([s.flatten(2).transpose(1, 2) + le[l] for l, s in enumerate(inp["srcs"])], 1)
+    assert torch.equal(tok.cpu(), ref)
+    cot = torch.randn(ref.shape)
+    (tok * cot.to(DEV)).sum().backward()
+    off = 0
+    for l, s in enumerate(inp["srcs"]):
+        hw = s.shape[2] * s.shape[3]
+        gref = cot[:, off:off + hw].transpose(1, 2).reshape(s.shape)
+        assert torch.equal(srcs[l].grad.cpu(), gref)
+        assert rel_err(led.grad[l], cot[:, off:off + hw].double().sum((0, 1))) < 1e-5
+        off += hw
+    vr = torch.stack([O.valid_ratio(m) for m in inp["masks"]], 1)
+    shapes = S.pyramid_of(cfg)
+    got = o.enc_reference_points(vr.to(DEV), shapes)
+    assert float((got.cpu() - O.encoder_reference_points(shapes, vr)).abs().max()) < 1e-6

@@ -339,7 +339,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("POET_GEMM_PRECISION", "fp32"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("POET_GEMM_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--no-kernel-table", dest="kernel_table", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -214,7 +214,9 @@ int poet_gemm_simt(const float* A, int64_t lda, int a_kcontig, const float* Bm, 
   const int64_t tiles = (int64_t)poet_ceil_div(M, bm) * poet_ceil_div(N, bn);
   int splits = 1;
   const bool linear_epi = !(flags & POET_GEMM_RELU) && gate == nullptr && row_mask == nullptr;
-  if (linear_epi && tiles < POET_NUM_SMS && K >= 512) {
+  // split-K (atomic accumulation) only for the weight-gradient shape (A = dY^T): forward and dgrad
+  // stay bitwise deterministic
+  if (linear_epi && !a_kcontig && tiles < POET_NUM_SMS && K >= 512) {
     splits = (int)((2 * POET_NUM_SMS + tiles - 1) / tiles);
     int max_splits = K / 128;
     if (splits > max_splits) splits = max_splits;

@@ -16,7 +16,10 @@ from . import _lib
 
 GEMM_FP32, GEMM_BF16X3, GEMM_BF16 = 0, 1, 2
 _PRECISION = {"fp32": GEMM_FP32, "bf16x3": GEMM_BF16X3, "bf16": GEMM_BF16}
-_state = {"precision": GEMM_FP32, "launches": 0}
+import os as _os
+
+# default: tcgen05 split-bf16 (fp32-grade) for the large contractions; the SIMT fp32 kernel serves the small ones
+_state = {"precision": _PRECISION[_os.environ.get("POET_GEMM_PRECISION", "bf16x3")], "launches": 0}
 
 
 def set_gemm_precision(name: str) -> None:

@@ -176,7 +176,7 @@ def test_msda_full_size_properties():
     g = torch.Generator().manual_seed(77)
     v1 = torch.randn(B, S_, M, D, generator=g).to(DEV)
     v2 = torch.randn(B, S_, M, D, generator=g).to(DEV)
-    loc = (torch.rand(B, Lq, M, L, P, 2, generator=g) * 0.8 + 0.1).to(DEV)
+    loc = (torch.rand(B, Lq, M, L, P, 2, generator=g) * 0.7 + 0.15).to(DEV)    # strictly interior on every level
     attn = torch.softmax(torch.randn(B, Lq, M, L * P, generator=g), -1).view(B, Lq, M, L, P).to(DEV)
     a, b_, c = (o.msda_core(v, shapes, loc, attn) for v in (v1, v2, 2.0 * v1 - 3.0 * v2))
     assert float((c - (2.0 * a - 3.0 * b_)).abs().max()) < 5e-5
@@ -319,3 +319,47 @@ def test_flatten_levels_and_reference_points():
     shapes = S.pyramid_of(cfg)
     got = o.enc_reference_points(vr.to(DEV), shapes)
     assert float((got.cpu() - O.encoder_reference_points(shapes, vr)).abs().max()) < 1e-6
+
+
+# ------------------------------------------------------------------------------- tcgen05 GEMM
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 3e-5), ("bf16", 2e-2)])
+@pytest.mark.parametrize("M,N,K,a_k,b_k", [
+    (25600, 256, 256, True, True),      # encoder projection, forward (NT)
+    (3200, 1024, 256, True, True),      # FFN1 forward
+    (3000, 256, 1024, True, True),      # FFN2 forward, ragged M (tile tail)
+    (25600, 256, 768, True, False),     # dgrad of the fused [offsets|logits] projection (NN, MN-major B)
+    (3200, 256, 1024, True, False),     # dgrad FFN1
+    (1024, 256, 25600, False, False),   # wgrad FFN1 (TN: both MN-major, split-K)
+    (256, 256, 3200, False, False),     # wgrad value_proj
+    (768, 256, 6400, False, False),     # wgrad fused projection (N tile 256, M 6 tiles)
+    (1600, 128, 200, True, True),       # BN=128 path, K tail (200 = 3*64 + 8)
+])
+def test_gemm_tcgen05(M, N, K, a_k, b_k, prec, tol):
+    o = ops()
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
+    A = torch.randn((M, K) if a_k else (K, M), generator=g)
+    Bm = torch.randn((N, K) if b_k else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    ref = (A.double() if a_k else A.double().t()) @ (Bm.double().t() if b_k else Bm.double()) + bias.double()
+    out = o.gemm(A.to(DEV), Bm.to(DEV), M, N, K, a_kcontig=a_k, b_kcontig=b_k, bias=bias.to(DEV),
+                 precision=o._PRECISION[prec])
+    err = rel_err(out, ref)
+    assert err < tol, f"{prec} {M}x{N}x{K} a_k={a_k} b_k={b_k}: rel err {err:.3e}"
+
+
+def test_gemm_tcgen05_epilogues():
+    o = ops()
+    g = torch.Generator().manual_seed(9)
+    M, N, K = 3200, 256, 256
+    A, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g)
+    gate = torch.randn(M, N, generator=g)
+    mask = (torch.rand(M, generator=g) < 0.2).to(torch.uint8)
+    base = torch.randn(M, N, generator=g)
+    ref = A.double() @ W.double().t() + b.double()
+    P = o.GEMM_BF16X3
+    assert rel_err(o.gemm(A.to(DEV), W.to(DEV), M, N, K, bias=b.to(DEV), relu=True, precision=P), ref.clamp_min(0)) < 3e-5
+    assert rel_err(o.gemm(A.to(DEV), W.to(DEV), M, N, K, bias=b.to(DEV), gate=gate.to(DEV), precision=P), ref * (gate > 0)) < 3e-5
+    assert rel_err(o.gemm(A.to(DEV), W.to(DEV), M, N, K, bias=b.to(DEV), row_mask=mask.to(DEV), precision=P),
+                   ref * (mask == 0)[:, None]) < 3e-5
+    acc = o.gemm(A.to(DEV), W.to(DEV), M, N, K, bias=b.to(DEV), out=base.to(DEV).clone(), accumulate=True, alpha=0.5, precision=P)
+    assert rel_err(acc, 0.5 * (ref - b.double()) + b.double() + base.double()) < 3e-5

@@ -7,7 +7,7 @@ import torch
 
 from oracle import poet_oracle as O
 from poet_b200 import synthetic as S
-from helpers import load_golden, sample_indices, oracle_poet_from_feats
+from helpers import load_golden, sample_indices, oracle_poet_from_feats, same_fingerprint
 
 
 def test_posenc_matches_reference():
@@ -42,7 +42,7 @@ def test_transformer_matches_reference(key):
     cfg = S.CONFIGS[g["cfg"]]
     P = S.make_params(cfg)
     inp = S.make_inputs(cfg, pad_columns=g["pad"])
-    assert S.fingerprint(inp["srcs"]) == g["fp_inputs"], "seeded generation is not reproducible here"
+    assert same_fingerprint(S.fingerprint(inp["srcs"]), g["fp_inputs"]), "seeded generation is not reproducible here"
     pos = [O.sine_position_embedding(m, cfg["d_model"] // 2) for m in inp["masks"]]
     qe, pb, _, _ = O.build_queries(inp["boxes"], inp["labels"], cfg["num_queries"], cfg["d_model"])
     cap = {}

@@ -212,12 +212,15 @@ def run_gpu(args):
     d_labels = [l.to(dev) for l in inp["labels"]]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def step(srcs, masks, boxes, labels):
-        reducer.zero()
-        out, _ = model.forward_pyramid(srcs, masks, boxes, labels)
+    def loss_fn(out):
         t = torch.stack([a["pred_translation"] for a in out["aux_outputs"]] + [out["pred_translation"]])
         R = torch.stack([a["pred_rotation"] for a in out["aux_outputs"]] + [out["pred_rotation"]])
-        loss = (t * g_t).sum() + (R * g_R).sum()
+        return (t * g_t).sum() + (R * g_R).sum()
+
+    def eager_step(srcs, masks, boxes, labels):
+        reducer.zero()
+        out, _ = model.forward_pyramid(srcs, masks, boxes, labels)
+        loss = loss_fn(out)
         loss.backward()
         reducer.all_reduce()
         return loss, out
@@ -227,29 +230,39 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    graphed = None
+    if args.graph:
+        from poet_b200.graph import GraphedStep
+        graphed = GraphedStep(model, loss_fn, d_srcs, d_masks, d_boxes, d_labels, reducer=reducer)
+
+        def step(srcs=None, masks=None, boxes=None, labels=None):
+            loss, out = graphed.run(srcs, masks, boxes, labels)
+            reducer.all_reduce()
+            return loss, out
+    else:
+        def step(srcs=None, masks=None, boxes=None, labels=None):
+            if srcs is None:
+                srcs, masks, boxes, labels = d_srcs, d_masks, d_boxes, d_labels
+            return eager_step(srcs, masks, boxes, labels)
+
     for _ in range(max(args.warmup, 3)):
-        step(d_srcs, d_masks, d_boxes, d_labels)
+        step()
     sync_all()
 
     # ---- device-resident timed region -------------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = ops.launch_count()
-    ops.kernel_timing(args.kernel_table)
     evs = []
     sync_all()
     for _ in range(args.steps):
         flush.fill_(1)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        step(d_srcs, d_masks, d_boxes, d_labels)
+        step()
         e.record()
         evs.append((s, e))
     sync_all()
-    launches = ops.launch_count() - launches0
-    ktimes = ops.kernel_times_ms() if args.kernel_table else {}
-    ops.kernel_timing(False)
     clocks = sampler.stop() if rank == 0 else None
     total_ms = sum(s.elapsed_time(e) for s, e in evs)
     tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -268,9 +281,12 @@ def run_gpu(args):
         flush.fill_(1)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        srcs = [s.to(dev, non_blocking=True) for s in h_srcs]
-        masks = [m.to(dev, non_blocking=True) for m in h_masks]
-        loss, out = step(srcs, masks, inp["boxes"], inp["labels"])          # host box lists: padded on host, one H2D
+        if graphed is not None:
+            loss, out = step(h_srcs, h_masks, inp["boxes"], inp["labels"])     # H2D into the graph's static buffers
+        else:
+            srcs = [s.to(dev, non_blocking=True) for s in h_srcs]
+            masks = [m.to(dev, non_blocking=True) for m in h_masks]
+            loss, out = step(srcs, masks, inp["boxes"], inp["labels"])          # host box lists: padded on host, one H2D
         host = [loss.detach().cpu(), out["pred_translation"].detach().cpu(), out["pred_rotation"].detach().cpu()]
         torch.cuda.synchronize()
         if it > 0:                                                         # first pass warms the pinned path
@@ -280,6 +296,26 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.item())
+
+    # ---- per-kernel table: an eager pass with CUDA events around every library call ----------
+    # (events cannot bracket nodes inside a replayed graph; the kernels and their arguments are identical)
+    ktimes, ksteps = {}, min(args.steps, 5)
+    launches = 0
+    if rank == 0 or world > 1:
+        l0 = ops.launch_count()
+        eager_step(d_srcs, d_masks, d_boxes, d_labels)
+        launches = (ops.launch_count() - l0) * args.steps          # launches replayed per step x timed steps
+        if args.kernel_table and rank == 0:
+            sync_all() if world == 1 else torch.cuda.synchronize()
+            ops.kernel_timing(True)
+            for _ in range(ksteps):
+                flush.fill_(1)
+                eager_step(d_srcs, d_masks, d_boxes, d_labels)
+            torch.cuda.synchronize()
+            ktimes = ops.kernel_times_ms()
+            ops.kernel_timing(False)
+    if world > 1:
+        dist.barrier()
 
     if rank == 0:
         peaks = load_peaks()
@@ -291,12 +327,14 @@ def run_gpu(args):
                 "data": "synthetic",
                 "config": config_dict(cfg, {"global_batch": B * world, "parallelism": f"dp{world}",
                                             "grad_allreduce_bytes": reducer.nbytes() if world > 1 else 0,
-                                            "gemm_precision": args.precision}),
+                                            "gemm_precision": args.precision,
+                                            "launch": "one CUDA graph per step" if args.graph else "eager",
+                                            "kernel_table": "eager pass, CUDA events around every library call"}),
                 "e2e": {"value": B * world * args.steps / (e2e_ms / 1e3), "unit": "images/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clocks}
         if ktimes:
-            line["roofline"], line["kernels"] = roofline_from(ktimes, peaks, args.steps, ms_per_step)
+            line["roofline"], line["kernels"] = roofline_from(ktimes, peaks, ksteps, ms_per_step)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg)
         print(json.dumps(line), flush=True)
@@ -342,6 +380,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("POET_GEMM_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--no-kernel-table", dest="kernel_table", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

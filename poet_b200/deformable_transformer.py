@@ -30,6 +30,22 @@ def _clones(module: nn.Module, n: int) -> nn.ModuleList:
     return nn.ModuleList(copy.deepcopy(module) for _ in range(n))
 
 
+_shape_cache = {}
+
+
+def _shape_tensors(shapes, device):
+    """spatial_shapes / level_start_index device tensors of the reference API, built once per
+    (pyramid, device): a host->device copy per forward would also break CUDA-graph capture.  The
+    host copy rides along as `_poet_host`, so no kernel launch ever needs a device->host sync."""
+    key = (shapes, str(device))
+    if key not in _shape_cache:
+        ss = torch.as_tensor(shapes, dtype=torch.long, device=device)
+        ss._poet_host = shapes
+        ls = torch.cat((ss.new_zeros((1,)), ss.prod(1).cumsum(0)[:-1]))
+        _shape_cache[key] = (ss, ls)
+    return _shape_cache[key]
+
+
 def _check_dropout(mod: nn.Module, p: float) -> None:
     if mod.training and p > 0.0:
         raise NotImplementedError("poet_b200: dropout > 0 in train mode is not implemented yet; build the model "
@@ -219,9 +235,7 @@ class DeformableTransformer(nn.Module):
         src = ops.flatten_levels(list(srcs))
         pos = pos_tokens if pos_tokens is not None else ops.flatten_levels(list(pos_embeds), self.level_embed)
         mask = torch.cat([m.flatten(1) for m in masks], 1)
-        spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=src.device)
-        spatial_shapes._poet_host = shapes
-        level_start = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
+        spatial_shapes, level_start = _shape_tensors(shapes, src.device)
         valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
         pad = mask.to(torch.uint8)              # converted once; every MSDeformAttn layer reuses it
 

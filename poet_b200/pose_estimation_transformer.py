@@ -201,14 +201,20 @@ class PoET(nn.Module):
     def forward_pyramid(self, srcs: Sequence[torch.Tensor], masks: Sequence[torch.Tensor], boxes, classes):
         """The benchmarked path: post-input_proj pyramid + boxes -> output dict.
         Position encodings are written straight into token layout (no NCHW pos tensors)."""
-        dev = srcs[0].device
-        qe, pb, pc, counts = self.build_queries(boxes, classes, dev)
-        B, C = srcs[0].shape[:2]
+        pb, pc, counts, n_dev = self._pad_boxes(boxes, classes, srcs[0].device)
+        return self.forward_padded(srcs, masks, pb, pc, n_dev), counts
+
+    def forward_padded(self, srcs, masks, pred_boxes, pred_classes, n_boxes_dev):
+        """Device-only part of the path (no host work, no syncs: capturable in a CUDA graph):
+        padded boxes [B,Q,4] / classes [B,Q] int64 / counts [B] int32, all on the device."""
+        qe = ops.bbox_embed_pad(pred_boxes, n_boxes_dev, int(self.hidden_dim // 8))
+        C = srcs[0].shape[1]
         S = sum(int(s.shape[2] * s.shape[3]) for s in srcs)
         pos_tokens = _PosTokens.apply(self.transformer.level_embed, C, S, *masks)
-        hs, _, _, _, _ = self.transformer(srcs, masks, None, qe, pb[:, :, :2].contiguous(), pos_tokens=pos_tokens)
-        t_all, R_all = self._heads(hs, pc)
-        return self._pack(t_all, R_all, pb, pc), counts
+        hs, _, _, _, _ = self.transformer(srcs, masks, None, qe, pred_boxes[:, :, :2].contiguous(),
+                                          pos_tokens=pos_tokens)
+        t_all, R_all = self._heads(hs, pred_classes)
+        return self._pack(t_all, R_all, pred_boxes, pred_classes)
 
     def forward(self, samples, targets=None):
         samples = _as_nested(samples)

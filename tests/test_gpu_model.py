@@ -16,6 +16,24 @@ DEV = "cuda:0"
 TOL_T, TOL_R = 1e-4, 1e-3
 
 
+# Gradient tolerances per GEMM precision.  The network is only piecewise smooth (ReLU kinks, bilinear
+# cell edges): an implementation whose forward differs from the oracle by eps flips a fraction ~eps of
+# those units, and every flip changes that unit's gradient by O(1).  fp32 kernels (eps ~1e-7) therefore
+# agree with the oracle's gradients to ~1e-3, the split-bf16 tensor-core path (eps ~1e-5) to ~1e-2,
+# while the forward outputs of both stay inside the 1e-4 / 1e-3 budget.  See DESIGN.md "gradient parity".
+GRAD_TOL = {"fp32": dict(l2=5e-3, elem=1e-3, frac=1e-2, mx=5e-2, samp=5e-3),
+            "bf16x3": dict(l2=2e-2, elem=5e-3, frac=2e-2, mx=1e-1, samp=3e-2)}
+
+
+@pytest.fixture(params=["fp32", "bf16x3"])
+def precision(request):
+    from poet_b200 import ops
+    old = ops.get_gemm_precision()
+    ops.set_gemm_precision(request.param)
+    yield request.param
+    ops.set_gemm_precision(old)
+
+
 def build_model(cfg, P):
     from poet_b200.deformable_transformer import DeformableTransformer
     from poet_b200.pose_estimation_transformer import PoET
@@ -34,7 +52,7 @@ def stack_outputs(out):
 
 @pytest.mark.parametrize("key", ["transformer/tiny/pad0", "transformer/tiny/pad1", "transformer/tiny16/pad1",
                                  "transformer/cfg1/pad0"])
-def test_transformer_vs_reference_golden(key):
+def test_transformer_vs_reference_golden(key, precision):
     """DeformableTransformer.forward with the reference's call signature (NCHW srcs/pos) vs the fixture."""
     from poet_b200 import ops
     g = load_golden(key)
@@ -54,7 +72,7 @@ def test_transformer_vs_reference_golden(key):
 
 
 @pytest.mark.parametrize("key", ["poet/tiny/pad1", "poet/tiny16/pad0", "poet/cfg1/pad0", "poet/cfg2_b2/pad1"])
-def test_poet_path_vs_reference_golden(key):
+def test_poet_path_vs_reference_golden(key, precision):
     """forward_pyramid + backward vs the fixture from the reference PoET (input_proj done by the oracle,
     which is outside the CUDA path: SURVEY.md §8f N1)."""
     g = load_golden(key)
@@ -79,16 +97,17 @@ def test_poet_path_vs_reference_golden(key):
         flat = p.grad.detach().cpu().flatten()
         scale = max(rec["norm"] / math.sqrt(flat.numel()), 1e-6)                 # RMS of the reference gradient
         err = (flat[sample_indices(flat.numel())] - rec["samples"]).abs()
-        # knife-edge ReLU / pixel-edge flips (see assert_grad_close): allow 1% of the samples to be off
-        assert float((err > 5e-3 * scale + 1e-5).double().mean()) <= 0.01, name
-        assert float(err.max()) < 0.2 * scale + 1e-5, name
-        assert abs(float(flat.double().norm()) - rec["norm"]) < 5e-3 * max(rec["norm"], 1e-3), name
+        tol = GRAD_TOL[precision]
+        # knife-edge ReLU / pixel-edge flips (see GRAD_TOL): allow 1% of the samples to be off
+        assert float((err > tol["samp"] * scale + 1e-5).double().mean()) <= 0.01, name
+        assert float(err.max()) < 10 * tol["samp"] * scale + 1e-5, name
+        assert abs(float(flat.double().norm()) - rec["norm"]) < tol["l2"] * max(rec["norm"], 1e-3), name
         checked += 1
     assert checked > 20
 
 
 @pytest.mark.parametrize("name,pad", [("tiny16", True), ("cfg1", False), ("cfg2_b2", True)])
-def test_poet_path_vs_oracle_all_grads(name, pad):
+def test_poet_path_vs_oracle_all_grads(name, pad, precision):
     """Every output of every decoder layer and the gradient of every parameter and of the input
     pyramid vs the oracle (fp32 CPU) on identical seeded inputs."""
     cfg = S.CONFIGS[name]
@@ -113,23 +132,22 @@ def test_poet_path_vs_oracle_all_grads(name, pad):
         if ref is None:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
             continue
-        assert_grad_close(p.grad.cpu(), ref, k)
+        assert_grad_close(p.grad.cpu(), ref, k, precision)
     for l, (s_d, s_r) in enumerate(zip(d_srcs, r_srcs)):
-        assert_grad_close(s_d.grad.cpu(), s_r.grad, f"srcs[{l}]")
+        assert_grad_close(s_d.grad.cpu(), s_r.grad, f"srcs[{l}]", precision)
 
 
-def assert_grad_close(got, ref, name):
-    """Two fp32 implementations of this network cannot agree element-wise to fp32 precision on every
-    gradient: ReLU units within rounding of 0 and bilinear samples within rounding of a pixel edge flip
-    between implementations (the oracle's own fp32-vs-fp64 gradients differ by up to 1.6e-3 of max on
-    cfg2_b2 for exactly this reason).  So: relative L2 error <= 5e-3, at most 1% of the
-    elements off by more than 1e-3 of max, and nothing off by more than 5% of max."""
+def assert_grad_close(got, ref, name, precision):
+    """Relative L2 error, fraction of elements off by more than `elem` of max, and worst element, against
+    the per-precision budget of GRAD_TOL (the oracle's own fp32-vs-fp64 gradients differ by up to 1.6e-3
+    of max on cfg2_b2 for the same reason)."""
+    tol = GRAD_TOL[precision]
     scale = float(ref.abs().max()) + 1e-12
     err = (got.double() - ref.double()).abs()
     rel_l2 = float(err.norm() / (ref.double().norm() + 1e-12))
-    assert rel_l2 < 5e-3, (name, "rel_l2", rel_l2)
-    assert float((err > 1e-3 * scale).double().mean()) < 1e-2, (name, "bad fraction")
-    assert float(err.max()) < 5e-2 * scale + 1e-7, (name, "max", float(err.max()), scale)
+    assert rel_l2 < tol["l2"], (name, "rel_l2", rel_l2)
+    assert float((err > tol["elem"] * scale).double().mean()) < tol["frac"], (name, "bad fraction")
+    assert float(err.max()) < tol["mx"] * scale + 1e-7, (name, "max", float(err.max()), scale)
 
 
 def test_msdeformattn_seam_matches_oracle_module():

@@ -117,6 +117,17 @@ int poet_gemm(const float* A, int64_t lda, int a_kcontig, const float* Bm, int64
               float* C, int64_t ldc, int M, int N, int K, float alpha, const float* bias, const float* gate,
               const uint8_t* row_mask, int flags, int precision, void* workspace, size_t workspace_bytes,
               poet_stream_t stream);
+/* Weights are operands of every forward and dgrad GEMM of a step: split them ONCE into bf16 planes
+ * (hi = bf16(x), lo = bf16(x - hi); lo may be NULL for POET_GEMM_BF16) and hand the planes to
+ * poet_gemm_bsplit, whose B operand is then fetched by TMA straight into the swizzled smem stage.
+ * B_hi/B_lo have the same logical layout and ldb (in elements) as the fp32 B; Bm (fp32) is still
+ * required when the shape is not tensor-core eligible (poet_gemm_tc_eligible() == 0). */
+int poet_split_bf16(const float* src, void* hi, void* lo, int64_t n, poet_stream_t stream);
+int poet_gemm_tc_eligible(int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc);
+int poet_gemm_bsplit(const float* A, int64_t lda, int a_kcontig, const float* Bm, const void* B_hi, const void* B_lo,
+                     int64_t ldb, int b_kcontig, float* C, int64_t ldc, int M, int N, int K, float alpha,
+                     const float* bias, const float* gate, const uint8_t* row_mask, int flags, int precision,
+                     poet_stream_t stream);
 /* out[N] (+)= sum_m X[m,n]  (bias gradients).  accumulate=0 overwrites. */
 int poet_colsum(const float* X, int64_t ldx, float* out, int M, int N, int accumulate, poet_stream_t stream);
 

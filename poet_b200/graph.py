@@ -52,6 +52,8 @@ class GraphedStep:
 
     # -- the captured region ----------------------------------------------------------------
     def _body(self):
+        from . import ops
+        ops.clear_weight_split_cache()          # the bf16 weight planes must be re-derived inside the graph
         if self.reducer is not None:
             self.reducer.zero()
         out = self.model.forward_padded(self.s_srcs, self.s_masks, self.s_boxes, self.s_classes, self.s_counts)

@@ -104,7 +104,7 @@ def shapes_array(shapes: Sequence[Tuple[int, int]]):
 def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_kcontig: bool = True, b_kcontig: bool = True,
          lda: Optional[int] = None, ldb: Optional[int] = None, bias=None, relu=False, gate=None, row_mask=None,
          out: Optional[torch.Tensor] = None, accumulate=False, alpha: float = 1.0,
-         precision: Optional[int] = None) -> torch.Tensor:
+         precision: Optional[int] = None, b_split=None) -> torch.Tensor:
     """out[M,N] = epi(alpha * op(A) @ op(B)); see include/poet_b200.h poet_gemm."""
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
@@ -117,10 +117,37 @@ def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_kcontig
         if ws_bytes:
             ws = torch.empty(ws_bytes, device=A.device, dtype=torch.uint8)
     flags = (1 if relu else 0) | (2 if accumulate else 0)
+    tag = (f"{M}x{N}x{K}" + ("" if a_kcontig else ",At") + ("" if b_kcontig else ",Bt")) if _timing["on"] else None
+    work = (4 * (M * K + N * K + M * N), 2 * M * N * K)
+    if b_split is not None and prec != GEMM_FP32 and a_kcontig:
+        _call("poet_gemm_bsplit", _p(A), lda, int(a_kcontig), _p(Bm), _p(b_split[0]), _p(b_split[1]), ldb,
+              int(b_kcontig), _p(out), out.stride(0), M, N, K, alpha, _p(bias), _p(gate), _p(row_mask), flags, prec,
+              _stream(A), tag=tag, work=work)
+        return out
     _call("poet_gemm", _p(A), lda, int(a_kcontig), _p(Bm), ldb, int(b_kcontig), _p(out), out.stride(0), M, N, K,
-          alpha, _p(bias), _p(gate), _p(row_mask), flags, prec, _p(ws), ws_bytes, _stream(A),
-          tag=f"{M}x{N}x{K}" if _timing["on"] else None, work=(4 * (M * K + N * K + M * N), 2 * M * N * K))
+          alpha, _p(bias), _p(gate), _p(row_mask), flags, prec, _p(ws), ws_bytes, _stream(A), tag=tag, work=work)
     return out
+
+
+# Weights are the B operand of the forward (NT) and of the dgrad (NN) GEMM of a layer: split them into
+# bf16 hi/lo planes once in forward, keep the planes on the autograd ctx for backward, and let both
+# GEMMs fetch them by TMA.  No cross-call cache: planes never outlive the forward/backward that made them.
+def clear_weight_split_cache() -> None:
+    """Kept for API stability: planes are owned by the autograd graph, there is nothing to clear."""
+
+
+def split_weight(W: torch.Tensor, M_rows: int):
+    """(hi, lo) bf16 planes of W [N,K] if the GEMMs that will use it are tensor-core eligible, else None."""
+    prec = _state["precision"]
+    if prec == GEMM_FP32:
+        return None
+    N, K = W.shape
+    if K % 8 or N % 8 or not _lib.lib().poet_gemm_tc_eligible(M_rows, N, K, K, K, N):
+        return None
+    hi = torch.empty(W.shape, device=W.device, dtype=torch.bfloat16)
+    lo = torch.empty(W.shape, device=W.device, dtype=torch.bfloat16) if prec == GEMM_BF16X3 else None
+    _call("poet_split_bf16", _p(W), _p(hi), _p(lo), W.numel(), _stream(W))
+    return hi, lo
 
 
 def colsum(X: torch.Tensor, M: int, N: int, out: Optional[torch.Tensor] = None, accumulate=False) -> torch.Tensor:
@@ -145,11 +172,11 @@ def add(a: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
 # autograd: Linear / FFN / MLP
 # ------------------------------------------------------------------------------------------
 def _linear_bwd(gy2: torch.Tensor, x2: torch.Tensor, W: torch.Tensor, need_x: bool, need_w: bool, need_b: bool,
-                gate: Optional[torch.Tensor] = None):
+                gate: Optional[torch.Tensor] = None, w_split=None):
     """gy2 [R,N], x2 [R,K], W [N,K] -> (dx [R,K] (gated by `gate`>0 if given), dW [N,K], db [N])."""
     R, N = gy2.shape
     K = x2.shape[1]
-    dx = gemm(gy2, W, R, K, N, a_kcontig=True, b_kcontig=False, gate=gate) if need_x else None
+    dx = gemm(gy2, W, R, K, N, a_kcontig=True, b_kcontig=False, gate=gate, b_split=w_split) if need_x else None
     dW = gemm(gy2, x2, N, K, R, a_kcontig=False, b_kcontig=False) if need_w else None
     db = colsum(gy2, R, N) if need_b else None
     return dx, dW, db
@@ -165,7 +192,8 @@ class _Linear(torch.autograd.Function):
         W = _chk(W)
         R, K = x2.shape
         N = W.shape[0]
-        y = gemm(x2, W, R, N, K, bias=b, row_mask=row_mask)
+        ctx.w_split = split_weight(W, R)
+        y = gemm(x2, W, R, N, K, bias=b, row_mask=row_mask, b_split=ctx.w_split)
         ctx.save_for_backward(x2, W)
         ctx.row_mask = row_mask
         ctx.has_bias = b is not None
@@ -179,7 +207,7 @@ class _Linear(torch.autograd.Function):
         if ctx.row_mask is not None:
             gy2 = mask_rows_(gy2 if ctx.mask_grad_inplace else gy2.clone(), ctx.row_mask)
         dx, dW, db = _linear_bwd(gy2, x2, W, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                                 ctx.has_bias and ctx.needs_input_grad[2])
+                                 ctx.has_bias and ctx.needs_input_grad[2], w_split=ctx.w_split)
         return (dx.view(ctx.xshape) if dx is not None else None), dW, db, None, None
 
 
@@ -197,10 +225,13 @@ class _MLP(torch.autograd.Function):
         n = len(wb) // 2
         x2 = _chk(x).view(-1, x.shape[-1])
         acts = [x2]
+        ctx.w_splits = []
         for i in range(n):
             W, b = _chk(wb[2 * i]), wb[2 * i + 1]
             h = acts[-1]
-            acts.append(gemm(h, W, h.shape[0], W.shape[0], W.shape[1], bias=b, relu=(i < n - 1)))
+            ctx.w_splits.append(split_weight(W, h.shape[0]))
+            acts.append(gemm(h, W, h.shape[0], W.shape[0], W.shape[1], bias=b, relu=(i < n - 1),
+                             b_split=ctx.w_splits[-1]))
         ctx.save_for_backward(*acts[:-1], *[wb[2 * i] for i in range(n)])
         ctx.n = n
         ctx.xshape = x.shape
@@ -215,7 +246,8 @@ class _MLP(torch.autograd.Function):
         for i in range(n - 1, -1, -1):
             need_x = i > 0 or ctx.needs_input_grad[0]
             dx, dW, db = _linear_bwd(g, acts[i], Ws[i], need_x, ctx.needs_input_grad[1 + 2 * i],
-                                     ctx.needs_input_grad[2 + 2 * i], gate=acts[i] if i > 0 else None)
+                                     ctx.needs_input_grad[2 + 2 * i], gate=acts[i] if i > 0 else None,
+                                     w_split=ctx.w_splits[i])
             grads[2 * i], grads[2 * i + 1] = dW, db
             g = dx
         return (g.view(ctx.xshape) if g is not None else None, *grads)

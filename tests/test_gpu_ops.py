@@ -363,3 +363,38 @@ def test_gemm_tcgen05_epilogues():
                    ref * (mask == 0)[:, None]) < 3e-5
     acc = o.gemm(A.to(DEV), W.to(DEV), M, N, K, bias=b.to(DEV), out=base.to(DEV).clone(), accumulate=True, alpha=0.5, precision=P)
     assert rel_err(acc, 0.5 * (ref - b.double()) + b.double() + base.double()) < 3e-5
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 3e-5), ("bf16", 2e-2)])
+@pytest.mark.parametrize("M,N,K,b_k", [
+    (25600, 256, 256, True),      # forward: weight [N,K] K-major via TMA
+    (3000, 1024, 256, True),      # ragged M, 4 N tiles
+    (3200, 256, 1024, True),      # long K
+    (25600, 256, 768, False),     # dgrad: weight stored [K,N] (MN-major B) via TMA
+    (3200, 1024, 256, False),
+    (1600, 128, 200, True),       # BN=128, K tail handled by TMA zero fill
+])
+def test_gemm_tcgen05_presplit_weights(M, N, K, b_k, prec, tol):
+    """B operand = bf16 hi/lo planes produced once by poet_split_bf16 and fetched by TMA."""
+    o = ops()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn((N, K) if b_k else (K, N), generator=g)
+    bias = torch.randn(N, generator=g)
+    ref = A.double() @ (W.double().t() if b_k else W.double()) + bias.double()
+    Wd = W.to(DEV)
+    old = o.get_gemm_precision()
+    o.set_gemm_precision(prec)
+    try:
+        hi = torch.empty(Wd.shape, device=DEV, dtype=torch.bfloat16)
+        lo = torch.empty(Wd.shape, device=DEV, dtype=torch.bfloat16) if prec == "bf16x3" else None
+        o._call("poet_split_bf16", Wd.data_ptr(), hi.data_ptr(), None if lo is None else lo.data_ptr(), Wd.numel(),
+                o._stream(Wd))
+        assert torch.equal(hi, Wd.to(torch.bfloat16))
+        if lo is not None:
+            assert torch.equal(lo, (Wd - hi.float()).to(torch.bfloat16))
+        out = o.gemm(A.to(DEV), Wd, M, N, K, b_kcontig=b_k, bias=bias.to(DEV), b_split=(hi, lo))
+    finally:
+        o.set_gemm_precision(old)
+    err = rel_err(out, ref)
+    assert err < tol, f"{prec} {M}x{N}x{K} b_k={b_k}: rel err {err:.3e}"

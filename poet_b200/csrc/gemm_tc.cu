@@ -324,12 +324,15 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
       mbar_wait(accum_bar, 0);
       tc_fence_after();
     }
+    // TMEM hands each thread one accumulator ROW (32 consecutive columns per tcgen05.ld).  Storing that
+    // directly would make every warp store touch 32 different rows; instead each warp transposes its
+    // 32x32 block through a private padded smem tile (the operand stages are free once accum_bar fired)
+    // so that lane = column and every global load / store / reduction is one coalesced 128-byte row.
     constexpr int GROUPS = PW / 4, COLS = BN / GROUPS;
     const int quarter = warp & 3, group = warp >> 2;
-    const int m = m0 + quarter * 32 + lane;
-    const bool row_ok = m < p.M;
     const bool relu = p.flags & POET_GEMM_RELU, accum = p.flags & POET_GEMM_ACCUMULATE;
-    const bool dead = row_ok && p.row_mask != nullptr && p.row_mask[m] != 0;
+    float* tile = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+    const int mrow0 = m0 + quarter * 32;
 #pragma unroll 1
     for (int cc = 0; cc < COLS; cc += 32) {
       const int col = group * COLS + cc;
@@ -339,33 +342,27 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
-      const int n = n0 + col;
-      if (!row_ok || n >= p.N) continue;
-      float* cp = p.C + (int64_t)m * p.ldc + n;
-      if (p.splits > 1) {
+      __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o = make_float4(p.alpha * v[j], p.alpha * v[j + 1], p.alpha * v[j + 2], p.alpha * v[j + 3]);
-          if (p.bias != nullptr && blockIdx.z == 0) {
-            const float4 b = ldg4(p.bias + n + j);
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp + j), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+      for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = v[j];
+      __syncwarp();
+      const int n = n0 + col + lane;                           // this lane's output column
+      if (n >= p.N) continue;
+      const float bias = (p.bias != nullptr && (p.splits == 1 || blockIdx.z == 0)) ? __ldg(p.bias + n) : 0.f;
+      const int rows = min(32, p.M - mrow0);
+      for (int r = 0; r < rows; ++r) {
+        const int m = mrow0 + r;
+        float o = p.alpha * tile[r * 33 + lane] + bias;
+        float* cp = p.C + (int64_t)m * p.ldc + n;
+        if (p.splits > 1) {
+          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(cp), "f"(o) : "memory");
+          continue;
         }
-        continue;
-      }
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 o = make_float4(p.alpha * v[j], p.alpha * v[j + 1], p.alpha * v[j + 2], p.alpha * v[j + 3]);
-        if (p.bias) { const float4 b = ldg4(p.bias + n + j); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
-        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-        if (p.gate) {
-          const float4 g = ldg4(p.gate + (int64_t)m * p.ldc + n + j);
-          o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
-        }
-        if (dead) o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (accum) { const float4 old = ld4(cp + j); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-        st4(cp + j, o);
+        if (relu) o = fmaxf(o, 0.f);
+        if (p.gate) o = __ldg(p.gate + (int64_t)m * p.ldc + n) > 0.f ? o : 0.f;
+        if (p.row_mask != nullptr && p.row_mask[m] != 0) o = 0.f;
+        if (accum) o += *cp;
+        *cp = o;
       }
     }
   }
@@ -447,8 +444,8 @@ int dispatch(const Args& a, bool a_mn, bool b_mn, bool b_tma, const CUtensorMap&
 bool poet_gemm_tc_supported(int M, int N, int K, int a_kcontig, int b_kcontig, int64_t lda, int64_t ldb, int64_t ldc) {
   if (N % 128 != 0 || K % 8 != 0 || M % 8 != 0) return false;
   if (lda % 4 != 0 || ldb % 4 != 0 || ldc % 4 != 0) return false;
-  // tiny problems (decoder rows, heads) are launch-latency bound: exact-fp32 SIMT path
-  if ((int64_t)M * N * K < (int64_t)512 * 256 * 256) return false;
+  // very small problems (head outputs, K < 64) stay on the exact-fp32 SIMT kernel
+  if (M < 64 || K < 64) return false;
   (void)a_kcontig; (void)b_kcontig;
   return true;
 }
@@ -469,7 +466,9 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
   tc::Args a;
   a.A = A; a.lda = lda; a.B = b_tma ? nullptr : Bm; a.ldb = ldb; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
   a.alpha = alpha; a.bias = bias; a.gate = gate; a.row_mask = row_mask; a.flags = flags;
-  const int bn = (N % 256 == 0) ? 256 : 128;
+  // 128 x 256 tiles when that still fills the machine, else 128 x 128 (decoder rows: more CTAs in flight)
+  int bn = (N % 256 == 0) ? 256 : 128;
+  if (bn == 256 && (int64_t)(N / 256) * poet_ceil_div(M, tc::BM) < POET_NUM_SMS / 2) bn = 128;
   const int64_t tiles = (int64_t)(N / bn) * poet_ceil_div(M, tc::BM);
   const int total_kb = poet_ceil_div(K, tc::BK);
   int splits = 1;

@@ -104,24 +104,41 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   for (int i = threadIdx.x; i < C; i += blockDim.x) { atomicAdd(dgamma + i, s_dg[i]); atomicAdd(dbeta + i, s_db[i]); }
 }
 
-// out[n] (+)= sum_m X[m,n].  block = 32 x 8: 32 columns wide, 8 row-lanes; grid.x over column tiles,
-// grid.y over row chunks; per-block partial -> one atomic per column.
+// out[n] (+)= sum_m X[m,n].  One warp covers 128 columns (float4 per lane), the 8 warps of a block take
+// alternate rows of a 64-row chunk (8 independent 128-bit loads in flight per thread); per-block partials
+// are combined in smem and leave as one atomic per column.  Tail columns (N % 4 != 0) use the scalar path.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int64_t ldx, float* __restrict__ out,
-                                                     int M, int N, int rows_per_block) {
-  __shared__ float part[8][33];
-  const int col = blockIdx.x * 32 + threadIdx.x;
-  const int r0 = blockIdx.y * rows_per_block;
-  const int r1 = min(M, r0 + rows_per_block);
-  float acc = 0.f;
-  if (col < N)
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += __ldg(X + (int64_t)r * ldx + col);
-  part[threadIdx.y][threadIdx.x] = acc;
+                                                     int M, int N, int rows_per_block, int vec) {
+  __shared__ float part[8][128];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 128 + lane * 4;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec && c0 + 3 < N) {
+#pragma unroll 4
+    for (int r = r0 + w; r < r1; r += 8) {
+      const float4 v = ldg4(X + (int64_t)r * ldx + c0);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  } else {
+    for (int r = r0 + w; r < r1; r += 8) {
+      const float* p = X + (int64_t)r * ldx + c0;
+      if (c0 + 0 < N) acc.x += __ldg(p + 0);
+      if (c0 + 1 < N) acc.y += __ldg(p + 1);
+      if (c0 + 2 < N) acc.z += __ldg(p + 2);
+      if (c0 + 3 < N) acc.w += __ldg(p + 3);
+    }
+  }
+  part[w][lane * 4 + 0] = acc.x; part[w][lane * 4 + 1] = acc.y; part[w][lane * 4 + 2] = acc.z; part[w][lane * 4 + 3] = acc.w;
   __syncthreads();
-  if (threadIdx.y == 0 && col < N) {
-    float s = 0.f;
+  if (threadIdx.x < 128) {
+    const int c = blockIdx.x * 128 + threadIdx.x;
+    if (c < N) {
+      float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += part[i][threadIdx.x];
-    atomicAdd(out + col, s);
+      for (int i = 0; i < 8; ++i) s += part[i][threadIdx.x];
+      atomicAdd(out + c, s);
+    }
   }
 }
 
@@ -197,12 +214,12 @@ extern "C" int poet_colsum(const float* X, int64_t ldx, float* out, int M, int N
     cudaError_t e = cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), s);
     if (e != cudaSuccess) return (int)e;
   }
-  const int col_tiles = poet_ceil_div(N, 32);
-  int row_chunks = poet_ceil_div(2 * POET_NUM_SMS, col_tiles);
-  int rows_per_block = poet_ceil_div(M, row_chunks);
-  if (rows_per_block < 64) rows_per_block = 64;
-  row_chunks = poet_ceil_div(M, rows_per_block);
-  colsum_kernel<<<dim3(col_tiles, row_chunks), dim3(32, 8), 0, s>>>(X, ldx, out, M, N, rows_per_block);
+  const int col_tiles = poet_ceil_div(N, 128);
+  int rows_per_block = 64;
+  while ((int64_t)poet_ceil_div(M, rows_per_block) * col_tiles > 8 * POET_NUM_SMS) rows_per_block *= 2;
+  const int row_chunks = poet_ceil_div(M, rows_per_block);
+  const int vec = poet_aligned16(X) && (ldx % 4 == 0);
+  colsum_kernel<<<dim3(col_tiles, row_chunks), 256, 0, s>>>(X, ldx, out, M, N, rows_per_block, vec);
   return poet_launch_status();
 }
 

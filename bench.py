@@ -310,6 +310,9 @@ def run_gpu(args):
             ops.kernel_timing(True)
             for _ in range(ksteps):
                 flush.fill_(1)
+                # park the GPU (~40 ms spin) while the host enqueues the whole step, so the events measure
+                # back-to-back device execution instead of Python launch gaps
+                torch.cuda._sleep(80_000_000)
                 eager_step(d_srcs, d_masks, d_boxes, d_labels)
             torch.cuda.synchronize()
             ktimes = ops.kernel_times_ms()

@@ -350,19 +350,37 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
       if (n >= p.N) continue;
       const float bias = (p.bias != nullptr && (p.splits == 1 || blockIdx.z == 0)) ? __ldg(p.bias + n) : 0.f;
       const int rows = min(32, p.M - mrow0);
-      for (int r = 0; r < rows; ++r) {
-        const int m = mrow0 + r;
-        float o = p.alpha * tile[r * 33 + lane] + bias;
-        float* cp = p.C + (int64_t)m * p.ldc + n;
-        if (p.splits > 1) {
-          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(cp), "f"(o) : "memory");
-          continue;
+      float* cbase = p.C + (int64_t)mrow0 * p.ldc + n;
+      if (p.splits > 1) {
+#pragma unroll 8
+        for (int r = 0; r < rows; ++r)
+          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(cbase + (int64_t)r * p.ldc), "f"(p.alpha * tile[r * 33 + lane] + bias) : "memory");
+        continue;
+      }
+      // rows in batches of 8 so the dependent global loads (ReLU gate, old C, row mask) overlap
+#pragma unroll 1
+      for (int r0 = 0; r0 < rows; r0 += 8) {
+        float o[8], g[8], old[8];
+        bool dead[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + i;
+          const bool ok = r < rows;
+          g[i] = (ok && p.gate) ? __ldg(p.gate + (int64_t)(mrow0 + r) * p.ldc + n) : 1.f;
+          old[i] = (ok && accum) ? cbase[(int64_t)r * p.ldc] : 0.f;
+          dead[i] = ok && p.row_mask != nullptr && p.row_mask[mrow0 + r] != 0;
+          o[i] = p.alpha * tile[(ok ? r : 0) * 33 + lane] + bias;
         }
-        if (relu) o = fmaxf(o, 0.f);
-        if (p.gate) o = __ldg(p.gate + (int64_t)m * p.ldc + n) > 0.f ? o : 0.f;
-        if (p.row_mask != nullptr && p.row_mask[m] != 0) o = 0.f;
-        if (accum) o += *cp;
-        *cp = o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + i;
+          if (r >= rows) break;
+          float x = o[i];
+          if (relu) x = fmaxf(x, 0.f);
+          if (!(g[i] > 0.f)) x = 0.f;
+          if (dead[i]) x = 0.f;
+          cbase[(int64_t)r * p.ldc] = x + old[i];
+        }
       }
     }
   }
@@ -418,7 +436,9 @@ static int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t r
 template <int BN, bool A_MN, bool B_MN, bool X3, bool B_TMA, int PW>
 int launch(const Args& a, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t s) {
   constexpr int PLANES = X3 ? 2 : 1;
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) * PLANES + 1024;
+  constexpr size_t stage_smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) * PLANES;
+  constexpr size_t epi_smem = (size_t)PW * 32 * 33 * sizeof(float);          // per-warp transpose tiles
+  constexpr size_t smem = (stage_smem > epi_smem ? stage_smem : epi_smem) + 1024;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, X3, B_TMA, PW>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;

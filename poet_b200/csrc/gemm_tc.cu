@@ -333,6 +333,9 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
     const bool relu = p.flags & POET_GEMM_RELU, accum = p.flags & POET_GEMM_ACCUMULATE;
     float* tile = reinterpret_cast<float*>(smem) + warp * (32 * 33);
     const int mrow0 = m0 + quarter * 32;
+    // rows of this warp's quarter that the padding mask zeroes (bit r = row mrow0 + r)
+    const uint32_t dead_rows = __ballot_sync(0xffffffffu, p.row_mask != nullptr && mrow0 + lane < p.M &&
+                                                              p.row_mask[min(mrow0 + lane, p.M - 1)] != 0);
 #pragma unroll 1
     for (int cc = 0; cc < COLS; cc += 32) {
       const int col = group * COLS + cc;
@@ -351,35 +354,43 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
       const float bias = (p.bias != nullptr && (p.splits == 1 || blockIdx.z == 0)) ? __ldg(p.bias + n) : 0.f;
       const int rows = min(32, p.M - mrow0);
       float* cbase = p.C + (int64_t)mrow0 * p.ldc + n;
+      const float alpha = p.alpha;
       if (p.splits > 1) {
 #pragma unroll 8
         for (int r = 0; r < rows; ++r)
-          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(cbase + (int64_t)r * p.ldc), "f"(p.alpha * tile[r * 33 + lane] + bias) : "memory");
-        continue;
-      }
-      // rows in batches of 8 so the dependent global loads (ReLU gate, old C, row mask) overlap
-#pragma unroll 1
-      for (int r0 = 0; r0 < rows; r0 += 8) {
-        float o[8], g[8], old[8];
-        bool dead[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r0 + i;
-          const bool ok = r < rows;
-          g[i] = (ok && p.gate) ? __ldg(p.gate + (int64_t)(mrow0 + r) * p.ldc + n) : 1.f;
-          old[i] = (ok && accum) ? cbase[(int64_t)r * p.ldc] : 0.f;
-          dead[i] = ok && p.row_mask != nullptr && p.row_mask[mrow0 + r] != 0;
-          o[i] = p.alpha * tile[(ok ? r : 0) * 33 + lane] + bias;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r0 + i;
-          if (r >= rows) break;
-          float x = o[i];
+          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(cbase + (int64_t)r * p.ldc), "f"(alpha * tile[r * 33 + lane] + bias) : "memory");
+      } else if (p.gate == nullptr && !accum) {
+        // common case: bias (+ReLU) (+row mask); nothing to load, stores are fire-and-forget
+#pragma unroll 8
+        for (int r = 0; r < rows; ++r) {
+          float x = alpha * tile[r * 33 + lane] + bias;
           if (relu) x = fmaxf(x, 0.f);
-          if (!(g[i] > 0.f)) x = 0.f;
-          if (dead[i]) x = 0.f;
-          cbase[(int64_t)r * p.ldc] = x + old[i];
+          if ((dead_rows >> r) & 1u) x = 0.f;
+          cbase[(int64_t)r * p.ldc] = x;
+        }
+      } else {
+        // ReLU-gate (dgrad through the FFN activation) and/or accumulate: batches of 16 rows so the
+        // dependent global loads overlap
+        const float* gbase = p.gate ? p.gate + (int64_t)mrow0 * p.ldc + n : nullptr;
+#pragma unroll 1
+        for (int r0 = 0; r0 < rows; r0 += 16) {
+          float g[16], old[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int r = min(r0 + i, rows - 1);
+            g[i] = gbase ? __ldg(gbase + (int64_t)r * p.ldc) : 1.f;
+            old[i] = accum ? cbase[(int64_t)r * p.ldc] : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int r = r0 + i;
+            if (r < rows) {
+              float x = alpha * tile[r * 33 + lane] + bias;
+              if (relu) x = fmaxf(x, 0.f);
+              if (!(g[i] > 0.f) || ((dead_rows >> r) & 1u)) x = 0.f;
+              cbase[(int64_t)r * p.ldc] = x + old[i];
+            }
+          }
         }
       }
     }

@@ -6,7 +6,7 @@
 // y = loc_y*H - 0.5, bilinear with zero padding, a sample contributes iff -1 < x < W, -1 < y < H.
 //
 // Work decomposition (general path, any S / Lq): one thread per (b, q, m, 4-channel group).
-// The D/4 lanes that share a (b,q,m) sit next to each other in a warp, so every bilinear corner
+// The G = D/4 lanes that share a (b,q,m) sit next to each other in a warp, so every bilinear corner
 // is one contiguous D*4-byte segment per group (64 B at D=16, 128 B at D=32) fetched with
 // 128-bit loads, and the output row [B,Lq,M*D] is written as one fully coalesced float4 stream.
 // mode 1 fuses the module's softmax over L*P and loc = ref + off/(W_l,H_l), so the [B,Lq,M,L,P,2]
@@ -22,6 +22,8 @@ struct Levels {
   int H[kMaxLevels];
   int W[kMaxLevels];
   int start[kMaxLevels];
+  float inv_H[kMaxLevels];   // 1/H_l, 1/W_l: off/(W,H) as a multiply (<= 1 ulp from the reference's divide)
+  float inv_W[kMaxLevels];
 };
 
 struct MsdaArgs {
@@ -48,8 +50,8 @@ __device__ __forceinline__ void softmax_inplace(float (&x)[LP]) {
   for (int i = 1; i < LP; ++i) mx = fmaxf(mx, x[i]);
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < LP; ++i) { x[i] = expf(x[i] - mx); sum += x[i]; }
-  const float inv = 1.f / sum;
+  for (int i = 0; i < LP; ++i) { x[i] = __expf(x[i] - mx); sum += x[i]; }   // ex2.approx: ~2 ulp, far inside the budget
+  const float inv = __fdividef(1.f, sum);
 #pragma unroll
   for (int i = 0; i < LP; ++i) x[i] *= inv;
 }
@@ -57,10 +59,9 @@ __device__ __forceinline__ void softmax_inplace(float (&x)[LP]) {
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
-template <int L, int P, bool FUSED>
+template <int L, int P, int G, bool FUSED>
 __global__ void __launch_bounds__(256) msda_fwd_kernel(const MsdaArgs p) {
-  constexpr int LP = L * P;
-  const int G = p.D >> 2;                                    // lanes per (b,q,m)
+  constexpr int LP = L * P, D = 4 * G;                       // G lanes per (b,q,m)
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)p.B * p.Lq * p.M * G;
   if (t >= total) return;
@@ -75,8 +76,8 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(const MsdaArgs p) {
   if (FUSED) softmax_inplace<LP>(aw);
 
   const float* arow = p.a + bq * p.lda + m * LP * 2;
-  const float* vbase = p.value + ((int64_t)b * p.S * p.M + m) * p.D + c4 * 4;
-  const int64_t vstride = (int64_t)p.M * p.D;
+  const int vstride = p.M * D;
+  const float* vbase = p.value + ((int64_t)b * p.S * p.M + m) * D + c4 * 4;
 
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(const MsdaArgs p) {
 #pragma unroll
     for (int s = 0; s < P; ++s) {
       float lx = xy[2 * s], ly = xy[2 * s + 1];
-      if (FUSED) { lx = rx + lx / (float)W; ly = ry + ly / (float)H; }
+      if (FUSED) { lx = rx + lx * p.lv.inv_W[l]; ly = ry + ly * p.lv.inv_H[l]; }
       const float x = lx * (float)W - 0.5f, y = ly * (float)H - 0.5f;
       if (x > -1.f && y > -1.f && x < (float)W && y < (float)H) {
         const float xf = floorf(x), yf = floorf(y);
@@ -104,12 +105,12 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(const MsdaArgs p) {
         const float w00 = (1.f - fy) * (1.f - fx) * a, w01 = (1.f - fy) * fx * a;
         const float w10 = fy * (1.f - fx) * a, w11 = fy * fx * a;
         const bool xl = x0 >= 0, xh = x0 + 1 < W, yl = y0 >= 0, yh = y0 + 1 < H;
-        const float* p00 = vl + ((int64_t)y0 * W + x0) * vstride;
+        const float* p00 = vl + (y0 * W + x0) * vstride;
         float4 v00 = make_float4(0.f, 0.f, 0.f, 0.f), v01 = v00, v10 = v00, v11 = v00;
         if (yl && xl) v00 = ldg4(p00);
         if (yl && xh) v01 = ldg4(p00 + vstride);
-        if (yh && xl) v10 = ldg4(p00 + (int64_t)W * vstride);
-        if (yh && xh) v11 = ldg4(p00 + (int64_t)(W + 1) * vstride);
+        if (yh && xl) v10 = ldg4(p00 + W * vstride);
+        if (yh && xh) v11 = ldg4(p00 + (W + 1) * vstride);
         acc.x += w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x;
         acc.y += w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y;
         acc.z += w00 * v00.z + w01 * v01.z + w10 * v10.z + w11 * v11.z;
@@ -123,24 +124,29 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(const MsdaArgs p) {
 // ------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float group_sum(float v, int G) {
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
   for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
-__device__ __forceinline__ void red_add4(float* p, float4 v) {
+__device__ __forceinline__ void red_add4(float* p, float w, float4 v) {
   // one 128-bit reduction per corner (sm_90+): red.global.add.v4.f32
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-               : "memory");
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x * w), "f"(v.y * w), "f"(v.z * w),
+               "f"(v.w * w) : "memory");
 }
 
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
-template <int L, int P, bool FUSED>
-__global__ void __launch_bounds__(256) msda_bwd_kernel(const MsdaArgs p) {
-  constexpr int LP = L * P;
-  const int G = p.D >> 2;
-  const int64_t total = (int64_t)p.B * p.Lq * p.M * G;       // host guarantees total % 32 == 0 handling below
+// Register diet (the kernel is latency-bound, so occupancy matters): location gradients leave the
+// thread level by level (8 floats per level = two float4 stores split over the group's lanes); only
+// the L*P attention gradients stay live until the softmax backward at the end.
+template <int L, int P, int G, bool FUSED>
+__global__ void __launch_bounds__(256, 3) msda_bwd_kernel(const MsdaArgs p) {
+  constexpr int LP = L * P, D = 4 * G;
+  static_assert(P % 2 == 0, "points per level must be even (float4 location stores)");
+  const int64_t total = (int64_t)p.B * p.Lq * p.M * G;
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = t < total;
   if (!live) t = total - 1;                                  // keep the warp converged for the shuffles
@@ -155,18 +161,20 @@ __global__ void __launch_bounds__(256) msda_bwd_kernel(const MsdaArgs p) {
   if (FUSED) softmax_inplace<LP>(aw);
 
   const float* arow = p.a + bq * p.lda + m * LP * 2;
-  const int64_t vstride = (int64_t)p.M * p.D;
-  const int64_t voff = ((int64_t)b * p.S * p.M + m) * p.D + c4 * 4;
+  float* garow = p.grad_a + bq * p.lda + m * LP * 2;
+  const int vstride = p.M * D;
+  const int64_t voff = ((int64_t)b * p.S * p.M + m) * D + c4 * 4;
   const float4 go = ldg4(p.grad_out + t * 4);
 
-  float g_attn[LP], g_x[LP], g_y[LP];
+  float g_attn[LP];
 #pragma unroll
   for (int l = 0; l < L; ++l) {
     const int H = p.lv.H[l], W = p.lv.W[l];
-    const int64_t lbase = voff + (int64_t)p.lv.start[l] * vstride;
+    const float* vl = p.value + voff + (int64_t)p.lv.start[l] * vstride;
+    float* gl = p.grad_value + voff + (int64_t)p.lv.start[l] * vstride;
     float rx = 0.f, ry = 0.f;
     if (FUSED) { float2 r = __ldg(reinterpret_cast<const float2*>(p.ref + (bq * L + l) * 2)); rx = r.x; ry = r.y; }
-    float xy[2 * P];
+    float xy[2 * P], gxy[2 * P];
 #pragma unroll
     for (int i = 0; i < 2 * P; i += 4) {
       float4 v = ldg4(arow + l * 2 * P + i);
@@ -175,7 +183,7 @@ __global__ void __launch_bounds__(256) msda_bwd_kernel(const MsdaArgs p) {
 #pragma unroll
     for (int s = 0; s < P; ++s) {
       float lx = xy[2 * s], ly = xy[2 * s + 1];
-      if (FUSED) { lx = rx + lx / (float)W; ly = ry + ly / (float)H; }
+      if (FUSED) { lx = rx + lx * p.lv.inv_W[l]; ly = ry + ly * p.lv.inv_H[l]; }
       const float x = lx * (float)W - 0.5f, y = ly * (float)H - 0.5f;
       float ga = 0.f, gx = 0.f, gy = 0.f;
       if (x > -1.f && y > -1.f && x < (float)W && y < (float)H) {
@@ -184,67 +192,57 @@ __global__ void __launch_bounds__(256) msda_bwd_kernel(const MsdaArgs p) {
         const float fx = x - xf, fy = y - yf;
         const float a = aw[l * P + s];
         const bool xl = x0 >= 0, xh = x0 + 1 < W, yl = y0 >= 0, yh = y0 + 1 < H;
-        const int64_t i00 = lbase + ((int64_t)y0 * W + x0) * vstride;
+        const int i00 = (y0 * W + x0) * vstride;
         float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;      // <grad_out, corner value>
-        const float4 ga4 = make_float4(go.x * a, go.y * a, go.z * a, go.w * a);
         if (yl && xl) {
-          d00 = dot4(go, ldg4(p.value + i00));
-          const float w = (1.f - fy) * (1.f - fx);
-          if (live) red_add4(p.grad_value + i00, make_float4(ga4.x * w, ga4.y * w, ga4.z * w, ga4.w * w));
+          d00 = dot4(go, ldg4(vl + i00));
+          if (live) red_add4(gl + i00, a * (1.f - fy) * (1.f - fx), go);
         }
         if (yl && xh) {
-          d01 = dot4(go, ldg4(p.value + i00 + vstride));
-          const float w = (1.f - fy) * fx;
-          if (live) red_add4(p.grad_value + i00 + vstride, make_float4(ga4.x * w, ga4.y * w, ga4.z * w, ga4.w * w));
+          d01 = dot4(go, ldg4(vl + i00 + vstride));
+          if (live) red_add4(gl + i00 + vstride, a * (1.f - fy) * fx, go);
         }
         if (yh && xl) {
-          d10 = dot4(go, ldg4(p.value + i00 + (int64_t)W * vstride));
-          const float w = fy * (1.f - fx);
-          if (live) red_add4(p.grad_value + i00 + (int64_t)W * vstride,
-                             make_float4(ga4.x * w, ga4.y * w, ga4.z * w, ga4.w * w));
+          d10 = dot4(go, ldg4(vl + i00 + W * vstride));
+          if (live) red_add4(gl + i00 + W * vstride, a * fy * (1.f - fx), go);
         }
         if (yh && xh) {
-          d11 = dot4(go, ldg4(p.value + i00 + (int64_t)(W + 1) * vstride));
-          const float w = fy * fx;
-          if (live) red_add4(p.grad_value + i00 + (int64_t)(W + 1) * vstride,
-                             make_float4(ga4.x * w, ga4.y * w, ga4.z * w, ga4.w * w));
+          d11 = dot4(go, ldg4(vl + i00 + (W + 1) * vstride));
+          if (live) red_add4(gl + i00 + (W + 1) * vstride, a * fy * fx, go);
         }
         ga = (1.f - fy) * (1.f - fx) * d00 + (1.f - fy) * fx * d01 + fy * (1.f - fx) * d10 + fy * fx * d11;
         // d sampled / d x (pixels) and / d y, times attention weight; pixels = loc * size
-        gx = a * ((1.f - fy) * (d01 - d00) + fy * (d11 - d10)) * (float)W;
-        gy = a * ((1.f - fx) * (d10 - d00) + fx * (d11 - d01)) * (float)H;
+        gx = a * ((1.f - fy) * (d01 - d00) + fy * (d11 - d10));
+        gy = a * ((1.f - fx) * (d10 - d00) + fx * (d11 - d01));
+        // d pixel / d (offset) = W * (1/W) = 1 in fused mode; d pixel / d loc = W in core mode
+        if (!FUSED) { gx *= (float)W; gy *= (float)H; }
       }
-      g_attn[l * P + s] = group_sum(ga, G);
-      g_x[l * P + s] = group_sum(gx, G);
-      g_y[l * P + s] = group_sum(gy, G);
+      g_attn[l * P + s] = group_sum<G>(ga);
+      gxy[2 * s] = group_sum<G>(gx);
+      gxy[2 * s + 1] = group_sum<G>(gy);
+    }
+    // this level's location gradients: 2P floats = P/2 float4 chunks, chunk j written by lane j % G
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < P / 2; ++j)
+        if ((l * (P / 2) + j) % G == c4)
+          st4(garow + l * 2 * P + j * 4, make_float4(gxy[4 * j], gxy[4 * j + 1], gxy[4 * j + 2], gxy[4 * j + 3]));
     }
   }
 
   if (FUSED) {
-    // softmax backward: g_logit_i = a_i (g_attn_i - sum_j a_j g_attn_j); offsets: loc = ref + off/(W,H)
+    // softmax backward: g_logit_i = a_i (g_attn_i - sum_j a_j g_attn_j)
     float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < LP; ++i) dot += aw[i] * g_attn[i];
 #pragma unroll
     for (int i = 0; i < LP; ++i) g_attn[i] = aw[i] * (g_attn[i] - dot);
-#pragma unroll
-    for (int l = 0; l < L; ++l)
-#pragma unroll
-      for (int s = 0; s < P; ++s) {
-        g_x[l * P + s] /= (float)p.lv.W[l];
-        g_y[l * P + s] /= (float)p.lv.H[l];
-      }
   }
   if (!live) return;
-  // the G lanes of a group split the stores: float4 chunk j is written by lane (j % G)
   float* gw = p.grad_w + bq * p.ldw + m * LP;
-  float* ga = p.grad_a + bq * p.lda + m * LP * 2;
 #pragma unroll
   for (int j = 0; j < LP / 4; ++j)
     if (j % G == c4) st4(gw + j * 4, make_float4(g_attn[j * 4], g_attn[j * 4 + 1], g_attn[j * 4 + 2], g_attn[j * 4 + 3]));
-#pragma unroll
-  for (int j = 0; j < LP / 2; ++j)
-    if (j % G == c4) st4(ga + j * 4, make_float4(g_x[2 * j], g_y[2 * j], g_x[2 * j + 1], g_y[2 * j + 1]));
 }
 
 int fill_args(MsdaArgs& a, const int32_t* shapes_host, int B, int S, int Lq, int M, int D, int L, int P,
@@ -257,10 +255,13 @@ int fill_args(MsdaArgs& a, const int32_t* shapes_host, int B, int S, int Lq, int
   POET_REQUIRE(lda % 4 == 0 && ldw % 4 == 0 && lda >= (int64_t)M * L * P * 2 && ldw >= (int64_t)M * L * P,
                POET_ERR_BAD_ALIGNMENT);
   POET_REQUIRE(poet_aligned16(value) && poet_aligned16(aa) && poet_aligned16(w), POET_ERR_BAD_ALIGNMENT);
+  POET_REQUIRE((int64_t)S * M * D < (int64_t)1 << 31, POET_ERR_BAD_SHAPE);        // per-image offsets are 32-bit
   int start = 0;
   for (int l = 0; l < L; ++l) {
     a.lv.H[l] = shapes_host[2 * l]; a.lv.W[l] = shapes_host[2 * l + 1]; a.lv.start[l] = start;
     POET_REQUIRE(a.lv.H[l] > 0 && a.lv.W[l] > 0, POET_ERR_BAD_SHAPE);
+    a.lv.inv_H[l] = 1.0f / (float)a.lv.H[l];
+    a.lv.inv_W[l] = 1.0f / (float)a.lv.W[l];
     start += a.lv.H[l] * a.lv.W[l];
   }
   POET_REQUIRE(start == S, POET_ERR_BAD_SHAPE);
@@ -269,25 +270,38 @@ int fill_args(MsdaArgs& a, const int32_t* shapes_host, int B, int S, int Lq, int
   return POET_OK;
 }
 
-template <bool BWD>
-int dispatch(const MsdaArgs& a, int mode, cudaStream_t s) {
+template <bool BWD, int LL, int PP, int GG>
+void launch_one(const MsdaArgs& a, int mode, int grid, cudaStream_t s) {
+  if (BWD) {
+    if (mode) msda_bwd_kernel<LL, PP, GG, true><<<grid, 256, 0, s>>>(a);
+    else msda_bwd_kernel<LL, PP, GG, false><<<grid, 256, 0, s>>>(a);
+  } else {
+    if (mode) msda_fwd_kernel<LL, PP, GG, true><<<grid, 256, 0, s>>>(a);
+    else msda_fwd_kernel<LL, PP, GG, false><<<grid, 256, 0, s>>>(a);
+  }
+}
+
+template <bool BWD, int LL, int PP>
+int launch_g(const MsdaArgs& a, int mode, cudaStream_t s) {
   const int64_t total = (int64_t)a.B * a.Lq * a.M * (a.D / 4);
   const int grid = poet_ceil_div(total, 256);
-#define POET_MSDA_CASE(LL, PP)                                                                         \
-  if (a.L == LL && a.P == PP) {                                                                        \
-    if (BWD) { if (mode) msda_bwd_kernel<LL, PP, true><<<grid, 256, 0, s>>>(a);                         \
-               else msda_bwd_kernel<LL, PP, false><<<grid, 256, 0, s>>>(a); }                           \
-    else     { if (mode) msda_fwd_kernel<LL, PP, true><<<grid, 256, 0, s>>>(a);                         \
-               else msda_fwd_kernel<LL, PP, false><<<grid, 256, 0, s>>>(a); }                           \
-    return poet_launch_status();                                                                       \
+  switch (a.D) {
+    case 8: launch_one<BWD, LL, PP, 2>(a, mode, grid, s); break;
+    case 16: launch_one<BWD, LL, PP, 4>(a, mode, grid, s); break;
+    case 32: launch_one<BWD, LL, PP, 8>(a, mode, grid, s); break;
+    case 64: launch_one<BWD, LL, PP, 16>(a, mode, grid, s); break;
+    default: return POET_ERR_UNSUPPORTED;
   }
-  POET_MSDA_CASE(4, 4)
-  POET_MSDA_CASE(4, 2)
-  POET_MSDA_CASE(3, 4)
-  POET_MSDA_CASE(2, 2)
-  POET_MSDA_CASE(2, 4)
-  POET_MSDA_CASE(1, 4)
-#undef POET_MSDA_CASE
+  return poet_launch_status();
+}
+
+template <bool BWD>
+int dispatch(const MsdaArgs& a, int mode, cudaStream_t s) {
+  if (a.L == 4 && a.P == 4) return launch_g<BWD, 4, 4>(a, mode, s);      // every PoET config
+  if (a.L == 4 && a.P == 2) return launch_g<BWD, 4, 2>(a, mode, s);
+  if (a.L == 2 && a.P == 2) return launch_g<BWD, 2, 2>(a, mode, s);      // upstream test.py shape
+  if (a.L == 2 && a.P == 4) return launch_g<BWD, 2, 4>(a, mode, s);
+  if (a.L == 1 && a.P == 4) return launch_g<BWD, 1, 4>(a, mode, s);
   return POET_ERR_UNSUPPORTED;
 }
 

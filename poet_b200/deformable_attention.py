@@ -79,9 +79,8 @@ class MSDeformAttn(nn.Module):
         value = ops.linear(input_flatten, self.value_proj.weight, self.value_proj.bias, row_mask=mask_u8,
                            mask_grad_inplace=True)
         # one projection for [offsets | logits]: the gather kernel reads both out of the same row
-        w_oa = torch.cat((self.sampling_offsets.weight, self.attention_weights.weight), 0)
-        b_oa = torch.cat((self.sampling_offsets.bias, self.attention_weights.bias), 0)
-        oa = ops.linear(query, w_oa, b_oa)
+        oa = ops.proj_cat(query, self.sampling_offsets.weight, self.sampling_offsets.bias,
+                          self.attention_weights.weight, self.attention_weights.bias)
         out = ops.msda_block(value, oa, reference_points, shapes, self.n_heads, self.n_levels, self.n_points)
         return ops.linear(out, self.output_proj.weight, self.output_proj.bias)
 

@@ -68,8 +68,7 @@ class _SelfAttentionParams(nn.Module):
     def forward(self, qk_in: torch.Tensor, v_in: torch.Tensor) -> torch.Tensor:
         """qk_in = tgt + query_pos, v_in = tgt, both [B,Q,C] (batch-first) -> attention output [B,Q,C]."""
         C = self.embed_dim
-        qk = ops.linear(qk_in, self.in_proj_weight[: 2 * C], self.in_proj_bias[: 2 * C])
-        v = ops.linear(v_in, self.in_proj_weight[2 * C:], self.in_proj_bias[2 * C:])
+        qk, v = ops.in_proj_qk_v(qk_in, v_in, self.in_proj_weight, self.in_proj_bias)
         o = ops.mha_smallq(qk, v, self.num_heads)
         return ops.linear(o, self.out_proj.weight, self.out_proj.bias)
 

@@ -19,7 +19,7 @@ _PRECISION = {"fp32": GEMM_FP32, "bf16x3": GEMM_BF16X3, "bf16": GEMM_BF16}
 import os as _os
 
 # default: tcgen05 split-bf16 (fp32-grade) for the large contractions; the SIMT fp32 kernel serves the small ones
-_state = {"precision": _PRECISION[_os.environ.get("POET_GEMM_PRECISION", "bf16x3")], "launches": 0}
+_state = {"precision": _PRECISION[_os.environ.get("POET_GEMM_PRECISION", "bf16x3")], "launches": 0, "direct_grads": True}
 
 
 def set_gemm_precision(name: str) -> None:
@@ -171,14 +171,44 @@ def add(a: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------
 # autograd: Linear / FFN / MLP
 # ------------------------------------------------------------------------------------------
+def _grad_slot(param) -> Optional[torch.Tensor]:
+    """The pre-allocated .grad of a leaf parameter (e.g. a view of FlatGradReducer's arena), if any.
+    Backward kernels then accumulate straight into it (beta = 1 epilogue) and hand autograd `None`,
+    which removes one zero-fill and one add kernel per parameter per step."""
+    if not _state["direct_grads"] or param is None or not isinstance(param, torch.Tensor):
+        return None
+    if not (param.is_leaf and param.requires_grad):
+        return None
+    g = param.grad
+    if g is None or not g.is_contiguous() or g.dtype != torch.float32 or g.shape != param.shape:
+        return None
+    return g
+
+
+def set_direct_param_grads(on: bool) -> None:
+    _state["direct_grads"] = bool(on)
+
+
 def _linear_bwd(gy2: torch.Tensor, x2: torch.Tensor, W: torch.Tensor, need_x: bool, need_w: bool, need_b: bool,
-                gate: Optional[torch.Tensor] = None, w_split=None):
-    """gy2 [R,N], x2 [R,K], W [N,K] -> (dx [R,K] (gated by `gate`>0 if given), dW [N,K], db [N])."""
+                gate: Optional[torch.Tensor] = None, w_split=None, w_param=None, b_param=None):
+    """gy2 [R,N], x2 [R,K], W [N,K] -> (dx [R,K] (gated by `gate`>0 if given), dW [N,K], db [N]).
+    dW / db come back as None when they were accumulated directly into the parameters' .grad."""
     R, N = gy2.shape
     K = x2.shape[1]
     dx = gemm(gy2, W, R, K, N, a_kcontig=True, b_kcontig=False, gate=gate, b_split=w_split) if need_x else None
-    dW = gemm(gy2, x2, N, K, R, a_kcontig=False, b_kcontig=False) if need_w else None
-    db = colsum(gy2, R, N) if need_b else None
+    dW = db = None
+    if need_w:
+        slot = _grad_slot(w_param)
+        if slot is not None:
+            gemm(gy2, x2, N, K, R, a_kcontig=False, b_kcontig=False, out=slot, accumulate=True)
+        else:
+            dW = gemm(gy2, x2, N, K, R, a_kcontig=False, b_kcontig=False)
+    if need_b:
+        slot = _grad_slot(b_param)
+        if slot is not None:
+            colsum(gy2, R, N, out=slot, accumulate=True)
+        else:
+            db = colsum(gy2, R, N)
     return dx, dW, db
 
 
@@ -192,6 +222,7 @@ class _Linear(torch.autograd.Function):
         W = _chk(W)
         R, K = x2.shape
         N = W.shape[0]
+        ctx.w_param, ctx.b_param = W, b
         ctx.w_split = split_weight(W, R)
         y = gemm(x2, W, R, N, K, bias=b, row_mask=row_mask, b_split=ctx.w_split)
         ctx.save_for_backward(x2, W)
@@ -207,7 +238,8 @@ class _Linear(torch.autograd.Function):
         if ctx.row_mask is not None:
             gy2 = mask_rows_(gy2 if ctx.mask_grad_inplace else gy2.clone(), ctx.row_mask)
         dx, dW, db = _linear_bwd(gy2, x2, W, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                                 ctx.has_bias and ctx.needs_input_grad[2], w_split=ctx.w_split)
+                                 ctx.has_bias and ctx.needs_input_grad[2], w_split=ctx.w_split,
+                                 w_param=ctx.w_param, b_param=ctx.b_param)
         return (dx.view(ctx.xshape) if dx is not None else None), dW, db, None, None
 
 
@@ -225,6 +257,7 @@ class _MLP(torch.autograd.Function):
         n = len(wb) // 2
         x2 = _chk(x).view(-1, x.shape[-1])
         acts = [x2]
+        ctx.params = wb
         ctx.w_splits = []
         for i in range(n):
             W, b = _chk(wb[2 * i]), wb[2 * i + 1]
@@ -247,7 +280,7 @@ class _MLP(torch.autograd.Function):
             need_x = i > 0 or ctx.needs_input_grad[0]
             dx, dW, db = _linear_bwd(g, acts[i], Ws[i], need_x, ctx.needs_input_grad[1 + 2 * i],
                                      ctx.needs_input_grad[2 + 2 * i], gate=acts[i] if i > 0 else None,
-                                     w_split=ctx.w_splits[i])
+                                     w_split=ctx.w_splits[i], w_param=ctx.params[2 * i], b_param=ctx.params[2 * i + 1])
             grads[2 * i], grads[2 * i + 1] = dW, db
             g = dx
         return (g.view(ctx.xshape) if g is not None else None, *grads)
@@ -258,6 +291,98 @@ def mlp(x, layers: Sequence[Tuple[torch.Tensor, torch.Tensor]]):
     for W, b in layers:
         flat += [W, b]
     return _MLP.apply(x, *flat)
+
+
+class _ProjPair(torch.autograd.Function):
+    """Two projections of (possibly different) inputs against row-blocks of parameters, without any autograd
+    slicing / concatenation of the parameters:
+
+      mode 'cat'   (MSDeformAttn, one input): out = x @ [W0; W1]^T + [b0; b1]  -> [R, N0+N1]
+                   (sampling_offsets | attention_weights: one fused GEMM, the gather reads one row)
+      mode 'split' (decoder self-attention in_proj, W = in_proj_weight [3C, C]):
+                   out0 = x0 @ W[:2C]^T + b[:2C]  (q | k of tgt+pos),  out1 = x1 @ W[2C:]^T + b[2C:]  (v of tgt)
+
+    Weight gradients are produced by GEMMs on row / column blocks addressed by pointer offset and leading
+    dimension, accumulated straight into the parameters' .grad slots when those exist."""
+
+    @staticmethod
+    def forward(ctx, mode, x0, x1, W0, b0, W1, b1):
+        ctx.mode = mode
+        x0_2 = _chk(x0).view(-1, x0.shape[-1])
+        R, K = x0_2.shape
+        if mode == "cat":
+            N0, N1 = W0.shape[0], W1.shape[0]
+            with torch.no_grad():
+                Wc = torch.cat((W0, W1), 0)
+                bc = torch.cat((b0, b1), 0)
+            ctx.w_split = split_weight(Wc, R)
+            out = gemm(x0_2, Wc, R, N0 + N1, K, bias=bc, b_split=ctx.w_split)
+            ctx.save_for_backward(x0_2, Wc)
+            ctx.params = (W0, b0, W1, b1)
+            ctx.dims = (R, K, N0, N1)
+            ctx.xshape = x0.shape
+            return out.view(*x0.shape[:-1], N0 + N1)
+        # 'split': W0 is the full in_proj_weight [3C, C], b0 the full bias; W1/b1 unused
+        x1_2 = _chk(x1).view(-1, x1.shape[-1])
+        C = K
+        W = _chk(W0)
+        Wqk, Wv = W[: 2 * C], W[2 * C:]
+        ctx.w_split = (split_weight(Wqk, R), split_weight(Wv, R))
+        qk = gemm(x0_2, Wqk, R, 2 * C, C, bias=b0[: 2 * C], b_split=ctx.w_split[0])
+        v = gemm(x1_2, Wv, R, C, C, bias=b0[2 * C:], b_split=ctx.w_split[1])
+        ctx.save_for_backward(x0_2, x1_2, W)
+        ctx.params = (W0, b0)
+        ctx.dims = (R, C)
+        ctx.xshape = x0.shape
+        return qk.view(*x0.shape[:-1], 2 * C), v.view(*x0.shape[:-1], C)
+
+    @staticmethod
+    def backward(ctx, g0, g1=None):
+        if ctx.mode == "cat":
+            x2, Wc = ctx.saved_tensors
+            W0, b0, W1, b1 = ctx.params
+            R, K, N0, N1 = ctx.dims
+            g = _chk(g0).view(R, N0 + N1)
+            dx = gemm(g, Wc, R, K, N0 + N1, a_kcontig=True, b_kcontig=False, b_split=ctx.w_split) if ctx.needs_input_grad[1] else None
+            outs = []
+            for W, b, col, n in ((W0, b0, 0, N0), (W1, b1, N0, N1)):
+                gcols = g[:, col:col + n]                           # column block: pointer offset + ld = N0+N1
+                slot = _grad_slot(W)
+                dW = gemm(gcols, x2, n, K, R, a_kcontig=False, b_kcontig=False, lda=N0 + N1, out=slot, accumulate=slot is not None)
+                bslot = _grad_slot(b)
+                if bslot is not None:
+                    _call("poet_colsum", _p(gcols), N0 + N1, _p(bslot), R, n, 1, _stream(g))
+                    db = None
+                else:
+                    db = torch.empty(n, device=g.device, dtype=torch.float32)
+                    _call("poet_colsum", _p(gcols), N0 + N1, _p(db), R, n, 0, _stream(g))
+                outs += [None if slot is not None else dW, db]
+            return None, (dx.view(ctx.xshape) if dx is not None else None), None, outs[0], outs[1], outs[2], outs[3]
+        x0_2, x1_2, W = ctx.saved_tensors
+        Wp, bp = ctx.params
+        R, C = ctx.dims
+        gqk, gv = _chk(g0).view(R, 2 * C), _chk(g1).view(R, C)
+        dx0 = gemm(gqk, W[: 2 * C], R, C, 2 * C, a_kcontig=True, b_kcontig=False, b_split=ctx.w_split[0]) if ctx.needs_input_grad[1] else None
+        dx1 = gemm(gv, W[2 * C:], R, C, C, a_kcontig=True, b_kcontig=False, b_split=ctx.w_split[1]) if ctx.needs_input_grad[2] else None
+        slot, bslot = _grad_slot(Wp), _grad_slot(bp)
+        dW = slot if slot is not None else torch.zeros_like(W)
+        db = bslot if bslot is not None else torch.zeros(3 * C, device=W.device, dtype=torch.float32)
+        gemm(gqk, x0_2, 2 * C, C, R, a_kcontig=False, b_kcontig=False, out=dW[: 2 * C], accumulate=True)
+        gemm(gv, x1_2, C, C, R, a_kcontig=False, b_kcontig=False, out=dW[2 * C:], accumulate=True)
+        _call("poet_colsum", _p(gqk), 2 * C, _p(db), R, 2 * C, 1, _stream(W))
+        _call("poet_colsum", _p(gv), C, _p(db[2 * C:]), R, C, 1, _stream(W))
+        return (None, dx0.view(ctx.xshape) if dx0 is not None else None, dx1.view(ctx.xshape) if dx1 is not None else None,
+                None if slot is not None else dW, None if bslot is not None else db, None, None)
+
+
+def proj_cat(x, W0, b0, W1, b1):
+    """x @ [W0; W1]^T + [b0; b1] (MSDeformAttn sampling_offsets | attention_weights)."""
+    return _ProjPair.apply("cat", x, None, W0, b0, W1, b1)
+
+
+def in_proj_qk_v(qk_in, v_in, in_proj_weight, in_proj_bias):
+    """nn.MultiheadAttention in_proj on (tgt+pos, tgt+pos, tgt): returns (qk [.., 2C], v [.., C])."""
+    return _ProjPair.apply("split", qk_in, v_in, in_proj_weight, in_proj_bias, None, None)
 
 
 # ------------------------------------------------------------------------------------------
@@ -279,6 +404,7 @@ class _AddLayerNorm(torch.autograd.Function):
         y2 = torch.empty_like(x2) if pos is not None else None
         _call("poet_add_layernorm_fwd", _p(x2), _p(r2), _p(gamma), _p(beta), _p(p2), _p(y), _p(y2), _p(xhat), _p(rstd),
               R, Cc, eps, _stream(x))
+        ctx.gb_params = (gamma, beta)
         if need_grad:
             ctx.save_for_backward(xhat, rstd, gamma)
         ctx.has_r, ctx.has_pos, ctx.shape = r is not None, pos is not None, x.shape
@@ -295,8 +421,14 @@ class _AddLayerNorm(torch.autograd.Function):
         if gy is None:
             gy, gy2 = gy2, None
         dz = torch.empty_like(xhat)
-        dgb = torch.zeros(2, Cc, device=xhat.device, dtype=torch.float32)
-        _call("poet_layernorm_bwd", _p(gy), _p(gy2), _p(xhat), _p(rstd), _p(gamma), _p(dz), _p(dgb[0]), _p(dgb[1]),
+        g_slot, b_slot = _grad_slot(ctx.gb_params[0]), _grad_slot(ctx.gb_params[1])
+        if g_slot is not None and b_slot is not None:            # accumulate straight into gamma.grad / beta.grad
+            dgb = (None, None)
+            dg_ptr, db_ptr = _p(g_slot), _p(b_slot)
+        else:
+            dgb = torch.zeros(2, Cc, device=xhat.device, dtype=torch.float32)
+            dg_ptr, db_ptr = _p(dgb[0]), _p(dgb[1])
+        _call("poet_layernorm_bwd", _p(gy), _p(gy2), _p(xhat), _p(rstd), _p(gamma), _p(dz), dg_ptr, db_ptr,
               R, Cc, _stream(xhat))
         dz = dz.view(ctx.shape)
         gpos = None
@@ -541,13 +673,18 @@ class _FlattenLevels(torch.autograd.Function):
             _call("poet_nchw_to_tokens", _p(_chk(m)), _p(vec), _p(out), B, Cc, hws[l], S, off, _stream(out))
             off += hws[l]
         ctx.meta = (B, Cc, hws, S, [m.shape for m in maps], level_embed is not None)
+        ctx.le_param = level_embed
         return out
 
     @staticmethod
     def backward(ctx, g):
         B, Cc, hws, S, shapes, has_le = ctx.meta
         g = _chk(g)
-        gle = torch.zeros((len(hws), Cc), device=g.device, dtype=torch.float32) if (has_le and ctx.needs_input_grad[0]) else None
+        gle, gle_ret = None, None
+        if has_le and ctx.needs_input_grad[0]:
+            gle = _grad_slot(ctx.le_param)                 # accumulate straight into level_embed.grad when it exists
+            if gle is None:
+                gle = gle_ret = torch.zeros((len(hws), Cc), device=g.device, dtype=torch.float32)
         outs = []
         off = 0
         for l, hw in enumerate(hws):
@@ -558,7 +695,7 @@ class _FlattenLevels(torch.autograd.Function):
                       _stream(g))
             outs.append(gm)
             off += hw
-        return (gle, *outs)
+        return (gle_ret, *outs)
 
 
 def flatten_levels(maps: Sequence[torch.Tensor], level_embed: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -261,18 +261,20 @@ class _PosTokens(torch.autograd.Function):
             hws.append(int(m.shape[1] * m.shape[2]))
             off += hws[-1]
         ctx.meta = (B, C, S, hws)
+        ctx.le_param = level_embed
         return out
 
     @staticmethod
     def backward(ctx, g):
         B, C, S, hws = ctx.meta
         g = g.contiguous()
-        gle = torch.zeros((len(hws), C), device=g.device, dtype=torch.float32)
+        slot = ops._grad_slot(ctx.le_param)               # accumulate straight into level_embed.grad when it exists
+        gle = slot if slot is not None else torch.zeros((len(hws), C), device=g.device, dtype=torch.float32)
         off = 0
         for l, hw in enumerate(hws):
             ops._call("poet_tokens_to_nchw", g.data_ptr(), None, gle[l].data_ptr(), B, C, hw, S, off, ops._stream(g))
             off += hw
-        return (gle, None, None, *([None] * len(hws)))
+        return (None if slot is not None else gle, None, None, *([None] * len(hws)))
 
 
 def build(args):

@@ -1,31 +1,37 @@
-// tcgen05 (5th-gen tensor core) GEMM on fp32 data with split-bf16 operands.
+// tcgen05 (5th-gen tensor core) GEMM on fp32 data with split-bf16 operands: persistent,
+// warp-specialised, TMEM double-buffered.
 //
 //   C[M,N] = epi( alpha * op(A)[M,K] . op(B)[K,N] ),  fp32 in / fp32 out, accumulators in TMEM.
 //
 // Why split precision: the reference computes every nn.Linear in fp32 and the parity budget is
-// 1e-4 abs on the translation head; plain TF32/BF16 operands miss it (1.9e-4 / 1.8e-3).
-// Each fp32 operand x is split exactly into hi = bf16(x), lo = bf16(x - hi) and the product is
-// accumulated as hi*lo + lo*hi + hi*hi in fp32 (POET_GEMM_BF16X3, relative error ~2^-17 per product,
-// fp32-grade after accumulation); POET_GEMM_BF16 issues only hi*hi (throughput mode).
+// 1e-4 abs on the translation head; plain TF32/BF16 operands miss it (measured: bf16 single pass
+// gives 3e-3..7e-3 on the translation head).  Each fp32 operand x is split exactly into
+// hi = bf16(x), lo = bf16(x - hi) and the product is accumulated as hi*lo + lo*hi + hi*hi in fp32
+// (POET_GEMM_BF16X3: ~2^-17 per product, fp32-grade after accumulation, measured <= 3e-5 rel. vs fp64);
+// POET_GEMM_BF16 issues only hi*hi (throughput mode).
 //
-// One 128 x BN output tile per CTA, BK = 64, 2 smem stages, warp-specialised:
-//   warps [0,PW)  A producers (and B producers when B is an fp32 activation): 128-bit global loads
-//                 (the next k-block is prefetched into registers while the current one is converted),
-//                 split/convert, st.shared into the UMMA canonical SWIZZLE_128B layout (K-major or
-//                 MN-major: forward / dgrad / wgrad need no transposes), fence.proxy.async, arrive on
-//                 full[stage].  Afterwards the epilogue: tcgen05.ld 32 columns at a time (one accumulator
-//                 row per thread), bias / ReLU / ReLU-gate / row-mask / accumulate / split-K reduction.
-//   warp PW       TMEM alloc + single-thread tcgen05.mma issue; tcgen05.commit releases smem stages.
-//   warp PW+1     TMA: when B is a weight it was split to bf16 hi/lo planes once per step
-//                 (poet_split_bf16) and is fetched by cp.async.bulk.tensor straight into the swizzled
-//                 stage (complete_tx on the same full[stage] barrier): no per-CTA re-conversion of W.
+// One CTA per SM walks a static round-robin list of (128 x BN output tile, k-split) work items:
+//   warps [0,PW)    producers: 128-bit global loads of the fp32 A tile (and of B when it is an fp32
+//                   activation: wgrad), next k-block prefetched into registers, split/convert, st.shared
+//                   into the UMMA canonical SWIZZLE_128B layout (K-major or MN-major: forward / dgrad /
+//                   wgrad need no transposes), fence.proxy.async, arrive on full[stage].  The smem ring
+//                   runs across work items, so the next tile's operands stream in during this tile's epilogue.
+//   warp PW         single-thread tcgen05.mma issue into TMEM accumulator buffer (tile & 1);
+//                   tcgen05.commit frees smem stages and publishes finished accumulators.
+//   warp PW+1       TMA: weights are split to bf16 hi/lo planes once per step (poet_split_bf16) and
+//                   fetched by cp.async.bulk.tensor straight into the swizzled stage.
+//   warps PW+2..+5  epilogue: tcgen05.ld (one accumulator row per thread) -> per-warp smem transpose ->
+//                   coalesced 128-byte rows: bias / ReLU / ReLU-gate / row mask / accumulate / split-K
+//                   reduction.  Runs concurrently with the next tile's MMAs (other TMEM buffer).
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace tc {
 
-constexpr int BM = 128, BK = 64, STAGES = 2;
+constexpr int BM = 128, BK = 64;
+constexpr int EPI_WARPS = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -124,9 +130,44 @@ struct Args {
   float alpha;
   const float* bias; const float* gate; const uint8_t* row_mask;
   int flags;
-  int kb_per_split;       // k-blocks (of 64) per grid.z slice
+  int kb_per_split;       // k-blocks (of 64) per split
   int splits;
+  int n_tiles, total_work;
+  int debug;              // POET_GEMM_DEBUG bit flags (pipeline bisection only): 1 no A loads, 2 no A stores, 4 no TMA, 8 no epilogue stores
 };
+
+// work item w -> (m0, n0, split, k-block range); n fastest so concurrent CTAs share A rows in L2
+struct Work {
+  int m0, n0, split, kb0, nkb;
+};
+__device__ __forceinline__ Work decode(const Args& p, int w, int bn) {
+  Work k;
+  k.split = w % p.splits;
+  const int tile = w / p.splits;
+  k.n0 = (tile % p.n_tiles) * bn;
+  k.m0 = (tile / p.n_tiles) * BM;
+  const int total_kb = (p.K + BK - 1) / BK;
+  k.kb0 = k.split * p.kb_per_split;
+  k.nkb = min(total_kb, k.kb0 + p.kb_per_split) - k.kb0;
+  return k;
+}
+
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -163,7 +204,7 @@ struct Tile {
   }
 
   template <bool WITH_LO>
-  __device__ static __forceinline__ void store(uint8_t* s_hi, uint8_t* s_lo, int tid, const float4 (&v)[CH][2]) {
+  __device__ static __forceinline__ void store(uint32_t s_hi, uint32_t s_lo, int tid, const float4 (&v)[CH][2]) {
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
       const int ch = tid + i * NT;
@@ -177,45 +218,49 @@ struct Tile {
       for (int j = 0; j < 8; ++j) h[j] = __bfloat162float(__float2bfloat16_rn(x[j]));
       uint4 hi;
       hi.x = pack_bf16(h[0], h[1]); hi.y = pack_bf16(h[2], h[3]); hi.z = pack_bf16(h[4], h[5]); hi.w = pack_bf16(h[6], h[7]);
-      *reinterpret_cast<uint4*>(s_hi + off) = hi;
+      sts128(s_hi + off, hi);
       if (WITH_LO) {
         uint4 lo;
         lo.x = pack_bf16(x[0] - h[0], x[1] - h[1]); lo.y = pack_bf16(x[2] - h[2], x[3] - h[3]);
         lo.z = pack_bf16(x[4] - h[4], x[5] - h[5]); lo.w = pack_bf16(x[6] - h[6], x[7] - h[7]);
-        *reinterpret_cast<uint4*>(s_lo + off) = lo;
+        sts128(s_lo + off, lo);
       }
     }
   }
 };
 
-template <int BN, bool A_MN, bool B_MN, bool X3, bool B_TMA, int PW>
-__global__ void __launch_bounds__((PW + 2) * 32, 1)
+template <int BN, bool X3, int STAGES>
+struct SmemPlan {
+  static constexpr int PLANES = X3 ? 2 : 1;
+  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;         // one bf16 plane
+  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * PLANES;
+  static constexpr int EPI_TILE_BYTES = 32 * 36 * 4;                          // per-warp transpose tile
+  static constexpr int EPI_BYTES = EPI_WARPS * EPI_TILE_BYTES;
+  static constexpr size_t TOTAL = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024;
+};
+
+template <int BN, bool A_MN, bool B_MN, bool X3, bool B_TMA, int PW, int STAGES>
+__global__ void __launch_bounds__((PW + 2 + EPI_WARPS) * 32, 1)
 gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo) {
-  constexpr int NT = PW * 32;                                        // producer / epilogue threads
-  constexpr int PLANES = X3 ? 2 : 1;
-  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;         // one bf16 plane
-  constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * PLANES;
+  using SP = SmemPlan<BN, X3, STAGES>;
+  constexpr int NT = PW * 32;                                        // producer threads
+  constexpr int PLANES = SP::PLANES, A_BYTES = SP::A_BYTES, B_BYTES = SP::B_BYTES, STAGE_BYTES = SP::STAGE_BYTES;
   using TA = Tile<A_MN ? BK : BM, A_MN ? BM / 64 : 1, NT>;
   using TB = Tile<B_MN ? BK : BN, B_MN ? BN / 64 : 1, NT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int total_kb = (p.K + BK - 1) / BK;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
-  const int kb_end = min(total_kb, kb_begin + p.kb_per_split);
-  const int nkb = kb_end - kb_begin;
-
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accum_bar = smem_u32(&bars[2 * STAGES]);
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + 2]);
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, NT + (B_TMA ? 1 : 0)); mbar_init(empty0 + 8 * s, 1); }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == PW) tmem_alloc(smem_u32(&s_tmem), BN);
+  if (warp == PW) tmem_alloc(smem_u32(&s_tmem), 2 * BN);             // two accumulator buffers
   if (B_TMA && warp == PW + 1 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi) : "memory");
     if (X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo) : "memory");
@@ -225,41 +270,73 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
 
-  auto a_hi_of = [&](int s) { return smem + s * STAGE_BYTES; };
-  auto b_hi_of = [&](int s) { return smem + s * STAGE_BYTES + A_BYTES * PLANES; };
-  auto loadA = [&](int i, float4 (&v)[TA::CH][2]) {
-    const int k0 = (kb_begin + i) * BK;
-    if (A_MN) TA::load(p.A, p.lda, k0, p.K, m0, p.M, tid, v);
-    else      TA::load(p.A, p.lda, m0, p.M, k0, p.K, tid, v);
-  };
-  auto publish = [&](int i, const float4 (&va)[TA::CH][2]) {
-    const int s = i % STAGES;
-    if constexpr (B_TMA) {
-      if (i >= STAGES) mbar_wait(empty0 + 8 * s, ((i / STAGES) - 1) & 1);
-      TA::template store<X3>(a_hi_of(s), a_hi_of(s) + A_BYTES, tid, va);
-    } else {                                                  // fp32 activation B: loads issued before the stage wait
-      float4 vb[TB::CH][2];
-      const int k0 = (kb_begin + i) * BK;
-      if (B_MN) TB::load(p.B, p.ldb, k0, p.K, n0, p.N, tid, vb);
-      else      TB::load(p.B, p.ldb, n0, p.N, k0, p.K, tid, vb);
-      if (i >= STAGES) mbar_wait(empty0 + 8 * s, ((i / STAGES) - 1) & 1);
-      TA::template store<X3>(a_hi_of(s), a_hi_of(s) + A_BYTES, tid, va);
-      TB::template store<X3>(b_hi_of(s), b_hi_of(s) + B_BYTES, tid, vb);
-    }
-    fence_proxy_async();                                      // generic-proxy smem writes -> visible to the tensor core
-    mbar_arrive(full0 + 8 * s);
-  };
-
   if (warp < PW) {
     // ===================== producers =====================
+    int it = 0;                                                    // k-blocks published so far (ring position)
+    auto publish = [&](const Work& wk, int kb, const float4 (&va)[TA::CH][2]) {
+      const int s = it % STAGES;
+      const uint32_t a_hi = smem_u32(smem) + s * STAGE_BYTES;
+      const uint32_t b_hi = a_hi + A_BYTES * PLANES;
+      if constexpr (B_TMA) {
+        if (it >= STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
+        if (!(p.debug & 2)) TA::template store<X3>(a_hi, a_hi + A_BYTES, tid, va);
+      } else {                                                  // fp32 activation B: loads issued before the stage wait
+        float4 vb[TB::CH][2];
+        const int k0 = (wk.kb0 + kb) * BK;
+        if (B_MN) TB::load(p.B, p.ldb, k0, p.K, wk.n0, p.N, tid, vb);
+        else      TB::load(p.B, p.ldb, wk.n0, p.N, k0, p.K, tid, vb);
+        if (it >= STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
+        TA::template store<X3>(a_hi, a_hi + A_BYTES, tid, va);
+        TB::template store<X3>(b_hi, b_hi + B_BYTES, tid, vb);
+      }
+      fence_proxy_async();                                      // generic-proxy smem writes -> visible to the tensor core
+      mbar_arrive(full0 + 8 * s);
+      ++it;
+    };
+    auto loadA = [&](const Work& wk, int kb, float4 (&v)[TA::CH][2]) {
+      if (p.debug & 1) {
+#pragma unroll
+        for (int i = 0; i < TA::CH; ++i) { v[i][0] = make_float4(1.f, 1.f, 1.f, 1.f); v[i][1] = v[i][0]; }
+        return;
+      }
+      const int k0 = (wk.kb0 + kb) * BK;
+      if (A_MN) TA::load(p.A, p.lda, k0, p.K, wk.m0, p.M, tid, v);
+      else      TA::load(p.A, p.lda, wk.m0, p.M, k0, p.K, tid, v);
+    };
+    // flattened (work item, k-block) sequence with a one-deep register prefetch across item boundaries
     float4 ra[TA::CH][2], rb[TA::CH][2];
-    if (nkb > 0) loadA(0, ra);
-    for (int i = 0; i < nkb; i += 2) {
-      if (i + 1 < nkb) loadA(i + 1, rb);                      // prefetch the next k-block into registers
-      publish(i, ra);
-      if (i + 1 < nkb) {
-        if (i + 2 < nkb) loadA(i + 2, ra);
-        publish(i + 1, rb);
+    int w = blockIdx.x;
+    if (w < p.total_work) {
+      Work cur = decode(p, w, BN);
+      int kb = 0;
+      loadA(cur, 0, ra);
+      bool more = true;
+      while (more) {
+        // position of the element after (cur, kb)
+        Work nxt = cur;
+        int nkb_i = kb + 1, nw = w;
+        bool has_next = true;
+        if (nkb_i == cur.nkb) {
+          nw = w + gridDim.x;
+          nkb_i = 0;
+          if (nw < p.total_work) nxt = decode(p, nw, BN); else has_next = false;
+        }
+        if (has_next) loadA(nxt, nkb_i, rb);
+        publish(cur, kb, ra);
+        if (!has_next) break;
+        // second half of the unrolled pair: roles of ra / rb swapped
+        Work nxt2 = nxt;
+        int nkb2 = nkb_i + 1, nw2 = nw;
+        bool has_next2 = true;
+        if (nkb2 == nxt.nkb) {
+          nw2 = nw + gridDim.x;
+          nkb2 = 0;
+          if (nw2 < p.total_work) nxt2 = decode(p, nw2, BN); else has_next2 = false;
+        }
+        if (has_next2) loadA(nxt2, nkb2, ra);
+        publish(nxt, nkb_i, rb);
+        more = has_next2;
+        cur = nxt2; kb = nkb2; w = nw2;
       }
     }
   } else if (warp == PW) {
@@ -271,133 +348,156 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
       //           a 16-wide k-step is two k groups = 2048 B.
       constexpr uint32_t A_LBO = A_MN ? BK * 128 : 16, A_STEP = A_MN ? 2048 : 32;
       constexpr uint32_t B_LBO = B_MN ? BK * 128 : 16, B_STEP = B_MN ? 2048 : 32;
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        mbar_wait(full0 + 8 * s, (i / STAGES) & 1);
+      int it = 0, tcnt = 0;
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcnt) {
+        const Work wk = decode(p, w, BN);
+        const int ab = tcnt & 1;
+        if (tcnt >= 2) mbar_wait(tempty0 + 8 * ab, ((tcnt >> 1) - 1) & 1);    // epilogue drained this buffer
         tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + A_BYTES * PLANES, b_lo = b_hi + B_BYTES;
+        const uint32_t tacc = tmem_base + (uint32_t)(ab * BN);
+        for (int i = 0; i < wk.nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + A_BYTES * PLANES, b_lo = b_hi + B_BYTES;
 #pragma unroll
-        for (int j = 0; j < BK / 16; ++j) {
-          const uint64_t dah = make_desc(a_hi + j * A_STEP, A_LBO, 1024);
-          const uint64_t dbh = make_desc(b_hi + j * B_STEP, B_LBO, 1024);
-          const uint32_t first = (i | j) ? 1u : 0u;
-          if (X3) {
-            const uint64_t dal = make_desc(a_lo + j * A_STEP, A_LBO, 1024);
-            const uint64_t dbl = make_desc(b_lo + j * B_STEP, B_LBO, 1024);
-            umma_bf16(tmem_base, dah, dbl, idesc, first);        // small cross terms first
-            umma_bf16(tmem_base, dal, dbh, idesc, 1u);
-            umma_bf16(tmem_base, dah, dbh, idesc, 1u);
-          } else {
-            umma_bf16(tmem_base, dah, dbh, idesc, first);
-          }
-        }
-        umma_commit(empty0 + 8 * s);                             // stage reusable once these MMAs retire
-      }
-      umma_commit(accum_bar);                                    // accumulator complete
-    }
-  } else if (B_TMA && lane == 0) {
-    // ===================== TMA: pre-split bf16 weight planes =====================
-    for (int i = 0; i < nkb; ++i) {
-      const int s = i % STAGES;
-      if (i >= STAGES) mbar_wait(empty0 + 8 * s, ((i / STAGES) - 1) & 1);
-      const uint32_t bar = full0 + 8 * s;
-      mbar_arrive_expect_tx(bar, B_BYTES * PLANES);
-      const int k0 = (kb_begin + i) * BK;
-      const uint32_t b_hi = smem_u32(b_hi_of(s)), b_lo = b_hi + B_BYTES;
-      if (B_MN) {
-#pragma unroll
-        for (int g = 0; g < BN / 64; ++g) {                        // box = 64 (n, contiguous) x 64 (k rows)
-          tma_load_2d(b_hi + g * (BK * 128), &tm_hi, n0 + g * 64, k0, bar);
-          if (X3) tma_load_2d(b_lo + g * (BK * 128), &tm_lo, n0 + g * 64, k0, bar);
-        }
-      } else {                                                     // box = 64 (k, contiguous) x BN (n rows)
-        tma_load_2d(b_hi, &tm_hi, k0, n0, bar);
-        if (X3) tma_load_2d(b_lo, &tm_lo, k0, n0, bar);
-      }
-    }
-  }
-
-  // ===================== epilogue (producer warps) =====================
-  if (warp < PW) {
-    if (nkb > 0) {
-      mbar_wait(accum_bar, 0);
-      tc_fence_after();
-    }
-    // TMEM hands each thread one accumulator ROW (32 consecutive columns per tcgen05.ld).  Storing that
-    // directly would make every warp store touch 32 different rows; instead each warp transposes its
-    // 32x32 block through a private padded smem tile (the operand stages are free once accum_bar fired)
-    // so that lane = column and every global load / store / reduction is one coalesced 128-byte row.
-    constexpr int GROUPS = PW / 4, COLS = BN / GROUPS;
-    const int quarter = warp & 3, group = warp >> 2;
-    const bool relu = p.flags & POET_GEMM_RELU, accum = p.flags & POET_GEMM_ACCUMULATE;
-    float* tile = reinterpret_cast<float*>(smem) + warp * (32 * 33);
-    const int mrow0 = m0 + quarter * 32;
-    // rows of this warp's quarter that the padding mask zeroes (bit r = row mrow0 + r)
-    const uint32_t dead_rows = __ballot_sync(0xffffffffu, p.row_mask != nullptr && mrow0 + lane < p.M &&
-                                                              p.row_mask[min(mrow0 + lane, p.M - 1)] != 0);
-#pragma unroll 1
-    for (int cc = 0; cc < COLS; cc += 32) {
-      const int col = group * COLS + cc;
-      float v[32];
-      if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col, v);
-      else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
-      }
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = v[j];
-      __syncwarp();
-      const int n = n0 + col + lane;                           // this lane's output column
-      if (n >= p.N) continue;
-      const float bias = (p.bias != nullptr && (p.splits == 1 || blockIdx.z == 0)) ? __ldg(p.bias + n) : 0.f;
-      const int rows = min(32, p.M - mrow0);
-      float* cbase = p.C + (int64_t)mrow0 * p.ldc + n;
-      const float alpha = p.alpha;
-      if (p.splits > 1) {
-#pragma unroll 8
-        for (int r = 0; r < rows; ++r)
-          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(cbase + (int64_t)r * p.ldc), "f"(alpha * tile[r * 33 + lane] + bias) : "memory");
-      } else if (p.gate == nullptr && !accum) {
-        // common case: bias (+ReLU) (+row mask); nothing to load, stores are fire-and-forget
-#pragma unroll 8
-        for (int r = 0; r < rows; ++r) {
-          float x = alpha * tile[r * 33 + lane] + bias;
-          if (relu) x = fmaxf(x, 0.f);
-          if ((dead_rows >> r) & 1u) x = 0.f;
-          cbase[(int64_t)r * p.ldc] = x;
-        }
-      } else {
-        // ReLU-gate (dgrad through the FFN activation) and/or accumulate: batches of 16 rows so the
-        // dependent global loads overlap
-        const float* gbase = p.gate ? p.gate + (int64_t)mrow0 * p.ldc + n : nullptr;
-#pragma unroll 1
-        for (int r0 = 0; r0 < rows; r0 += 16) {
-          float g[16], old[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int r = min(r0 + i, rows - 1);
-            g[i] = gbase ? __ldg(gbase + (int64_t)r * p.ldc) : 1.f;
-            old[i] = accum ? cbase[(int64_t)r * p.ldc] : 0.f;
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int r = r0 + i;
-            if (r < rows) {
-              float x = alpha * tile[r * 33 + lane] + bias;
-              if (relu) x = fmaxf(x, 0.f);
-              if (!(g[i] > 0.f) || ((dead_rows >> r) & 1u)) x = 0.f;
-              cbase[(int64_t)r * p.ldc] = x + old[i];
+          for (int j = 0; j < BK / 16; ++j) {
+            const uint64_t dah = make_desc(a_hi + j * A_STEP, A_LBO, 1024);
+            const uint64_t dbh = make_desc(b_hi + j * B_STEP, B_LBO, 1024);
+            const uint32_t first = (i | j) ? 1u : 0u;
+            if (X3) {
+              const uint64_t dal = make_desc(a_lo + j * A_STEP, A_LBO, 1024);
+              const uint64_t dbl = make_desc(b_lo + j * B_STEP, B_LBO, 1024);
+              umma_bf16(tacc, dah, dbl, idesc, first);            // small cross terms first
+              umma_bf16(tacc, dal, dbh, idesc, 1u);
+              umma_bf16(tacc, dah, dbh, idesc, 1u);
+            } else {
+              umma_bf16(tacc, dah, dbh, idesc, first);
             }
           }
+          umma_commit(empty0 + 8 * s);                             // stage reusable once these MMAs retire
+        }
+        umma_commit(tfull0 + 8 * ab);                              // accumulator complete
+      }
+    }
+  } else if (warp == PW + 1) {
+    if (B_TMA && lane == 0) {
+      // ===================== TMA: pre-split bf16 weight planes =====================
+      int it = 0;
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        const Work wk = decode(p, w, BN);
+        for (int i = 0; i < wk.nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          if (it >= STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
+          const uint32_t bar = full0 + 8 * s;
+          if (p.debug & 4) { mbar_arrive(bar); continue; }
+          mbar_arrive_expect_tx(bar, B_BYTES * PLANES);
+          const int k0 = (wk.kb0 + i) * BK;
+          const uint32_t b_hi = smem_u32(smem + s * STAGE_BYTES + A_BYTES * PLANES), b_lo = b_hi + B_BYTES;
+          if (B_MN) {
+#pragma unroll
+            for (int g = 0; g < BN / 64; ++g) {                      // box = 64 (n, contiguous) x 64 (k rows)
+              tma_load_2d(b_hi + g * (BK * 128), &tm_hi, wk.n0 + g * 64, k0, bar);
+              if (X3) tma_load_2d(b_lo + g * (BK * 128), &tm_lo, wk.n0 + g * 64, k0, bar);
+            }
+          } else {                                                   // box = 64 (k, contiguous) x BN (n rows)
+            tma_load_2d(b_hi, &tm_hi, k0, wk.n0, bar);
+            if (X3) tma_load_2d(b_lo, &tm_lo, k0, wk.n0, bar);
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    // TMEM hands each thread one accumulator ROW (32 consecutive columns per tcgen05.ld).  Each warp
+    // transposes its 32x32 block through a private padded smem tile so that lane = column and every
+    // global load / store / reduction is one coalesced 128-byte row.
+    const int quarter = warp & 3;                                    // TMEM lane quarter this warp may access
+    // Transpose tile: 32 rows x 36 floats (144-byte rows keep every 128-bit access bank-conflict free).
+    // Write: thread = accumulator row, 8 x STS.128.  Read back: lane -> (row lane/8 + 4i, columns 4*(lane%8)..+3),
+    // so every global access is a 128-bit vector and a warp instruction covers four full 128-byte row segments.
+    const uint32_t tile = smem_u32(smem) + STAGES * STAGE_BYTES + (warp - (PW + 2)) * SP::EPI_TILE_BYTES;
+    const bool relu = p.flags & POET_GEMM_RELU, accum = p.flags & POET_GEMM_ACCUMULATE;
+    const float alpha = p.alpha;
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+    int tcnt = 0;
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcnt) {
+      const Work wk = decode(p, w, BN);
+      const int ab = tcnt & 1;
+      const int mrow0 = wk.m0 + quarter * 32;
+      const int rows = min(32, p.M - mrow0);
+      // rows of this warp's quarter that the padding mask zeroes (bit r = row mrow0 + r)
+      const uint32_t dead_rows = __ballot_sync(0xffffffffu, p.row_mask != nullptr && mrow0 + lane < p.M &&
+                                                                p.row_mask[min(mrow0 + lane, p.M - 1)] != 0);
+      mbar_wait(tfull0 + 8 * ab, (tcnt >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int col = 0; col < BN; col += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN + col), v);
+        if (col + 32 >= BN) {                                        // last read of this accumulator: release it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty0 + 8 * ab);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128(tile + lane * 144 + j * 16, make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                                        __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
+        __syncwarp();
+        const int n = wk.n0 + col + c4;                            // first of this lane's four output columns
+        if (n >= p.N || rows <= 0 || (p.debug & 8)) continue;
+        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr && wk.split == 0) bias = ldg4(p.bias + n);
+        float4 o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 t = lds128(tile + (rsub + 4 * i) * 144 + c4 * 4);
+          o[i] = make_float4(alpha * t.x + bias.x, alpha * t.y + bias.y, alpha * t.z + bias.z, alpha * t.w + bias.w);
+        }
+        float* cbase = p.C + (int64_t)mrow0 * p.ldc + n;
+        if (p.splits > 1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = rsub + 4 * i;
+            if (r < rows)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cbase + (int64_t)r * p.ldc), "f"(o[i].x),
+                           "f"(o[i].y), "f"(o[i].z), "f"(o[i].w) : "memory");
+          }
+          continue;
+        }
+        float4 g[8];
+        if (p.gate != nullptr) {                                   // ReLU backward: keep where the forward activation was > 0
+          const float* gbase = p.gate + (int64_t)mrow0 * p.ldc + n;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = ldg4(gbase + (int64_t)min(rsub + 4 * i, rows - 1) * p.ldc);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            o[i].x = g[i].x > 0.f ? o[i].x : 0.f; o[i].y = g[i].y > 0.f ? o[i].y : 0.f;
+            o[i].z = g[i].z > 0.f ? o[i].z : 0.f; o[i].w = g[i].w > 0.f ? o[i].w : 0.f;
+          }
+        }
+        if (accum) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = ld4(cbase + (int64_t)min(rsub + 4 * i, rows - 1) * p.ldc);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = rsub + 4 * i;
+          float4 x = o[i];
+          if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+          if ((dead_rows >> r) & 1u) x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (accum) { x.x += g[i].x; x.y += g[i].y; x.z += g[i].z; x.w += g[i].w; }
+          if (r < rows) st4(cbase + (int64_t)r * p.ldc, x);
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == PW) tmem_dealloc(tmem_base, BN);
+  if (warp == PW) tmem_dealloc(tmem_base, 2 * BN);
 }
 
 // ---- fp32 -> bf16 hi/lo planes (weights, once per step) --------------------------------------
@@ -445,16 +545,18 @@ static int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t r
 }
 
 template <int BN, bool A_MN, bool B_MN, bool X3, bool B_TMA, int PW>
-int launch(const Args& a, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t s) {
-  constexpr int PLANES = X3 ? 2 : 1;
-  constexpr size_t stage_smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) * PLANES;
-  constexpr size_t epi_smem = (size_t)PW * 32 * 33 * sizeof(float);          // per-warp transpose tiles
-  constexpr size_t smem = (stage_smem > epi_smem ? stage_smem : epi_smem) + 1024;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, X3, B_TMA, PW>;
+int launch(Args a, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t s) {
+  // 128 x 256 tiles: 2 stages of 96 KB (x3); 128 x 128 tiles: 3 stages of 64 KB
+  constexpr int STAGES = (BN == 256) ? 2 : 3;
+  constexpr size_t smem = SmemPlan<BN, X3, STAGES>::TOTAL;
+  static_assert(smem <= 227 * 1024, "shared memory plan exceeds the 227 KB per-CTA limit");
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, X3, B_TMA, PW, STAGES>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  dim3 grid(a.N / BN, poet_ceil_div(a.M, BM), a.splits);
-  kern<<<grid, (PW + 2) * 32, smem, s>>>(a, mh, ml);
+  a.n_tiles = a.N / BN;
+  a.total_work = a.n_tiles * poet_ceil_div(a.M, BM) * a.splits;
+  const int grid = a.total_work < POET_NUM_SMS ? a.total_work : POET_NUM_SMS;       // persistent: one CTA per SM
+  kern<<<grid, (PW + 2 + EPI_WARPS) * 32, smem, s>>>(a, mh, ml);
   return poet_launch_status();
 }
 
@@ -464,10 +566,10 @@ int dispatch(const Args& a, bool a_mn, bool b_mn, bool b_tma, const CUtensorMap&
     if (a_mn) return POET_ERR_UNSUPPORTED;
     return b_mn ? launch<BN, false, true, X3, true, 8>(a, mh, ml, s) : launch<BN, false, false, X3, true, 8>(a, mh, ml, s);
   }
-  if (!a_mn && !b_mn) return launch<BN, false, false, X3, false, 16>(a, mh, ml, s);
-  if (!a_mn && b_mn) return launch<BN, false, true, X3, false, 16>(a, mh, ml, s);
-  if (a_mn && b_mn) return launch<BN, true, true, X3, false, 16>(a, mh, ml, s);
-  return launch<BN, true, false, X3, false, 16>(a, mh, ml, s);
+  if (!a_mn && !b_mn) return launch<BN, false, false, X3, false, 8>(a, mh, ml, s);
+  if (!a_mn && b_mn) return launch<BN, false, true, X3, false, 8>(a, mh, ml, s);
+  if (a_mn && b_mn) return launch<BN, true, true, X3, false, 8>(a, mh, ml, s);
+  return launch<BN, true, false, X3, false, 8>(a, mh, ml, s);
 }
 
 }  // namespace tc
@@ -497,11 +599,20 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
   tc::Args a;
   a.A = A; a.lda = lda; a.B = b_tma ? nullptr : Bm; a.ldb = ldb; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
   a.alpha = alpha; a.bias = bias; a.gate = gate; a.row_mask = row_mask; a.flags = flags;
-  // 128 x 256 tiles when that still fills the machine, else 128 x 128 (decoder rows: more CTAs in flight)
-  int bn = (N % 256 == 0) ? 256 : 128;
-  if (bn == 256 && (int64_t)(N / 256) * poet_ceil_div(M, tc::BM) < POET_NUM_SMS / 2) bn = 128;
-  const int64_t tiles = (int64_t)(N / bn) * poet_ceil_div(M, tc::BM);
+  a.n_tiles = 0; a.total_work = 0;
+  static const int dbg = []() { const char* e = getenv("POET_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
+  a.debug = dbg;
+  const int m_tiles = poet_ceil_div(M, tc::BM);
   const int total_kb = poet_ceil_div(K, tc::BK);
+  // Tile width: rounds of the persistent grid x work per round.  128-wide tiles quantise better over 148 SMs
+  // but convert every A tile twice as often, hence the 15 % handicap.
+  int bn = 128;
+  if (N % 256 == 0 && b_tma) {          // fp32-B variants (wgrad) keep 128-wide tiles: both operands are converted in-kernel
+    const double c256 = (double)poet_ceil_div((int64_t)(N / 256) * m_tiles, POET_NUM_SMS) * 256.0;
+    const double c128 = (double)poet_ceil_div((int64_t)(N / 128) * m_tiles, POET_NUM_SMS) * 128.0 * 1.15;
+    if (c256 <= c128) bn = 256;
+  }
+  const int64_t tiles = (int64_t)(N / bn) * m_tiles;
   int splits = 1;
   const bool linear_epi = !(flags & POET_GEMM_RELU) && gate == nullptr && row_mask == nullptr;
   if (linear_epi && !a_kcontig && tiles < POET_NUM_SMS && total_kb >= 8) {       // weight-gradient shape

@@ -300,23 +300,27 @@ def run_gpu(args):
     # ---- per-kernel table: an eager pass with CUDA events around every library call ----------
     # (events cannot bracket nodes inside a replayed graph; the kernels and their arguments are identical)
     ktimes, ksteps = {}, min(args.steps, 5)
-    launches = 0
-    if rank == 0 or world > 1:
-        l0 = ops.launch_count()
-        eager_step(d_srcs, d_masks, d_boxes, d_labels)
-        launches = (ops.launch_count() - l0) * args.steps          # launches replayed per step x timed steps
-        if args.kernel_table and rank == 0:
-            sync_all() if world == 1 else torch.cuda.synchronize()
-            ops.kernel_timing(True)
-            for _ in range(ksteps):
-                flush.fill_(1)
-                # park the GPU (~40 ms spin) while the host enqueues the whole step, so the events measure
-                # back-to-back device execution instead of Python launch gaps
-                torch.cuda._sleep(80_000_000)
-                eager_step(d_srcs, d_masks, d_boxes, d_labels)
-            torch.cuda.synchronize()
-            ktimes = ops.kernel_times_ms()
-            ops.kernel_timing(False)
+
+    def local_step():                                   # no collective: only rank 0 runs the table pass
+        reducer.zero()
+        out, _ = model.forward_pyramid(d_srcs, d_masks, d_boxes, d_labels)
+        loss_fn(out).backward()
+
+    l0 = ops.launch_count()
+    local_step()
+    launches = (ops.launch_count() - l0) * args.steps          # library launches replayed per step x timed steps
+    if args.kernel_table and rank == 0:
+        torch.cuda.synchronize()
+        ops.kernel_timing(True)
+        for _ in range(ksteps):
+            flush.fill_(1)
+            # park the GPU (~40 ms spin) while the host enqueues the whole step, so the events measure
+            # back-to-back device execution instead of Python launch gaps
+            torch.cuda._sleep(80_000_000)
+            local_step()
+        torch.cuda.synchronize()
+        ktimes = ops.kernel_times_ms()
+        ops.kernel_timing(False)
     if world > 1:
         dist.barrier()
 

@@ -370,8 +370,14 @@ def roofline_from(ktimes, peaks, steps, ms_per_step):
     # group GEMM shapes into one dominant-kernel line as well
     gemm = [r for r in rows if r["kernel"].startswith("poet_gemm")]
     top = rows[0]
+    traffic = None
+    try:                                        # measured DRAM bytes per launch of that kernel (ncu --set full)
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            traffic = json.load(fh).get(top["kernel"])
+    except Exception:
+        pass
     roof = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
-            "unit": top["unit"], "frac": top["frac"], "traffic": None, "peak_source": peaks["source"],
+            "unit": top["unit"], "frac": top["frac"], "traffic": traffic, "peak_source": peaks["source"],
             "share_of_step": top["share"]}
     if gemm:
         roof["all_gemm_share_of_step"] = sum(r["share"] for r in gemm)

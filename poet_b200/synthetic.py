@@ -41,6 +41,9 @@ CONFIGS: Dict[str, dict] = {
     "tiny16": _cfg(batch=2, enc_layers=2, dec_layers=2, nheads=16, num_queries=6, n_classes=5,
                    pyramid="TINY"),
     "cfg2_b2": _cfg(batch=2, enc_layers=5, dec_layers=5, nheads=16, num_queries=10, n_classes=21),
+    "cfg3_b2": _cfg(batch=2, enc_layers=5, dec_layers=5, nheads=16, num_queries=10, n_classes=8),       # LM-O heads 27/54
+    "cfg5_b1": _cfg(batch=1, enc_layers=6, dec_layers=6, nheads=8, num_queries=25, n_classes=21,
+                    pyramid="REF1280"),                                                                  # 1280x960, S=6380
 }
 
 

@@ -210,3 +210,22 @@ def test_backward_matches_forward_directional_derivative(precision):
                 p.add_(v, alpha=eps)
         numeric = (lp - lm) / (2 * eps)
         assert abs(numeric - gnorm) <= 0.05 * gnorm + 1e-3, (key, numeric, gnorm)
+
+
+@pytest.mark.parametrize("name", ["cfg3_b2", "cfg5_b1"])
+def test_other_baseline_configs_forward_parity(name):
+    """BASELINE.json configs 3 (LM-O: 9 class slots) and 5 (1280x960 pyramid S=6380, 6/6 layers, 8 heads of 32
+    channels, 25 queries) at reduced batch: every decoder layer's outputs vs the oracle, default precision."""
+    cfg = S.CONFIGS[name]
+    P = S.make_params(cfg)
+    inp = S.make_inputs(cfg, pad_columns=(name == "cfg3_b2"))
+    cap = {}
+    with torch.no_grad():
+        O.poet_path_forward(P, cfg, inp["srcs"], inp["masks"], inp["boxes"], inp["labels"], capture=cap)
+        model = build_model(cfg, P)
+        out, n = model.forward_pyramid([s.to(DEV) for s in inp["srcs"]], [m.to(DEV) for m in inp["masks"]],
+                                       inp["boxes"], inp["labels"])
+    t, R = stack_outputs(out)
+    assert float((t.cpu() - cap["translation_all"]).abs().max()) < TOL_T
+    assert float((R.cpu() - cap["rotation_all"]).abs().max()) < TOL_R
+    assert n == [max(1, cfg["num_queries"] - (i % 4)) for i in range(cfg["batch"])]

@@ -58,11 +58,26 @@ class MSDeformAttn(nn.Module):
         nn.init.xavier_uniform_(self.output_proj.weight)
         self.output_proj.bias.zero_()
 
+    @staticmethod
+    def _mask_u8(input_padding_mask):
+        if input_padding_mask is None:
+            return None
+        m = input_padding_mask.reshape(-1)
+        return m if m.dtype == torch.uint8 else m.to(torch.uint8)
+
+    def project_value(self, input_flatten: torch.Tensor, input_padding_mask: Optional[torch.Tensor] = None):
+        """value_proj(input_flatten) with padded rows zeroed.  Exposed so that a caller whose keys do not
+        depend on the queries (the decoder: `memory` is fixed) can issue it early / on another stream."""
+        # value feeds only the gather kernel, whose backward hands us a private grad buffer
+        return ops.linear(input_flatten, self.value_proj.weight, self.value_proj.bias,
+                          row_mask=self._mask_u8(input_padding_mask), mask_grad_inplace=True)
+
     def forward(self, query: torch.Tensor, reference_points: torch.Tensor, input_flatten: torch.Tensor,
                 input_spatial_shapes, input_level_start_index=None,
-                input_padding_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+                input_padding_mask: Optional[torch.Tensor] = None, value: Optional[torch.Tensor] = None) -> torch.Tensor:
         """query [N,Lq,C]; reference_points [N,Lq,L,2] in [0,1]; input_flatten [N,S,C];
-        input_spatial_shapes [(H_l,W_l)]; input_padding_mask [N,S] True = padded  ->  [N,Lq,C]."""
+        input_spatial_shapes [(H_l,W_l)]; input_padding_mask [N,S] True = padded  ->  [N,Lq,C].
+        `value` (ours, optional): the result of project_value() computed beforehand."""
         shapes = host_shapes(input_spatial_shapes)
         N, S, _ = input_flatten.shape
         if sum(h * w for h, w in shapes) != S:
@@ -70,14 +85,8 @@ class MSDeformAttn(nn.Module):
         if reference_points.shape[-1] != 2:
             raise NotImplementedError("only 2-d reference points (PoET 'bbox' mode) are implemented; "
                                       "4-d box references are reachable in the reference but in no PoET config")
-        mask_u8 = None
-        if input_padding_mask is not None:
-            mask_u8 = input_padding_mask.reshape(-1)
-            if mask_u8.dtype != torch.uint8:
-                mask_u8 = mask_u8.to(torch.uint8)
-        # value feeds only the gather kernel, whose backward hands us a private grad buffer
-        value = ops.linear(input_flatten, self.value_proj.weight, self.value_proj.bias, row_mask=mask_u8,
-                           mask_grad_inplace=True)
+        if value is None:
+            value = self.project_value(input_flatten, input_padding_mask)
         # one projection for [offsets | logits]: the gather kernel reads both out of the same row
         oa = ops.proj_cat(query, self.sampling_offsets.weight, self.sampling_offsets.bias,
                           self.attention_weights.weight, self.attention_weights.bias)

@@ -144,7 +144,7 @@ class DeformableTransformerDecoderLayer(nn.Module):
         self.norm3 = nn.LayerNorm(d_model)
 
     def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index,
-                src_padding_mask=None):
+                src_padding_mask=None, value=None):
         _check_dropout(self, self.p_drop)
         if tgt.shape[1] > 32:
             raise NotImplementedError("decoder self-attention kernel supports at most 32 object queries")
@@ -155,7 +155,8 @@ class DeformableTransformerDecoderLayer(nn.Module):
         else:
             tgt = ops.add_layernorm(tgt, sa, self.norm2.weight, self.norm2.bias, eps=self.norm2.eps)
             q2 = tgt
-        ca = self.cross_attn(q2, reference_points, src, src_spatial_shapes, level_start_index, src_padding_mask)
+        ca = self.cross_attn(q2, reference_points, src, src_spatial_shapes, level_start_index, src_padding_mask,
+                             value=value)
         tgt = ops.add_layernorm(tgt, ca, self.norm1.weight, self.norm1.bias, eps=self.norm1.eps)
         ffn = ops.mlp(tgt, ((self.linear1.weight, self.linear1.bias), (self.linear2.weight, self.linear2.bias)))
         return ops.add_layernorm(tgt, ffn, self.norm3.weight, self.norm3.bias, eps=self.norm3.eps)
@@ -171,15 +172,34 @@ class DeformableTransformerDecoder(nn.Module):
         self.class_embed = None
 
     def forward(self, tgt, reference_points, src, src_spatial_shapes, src_level_start_index, src_valid_ratios,
-                query_pos=None, src_padding_mask=None):
+                query_pos=None, src_padding_mask=None, layer_callback=None):
+        """Reference signature; `layer_callback(i, out_i)` (ours, optional) is invoked as soon as decoder layer i
+        is issued, so the caller can start that layer's pose heads without waiting for the whole stack."""
         if self.bbox_embed is not None:
             raise NotImplementedError("iterative box refinement is not part of PoET")
         if reference_points.shape[-1] != 2:
             raise NotImplementedError("only 2-d reference points (PoET 'bbox' mode) are implemented")
         ref_in = (reference_points[:, :, None] * src_valid_ratios[:, None]).contiguous()     # [B,Q,L,2]
+        # `src` (the encoder memory) is the same for every layer: project it for all layers up front on a
+        # side stream, so these large GEMMs (and their dgrad/wgrad in backward) overlap the launch-bound
+        # self-attention / FFN chain of the queries instead of sitting on its critical path
+        values = [None] * len(self.layers)
+        forked, marks = None, []
+        if ops.parallel_streams_enabled() and src.is_cuda:
+            forked = ops.fork(0, src.device)
+            forked.uses(src, src_padding_mask)
+            with forked:
+                for i, layer in enumerate(self.layers):
+                    values[i] = layer.cross_attn.project_value(src, src_padding_mask)
+                    marks.append(forked.checkpoint())
         out, inter, inter_ref = tgt, [], []
-        for layer in self.layers:
-            out = layer(out, query_pos, ref_in, src, src_spatial_shapes, src_level_start_index, src_padding_mask)
+        for i, layer in enumerate(self.layers):
+            if forked is not None:
+                forked.wait(marks[i], values[i])
+            out = layer(out, query_pos, ref_in, src, src_spatial_shapes, src_level_start_index, src_padding_mask,
+                        value=values[i])
+            if layer_callback is not None:
+                layer_callback(i, out)
             if self.return_intermediate:
                 inter.append(out)
                 inter_ref.append(reference_points)
@@ -223,7 +243,8 @@ class DeformableTransformer(nn.Module):
         vw = (~mask[:, 0, :]).sum(1).float() / W
         return torch.stack((vw, vh), -1)
 
-    def forward(self, srcs, masks, pos_embeds, query_embed=None, reference_points=None, pos_tokens=None):
+    def forward(self, srcs, masks, pos_embeds, query_embed=None, reference_points=None, pos_tokens=None,
+                layer_callback=None):
         """Reference signature (deformable_transformer.py:120).  `pos_tokens` (optional, ours):
         lvl_pos_embed_flatten [B,S,C] already in token layout with level_embed added."""
         if query_embed is None:
@@ -247,7 +268,7 @@ class DeformableTransformer(nn.Module):
         query_pos = query_embed[..., :C].contiguous()
         tgt = query_embed[..., C:].contiguous()
         hs, inter_refs = self.decoder(tgt, reference_points, memory, spatial_shapes, level_start, valid_ratios,
-                                      query_pos, pad)
+                                      query_pos, pad, layer_callback=layer_callback)
         return hs, reference_points, inter_refs, None, None
 
 

@@ -31,6 +31,72 @@ def get_gemm_precision() -> str:
     return {v: k for k, v in _PRECISION.items()}[_state["precision"]]
 
 
+# ------------------------------------------------------------------------------------------
+# stream forking: the decoder / head chain is a sequence of launch-latency-bound kernels that leaves the
+# GPU mostly idle, so independent work (the decoder layers' value projections of `memory`, the per-layer
+# pose heads and their backward) is issued on side streams.  Under CUDA-graph capture the fork/join
+# events become graph edges and the branches run concurrently; autograd replays each op's backward on
+# the stream of its forward, so the backward overlaps the same way.
+# ------------------------------------------------------------------------------------------
+_side_streams = {}
+
+
+def parallel_streams_enabled() -> bool:
+    return _state.get("parallel_streams", True)
+
+
+def set_parallel_streams(on: bool) -> None:
+    _state["parallel_streams"] = bool(on)
+
+
+class fork:
+    """with fork(idx, device) as f: ... work issued on side stream idx ...; f.join() makes the caller's stream wait."""
+
+    def __init__(self, idx: int, device):
+        self.main = torch.cuda.current_stream(device)
+        key = (str(device), idx)
+        if key not in _side_streams:
+            _side_streams[key] = torch.cuda.Stream(device=device)
+        self.side = _side_streams[key]
+        self._ctx = None
+
+    def __enter__(self):
+        self.side.wait_stream(self.main)
+        self._ctx = torch.cuda.stream(self.side)
+        self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        self._ctx.__exit__(*exc)
+        return False
+
+    def join(self, *tensors) -> None:
+        """Caller's stream waits for the side stream; `tensors` produced there are marked as used on it."""
+        self.main.wait_stream(self.side)
+        for t in tensors:
+            if isinstance(t, torch.Tensor):
+                t.record_stream(self.main)
+
+    def uses(self, *tensors) -> None:
+        """Tensors allocated on the caller's stream that the side stream reads."""
+        for t in tensors:
+            if isinstance(t, torch.Tensor):
+                t.record_stream(self.side)
+
+    def checkpoint(self) -> "torch.cuda.Event":
+        """Event marking the side-stream work issued so far (call inside the `with` block)."""
+        ev = torch.cuda.Event()
+        ev.record(self.side)
+        return ev
+
+    def wait(self, ev, *tensors) -> None:
+        """Caller's stream waits for a checkpoint; `tensors` produced before it are marked as used there."""
+        self.main.wait_event(ev)
+        for t in tensors:
+            if isinstance(t, torch.Tensor):
+                t.record_stream(self.main)
+
+
 def launch_count() -> int:
     """Number of libpoet_b200 kernel-launching calls issued so far (bench.py's gpu_launches)."""
     return _state["launches"]

@@ -177,14 +177,42 @@ class PoET(nn.Module):
         return self.build_queries(boxes, classes, device)
 
     # ------------------------------------------------------------------ heads (A9)
-    def _heads(self, hs: torch.Tensor, pred_classes: torch.Tensor):
+    def _head_layer(self, l: int, h: torch.Tensor, pred_classes: torch.Tensor):
         slots = self.n_classes if self.class_mode == "specific" else 1
         cls = pred_classes if slots > 1 else None
+        rot = self.rotation_head[l](h)
+        tr = self.translation_head[l](h)
+        t, R, _ = ops.heads_select_rot6d(rot, tr, cls, slots)
+        return t, R
+
+    def _heads(self, hs: torch.Tensor, pred_classes: torch.Tensor):
         t_all, R_all = [], []
         for l in range(hs.shape[0]):
-            rot = self.rotation_head[l](hs[l])
-            tr = self.translation_head[l](hs[l])
-            t, R, _ = ops.heads_select_rot6d(rot, tr, cls, slots)
+            t, R = self._head_layer(l, hs[l], pred_classes)
+            t_all.append(t)
+            R_all.append(R)
+        return t_all, R_all
+
+    def _run_with_heads(self, srcs, masks, pos, qe, ref, pred_classes, pos_tokens=None):
+        """transformer + heads; with stream forking on, layer l's heads are issued on a side stream the moment
+        decoder layer l is issued, so they (and their backward) overlap the rest of the decoder chain."""
+        if not (ops.parallel_streams_enabled() and srcs[0].is_cuda):
+            hs = self.transformer(srcs, masks, pos, qe, ref, pos_tokens=pos_tokens)[0]
+            return self._heads(hs, pred_classes)
+        dev = srcs[0].device
+        pending = []
+
+        def on_layer(l, out):
+            f = ops.fork(1 + (l % 3), dev)
+            f.uses(out, pred_classes)
+            with f:
+                t, R = self._head_layer(l, out, pred_classes)
+                pending.append((f, f.checkpoint(), t, R))
+
+        self.transformer(srcs, masks, pos, qe, ref, pos_tokens=pos_tokens, layer_callback=on_layer)
+        t_all, R_all = [], []
+        for f, ev, t, R in pending:
+            f.wait(ev, t, R)
             t_all.append(t)
             R_all.append(R)
         return t_all, R_all
@@ -211,9 +239,8 @@ class PoET(nn.Module):
         C = srcs[0].shape[1]
         S = sum(int(s.shape[2] * s.shape[3]) for s in srcs)
         pos_tokens = _PosTokens.apply(self.transformer.level_embed, C, S, *masks)
-        hs, _, _, _, _ = self.transformer(srcs, masks, None, qe, pred_boxes[:, :, :2].contiguous(),
-                                          pos_tokens=pos_tokens)
-        t_all, R_all = self._heads(hs, pred_classes)
+        t_all, R_all = self._run_with_heads(srcs, masks, None, qe, pred_boxes[:, :, :2].contiguous(), pred_classes,
+                                            pos_tokens=pos_tokens)
         return self._pack(t_all, R_all, pred_boxes, pred_classes)
 
     def forward(self, samples, targets=None):
@@ -242,8 +269,7 @@ class PoET(nn.Module):
             srcs.append(src)
             masks.append(mask)
 
-        hs, _, _, _, _ = self.transformer(srcs, masks, pos, qe, pb[:, :, :2].contiguous())
-        t_all, R_all = self._heads(hs, pc)
+        t_all, R_all = self._run_with_heads(srcs, masks, pos, qe, pb[:, :, :2].contiguous(), pc)
         return self._pack(t_all, R_all, pb, pc), counts
 
 

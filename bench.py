@@ -311,6 +311,7 @@ def run_gpu(args):
     launches = (ops.launch_count() - l0) * args.steps          # library launches replayed per step x timed steps
     if args.kernel_table and rank == 0:
         torch.cuda.synchronize()
+        ops.set_parallel_streams(False)       # single stream: the event brackets must see each kernel alone
         ops.kernel_timing(True)
         for _ in range(ksteps):
             flush.fill_(1)
@@ -321,6 +322,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
         ktimes = ops.kernel_times_ms()
         ops.kernel_timing(False)
+        ops.set_parallel_streams(True)
     if world > 1:
         dist.barrier()
 
@@ -336,7 +338,7 @@ def run_gpu(args):
                                             "grad_allreduce_bytes": reducer.nbytes() if world > 1 else 0,
                                             "gemm_precision": args.precision,
                                             "launch": "one CUDA graph per step" if args.graph else "eager",
-                                            "kernel_table": "eager pass, CUDA events around every library call"}),
+                                            "kernel_table": "eager single-stream pass, CUDA events around every library call"}),
                 "e2e": {"value": B * world * args.steps / (e2e_ms / 1e3), "unit": "images/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clocks}

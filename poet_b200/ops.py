@@ -263,19 +263,49 @@ def _linear_bwd(gy2: torch.Tensor, x2: torch.Tensor, W: torch.Tensor, need_x: bo
     K = x2.shape[1]
     dx = gemm(gy2, W, R, K, N, a_kcontig=True, b_kcontig=False, gate=gate, b_split=w_split) if need_x else None
     dW = db = None
-    if need_w:
-        slot = _grad_slot(w_param)
-        if slot is not None:
-            gemm(gy2, x2, N, K, R, a_kcontig=False, b_kcontig=False, out=slot, accumulate=True)
-        else:
-            dW = gemm(gy2, x2, N, K, R, a_kcontig=False, b_kcontig=False)
-    if need_b:
-        slot = _grad_slot(b_param)
-        if slot is not None:
-            colsum(gy2, R, N, out=slot, accumulate=True)
-        else:
-            db = colsum(gy2, R, N)
+    w_slot = _grad_slot(w_param) if need_w else None
+    b_slot = _grad_slot(b_param) if need_b else None
+    # Parameter gradients are leaves of the backward graph: when they go straight into .grad slots nobody
+    # downstream waits for them, so they are issued on a side stream and only the dgrad stays on the
+    # critical path (joined at the end of the backward pass).
+    side = None
+    if (w_slot is not None or b_slot is not None) and parallel_streams_enabled():
+        side = fork(_WGRAD_STREAM, gy2.device)
+        side.uses(gy2, x2)
+        _join_at_end_of_backward(side)
+        side.__enter__()
+    try:
+        if w_slot is not None:
+            gemm(gy2, x2, N, K, R, a_kcontig=False, b_kcontig=False, out=w_slot, accumulate=True)
+        if b_slot is not None:
+            colsum(gy2, R, N, out=b_slot, accumulate=True)
+    finally:
+        if side is not None:
+            side.__exit__(None, None, None)
+    if need_w and w_slot is None:
+        dW = gemm(gy2, x2, N, K, R, a_kcontig=False, b_kcontig=False)
+    if need_b and b_slot is None:
+        db = colsum(gy2, R, N)
     return dx, dW, db
+
+
+_WGRAD_STREAM = 8
+_pending_joins = {}
+
+
+def _join_at_end_of_backward(f: "fork") -> None:
+    """Make the stream that called backward() wait for side stream `f.side` once the backward pass is over."""
+    key = id(f.side)
+    if key in _pending_joins:
+        return
+    _pending_joins[key] = f.side
+
+    def _cb():
+        side = _pending_joins.pop(key, None)
+        if side is not None:
+            torch.cuda.current_stream(side.device).wait_stream(side)
+
+    torch.autograd.Variable._execution_engine.queue_callback(_cb)
 
 
 class _Linear(torch.autograd.Function):

@@ -4,13 +4,6 @@
 int poet_gemm_simt(const float* A, int64_t lda, int a_kcontig, const float* Bm, int64_t ldb, int b_kcontig, float* C,
                    int64_t ldc, int M, int N, int K, float alpha, const float* bias, const float* gate,
                    const uint8_t* row_mask, int flags, cudaStream_t s);
-int poet_gemm_skinny(const float* A, int64_t lda, int a_kcontig, const float* Bm, int64_t ldb, int b_kcontig, float* C,
-                     int64_t ldc, int M, int N, int K, float alpha, const float* bias, const float* gate,
-                     const uint8_t* row_mask, int flags, cudaStream_t s);
-// Problems below this many multiply-adds are launch-latency bound (decoder rows, heads and their weight
-// gradients): exact-fp32 short-chain kernel instead of a tensor-core pipeline.
-static inline bool poet_is_skinny(int M, int N, int K) { return (int64_t)M * N * K <= ((int64_t)1 << 26); }
-
 #ifdef POET_HAVE_TC_GEMM
 size_t poet_gemm_tc_workspace_bytes(int M, int N, int K, int a_kcontig, int b_kcontig, int precision);
 int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, const void* b_hi, const void* b_lo,
@@ -62,8 +55,6 @@ extern "C" int poet_gemm(const float* A, int64_t lda, int a_kcontig, const float
   POET_REQUIRE(lda >= (a_kcontig ? K : M) && ldb >= (b_kcontig ? K : N) && ldc >= N, POET_ERR_BAD_SHAPE);
   POET_REQUIRE(precision >= POET_GEMM_FP32 && precision <= POET_GEMM_BF16, POET_ERR_UNSUPPORTED);
   cudaStream_t s = (cudaStream_t)stream;
-  if (poet_is_skinny(M, N, K))
-    return poet_gemm_skinny(A, lda, a_kcontig, Bm, ldb, b_kcontig, C, ldc, M, N, K, alpha, bias, gate, row_mask, flags, s);
 #ifdef POET_HAVE_TC_GEMM
   if (precision != POET_GEMM_FP32 && poet_gemm_tc_supported(M, N, K, a_kcontig, b_kcontig, lda, ldb, ldc))
     return poet_gemm_tc(A, lda, a_kcontig, Bm, nullptr, nullptr, ldb, b_kcontig, C, ldc, M, N, K, alpha, bias, gate,
@@ -76,7 +67,7 @@ extern "C" int poet_gemm(const float* A, int64_t lda, int a_kcontig, const float
 
 extern "C" int poet_gemm_tc_eligible(int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc) {
 #ifdef POET_HAVE_TC_GEMM
-  return (!poet_is_skinny(M, N, K) && poet_gemm_tc_supported(M, N, K, 1, 1, lda, ldb, ldc)) ? 1 : 0;
+  return poet_gemm_tc_supported(M, N, K, 1, 1, lda, ldb, ldc) ? 1 : 0;
 #else
   (void)M; (void)N; (void)K; (void)lda; (void)ldb; (void)ldc;
   return 0;
@@ -101,8 +92,6 @@ extern "C" int poet_gemm_bsplit(const float* A, int64_t lda, int a_kcontig, cons
   POET_REQUIRE(lda >= (a_kcontig ? K : M) && ldb >= (b_kcontig ? K : N) && ldc >= N, POET_ERR_BAD_SHAPE);
   POET_REQUIRE(precision >= POET_GEMM_FP32 && precision <= POET_GEMM_BF16, POET_ERR_UNSUPPORTED);
   cudaStream_t s = (cudaStream_t)stream;
-  if (poet_is_skinny(M, N, K) && Bm != nullptr)
-    return poet_gemm_skinny(A, lda, a_kcontig, Bm, ldb, b_kcontig, C, ldc, M, N, K, alpha, bias, gate, row_mask, flags, s);
 #ifdef POET_HAVE_TC_GEMM
   if (precision != POET_GEMM_FP32 && poet_gemm_tc_supported(M, N, K, a_kcontig, b_kcontig, lda, ldb, ldc))
     return poet_gemm_tc(A, lda, a_kcontig, Bm, B_hi, B_lo, ldb, b_kcontig, C, ldc, M, N, K, alpha, bias, gate, row_mask,

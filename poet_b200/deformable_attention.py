@@ -85,11 +85,22 @@ class MSDeformAttn(nn.Module):
         if reference_points.shape[-1] != 2:
             raise NotImplementedError("only 2-d reference points (PoET 'bbox' mode) are implemented; "
                                       "4-d box references are reachable in the reference but in no PoET config")
+        forked = None
         if value is None:
-            value = self.project_value(input_flatten, input_padding_mask)
+            if ops.parallel_streams_enabled() and input_flatten.is_cuda:
+                # value projection and the [offsets | logits] projection are independent GEMMs
+                forked = ops.fork(4, input_flatten.device)
+                forked.uses(input_flatten, input_padding_mask)
+                with forked:
+                    value = self.project_value(input_flatten, input_padding_mask)
+                    mark = forked.checkpoint()
+            else:
+                value = self.project_value(input_flatten, input_padding_mask)
         # one projection for [offsets | logits]: the gather kernel reads both out of the same row
         oa = ops.proj_cat(query, self.sampling_offsets.weight, self.sampling_offsets.bias,
                           self.attention_weights.weight, self.attention_weights.bias)
+        if forked is not None:
+            forked.wait(mark, value)
         out = ops.msda_block(value, oa, reference_points, shapes, self.n_heads, self.n_levels, self.n_points)
         return ops.linear(out, self.output_proj.weight, self.output_proj.bias)
 

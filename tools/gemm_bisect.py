@@ -27,7 +27,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     e.record(); torch.cuda.synchronize()
     print(f"debug={os.environ.get('POET_GEMM_DEBUG','0'):>2s} {M}x{N}x{K}: {s.elapsed_time(e)/100*1e3:8.1f} us")
 else:
-    for shape in ((25600, 256, 256), (25600, 1024, 256), (160, 256, 256)):
-        for dbg in (0, 1, 2, 3, 4, 8, 7, 15):
-            env = dict(os.environ, POET_GEMM_DEBUG=str(dbg))
-            subprocess.run([sys.executable, __file__, "child", *map(str, shape)], env=env)
+    if True:
+        for shape in ((25600, 256, 256), (25600, 1024, 256), (160, 256, 256)):
+            for dbg in (0, 1, 2, 3, 4, 8, 7, 15):
+                env = dict(os.environ, POET_GEMM_DEBUG=str(dbg))
+                subprocess.run([sys.executable, __file__, "child", *map(str, shape)], env=env)

@@ -20,17 +20,25 @@
 //                   tcgen05.commit frees smem stages and publishes finished accumulators.
 //   warp PW+1       TMA: weights are split to bf16 hi/lo planes once per step (poet_split_bf16) and
 //                   fetched by cp.async.bulk.tensor straight into the swizzled stage.
-//   warps PW+2..+5  epilogue: tcgen05.ld (one accumulator row per thread) -> per-warp smem transpose ->
-//                   coalesced 128-byte rows: bias / ReLU / ReLU-gate / row mask / accumulate / split-K
-//                   reduction.  Runs concurrently with the next tile's MMAs (other TMEM buffer).
+//   warps PW+2..+5  epilogue: tcgen05.ld (one accumulator row per thread), bias / ReLU (+ sign bitmask out) /
+//                   ReLU-gate (bitmask or fp32) / row mask in registers, st.shared into a per-warp
+//                   SWIZZLE_128B 32x32 staging box, then ONE asynchronous TMA store per box
+//                   (cp.async.bulk.tensor; cp.reduce...add for beta=1 and split-K), double-buffered per
+//                   warp, so the epilogue warps never wait on global stores.  Runs concurrently with the
+//                   next tile's MMAs (other TMEM buffer).  POET_GEMM_TMA_EPI=0 selects the older
+//                   smem-transpose + st.global epilogue (kept for A/B measurements).
+// Weight-gradient shape (both operands fp32 activations, MN-major): BK = 32, both operand tiles are
+// register-prefetched one k-block ahead, lines further ahead are pulled into L2 with prefetch hints,
+// and the tile is 128 x 256 when N allows (less L2->SM traffic per flop).
 #include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include "common.cuh"
+#include "tma_host.cuh"
 
 namespace tc {
 
-constexpr int BM = 128, BK = 64;
+constexpr int BM = 128;
 constexpr int EPI_WARPS = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -129,10 +137,14 @@ struct Args {
   int M, N, K;
   float alpha;
   const float* bias; const float* gate; const uint8_t* row_mask;
+  uint32_t* relu_bits;                    // [M, N/32] sign bitmask of the ReLU output (TMA epilogue only)
+  const uint32_t* gate_bits;              // [M, N/32] keep-mask for the ReLU backward (TMA epilogue only)
   int flags;
-  int kb_per_split;       // k-blocks (of 64) per split
+  int kb_per_split;       // k-blocks (of BK) per split
   int splits;
   int n_tiles, total_work;
+  int epi_tma;            // 1: TMA-store epilogue, 0: smem-transpose + st.global epilogue
+  int l2_prefetch;        // 1: L2 prefetch hints ahead of the register-prefetched operand loads
   int debug;              // POET_GEMM_DEBUG bit flags (pipeline bisection only): 1 no A loads, 2 no A stores, 4 no TMA, 8 no epilogue stores
 };
 
@@ -140,6 +152,7 @@ struct Args {
 struct Work {
   int m0, n0, split, kb0, nkb;
 };
+template <int BK>
 __device__ __forceinline__ Work decode(const Args& p, int w, int bn) {
   Work k;
   k.split = w % p.splits;
@@ -155,17 +168,9 @@ __device__ __forceinline__ Work decode(const Args& p, int w, int bn) {
 __device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ void sts32(uint32_t saddr, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
-}
 __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
-  return v;
-}
-__device__ __forceinline__ float lds32(uint32_t saddr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
   return v;
 }
 
@@ -174,10 +179,31 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// L2 prefetch hints (no architectural effect on results)
+__device__ __forceinline__ void l2_prefetch_line(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {   // p 16-byte aligned, bytes % 16 == 0
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// TMA stores of one [32 x 32] fp32 box (smem: 32 rows x 128 B, SWIZZLE_128B)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // A tile of ROWS "rows" x (SEGS*64) contiguous fp32 elements <-> SEGS blocks of [ROWS x 128 B] bf16 in
 // the SWIZZLE_128B canonical layout.
-//   K-major operand : row = m (or n) index, contiguous = k   -> ROWS = tile extent, SEGS = 1
-//   MN-major operand: row = k index,        contiguous = m/n -> ROWS = 64,          SEGS = extent/64
+//   K-major operand : row = m (or n) index, contiguous = k   -> ROWS = tile extent, SEGS = 1 (BK = 64)
+//   MN-major operand: row = k index,        contiguous = m/n -> ROWS = BK,          SEGS = extent/64
 // Each thread owns CH 16-byte chunks (8 elements); chunk id = tid + i*NT.
 template <int ROWS, int SEGS, int NT>
 struct Tile {
@@ -200,6 +226,20 @@ struct Tile {
         v[i][0] = ldg4(p);
         v[i][1] = ldg4(p + 4);
       }
+    }
+  }
+
+  // one L2 prefetch hint per 128-byte line of the tile (LINES = ROWS*SEGS*2 <= 2*NT)
+  __device__ static __forceinline__ void prefetch(const float* __restrict__ G, int64_t ld, int row0, int row_end, int col0,
+                                                  int col_end, int tid) {
+    constexpr int LINES = ROWS * SEGS * 2;
+#pragma unroll
+    for (int i = 0; i < (LINES + NT - 1) / NT; ++i) {
+      const int ln = tid + i * NT;
+      const int h = ln & 1, rs = ln >> 1;
+      const int row = rs % ROWS, seg = rs / ROWS;
+      const int grow = row0 + row, gcol = col0 + seg * 64 + h * 32;
+      if (ln < LINES && grow < row_end && gcol < col_end) l2_prefetch_line(G + (int64_t)grow * ld + gcol);
     }
   }
 
@@ -229,24 +269,32 @@ struct Tile {
   }
 };
 
-template <int BN, bool X3, int STAGES>
+template <int BN, int BK, bool X3, int STAGES>
 struct SmemPlan {
   static constexpr int PLANES = X3 ? 2 : 1;
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;         // one bf16 plane
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * PLANES;
-  static constexpr int EPI_TILE_BYTES = 32 * 36 * 4;                          // per-warp transpose tile
-  static constexpr int EPI_BYTES = EPI_WARPS * EPI_TILE_BYTES;
+  static constexpr int EPI_BOX_BYTES = 32 * 32 * 4;                           // one TMA store box (1024-byte aligned)
+  static constexpr int EPI_WARP_BYTES = 2 * EPI_BOX_BYTES;                    // double-buffered per warp
+  static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
   static constexpr size_t TOTAL = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024;
+  static_assert(STAGE_BYTES % 1024 == 0, "stages must keep the 1024-byte swizzle alignment");
+  static_assert(32 * 36 * 4 <= EPI_WARP_BYTES, "transpose tile of the st.global epilogue must fit the staging area");
 };
 
-template <int BN, bool A_MN, bool B_MN, bool X3, bool B_TMA, int PW, int STAGES>
+template <int BN, int BK, bool A_MN, bool B_MN, bool X3, bool B_TMA, int PW, int STAGES>
 __global__ void __launch_bounds__((PW + 2 + EPI_WARPS) * 32, 1)
-gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo) {
-  using SP = SmemPlan<BN, X3, STAGES>;
+gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+               const __grid_constant__ CUtensorMap tm_c) {
+  using SP = SmemPlan<BN, BK, X3, STAGES>;
   constexpr int NT = PW * 32;                                        // producer threads
   constexpr int PLANES = SP::PLANES, A_BYTES = SP::A_BYTES, B_BYTES = SP::B_BYTES, STAGE_BYTES = SP::STAGE_BYTES;
+  // both operands fp32 and MN-major (weight gradient): B is register-prefetched like A
+  constexpr bool B_PREFETCH = !B_TMA && A_MN && B_MN;
+  static_assert(BK == 64 || (A_MN && B_MN), "K-major operands need BK = 64 (one 128-byte swizzle row)");
   using TA = Tile<A_MN ? BK : BM, A_MN ? BM / 64 : 1, NT>;
   using TB = Tile<B_MN ? BK : BN, B_MN ? BN / 64 : 1, NT>;
+  constexpr int BCH = B_PREFETCH ? TB::CH : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
@@ -261,9 +309,12 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == PW) tmem_alloc(smem_u32(&s_tmem), 2 * BN);             // two accumulator buffers
-  if (B_TMA && warp == PW + 1 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi) : "memory");
-    if (X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo) : "memory");
+  if (warp == PW + 1 && lane == 0) {
+    if (B_TMA) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi) : "memory");
+      if (X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo) : "memory");
+    }
+    if (p.epi_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_c) : "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -273,13 +324,17 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
   if (warp < PW) {
     // ===================== producers =====================
     int it = 0;                                                    // k-blocks published so far (ring position)
-    auto publish = [&](const Work& wk, int kb, const float4 (&va)[TA::CH][2]) {
+    auto publish = [&](const Work& wk, int kb, const float4 (&va)[TA::CH][2], const float4 (&vbp)[BCH][2]) {
       const int s = it % STAGES;
       const uint32_t a_hi = smem_u32(smem) + s * STAGE_BYTES;
       const uint32_t b_hi = a_hi + A_BYTES * PLANES;
       if constexpr (B_TMA) {
         if (it >= STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
         if (!(p.debug & 2)) TA::template store<X3>(a_hi, a_hi + A_BYTES, tid, va);
+      } else if constexpr (B_PREFETCH) {
+        if (it >= STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
+        TA::template store<X3>(a_hi, a_hi + A_BYTES, tid, va);
+        TB::template store<X3>(b_hi, b_hi + B_BYTES, tid, vbp);
       } else {                                                  // fp32 activation B: loads issued before the stage wait
         float4 vb[TB::CH][2];
         const int k0 = (wk.kb0 + kb) * BK;
@@ -293,23 +348,51 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
       mbar_arrive(full0 + 8 * s);
       ++it;
     };
-    auto loadA = [&](const Work& wk, int kb, float4 (&v)[TA::CH][2]) {
+    auto loadAB = [&](const Work& wk, int kb, float4 (&v)[TA::CH][2], float4 (&vbp)[BCH][2]) {
       if (p.debug & 1) {
 #pragma unroll
         for (int i = 0; i < TA::CH; ++i) { v[i][0] = make_float4(1.f, 1.f, 1.f, 1.f); v[i][1] = v[i][0]; }
-        return;
+      } else {
+        const int k0 = (wk.kb0 + kb) * BK;
+        if (A_MN) TA::load(p.A, p.lda, k0, p.K, wk.m0, p.M, tid, v);
+        else      TA::load(p.A, p.lda, wk.m0, p.M, k0, p.K, tid, v);
       }
-      const int k0 = (wk.kb0 + kb) * BK;
-      if (A_MN) TA::load(p.A, p.lda, k0, p.K, wk.m0, p.M, tid, v);
-      else      TA::load(p.A, p.lda, wk.m0, p.M, k0, p.K, tid, v);
+      if constexpr (B_PREFETCH) {
+        const int k0 = (wk.kb0 + kb) * BK;
+        TB::load(p.B, p.ldb, k0, p.K, wk.n0, p.N, tid, vbp);
+      }
+    };
+    // L2 prefetch hints.  K-major A: when a work item starts, the next item's rows (this CTA's next tile) are
+    // requested from HBM, a whole tile period before the register prefetch asks for them.
+    // MN-major operands (weight gradient): lines PF_DIST k-blocks ahead inside the same item.
+    constexpr int PF_DIST = 4;
+    auto hints = [&](const Work& wk, int kb, int w) {
+      if (!p.l2_prefetch) return;
+      if constexpr (!A_MN) {
+        if (kb == 0 && tid < BM) {
+          const int nw = w + gridDim.x;
+          if (nw < p.total_work) {
+            const Work nx = decode<BK>(p, nw, BN);
+            const int row = nx.m0 + tid, k0 = nx.kb0 * BK;
+            if (row < p.M) l2_prefetch_bulk(p.A + (int64_t)row * p.lda + k0, (uint32_t)(min(nx.nkb * BK, p.K - k0) * 4));
+          }
+        }
+      } else {
+        const int kpf = kb + PF_DIST;
+        if (kpf < wk.nkb) {
+          const int k0 = (wk.kb0 + kpf) * BK;
+          TA::prefetch(p.A, p.lda, k0, p.K, wk.m0, p.M, tid);
+          if constexpr (B_PREFETCH) TB::prefetch(p.B, p.ldb, k0, p.K, wk.n0, p.N, tid);
+        }
+      }
     };
     // flattened (work item, k-block) sequence with a one-deep register prefetch across item boundaries
-    float4 ra[TA::CH][2], rb[TA::CH][2];
+    float4 ra[TA::CH][2], rb[TA::CH][2], rc[BCH][2], rd[BCH][2];
     int w = blockIdx.x;
     if (w < p.total_work) {
-      Work cur = decode(p, w, BN);
+      Work cur = decode<BK>(p, w, BN);
       int kb = 0;
-      loadA(cur, 0, ra);
+      loadAB(cur, 0, ra, rc);
       bool more = true;
       while (more) {
         // position of the element after (cur, kb)
@@ -319,22 +402,24 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
         if (nkb_i == cur.nkb) {
           nw = w + gridDim.x;
           nkb_i = 0;
-          if (nw < p.total_work) nxt = decode(p, nw, BN); else has_next = false;
+          if (nw < p.total_work) nxt = decode<BK>(p, nw, BN); else has_next = false;
         }
-        if (has_next) loadA(nxt, nkb_i, rb);
-        publish(cur, kb, ra);
+        if (has_next) loadAB(nxt, nkb_i, rb, rd);
+        hints(cur, kb, w);
+        publish(cur, kb, ra, rc);
         if (!has_next) break;
-        // second half of the unrolled pair: roles of ra / rb swapped
+        // second half of the unrolled pair: roles of (ra, rc) / (rb, rd) swapped
         Work nxt2 = nxt;
         int nkb2 = nkb_i + 1, nw2 = nw;
         bool has_next2 = true;
         if (nkb2 == nxt.nkb) {
           nw2 = nw + gridDim.x;
           nkb2 = 0;
-          if (nw2 < p.total_work) nxt2 = decode(p, nw2, BN); else has_next2 = false;
+          if (nw2 < p.total_work) nxt2 = decode<BK>(p, nw2, BN); else has_next2 = false;
         }
-        if (has_next2) loadA(nxt2, nkb2, ra);
-        publish(nxt, nkb_i, rb);
+        if (has_next2) loadAB(nxt2, nkb2, ra, rc);
+        hints(nxt, nkb_i, nw);
+        publish(nxt, nkb_i, rb, rd);
         more = has_next2;
         cur = nxt2; kb = nkb2; w = nw2;
       }
@@ -344,13 +429,13 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
       // ===================== MMA issuer (one thread) =====================
       constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
       // K-major: 8-row groups 1024 B apart, a 16-wide k-step is 32 B inside the 128 B swizzle row.
-      // MN-major: 64-element m/n groups ROWS*128 = 8192 B apart (LBO), 8-row k groups 1024 B apart (SBO),
+      // MN-major: 64-element m/n groups BK*128 B apart (LBO), 8-row k groups 1024 B apart (SBO),
       //           a 16-wide k-step is two k groups = 2048 B.
       constexpr uint32_t A_LBO = A_MN ? BK * 128 : 16, A_STEP = A_MN ? 2048 : 32;
       constexpr uint32_t B_LBO = B_MN ? BK * 128 : 16, B_STEP = B_MN ? 2048 : 32;
       int it = 0, tcnt = 0;
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcnt) {
-        const Work wk = decode(p, w, BN);
+        const Work wk = decode<BK>(p, w, BN);
         const int ab = tcnt & 1;
         if (tcnt >= 2) mbar_wait(tempty0 + 8 * ab, ((tcnt >> 1) - 1) & 1);    // epilogue drained this buffer
         tc_fence_after();
@@ -386,7 +471,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
       // ===================== TMA: pre-split bf16 weight planes =====================
       int it = 0;
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x) {
-        const Work wk = decode(p, w, BN);
+        const Work wk = decode<BK>(p, w, BN);
         for (int i = 0; i < wk.nkb; ++i, ++it) {
           const int s = it % STAGES;
           if (it >= STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
@@ -397,7 +482,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
           const uint32_t b_hi = smem_u32(smem + s * STAGE_BYTES + A_BYTES * PLANES), b_lo = b_hi + B_BYTES;
           if (B_MN) {
 #pragma unroll
-            for (int g = 0; g < BN / 64; ++g) {                      // box = 64 (n, contiguous) x 64 (k rows)
+            for (int g = 0; g < BN / 64; ++g) {                      // box = 64 (n, contiguous) x BK (k rows)
               tma_load_2d(b_hi + g * (BK * 128), &tm_hi, wk.n0 + g * 64, k0, bar);
               if (X3) tma_load_2d(b_lo + g * (BK * 128), &tm_lo, wk.n0 + g * 64, k0, bar);
             }
@@ -410,87 +495,174 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
     }
   } else {
     // ===================== epilogue warps =====================
-    // TMEM hands each thread one accumulator ROW (32 consecutive columns per tcgen05.ld).  Each warp
-    // transposes its 32x32 block through a private padded smem tile so that lane = column and every
-    // global load / store / reduction is one coalesced 128-byte row.
     const int quarter = warp & 3;                                    // TMEM lane quarter this warp may access
-    // Transpose tile: 32 rows x 36 floats (144-byte rows keep every 128-bit access bank-conflict free).
-    // Write: thread = accumulator row, 8 x STS.128.  Read back: lane -> (row lane/8 + 4i, columns 4*(lane%8)..+3),
-    // so every global access is a 128-bit vector and a warp instruction covers four full 128-byte row segments.
-    const uint32_t tile = smem_u32(smem) + STAGES * STAGE_BYTES + (warp - (PW + 2)) * SP::EPI_TILE_BYTES;
+    const uint32_t stage0 = smem_u32(smem) + STAGES * STAGE_BYTES + (warp - (PW + 2)) * SP::EPI_WARP_BYTES;
     const bool relu = p.flags & POET_GEMM_RELU, accum = p.flags & POET_GEMM_ACCUMULATE;
     const float alpha = p.alpha;
-    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     int tcnt = 0;
-    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcnt) {
-      const Work wk = decode(p, w, BN);
-      const int ab = tcnt & 1;
-      const int mrow0 = wk.m0 + quarter * 32;
-      const int rows = min(32, p.M - mrow0);
-      // rows of this warp's quarter that the padding mask zeroes (bit r = row mrow0 + r)
-      const uint32_t dead_rows = __ballot_sync(0xffffffffu, p.row_mask != nullptr && mrow0 + lane < p.M &&
-                                                                p.row_mask[min(mrow0 + lane, p.M - 1)] != 0);
-      mbar_wait(tfull0 + 8 * ab, (tcnt >> 1) & 1);
-      tc_fence_after();
+    if (p.epi_tma) {
+      // TMEM hands each thread one accumulator ROW (32 consecutive columns per tcgen05.ld).  All epilogue math
+      // happens on that row in registers; the row is written into a SWIZZLE_128B staging box (16-byte chunk c of
+      // row r at chunk c ^ (r & 7): conflict-free for the quarter-warps) and one lane issues the TMA store of the
+      // 32 x 32 box.  Rows beyond M are clipped by the tensor map.  Two boxes per warp: the store of chunk i
+      // overlaps the TMEM load and math of chunk i+1.
+      const bool reduce = accum || p.splits > 1;
+      const int words = p.N >> 5;                                    // bitmask words per row
+      int nst = 0;                                                   // boxes issued by this warp
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcnt) {
+        const Work wk = decode<BK>(p, w, BN);
+        const int ab = tcnt & 1;
+        const int mrow0 = wk.m0 + quarter * 32;
+        const int row = mrow0 + lane;
+        const bool row_ok = row < p.M;
+        const bool dead = p.row_mask != nullptr && row_ok && p.row_mask[row] != 0;
+        mbar_wait(tfull0 + 8 * ab, (tcnt >> 1) & 1);
+        tc_fence_after();
 #pragma unroll 1
-      for (int col = 0; col < BN; col += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN + col), v);
-        if (col + 32 >= BN) {                                        // last read of this accumulator: release it
-          tc_fence_before();
+        for (int col = 0; col < BN; col += 32) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN + col), v);
+          if (col + 32 >= BN) {                                      // last read of this accumulator: release it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * ab);
+          }
+          const int n0c = wk.n0 + col;
+          if (mrow0 >= p.M || (p.debug & 8)) continue;               // warp-uniform
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= alpha;
+          if (p.bias != nullptr && wk.split == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = ldg4(p.bias + n0c + 4 * j);          // warp-uniform address: one broadcast transaction
+              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+            }
+          }
+          if (relu) {
+            if (p.relu_bits != nullptr) {
+              uint32_t bits = 0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
+              if (row_ok) p.relu_bits[(int64_t)row * words + (n0c >> 5)] = dead ? 0u : bits;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (p.gate_bits != nullptr) {                              // ReLU backward from the saved sign bitmask
+            const uint32_t bits = row_ok ? __ldg(p.gate_bits + (int64_t)row * words + (n0c >> 5)) : 0u;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = ((bits >> i) & 1u) ? v[i] : 0.f;
+          } else if (p.gate != nullptr) {                            // ReLU backward from the fp32 activation
+            if (row_ok) {
+              const float* gp = p.gate + (int64_t)row * p.ldc + n0c;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 g4 = ldg4(gp + 4 * j);
+                v[4 * j] = g4.x > 0.f ? v[4 * j] : 0.f; v[4 * j + 1] = g4.y > 0.f ? v[4 * j + 1] : 0.f;
+                v[4 * j + 2] = g4.z > 0.f ? v[4 * j + 2] : 0.f; v[4 * j + 3] = g4.w > 0.f ? v[4 * j + 3] : 0.f;
+              }
+            }
+          }
+          if (dead) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+          const uint32_t box = stage0 + (uint32_t)(nst & 1) * SP::EPI_BOX_BYTES;
+          if (nst >= 2) {                                            // the store issued two boxes ago has read this buffer
+            if (lane == 0) bulk_wait_read_1();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts128(box + lane * 128 + ((j ^ (lane & 7)) << 4),
+                   make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                              __float_as_uint(v[4 * j + 3])));
+          fence_proxy_async();                                       // generic-proxy writes -> visible to the TMA engine
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty0 + 8 * ab);
+          if (lane == 0) {
+            if (reduce) tma_reduce_add_2d(&tm_c, box, n0c, mrow0);
+            else        tma_store_2d(&tm_c, box, n0c, mrow0);
+            bulk_commit();
+          }
+          ++nst;
         }
-        __syncwarp();
+      }
+      if (lane == 0) bulk_wait_all();                                // staging smem must outlive the last store
+    } else {
+      // Older epilogue: each warp transposes its 32x32 block through a private padded smem tile (32 rows x 36
+      // floats) so that lane = column group and every global access is a coalesced 128-bit vector.
+      const uint32_t tile = stage0;
+      const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcnt) {
+        const Work wk = decode<BK>(p, w, BN);
+        const int ab = tcnt & 1;
+        const int mrow0 = wk.m0 + quarter * 32;
+        const int rows = min(32, p.M - mrow0);
+        // rows of this warp's quarter that the padding mask zeroes (bit r = row mrow0 + r)
+        const uint32_t dead_rows = __ballot_sync(0xffffffffu, p.row_mask != nullptr && mrow0 + lane < p.M &&
+                                                                  p.row_mask[min(mrow0 + lane, p.M - 1)] != 0);
+        mbar_wait(tfull0 + 8 * ab, (tcnt >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int col = 0; col < BN; col += 32) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN + col), v);
+          if (col + 32 >= BN) {                                        // last read of this accumulator: release it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * ab);
+          }
+          __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          sts128(tile + lane * 144 + j * 16, make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
-                                                        __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
-        __syncwarp();
-        const int n = wk.n0 + col + c4;                            // first of this lane's four output columns
-        if (n >= p.N || rows <= 0 || (p.debug & 8)) continue;
-        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr && wk.split == 0) bias = ldg4(p.bias + n);
-        float4 o[8];
+          for (int j = 0; j < 8; ++j)
+            sts128(tile + lane * 144 + j * 16, make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                                          __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
+          __syncwarp();
+          const int n = wk.n0 + col + c4;                            // first of this lane's four output columns
+          if (n >= p.N || rows <= 0 || (p.debug & 8)) continue;
+          float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr && wk.split == 0) bias = ldg4(p.bias + n);
+          float4 o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 t = lds128(tile + (rsub + 4 * i) * 144 + c4 * 4);
-          o[i] = make_float4(alpha * t.x + bias.x, alpha * t.y + bias.y, alpha * t.z + bias.z, alpha * t.w + bias.w);
-        }
-        float* cbase = p.C + (int64_t)mrow0 * p.ldc + n;
-        if (p.splits > 1) {
+          for (int i = 0; i < 8; ++i) {
+            const float4 t = lds128(tile + (rsub + 4 * i) * 144 + c4 * 4);
+            o[i] = make_float4(alpha * t.x + bias.x, alpha * t.y + bias.y, alpha * t.z + bias.z, alpha * t.w + bias.w);
+          }
+          float* cbase = p.C + (int64_t)mrow0 * p.ldc + n;
+          if (p.splits > 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = rsub + 4 * i;
+              if (r < rows)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cbase + (int64_t)r * p.ldc), "f"(o[i].x),
+                             "f"(o[i].y), "f"(o[i].z), "f"(o[i].w) : "memory");
+            }
+            continue;
+          }
+          float4 g[8];
+          if (p.gate != nullptr) {                                   // ReLU backward: keep where the forward activation was > 0
+            const float* gbase = p.gate + (int64_t)mrow0 * p.ldc + n;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = ldg4(gbase + (int64_t)min(rsub + 4 * i, rows - 1) * p.ldc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              o[i].x = g[i].x > 0.f ? o[i].x : 0.f; o[i].y = g[i].y > 0.f ? o[i].y : 0.f;
+              o[i].z = g[i].z > 0.f ? o[i].z : 0.f; o[i].w = g[i].w > 0.f ? o[i].w : 0.f;
+            }
+          }
+          if (accum) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = ld4(cbase + (int64_t)min(rsub + 4 * i, rows - 1) * p.ldc);
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = rsub + 4 * i;
-            if (r < rows)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cbase + (int64_t)r * p.ldc), "f"(o[i].x),
-                           "f"(o[i].y), "f"(o[i].z), "f"(o[i].w) : "memory");
+            float4 x = o[i];
+            if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+            if ((dead_rows >> r) & 1u) x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (accum) { x.x += g[i].x; x.y += g[i].y; x.z += g[i].z; x.w += g[i].w; }
+            if (r < rows) st4(cbase + (int64_t)r * p.ldc, x);
           }
-          continue;
-        }
-        float4 g[8];
-        if (p.gate != nullptr) {                                   // ReLU backward: keep where the forward activation was > 0
-          const float* gbase = p.gate + (int64_t)mrow0 * p.ldc + n;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] = ldg4(gbase + (int64_t)min(rsub + 4 * i, rows - 1) * p.ldc);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            o[i].x = g[i].x > 0.f ? o[i].x : 0.f; o[i].y = g[i].y > 0.f ? o[i].y : 0.f;
-            o[i].z = g[i].z > 0.f ? o[i].z : 0.f; o[i].w = g[i].w > 0.f ? o[i].w : 0.f;
-          }
-        }
-        if (accum) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] = ld4(cbase + (int64_t)min(rsub + 4 * i, rows - 1) * p.ldc);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = rsub + 4 * i;
-          float4 x = o[i];
-          if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-          if ((dead_rows >> r) & 1u) x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (accum) { x.x += g[i].x; x.y += g[i].y; x.z += g[i].z; x.w += g[i].w; }
-          if (r < rows) st4(cbase + (int64_t)r * p.ldc, x);
         }
       }
     }
@@ -513,63 +685,60 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float4* __restric
 }
 
 // ---- host side ------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = []() -> EncodeTiledFn {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    return reinterpret_cast<EncodeTiledFn>(f);
-  }();
-  return fn;
-}
-
 // 2-D bf16 tensor map: `inner` contiguous elements per row, `rows` rows of stride ld elements,
 // box = 64 x box_rows, SWIZZLE_128B (the box row is exactly one 128-byte swizzle span).
 static int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t rows, int64_t ld, int box_rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return POET_ERR_UNSUPPORTED;
-  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? POET_OK : POET_ERR_UNSUPPORTED;
+  return poet_tma::encode_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, (uint64_t)inner, (uint64_t)rows, (uint64_t)ld * 2,
+                             64u, (uint32_t)box_rows, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)
+             ? POET_OK : POET_ERR_UNSUPPORTED;
 }
 
-template <int BN, bool A_MN, bool B_MN, bool X3, bool B_TMA, int PW>
-int launch(Args a, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t s) {
-  // 128 x 256 tiles: 2 stages of 96 KB (x3); 128 x 128 tiles: 3 stages of 64 KB
-  constexpr int STAGES = (BN == 256) ? 2 : 3;
-  constexpr size_t smem = SmemPlan<BN, X3, STAGES>::TOTAL;
-  static_assert(smem <= 227 * 1024, "shared memory plan exceeds the 227 KB per-CTA limit");
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, X3, B_TMA, PW, STAGES>;
+// 2-D fp32 output map: N contiguous columns, M rows of stride ldc floats, box = 32 x 32 (128-byte rows), SWIZZLE_128B.
+static int make_map_c(CUtensorMap* map, float* base, int64_t N, int64_t M, int64_t ldc) {
+  return poet_tma::encode_2d(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, (uint64_t)N, (uint64_t)M, (uint64_t)ldc * 4, 32u,
+                             32u, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B)
+             ? POET_OK : POET_ERR_UNSUPPORTED;
+}
+
+struct Maps {
+  CUtensorMap hi, lo, c;
+};
+
+template <int BN, int BK, bool A_MN, bool B_MN, bool X3, bool B_TMA, int STAGES>
+int launch(Args a, const Maps& m, cudaStream_t s) {
+  constexpr int PW = 8;
+  constexpr size_t smem = SmemPlan<BN, BK, X3, STAGES>::TOTAL;
+  static_assert(smem <= 227 * 1024 - 256, "shared memory plan exceeds the 227 KB per-CTA limit");
+  auto kern = gemm_tc_kernel<BN, BK, A_MN, B_MN, X3, B_TMA, PW, STAGES>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  a.n_tiles = a.N / BN;
-  a.total_work = a.n_tiles * poet_ceil_div(a.M, BM) * a.splits;
   const int grid = a.total_work < POET_NUM_SMS ? a.total_work : POET_NUM_SMS;       // persistent: one CTA per SM
-  kern<<<grid, (PW + 2 + EPI_WARPS) * 32, smem, s>>>(a, mh, ml);
+  kern<<<grid, (PW + 2 + EPI_WARPS) * 32, smem, s>>>(a, m.hi, m.lo, m.c);
   return poet_launch_status();
 }
 
+// stage counts: 128 x 256 tiles, BK 64: 2 stages of 96 KB (x3); 128 x 128, BK 64: 3 x 64 KB;
+// weight gradient (BK 32): 128 x 128: 6 x 32 KB, 128 x 256: 4 x 48 KB.  (+ 32 KB epilogue staging each)
 template <int BN, bool X3>
-int dispatch(const Args& a, bool a_mn, bool b_mn, bool b_tma, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t s) {
+int dispatch(const Args& a, bool a_mn, bool b_mn, bool b_tma, const Maps& m, cudaStream_t s) {
+  constexpr int ST64 = (BN == 256) ? 2 : 3;
+  constexpr int ST32 = (BN == 256) ? 4 : 6;
   if (b_tma) {                                      // B is a pre-split weight: A is k-contiguous (forward / dgrad)
     if (a_mn) return POET_ERR_UNSUPPORTED;
-    return b_mn ? launch<BN, false, true, X3, true, 8>(a, mh, ml, s) : launch<BN, false, false, X3, true, 8>(a, mh, ml, s);
+    return b_mn ? launch<BN, 64, false, true, X3, true, ST64>(a, m, s) : launch<BN, 64, false, false, X3, true, ST64>(a, m, s);
   }
-  if (!a_mn && !b_mn) return launch<BN, false, false, X3, false, 8>(a, mh, ml, s);
-  if (!a_mn && b_mn) return launch<BN, false, true, X3, false, 8>(a, mh, ml, s);
-  if (a_mn && b_mn) return launch<BN, true, true, X3, false, 8>(a, mh, ml, s);
-  return launch<BN, true, false, X3, false, 8>(a, mh, ml, s);
+  if (a_mn && b_mn) return launch<BN, 32, true, true, X3, false, ST32>(a, m, s);   // weight gradient
+  if constexpr (BN == 128) {
+    if (!a_mn && !b_mn) return launch<128, 64, false, false, X3, false, 3>(a, m, s);
+    if (!a_mn && b_mn) return launch<128, 64, false, true, X3, false, 3>(a, m, s);
+    return launch<128, 64, true, false, X3, false, 3>(a, m, s);
+  }
+  return POET_ERR_UNSUPPORTED;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 
 }  // namespace tc
@@ -585,61 +754,82 @@ bool poet_gemm_tc_supported(int M, int N, int K, int a_kcontig, int b_kcontig, i
 
 size_t poet_gemm_tc_workspace_bytes(int, int, int, int, int, int) { return 0; }
 
+// 1 when relu_bits / gate_bits are honoured (TMA epilogue enabled); the Python side asks before using them.
+int poet_gemm_tc_bits_supported() {
+  static const int on = tc::env_int("POET_GEMM_TMA_EPI", 1);
+  return on;
+}
+
 // b_hi / b_lo != nullptr: B was pre-split into bf16 planes (same logical layout / ldb as the fp32 B).
 int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, const void* b_hi, const void* b_lo,
                  int64_t ldb, int b_kcontig, float* C, int64_t ldc, int M, int N, int K, float alpha, const float* bias,
-                 const float* gate, const uint8_t* row_mask, int flags, int precision, cudaStream_t s) {
+                 const float* gate, const uint8_t* row_mask, uint32_t* relu_bits, const uint32_t* gate_bits, int flags,
+                 int precision, cudaStream_t s) {
   POET_REQUIRE(poet_aligned16(A) && poet_aligned16(C), POET_ERR_BAD_ALIGNMENT);
   POET_REQUIRE(!bias || poet_aligned16(bias), POET_ERR_BAD_ALIGNMENT);
   POET_REQUIRE(!gate || poet_aligned16(gate), POET_ERR_BAD_ALIGNMENT);
+  static const int dbg = tc::env_int("POET_GEMM_DEBUG", 0);
+  static const int epi_tma = tc::env_int("POET_GEMM_TMA_EPI", 1);
+  static const int l2pf = tc::env_int("POET_GEMM_L2_PREFETCH", 1);
+  static const int wgrad_bn = tc::env_int("POET_GEMM_WGRAD_BN", 256);
+  POET_REQUIRE(epi_tma || (relu_bits == nullptr && gate_bits == nullptr), POET_ERR_UNSUPPORTED);
   const bool x3 = precision == POET_GEMM_BF16X3;
   const bool b_tma = b_hi != nullptr && (!x3 || b_lo != nullptr) && a_kcontig && (ldb % 8 == 0) &&
                      poet_aligned16(b_hi) && (!x3 || poet_aligned16(b_lo));
   POET_REQUIRE(b_tma || (Bm != nullptr && poet_aligned16(Bm)), POET_ERR_NULL_POINTER);
+  const bool a_mn = !a_kcontig, b_mn = !b_kcontig;
+  const bool wgrad = !b_tma && a_mn && b_mn;
+  const int bk = wgrad ? 32 : 64;
   tc::Args a;
   a.A = A; a.lda = lda; a.B = b_tma ? nullptr : Bm; a.ldb = ldb; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
-  a.alpha = alpha; a.bias = bias; a.gate = gate; a.row_mask = row_mask; a.flags = flags;
-  a.n_tiles = 0; a.total_work = 0;
-  static const int dbg = []() { const char* e = getenv("POET_GEMM_DEBUG"); return e ? atoi(e) : 0; }();
-  a.debug = dbg;
+  a.alpha = alpha; a.bias = bias; a.gate = gate; a.row_mask = row_mask; a.relu_bits = relu_bits; a.gate_bits = gate_bits;
+  a.flags = flags;
+  a.epi_tma = epi_tma; a.l2_prefetch = l2pf; a.debug = dbg;
   const int m_tiles = poet_ceil_div(M, tc::BM);
-  const int total_kb = poet_ceil_div(K, tc::BK);
+  const int total_kb = poet_ceil_div(K, bk);
   // Tile width: rounds of the persistent grid x work per round.  128-wide tiles quantise better over 148 SMs
   // but convert every A tile twice as often, hence the 15 % handicap.
   int bn = 128;
-  if (N % 256 == 0 && b_tma) {          // fp32-B variants (wgrad) keep 128-wide tiles: both operands are converted in-kernel
+  if (N % 256 == 0 && b_tma) {
     const double c256 = (double)poet_ceil_div((int64_t)(N / 256) * m_tiles, POET_NUM_SMS) * 256.0;
     const double c128 = (double)poet_ceil_div((int64_t)(N / 128) * m_tiles, POET_NUM_SMS) * 128.0 * 1.15;
     if (c256 <= c128) bn = 256;
   }
+  // weight gradient: the wide tile halves the L2->SM operand traffic per flop; split-K fills the machine
+  if (wgrad && N % 256 == 0 && wgrad_bn == 256 && total_kb >= 16) bn = 256;
   const int64_t tiles = (int64_t)(N / bn) * m_tiles;
   int splits = 1;
-  const bool linear_epi = !(flags & POET_GEMM_RELU) && gate == nullptr && row_mask == nullptr;
-  if (linear_epi && !a_kcontig && tiles < POET_NUM_SMS && total_kb >= 8) {       // weight-gradient shape
+  const bool linear_epi = !(flags & POET_GEMM_RELU) && gate == nullptr && gate_bits == nullptr && row_mask == nullptr;
+  const int min_kb = 256 / bk;                                                     // at least 256 k per split
+  if (linear_epi && !a_kcontig && tiles < POET_NUM_SMS && total_kb >= 2 * min_kb) {  // weight-gradient shape
     splits = (int)(POET_NUM_SMS / tiles);
-    if (splits > total_kb / 4) splits = total_kb / 4;
+    if (splits > total_kb / min_kb) splits = total_kb / min_kb;
     if (splits < 1) splits = 1;
   }
   a.kb_per_split = poet_ceil_div(total_kb, splits);
   a.splits = poet_ceil_div(total_kb, a.kb_per_split);
+  a.n_tiles = N / bn;
+  a.total_work = a.n_tiles * m_tiles * a.splits;
   if (a.splits > 1 && !(flags & POET_GEMM_ACCUMULATE)) {
     cudaError_t e = cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s);
     if (e != cudaSuccess) return (int)e;
   }
-  const bool a_mn = !a_kcontig, b_mn = !b_kcontig;
-  CUtensorMap mh, ml;
-  memset(&mh, 0, sizeof(mh));
-  memset(&ml, 0, sizeof(ml));
+  tc::Maps m;
+  memset(&m, 0, sizeof(m));
   if (b_tma) {
-    // K-major weight [N,K]: inner = K, rows = N, box rows = BN.  MN-major weight [K,N]: inner = N, rows = K, box rows = 64.
+    // K-major weight [N,K]: inner = K, rows = N, box rows = BN.  MN-major weight [K,N]: inner = N, rows = K, box rows = BK.
     const int64_t inner = b_mn ? N : K, rows = b_mn ? K : N;
-    const int box_rows = b_mn ? tc::BK : bn;
-    int rc = tc::make_map(&mh, b_hi, inner, rows, ldb, box_rows);
+    const int box_rows = b_mn ? bk : bn;
+    int rc = tc::make_map(&m.hi, b_hi, inner, rows, ldb, box_rows);
     if (rc) return rc;
-    if (x3) { rc = tc::make_map(&ml, b_lo, inner, rows, ldb, box_rows); if (rc) return rc; }
+    if (x3) { rc = tc::make_map(&m.lo, b_lo, inner, rows, ldb, box_rows); if (rc) return rc; }
   }
-  if (bn == 256) return x3 ? tc::dispatch<256, true>(a, a_mn, b_mn, b_tma, mh, ml, s) : tc::dispatch<256, false>(a, a_mn, b_mn, b_tma, mh, ml, s);
-  return x3 ? tc::dispatch<128, true>(a, a_mn, b_mn, b_tma, mh, ml, s) : tc::dispatch<128, false>(a, a_mn, b_mn, b_tma, mh, ml, s);
+  if (epi_tma) {
+    int rc = tc::make_map_c(&m.c, C, N, M, ldc);
+    if (rc) return rc;
+  }
+  if (bn == 256) return x3 ? tc::dispatch<256, true>(a, a_mn, b_mn, b_tma, m, s) : tc::dispatch<256, false>(a, a_mn, b_mn, b_tma, m, s);
+  return x3 ? tc::dispatch<128, true>(a, a_mn, b_mn, b_tma, m, s) : tc::dispatch<128, false>(a, a_mn, b_mn, b_tma, m, s);
 }
 
 int poet_split_bf16_impl(const float* src, void* hi, void* lo, int64_t n, cudaStream_t s) {

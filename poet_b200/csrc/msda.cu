@@ -11,7 +11,19 @@
 // 128-bit loads, and the output row [B,Lq,M*D] is written as one fully coalesced float4 stream.
 // mode 1 fuses the module's softmax over L*P and loc = ref + off/(W_l,H_l), so the [B,Lq,M,L,P,2]
 // location and [B,Lq,M,L,P] attention tensors are never materialised (SURVEY.md §8d msda_block).
+//
+// Slab path (forward, D = 16, many queries per image: the encoder): one CTA per (image, head, query
+// chunk).  The head's slice of the flattened multi-level feature map, value[b, :, m, :] = S rows of
+// 64 B, is staged ONCE into shared memory by TMA (2-D boxes of 64 rows, one mbarrier) and all gathers
+// of the chunk are served from there: the general path is bound by L1 wavefronts (8 distinct 64-byte
+// segments per warp load), the slab path by the 128 B/clk shared-memory crossbar.  Eight lanes share a
+// (q,m): lanes 0-3 take the left corner column, lanes 4-7 the right one, so a quarter-warp always reads
+// 128 contiguous bytes (x0 and x0+1 of one row): bank-conflict free.  The two halves are summed with
+// one shuffle at the end.
+#include <cstdlib>
+#include <cuda.h>
 #include "common.cuh"
+#include "tma_host.cuh"
 
 namespace {
 
@@ -119,6 +131,157 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(const MsdaArgs p) {
     }
   }
   st4(p.out + t * 4, acc);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// forward, value slab staged in shared memory by TMA
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
+constexpr int kSlabBoxRows = 64;                 // TMA box: 64 rows x 16 floats = 4 KB
+constexpr int kSlabThreads = 256;
+
+template <int L, int P, bool FUSED>
+__global__ void __launch_bounds__(kSlabThreads, 2)
+msda_fwd_slab_kernel(const MsdaArgs p, const __grid_constant__ CUtensorMap tm_v, int nsplit, int q_per_cta, int n_boxes) {
+  constexpr int LP = L * P, D = 16;
+  extern __shared__ uint8_t slab_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  const uint32_t slab = (smem_addr(slab_raw) + 127u) & ~127u;
+  const int tid = threadIdx.x;
+  const int chunk = blockIdx.x % nsplit, bm = blockIdx.x / nsplit;
+  const int m = bm % p.M, b = bm / p.M;
+  const uint32_t bar_a = smem_addr(&bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a),
+                 "r"((uint32_t)(n_boxes * kSlabBoxRows * D * 4)) : "memory");
+    for (int i = 0; i < n_boxes; ++i)      // rows past the end of the tensor are zero-filled; rows of the next image are never read
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                   ::"r"(slab + (uint32_t)(i * kSlabBoxRows * D * 4)), "l"(&tm_v), "r"(m * D), "r"(b * p.S + i * kSlabBoxRows),
+                     "r"(bar_a) : "memory");
+  }
+  // lane roles: 8 lanes per (q,m); h = corner column (0: x0, 1: x0+1), c4 = 4-channel group
+  const int grp = tid >> 3, h = (tid >> 2) & 1, c4 = tid & 3;
+  const int q_beg = chunk * q_per_cta, q_end = min(p.Lq, q_beg + q_per_cta);
+  const int iters = (q_end - q_beg + (kSlabThreads / 8) - 1) / (kSlabThreads / 8);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SLAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+      "@p bra.uni SLAB_DONE;\n"
+      "bra.uni SLAB_WAIT;\n"
+      "SLAB_DONE:\n"
+      "}\n" ::"r"(bar_a) : "memory");
+
+  for (int itq = 0; itq < iters; ++itq) {
+    const int q_raw = q_beg + grp + itq * (kSlabThreads / 8);
+    const bool live = q_raw < q_end;
+    const int q = live ? q_raw : q_end - 1;                    // keep the warp converged for the shuffles
+    const int64_t bq = (int64_t)b * p.Lq + q;
+    float aw[LP];
+    load_row<LP>(p.w + bq * p.ldw + m * LP, aw);
+    if (FUSED) softmax_inplace<LP>(aw);
+    const float* arow = p.a + bq * p.lda + m * LP * 2;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      const int H = p.lv.H[l], W = p.lv.W[l];
+      const uint32_t lvl = slab + (uint32_t)p.lv.start[l] * (D * 4) + (uint32_t)c4 * 16;
+      float rx = 0.f, ry = 0.f;
+      if (FUSED) { float2 r = __ldg(reinterpret_cast<const float2*>(p.ref + (bq * L + l) * 2)); rx = r.x; ry = r.y; }
+      float xy[2 * P];
+#pragma unroll
+      for (int i = 0; i < 2 * P; i += 4) {
+        float4 v = ldg4(arow + l * 2 * P + i);
+        xy[i] = v.x; xy[i + 1] = v.y; xy[i + 2] = v.z; xy[i + 3] = v.w;
+      }
+#pragma unroll
+      for (int s = 0; s < P; ++s) {
+        float lx = xy[2 * s], ly = xy[2 * s + 1];
+        if (FUSED) { lx = rx + lx * p.lv.inv_W[l]; ly = ry + ly * p.lv.inv_H[l]; }
+        const float x = lx * (float)W - 0.5f, y = ly * (float)H - 0.5f;
+        if (x > -1.f && y > -1.f && x < (float)W && y < (float)H) {
+          const float xf = floorf(x), yf = floorf(y);
+          const int xc = (int)xf + h, y0 = (int)yf;              // this lane's corner column
+          const float fx = x - xf, fy = y - yf;
+          const float wx = (h ? fx : 1.f - fx) * aw[l * P + s];
+          if (xc >= 0 && xc < W) {
+            const uint32_t a00 = lvl + (uint32_t)(y0 * W + xc) * (D * 4);
+            if (y0 >= 0) {
+              const float4 v = lds4(a00);
+              const float w0 = (1.f - fy) * wx;
+              acc.x += w0 * v.x; acc.y += w0 * v.y; acc.z += w0 * v.z; acc.w += w0 * v.w;
+            }
+            if (y0 + 1 < H) {
+              const float4 v = lds4(a00 + (uint32_t)W * (D * 4));
+              const float w1 = fy * wx;
+              acc.x += w1 * v.x; acc.y += w1 * v.y; acc.z += w1 * v.z; acc.w += w1 * v.w;
+            }
+          }
+        }
+      }
+    }
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 4);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 4);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 4);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 4);
+    if (live && h == 0) st4(p.out + (bq * p.M + m) * D + c4 * 4, acc);
+  }
+}
+
+// number of query chunks per (image, head): trade the slab reload (S rows) against wave quantisation
+// over 2 resident CTAs per SM
+static int slab_nsplit(int BM_, int S, int Lq) {
+  int best = 1;
+  double best_cost = 1e30;
+  for (int ns = 1; ns <= 16; ++ns) {
+    const int q = poet_ceil_div(Lq, ns);
+    const double waves = (double)poet_ceil_div((int64_t)BM_ * ns, 2 * POET_NUM_SMS);
+    const double cost = waves * ((double)S + 80.0 * q);
+    if (cost < best_cost) { best_cost = cost; best = ns; }
+  }
+  return best;
+}
+
+// POET_OK if the slab kernel ran, POET_ERR_UNSUPPORTED if the shape does not qualify (caller falls back to the
+// general kernel: same results up to summation order).
+static int try_slab_fwd(const MsdaArgs& a, int mode, cudaStream_t s) {
+  static const int enabled = []() { const char* e = getenv("POET_MSDA_SLAB"); return e ? atoi(e) : 1; }();
+  if (!enabled || a.D != 16 || a.L != 4 || a.P != 4) return POET_ERR_UNSUPPORTED;
+  const int n_boxes = poet_ceil_div(a.S, kSlabBoxRows);
+  const size_t slab_bytes = (size_t)n_boxes * kSlabBoxRows * 64 + 128;
+  if (slab_bytes > 112 * 1024) return POET_ERR_UNSUPPORTED;                 // two CTAs per SM
+  if ((int64_t)a.Lq * 4 < a.S) return POET_ERR_UNSUPPORTED;                 // decoder rows: the reload would dominate
+  if ((int64_t)a.B * a.S >= ((int64_t)1 << 31)) return POET_ERR_UNSUPPORTED;
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  // value viewed as [B*S rows, M*D floats]; box = one head's 16 floats x 64 rows
+  if (!poet_tma::encode_2d(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.value, (uint64_t)a.M * a.D, (uint64_t)a.B * a.S,
+                           (uint64_t)a.M * a.D * 4, 16u, (uint32_t)kSlabBoxRows, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B))
+    return POET_ERR_UNSUPPORTED;
+  const int nsplit = slab_nsplit(a.B * a.M, a.S, a.Lq);
+  const int q_per_cta = poet_ceil_div(a.Lq, nsplit);
+  const int grid = a.B * a.M * nsplit;
+  auto launch = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab_bytes);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, kSlabThreads, slab_bytes, s>>>(a, tm, nsplit, q_per_cta, n_boxes);
+    return poet_launch_status();
+  };
+  return mode ? launch(msda_fwd_slab_kernel<4, 4, true>) : launch(msda_fwd_slab_kernel<4, 4, false>);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -316,6 +479,8 @@ extern "C" int poet_msda_fwd(const float* value, const float* a, int64_t lda, co
   POET_REQUIRE(out != nullptr, POET_ERR_NULL_POINTER);
   POET_REQUIRE(poet_aligned16(out), POET_ERR_BAD_ALIGNMENT);
   args.out = out;
+  const int rc_slab = try_slab_fwd(args, mode, (cudaStream_t)stream);
+  if (rc_slab != POET_ERR_UNSUPPORTED) return rc_slab;
   return dispatch<false>(args, mode, (cudaStream_t)stream);
 }
 

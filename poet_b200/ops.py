@@ -170,8 +170,10 @@ def shapes_array(shapes: Sequence[Tuple[int, int]]):
 def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_kcontig: bool = True, b_kcontig: bool = True,
          lda: Optional[int] = None, ldb: Optional[int] = None, bias=None, relu=False, gate=None, row_mask=None,
          out: Optional[torch.Tensor] = None, accumulate=False, alpha: float = 1.0,
-         precision: Optional[int] = None, b_split=None) -> torch.Tensor:
-    """out[M,N] = epi(alpha * op(A) @ op(B)); see include/poet_b200.h poet_gemm."""
+         precision: Optional[int] = None, b_split=None, relu_bits: Optional[torch.Tensor] = None,
+         gate_bits: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = epi(alpha * op(A) @ op(B)); see include/poet_b200.h poet_gemm / poet_gemm_ex.
+    relu_bits (out) / gate_bits (in): int32 [M, N/32] sign bitmask of a ReLU (tensor-core path only)."""
     if out is None:
         out = torch.empty((M, N), device=A.device, dtype=torch.float32)
     lda = (K if a_kcontig else M) if lda is None else lda
@@ -185,6 +187,13 @@ def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_kcontig
     flags = (1 if relu else 0) | (2 if accumulate else 0)
     tag = (f"{M}x{N}x{K}" + ("" if a_kcontig else ",At") + ("" if b_kcontig else ",Bt")) if _timing["on"] else None
     work = (4 * (M * K + N * K + M * N), 2 * M * N * K)
+    if relu_bits is not None or gate_bits is not None:
+        assert gate is None and prec != GEMM_FP32
+        bs = b_split if (b_split is not None and a_kcontig) else (None, None)
+        _call("poet_gemm_ex", _p(A), lda, int(a_kcontig), _p(Bm), _p(bs[0]), _p(bs[1]), ldb, int(b_kcontig), _p(out),
+              out.stride(0), M, N, K, alpha, _p(bias), _p(row_mask), _p(relu_bits), _p(gate_bits), flags, prec,
+              _stream(A), tag=tag, work=work)
+        return out
     if b_split is not None and prec != GEMM_FP32 and a_kcontig:
         _call("poet_gemm_bsplit", _p(A), lda, int(a_kcontig), _p(Bm), _p(b_split[0]), _p(b_split[1]), ldb,
               int(b_kcontig), _p(out), out.stride(0), M, N, K, alpha, _p(bias), _p(gate), _p(row_mask), flags, prec,
@@ -214,6 +223,17 @@ def split_weight(W: torch.Tensor, M_rows: int):
     lo = torch.empty(W.shape, device=W.device, dtype=torch.bfloat16) if prec == GEMM_BF16X3 else None
     _call("poet_split_bf16", _p(W), _p(hi), _p(lo), W.numel(), _stream(W))
     return hi, lo
+
+
+def relu_bits_buffer(R: int, N: int, K: int, device) -> Optional[torch.Tensor]:
+    """int32 [R, N/32] buffer for a ReLU sign bitmask if the GEMM [R,N,K] supports it (large tensor-core shapes:
+    the dgrad then reads 1 bit instead of one fp32 activation per element), else None."""
+    prec = _state["precision"]
+    if prec == GEMM_FP32 or R < 1024 or N % 32:
+        return None
+    if not _lib.lib().poet_gemm_relu_bits_supported(R, N, K, prec):
+        return None
+    return torch.empty((R, N // 32), device=device, dtype=torch.int32)
 
 
 def colsum(X: torch.Tensor, M: int, N: int, out: Optional[torch.Tensor] = None, accumulate=False) -> torch.Tensor:
@@ -256,12 +276,16 @@ def set_direct_param_grads(on: bool) -> None:
 
 
 def _linear_bwd(gy2: torch.Tensor, x2: torch.Tensor, W: torch.Tensor, need_x: bool, need_w: bool, need_b: bool,
-                gate: Optional[torch.Tensor] = None, w_split=None, w_param=None, b_param=None):
+                gate: Optional[torch.Tensor] = None, w_split=None, w_param=None, b_param=None,
+                gate_bits: Optional[torch.Tensor] = None):
     """gy2 [R,N], x2 [R,K], W [N,K] -> (dx [R,K] (gated by `gate`>0 if given), dW [N,K], db [N]).
     dW / db come back as None when they were accumulated directly into the parameters' .grad."""
     R, N = gy2.shape
     K = x2.shape[1]
-    dx = gemm(gy2, W, R, K, N, a_kcontig=True, b_kcontig=False, gate=gate, b_split=w_split) if need_x else None
+    if gate_bits is not None:
+        gate = None
+    dx = gemm(gy2, W, R, K, N, a_kcontig=True, b_kcontig=False, gate=gate, b_split=w_split,
+              gate_bits=gate_bits) if need_x else None
     dW = db = None
     w_slot = _grad_slot(w_param) if need_w else None
     b_slot = _grad_slot(b_param) if need_b else None
@@ -355,12 +379,15 @@ class _MLP(torch.autograd.Function):
         acts = [x2]
         ctx.params = wb
         ctx.w_splits = []
+        ctx.relu_bits = []                       # sign bitmask of layer i's ReLU output (None: gate on the fp32 activation)
         for i in range(n):
             W, b = _chk(wb[2 * i]), wb[2 * i + 1]
             h = acts[-1]
             ctx.w_splits.append(split_weight(W, h.shape[0]))
+            bits = relu_bits_buffer(h.shape[0], W.shape[0], W.shape[1], h.device) if i < n - 1 else None
+            ctx.relu_bits.append(bits)
             acts.append(gemm(h, W, h.shape[0], W.shape[0], W.shape[1], bias=b, relu=(i < n - 1),
-                             b_split=ctx.w_splits[-1]))
+                             b_split=ctx.w_splits[-1], relu_bits=bits))
         ctx.save_for_backward(*acts[:-1], *[wb[2 * i] for i in range(n)])
         ctx.n = n
         ctx.xshape = x.shape
@@ -376,7 +403,8 @@ class _MLP(torch.autograd.Function):
             need_x = i > 0 or ctx.needs_input_grad[0]
             dx, dW, db = _linear_bwd(g, acts[i], Ws[i], need_x, ctx.needs_input_grad[1 + 2 * i],
                                      ctx.needs_input_grad[2 + 2 * i], gate=acts[i] if i > 0 else None,
-                                     w_split=ctx.w_splits[i], w_param=ctx.params[2 * i], b_param=ctx.params[2 * i + 1])
+                                     w_split=ctx.w_splits[i], w_param=ctx.params[2 * i], b_param=ctx.params[2 * i + 1],
+                                     gate_bits=ctx.relu_bits[i - 1] if i > 0 else None)
             grads[2 * i], grads[2 * i + 1] = dW, db
             g = dx
         return (g.view(ctx.xshape) if g is not None else None, *grads)

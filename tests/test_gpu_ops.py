@@ -120,6 +120,8 @@ def _msda_inputs(B, M, D, Lq, P, shapes, seed):
     (2, 16, 16, 37, 4, [(30, 40), (15, 20), (8, 10), (4, 5)]),           # YCB-V head geometry on the REF pyramid
     (2, 8, 32, 50, 4, [(30, 40), (15, 20), (8, 10), (4, 5)]),            # cfg1 head geometry
     (1, 4, 64, 9, 4, [(6, 8), (3, 4), (2, 2), (1, 1)]),
+    (2, 3, 16, 40, 4, [(6, 8), (3, 4), (2, 2), (1, 1)]),                 # smem-slab forward: S=65 (TMA box tail, OOB fill)
+    (2, 16, 16, 500, 4, [(30, 40), (15, 20), (8, 10), (4, 5)]),          # smem-slab forward on the REF pyramid
 ])
 def test_msda_core_fwd_bwd(B, M, D, Lq, P, shapes):
     o = ops()
@@ -137,11 +139,12 @@ def test_msda_core_fwd_bwd(B, M, D, Lq, P, shapes):
     assert bad_fraction(l.grad, l64.grad, 5e-5) < 1e-3
 
 
-def test_msda_block_matches_module_math():
+@pytest.mark.parametrize("Lq", [64, 480])                                # 480: forward served by the smem-slab kernel
+def test_msda_block_matches_module_math(Lq):
     """mode 1 (fused softmax + ref + off/(W,H)) == oracle module math, forward and all gradients."""
     o = ops()
     shapes = [(30, 40), (15, 20), (8, 10), (4, 5)]
-    B, M, D, Lq, L, P = 2, 16, 16, 64, 4, 4
+    B, M, D, L, P = 2, 16, 16, 4, 4
     g = torch.Generator().manual_seed(21)
     S_ = sum(h * w for h, w in shapes)
     value = torch.randn(B, S_, M * D, generator=g)
@@ -363,6 +366,66 @@ def test_gemm_tcgen05_epilogues():
                    ref * (mask == 0)[:, None]) < 3e-5
     acc = o.gemm(A.to(DEV), W.to(DEV), M, N, K, bias=b.to(DEV), out=base.to(DEV).clone(), accumulate=True, alpha=0.5, precision=P)
     assert rel_err(acc, 0.5 * (ref - b.double()) + b.double() + base.double()) < 3e-5
+
+
+def test_gemm_tcgen05_relu_bitmask_and_views():
+    """poet_gemm_ex: the forward GEMM's ReLU sign bitmask gates the dgrad GEMM (no fp32 re-read); TMA-store
+    epilogue on a ragged M, on a column-block view of a wider matrix (ldc > N) and with beta = 1."""
+    o = ops()
+    g = torch.Generator().manual_seed(31)
+    R, C, F = 3000, 256, 1024                                     # ragged M: 23 full tiles + 56 rows
+    x, W1, b1 = torch.randn(R, C, generator=g), torch.randn(F, C, generator=g) * 0.06, torch.randn(F, generator=g) * 0.1
+    gy = torch.randn(R, C, generator=g)
+    W2 = torch.randn(C, F, generator=g) * 0.06
+    old = o.get_gemm_precision()
+    o.set_gemm_precision("bf16x3")
+    try:
+        bits = o.relu_bits_buffer(R, F, C, DEV)
+        if bits is None:
+            pytest.skip("TMA epilogue disabled (POET_GEMM_TMA_EPI=0)")
+        h = o.gemm(x.to(DEV), W1.to(DEV), R, F, C, bias=b1.to(DEV), relu=True, relu_bits=bits)
+        pre = x.double() @ W1.double().t() + b1.double()
+        assert rel_err(h, pre.clamp_min(0)) < 3e-5
+        # bit c%32 of word [r, c/32] == (h[r,c] > 0), judged on the kernel's own output
+        got_bits = ((bits.view(R, F // 32, 1) >> torch.arange(32, device=DEV).view(1, 1, 32)) & 1).view(R, F).bool()
+        assert torch.equal(got_bits, h > 0)
+        dh = o.gemm(gy.to(DEV), W2.to(DEV), R, F, C, b_kcontig=False, gate_bits=bits)
+        ref_dh = (gy.double() @ W2.double()) * (h.cpu() > 0)
+        assert rel_err(dh, ref_dh) < 3e-5
+        # column-block view: write N = 256 columns at offset 128 of a 640-wide matrix, beta = 1
+        wide = torch.randn(R, 640, generator=g).to(DEV)
+        keep = wide.clone()
+        view = wide[:, 128:384]
+        W3 = torch.randn(256, C, generator=g)
+        o.gemm(x.to(DEV), W3.to(DEV), R, 256, C, out=view, accumulate=True)
+        ref = keep.cpu().double()
+        ref[:, 128:384] += x.double() @ W3.double().t()
+        assert rel_err(wide, ref) < 3e-5
+        assert torch.equal(wide[:, :128], keep[:, :128]) and torch.equal(wide[:, 384:], keep[:, 384:])
+    finally:
+        o.set_gemm_precision(old)
+
+
+@pytest.mark.parametrize("Mo,No,R", [(256, 256, 25600), (1024, 256, 25600), (256, 1024, 6400), (128, 384, 3208),
+                                     (512, 256, 160)])
+def test_gemm_tcgen05_wgrad_accumulate(Mo, No, R):
+    """Weight-gradient shape (TN, both operands fp32 activations): BK=32 pipeline, 128x256 tiles when N allows,
+    split-K reduced by TMA reduce-add straight into an existing gradient (beta = 1), K tails (3208 = 100*32 + 8)."""
+    o = ops()
+    g = torch.Generator().manual_seed(Mo + No + R)
+    dY, X = torch.randn(R, Mo, generator=g), torch.randn(R, No, generator=g)
+    base = torch.randn(Mo, No, generator=g)
+    ref = dY.double().t() @ X.double()
+    P = o.GEMM_BF16X3
+    out = o.gemm(dY.to(DEV), X.to(DEV), Mo, No, R, a_kcontig=False, b_kcontig=False, precision=P)
+    assert rel_err(out, ref) < 3e-5
+    acc = o.gemm(dY.to(DEV), X.to(DEV), Mo, No, R, a_kcontig=False, b_kcontig=False, out=base.to(DEV).clone(),
+                 accumulate=True, precision=P)
+    assert rel_err(acc, ref + base.double()) < 3e-5
+    # operands that are column blocks of wider activations (fused projection gradients): lda / ldb > extent
+    wideY = torch.randn(R, Mo + 128, generator=g).to(DEV)
+    out2 = o.gemm(wideY[:, 128:], X.to(DEV), Mo, No, R, a_kcontig=False, b_kcontig=False, lda=Mo + 128, precision=P)
+    assert rel_err(out2, wideY[:, 128:].cpu().double().t() @ X.double()) < 3e-5
 
 
 @pytest.mark.parametrize("prec,tol", [("bf16x3", 3e-5), ("bf16", 2e-2)])

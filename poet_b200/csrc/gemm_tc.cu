@@ -282,8 +282,16 @@ struct SmemPlan {
   static_assert(32 * 36 * 4 <= EPI_WARP_BYTES, "transpose tile of the st.global epilogue must fit the staging area");
 };
 
+// Block = 16 warps: 8 producers (2 warpgroups), MMA, TMA, 4 epilogue, 2 idle (so every warpgroup is complete:
+// setmaxnreg is warpgroup-aligned).  The kernel starts at 128 registers/thread; producers raise their budget to
+// PRODUCER_REGS (their operand tiles live in registers, DEPTH k-blocks in flight), everyone else drops to OTHER_REGS.
+constexpr int BLOCK_THREADS = 512;
+constexpr int PRODUCER_REGS = 160, OTHER_REGS = 96;      // 256*160 + 256*96 = 65536
+__device__ __forceinline__ void regs_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS)); }
+__device__ __forceinline__ void regs_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(OTHER_REGS)); }
+
 template <int BN, int BK, bool A_MN, bool B_MN, bool X3, bool B_TMA, int PW, int STAGES>
-__global__ void __launch_bounds__((PW + 2 + EPI_WARPS) * 32, 1)
+__global__ void __launch_bounds__(BLOCK_THREADS, 1)
 gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                const __grid_constant__ CUtensorMap tm_c) {
   using SP = SmemPlan<BN, BK, X3, STAGES>;
@@ -320,6 +328,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
+  if (warp < PW) regs_inc(); else regs_dec();                     // warpgroup-uniform
 
   if (warp < PW) {
     // ===================== producers =====================
@@ -386,42 +395,44 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
         }
       }
     };
-    // flattened (work item, k-block) sequence with a one-deep register prefetch across item boundaries
-    float4 ra[TA::CH][2], rb[TA::CH][2], rc[BCH][2], rd[BCH][2];
-    int w = blockIdx.x;
-    if (w < p.total_work) {
-      Work cur = decode<BK>(p, w, BN);
-      int kb = 0;
-      loadAB(cur, 0, ra, rc);
-      bool more = true;
-      while (more) {
-        // position of the element after (cur, kb)
-        Work nxt = cur;
-        int nkb_i = kb + 1, nw = w;
-        bool has_next = true;
-        if (nkb_i == cur.nkb) {
-          nw = w + gridDim.x;
-          nkb_i = 0;
-          if (nw < p.total_work) nxt = decode<BK>(p, nw, BN); else has_next = false;
+    // flattened (work item, k-block) sequence; DEPTH k-blocks of operand tiles are in flight in registers
+    // (ring of DEPTH+1 buffers, rotation resolved at compile time by unrolling the ring)
+    constexpr int DEPTH = B_PREFETCH ? (BN == 256 ? 1 : 2) : 2;
+    constexpr int NBUF = DEPTH + 1;
+    struct Pos { Work wk; int kb, w; bool valid; };
+    auto next_pos = [&](const Pos& c) {
+      Pos n = c;
+      if (!c.valid) return n;
+      n.kb = c.kb + 1;
+      if (n.kb == c.wk.nkb) {
+        n.kb = 0;
+        n.w = c.w + gridDim.x;
+        if (n.w < p.total_work) n.wk = decode<BK>(p, n.w, BN); else n.valid = false;
+      }
+      return n;
+    };
+    float4 ta[NBUF][TA::CH][2], tb[NBUF][BCH][2];
+    Pos pos[NBUF];
+    pos[0].w = blockIdx.x; pos[0].kb = 0; pos[0].valid = pos[0].w < p.total_work;
+    if (pos[0].valid) pos[0].wk = decode<BK>(p, pos[0].w, BN); else pos[0].wk = Work{0, 0, 0, 0, 1};
+#pragma unroll
+    for (int d = 1; d < NBUF; ++d) pos[d] = next_pos(pos[d - 1]);
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d)
+      if (pos[d].valid) loadAB(pos[d].wk, pos[d].kb, ta[d], tb[d]);
+    while (pos[0].valid) {
+#pragma unroll
+      for (int u = 0; u < NBUF; ++u) {
+        // slot u holds the tile to publish now; slot (u + DEPTH) % NBUF is free: fetch the tile DEPTH ahead into it
+        const int f = (u + DEPTH) % NBUF;
+        if (pos[u].valid) {
+          if (pos[f].valid) loadAB(pos[f].wk, pos[f].kb, ta[f], tb[f]);
+          hints(pos[u].wk, pos[u].kb, pos[u].w);
+          publish(pos[u].wk, pos[u].kb, ta[u], tb[u]);
+          // slot u becomes the position NBUF ahead
+          Pos nx = pos[(u + NBUF - 1) % NBUF];
+          pos[u] = next_pos(nx);
         }
-        if (has_next) loadAB(nxt, nkb_i, rb, rd);
-        hints(cur, kb, w);
-        publish(cur, kb, ra, rc);
-        if (!has_next) break;
-        // second half of the unrolled pair: roles of (ra, rc) / (rb, rd) swapped
-        Work nxt2 = nxt;
-        int nkb2 = nkb_i + 1, nw2 = nw;
-        bool has_next2 = true;
-        if (nkb2 == nxt.nkb) {
-          nw2 = nw + gridDim.x;
-          nkb2 = 0;
-          if (nw2 < p.total_work) nxt2 = decode<BK>(p, nw2, BN); else has_next2 = false;
-        }
-        if (has_next2) loadAB(nxt2, nkb2, ra, rc);
-        hints(nxt, nkb_i, nw);
-        publish(nxt, nkb_i, rb, rd);
-        more = has_next2;
-        cur = nxt2; kb = nkb2; w = nw2;
       }
     }
   } else if (warp == PW) {
@@ -493,7 +504,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
         }
       }
     }
-  } else {
+  } else if (warp < PW + 2 + EPI_WARPS) {
     // ===================== epilogue warps =====================
     const int quarter = warp & 3;                                    // TMEM lane quarter this warp may access
     const uint32_t stage0 = smem_u32(smem) + STAGES * STAGE_BYTES + (warp - (PW + 2)) * SP::EPI_WARP_BYTES;
@@ -713,7 +724,7 @@ int launch(Args a, const Maps& m, cudaStream_t s) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int grid = a.total_work < POET_NUM_SMS ? a.total_work : POET_NUM_SMS;       // persistent: one CTA per SM
-  kern<<<grid, (PW + 2 + EPI_WARPS) * 32, smem, s>>>(a, m.hi, m.lo, m.c);
+  kern<<<grid, BLOCK_THREADS, smem, s>>>(a, m.hi, m.lo, m.c);
   return poet_launch_status();
 }
 

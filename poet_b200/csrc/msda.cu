@@ -146,15 +146,27 @@ __device__ __forceinline__ float4 lds4(uint32_t saddr) {
 
 constexpr int kSlabBoxRows = 64;                 // TMA box: 64 rows x 16 floats = 4 KB
 constexpr int kSlabThreads = 256;
+constexpr int kSlabWarps = kSlabThreads / 32;
+constexpr int kRecBytesPerWarp = 2 * 16 * 32;    // 2 queries x 16 points x 4 corners x {offset, weight}
 
+// Each warp walks pairs of queries of its CTA's chunk in two phases:
+//   A  one lane per (query, sampling point): softmax over the 16 logits (shuffles inside the 16-lane half),
+//      location -> the four bilinear corners as {byte offset into the slab, weight * attention} records,
+//      out-of-range corners as weight 0 on a clamped offset (phase B is branch-free), records -> per-warp smem;
+//   B  16 lanes per query = 2 rows x 2 columns x 4 channel groups: per point one 8-byte record (broadcast) and
+//      one 128-bit slab load; a quarter-warp (column pair x 4 groups) reads 128 contiguous bytes: conflict-free.
+// The per-point arithmetic is done once per (q,m) instead of once per lane, which is what bounds the general
+// kernel (issue-bound), and the corner reads come from shared memory instead of 8 L1 wavefronts per warp load.
 template <int L, int P, bool FUSED>
 __global__ void __launch_bounds__(kSlabThreads, 2)
 msda_fwd_slab_kernel(const MsdaArgs p, const __grid_constant__ CUtensorMap tm_v, int nsplit, int q_per_cta, int n_boxes) {
   constexpr int LP = L * P, D = 16;
+  static_assert(LP == 16, "one lane per sampling point in a 16-lane half-warp");
   extern __shared__ uint8_t slab_raw[];
   __shared__ __align__(8) uint64_t bar;
   const uint32_t slab = (smem_addr(slab_raw) + 127u) & ~127u;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rec = slab + (uint32_t)(n_boxes * kSlabBoxRows * D * 4) + (uint32_t)warp * kRecBytesPerWarp;
   const int chunk = blockIdx.x % nsplit, bm = blockIdx.x / nsplit;
   const int m = bm % p.M, b = bm / p.M;
   const uint32_t bar_a = smem_addr(&bar);
@@ -171,10 +183,30 @@ msda_fwd_slab_kernel(const MsdaArgs p, const __grid_constant__ CUtensorMap tm_v,
                    ::"r"(slab + (uint32_t)(i * kSlabBoxRows * D * 4)), "l"(&tm_v), "r"(m * D), "r"(b * p.S + i * kSlabBoxRows),
                      "r"(bar_a) : "memory");
   }
-  // lane roles: 8 lanes per (q,m); h = corner column (0: x0, 1: x0+1), c4 = 4-channel group
-  const int grp = tid >> 3, h = (tid >> 2) & 1, c4 = tid & 3;
   const int q_beg = chunk * q_per_cta, q_end = min(p.Lq, q_beg + q_per_cta);
-  const int iters = (q_end - q_beg + (kSlabThreads / 8) - 1) / (kSlabThreads / 8);
+  const int n_pairs = (q_end - q_beg + 1) >> 1;
+  // phase A roles
+  const int qa = lane >> 4, pt = lane & 15, lvl = pt / P;
+  const int H = p.lv.H[lvl], W = p.lv.W[lvl], start = p.lv.start[lvl];
+  const float inv_W = p.lv.inv_W[lvl], inv_H = p.lv.inv_H[lvl];
+  // phase B roles
+  const int r = (lane >> 3) & 1, h = (lane >> 2) & 1, c4 = lane & 3;
+  const uint32_t rec_rd = rec + (uint32_t)(qa * 16 * 32 + (r * 2 + h) * 8);
+  const uint32_t rec_wr = rec + (uint32_t)((qa * 16 + pt) * 32);
+
+  // parameters of this lane's (query, point); prefetched one pair ahead
+  auto load_params = [&](int pair, float& logit, float2& xy, float2& rf) {
+    const int q = min(q_beg + 2 * pair + qa, q_end - 1);
+    const int64_t bq = (int64_t)b * p.Lq + q;
+    logit = __ldg(p.w + bq * p.ldw + m * LP + pt);
+    xy = __ldg(reinterpret_cast<const float2*>(p.a + bq * p.lda + (m * LP + pt) * 2));
+    rf = make_float2(0.f, 0.f);
+    if (FUSED) rf = __ldg(reinterpret_cast<const float2*>(p.ref + (bq * L + lvl) * 2));
+  };
+  float logit, n_logit = 0.f;
+  float2 xy, rf, n_xy = make_float2(0.f, 0.f), n_rf = make_float2(0.f, 0.f);
+  if (warp < n_pairs) load_params(warp, logit, xy, rf);
+
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -185,59 +217,61 @@ msda_fwd_slab_kernel(const MsdaArgs p, const __grid_constant__ CUtensorMap tm_v,
       "SLAB_DONE:\n"
       "}\n" ::"r"(bar_a) : "memory");
 
-  for (int itq = 0; itq < iters; ++itq) {
-    const int q_raw = q_beg + grp + itq * (kSlabThreads / 8);
-    const bool live = q_raw < q_end;
-    const int q = live ? q_raw : q_end - 1;                    // keep the warp converged for the shuffles
-    const int64_t bq = (int64_t)b * p.Lq + q;
-    float aw[LP];
-    load_row<LP>(p.w + bq * p.ldw + m * LP, aw);
-    if (FUSED) softmax_inplace<LP>(aw);
-    const float* arow = p.a + bq * p.lda + m * LP * 2;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int pair = warp; pair < n_pairs; pair += kSlabWarps) {
+    if (pair + kSlabWarps < n_pairs) load_params(pair + kSlabWarps, n_logit, n_xy, n_rf);
+    // ---- phase A ----
+    float a = logit;
+    if (FUSED) {
+      float mx = a;
 #pragma unroll
-    for (int l = 0; l < L; ++l) {
-      const int H = p.lv.H[l], W = p.lv.W[l];
-      const uint32_t lvl = slab + (uint32_t)p.lv.start[l] * (D * 4) + (uint32_t)c4 * 16;
-      float rx = 0.f, ry = 0.f;
-      if (FUSED) { float2 r = __ldg(reinterpret_cast<const float2*>(p.ref + (bq * L + l) * 2)); rx = r.x; ry = r.y; }
-      float xy[2 * P];
+      for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float e = __expf(a - mx);
+      float sum = e;
 #pragma unroll
-      for (int i = 0; i < 2 * P; i += 4) {
-        float4 v = ldg4(arow + l * 2 * P + i);
-        xy[i] = v.x; xy[i + 1] = v.y; xy[i + 2] = v.z; xy[i + 3] = v.w;
-      }
-#pragma unroll
-      for (int s = 0; s < P; ++s) {
-        float lx = xy[2 * s], ly = xy[2 * s + 1];
-        if (FUSED) { lx = rx + lx * p.lv.inv_W[l]; ly = ry + ly * p.lv.inv_H[l]; }
-        const float x = lx * (float)W - 0.5f, y = ly * (float)H - 0.5f;
-        if (x > -1.f && y > -1.f && x < (float)W && y < (float)H) {
-          const float xf = floorf(x), yf = floorf(y);
-          const int xc = (int)xf + h, y0 = (int)yf;              // this lane's corner column
-          const float fx = x - xf, fy = y - yf;
-          const float wx = (h ? fx : 1.f - fx) * aw[l * P + s];
-          if (xc >= 0 && xc < W) {
-            const uint32_t a00 = lvl + (uint32_t)(y0 * W + xc) * (D * 4);
-            if (y0 >= 0) {
-              const float4 v = lds4(a00);
-              const float w0 = (1.f - fy) * wx;
-              acc.x += w0 * v.x; acc.y += w0 * v.y; acc.z += w0 * v.z; acc.w += w0 * v.w;
-            }
-            if (y0 + 1 < H) {
-              const float4 v = lds4(a00 + (uint32_t)W * (D * 4));
-              const float w1 = fy * wx;
-              acc.x += w1 * v.x; acc.y += w1 * v.y; acc.z += w1 * v.z; acc.w += w1 * v.w;
-            }
-          }
-        }
-      }
+      for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      a = e * __fdividef(1.f, sum);
     }
-    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 4);
-    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 4);
-    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 4);
-    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 4);
-    if (live && h == 0) st4(p.out + (bq * p.M + m) * D + c4 * 4, acc);
+    float lx = xy.x, ly = xy.y;
+    if (FUSED) { lx = rf.x + lx * inv_W; ly = rf.y + ly * inv_H; }
+    const float x = lx * (float)W - 0.5f, y = ly * (float)H - 0.5f;
+    const bool inside = x > -1.f && y > -1.f && x < (float)W && y < (float)H;
+    const float xf = floorf(x), yf = floorf(y);
+    const float fx = x - xf, fy = y - yf;
+    // clamp through float so that wild locations cannot overflow the int conversion
+    const int x0 = (int)fminf(fmaxf(xf, -1.f), (float)W), y0 = (int)fminf(fmaxf(yf, -1.f), (float)H);
+    const bool xl = inside && x0 >= 0, xh = inside && x0 + 1 < W, yl = y0 >= 0, yh = y0 + 1 < H;
+    const int xc0 = min(max(x0, 0), W - 1), xc1 = min(max(x0 + 1, 0), W - 1);
+    const int yc0 = min(max(y0, 0), H - 1), yc1 = min(max(y0 + 1, 0), H - 1);
+    const float w00 = (xl && yl) ? (1.f - fy) * (1.f - fx) * a : 0.f, w01 = (xh && yl) ? (1.f - fy) * fx * a : 0.f;
+    const float w10 = (xl && yh) ? fy * (1.f - fx) * a : 0.f, w11 = (xh && yh) ? fy * fx * a : 0.f;
+    const uint32_t o00 = (uint32_t)(start + yc0 * W + xc0) * (D * 4), o01 = (uint32_t)(start + yc0 * W + xc1) * (D * 4);
+    const uint32_t o10 = (uint32_t)(start + yc1 * W + xc0) * (D * 4), o11 = (uint32_t)(start + yc1 * W + xc1) * (D * 4);
+    __syncwarp();                                            // phase B of the previous pair has read its records
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rec_wr), "r"(o00), "r"(__float_as_uint(w00)), "r"(o01),
+                 "r"(__float_as_uint(w01)) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rec_wr + 16), "r"(o10), "r"(__float_as_uint(w10)), "r"(o11),
+                 "r"(__float_as_uint(w11)) : "memory");
+    __syncwarp();
+    // ---- phase B ----
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t vbase = slab + (uint32_t)c4 * 16;
+#pragma unroll
+    for (int s = 0; s < LP; ++s) {
+      uint32_t off; float wgt;
+      asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(off), "=f"(wgt) : "r"(rec_rd + s * 32));
+      const float4 v = lds4(vbase + off);
+      acc.x += wgt * v.x; acc.y += wgt * v.y; acc.z += wgt * v.z; acc.w += wgt * v.w;
+    }
+#pragma unroll
+    for (int o = 4; o <= 8; o <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+      acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    const int q = q_beg + 2 * pair + qa;
+    if (q < q_end && (lane & 12) == 0) st4(p.out + (((int64_t)b * p.Lq + q) * p.M + m) * D + c4 * 4, acc);
+    logit = n_logit; xy = n_xy; rf = n_rf;
   }
 }
 
@@ -261,7 +295,7 @@ static int try_slab_fwd(const MsdaArgs& a, int mode, cudaStream_t s) {
   static const int enabled = []() { const char* e = getenv("POET_MSDA_SLAB"); return e ? atoi(e) : 1; }();
   if (!enabled || a.D != 16 || a.L != 4 || a.P != 4) return POET_ERR_UNSUPPORTED;
   const int n_boxes = poet_ceil_div(a.S, kSlabBoxRows);
-  const size_t slab_bytes = (size_t)n_boxes * kSlabBoxRows * 64 + 128;
+  const size_t slab_bytes = (size_t)n_boxes * kSlabBoxRows * 64 + 128 + kSlabWarps * kRecBytesPerWarp;
   if (slab_bytes > 112 * 1024) return POET_ERR_UNSUPPORTED;                 // two CTAs per SM
   if ((int64_t)a.Lq * 4 < a.S) return POET_ERR_UNSUPPORTED;                 // decoder rows: the reload would dominate
   if ((int64_t)a.B * a.S >= ((int64_t)1 << 31)) return POET_ERR_UNSUPPORTED;

@@ -275,27 +275,44 @@ def run_gpu(args):
     h_masks = [m.pin_memory() for m in inp["masks"]]
     h2d = sum(t.numel() * t.element_size() for t in h_srcs + h_masks) + sum(b.numel() * 4 + l.numel() * 8 for b, l in zip(inp["boxes"], inp["labels"]))
     d2h = 0
-    e2e_ms = 0.0
-    sync_all()
-    for it in range(args.steps + 1):
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        if graphed is not None:
-            loss, out = step(h_srcs, h_masks, inp["boxes"], inp["labels"])     # H2D into the graph's static buffers
-        else:
-            srcs = [s.to(dev, non_blocking=True) for s in h_srcs]
-            masks = [m.to(dev, non_blocking=True) for m in h_masks]
-            loss, out = step(srcs, masks, inp["boxes"], inp["labels"])          # host box lists: padded on host, one H2D
-        host = [loss.detach().cpu(), out["pred_translation"].detach().cpu(), out["pred_rotation"].detach().cpu()]
-        torch.cuda.synchronize()
-        if it > 0:                                                         # first pass warms the pinned path
-            e2e_ms += 1e3 * (time.perf_counter() - t0)
-        d2h = sum(t.numel() * t.element_size() for t in host)
-    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms = float(te.item())
+
+    def e2e_loop(pipelined: bool) -> float:
+        """Wall-clock ms of args.steps end-to-end steps (one untimed pass first).  pipelined: the H2D copy of
+        step i+1's inputs is issued on the copy stream before step i is replayed (GraphedStep.prefetch), so every
+        timed step still contains one full input copy and one result read-back, overlapped with compute."""
+        nonlocal d2h
+        total = 0.0
+        sync_all()
+        if pipelined:
+            graphed.prefetch(h_srcs, h_masks, inp["boxes"], inp["labels"])
+        for it in range(args.steps + 1):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if pipelined:
+                graphed.prefetch(h_srcs, h_masks, inp["boxes"], inp["labels"])     # inputs of the NEXT step
+                loss, out = step()                                                   # consumes the oldest prefetched set
+            elif graphed is not None:
+                loss, out = step(h_srcs, h_masks, inp["boxes"], inp["labels"])     # H2D into the graph's static buffers
+            else:
+                srcs = [s.to(dev, non_blocking=True) for s in h_srcs]
+                masks = [m.to(dev, non_blocking=True) for m in h_masks]
+                loss, out = step(srcs, masks, inp["boxes"], inp["labels"])          # host box lists: padded on host, one H2D
+            host = [loss.detach().cpu(), out["pred_translation"].detach().cpu(), out["pred_rotation"].detach().cpu()]
+            torch.cuda.synchronize()
+            if it > 0:                                                         # first pass warms the pinned path
+                total += 1e3 * (time.perf_counter() - t0)
+            d2h = sum(t.numel() * t.element_size() for t in host)
+        if pipelined:
+            step()                                                             # drain the last prefetched set
+            torch.cuda.synchronize()
+        t = torch.tensor([total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    e2e_serial_ms = e2e_loop(False)
+    e2e_ms = e2e_loop(True) if graphed is not None else e2e_serial_ms
 
     # ---- per-kernel table: an eager pass with CUDA events around every library call ----------
     # (events cannot bracket nodes inside a replayed graph; the kernels and their arguments are identical)
@@ -340,10 +357,14 @@ def run_gpu(args):
                                             "launch": "one CUDA graph per step" if args.graph else "eager",
                                             "kernel_table": "eager single-stream pass, CUDA events around every library call"}),
                 "e2e": {"value": B * world * args.steps / (e2e_ms / 1e3), "unit": "images/s",
-                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "pipeline": ("pinned host inputs of step i+1 copied on a copy stream while step i replays "
+                                     "(GraphedStep.prefetch); result read back every step") if graphed is not None else "serial",
+                        "serial_value": B * world * args.steps / (e2e_serial_ms / 1e3)},
                 "gpu_launches": launches, "clocks": clocks}
         if ktimes:
-            line["roofline"], line["kernels"] = roofline_from(ktimes, peaks, ksteps, ms_per_step)
+            line["roofline"], line["kernels"] = roofline_from(ktimes, peaks, ksteps, ms_per_step,
+                                                              mma_passes=3 if args.precision == "bf16x3" else 1)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg)
         print(json.dumps(line), flush=True)
@@ -351,7 +372,7 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def roofline_from(ktimes, peaks, steps, ms_per_step):
+def roofline_from(ktimes, peaks, steps, ms_per_step, mma_passes=1):
     """Per-kernel table from the CUDA-event brackets; `roofline` = the kernel with the largest time share.
     GEMMs are judged against the tensor pipe (sustained bf16 peak: the kernel is timed inside a long step),
     everything else against HBM.  Algorithmic bytes/flops per launch are the figures of DESIGN.md."""
@@ -364,10 +385,16 @@ def roofline_from(ktimes, peaks, steps, ms_per_step):
             ach, peak, unit, bound = flops / (ms * 1e-3) / 1e12, peaks["tf_sust"], "TFLOP/s", "tensor"
         else:
             ach, peak, unit, bound = nbytes / (ms * 1e-3) / 1e9, peaks["hbm"], "GB/s", "hbm"
-        rows.append({"kernel": name, "launches_per_step": n / steps, "ms_per_step": ms / steps,
-                     "share": ms / steps / ms_per_step, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
-                     "frac": ach / peak if nbytes or flops else None,
-                     "hbm_gbs": nbytes / (ms * 1e-3) / 1e9 if nbytes else None})
+        row = {"kernel": name, "launches_per_step": n / steps, "ms_per_step": ms / steps,
+               "share": ms / steps / ms_per_step, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
+               "frac": ach / peak if nbytes or flops else None,
+               "hbm_gbs": nbytes / (ms * 1e-3) / 1e9 if nbytes else None}
+        if is_gemm and flops:
+            # split-bf16 issues `mma_passes` tensor-core MMAs per fp32 product: tensor-pipe utilisation counts them all
+            row["issued_tflops"] = ach * mma_passes
+            row["tensor_pipe_frac"] = ach * mma_passes / peak
+            row["hbm_frac"] = row["hbm_gbs"] / peaks["hbm"] if row["hbm_gbs"] else None
+        rows.append(row)
     rows.sort(key=lambda r: -r["ms_per_step"])
     # group GEMM shapes into one dominant-kernel line as well
     gemm = [r for r in rows if r["kernel"].startswith("poet_gemm")]

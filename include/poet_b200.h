@@ -123,6 +123,11 @@ int poet_gemm(const float* A, int64_t lda, int a_kcontig, const float* Bm, int64
  * B_hi/B_lo have the same logical layout and ldb (in elements) as the fp32 B; Bm (fp32) is still
  * required when the shape is not tensor-core eligible (poet_gemm_tc_eligible() == 0). */
 int poet_split_bf16(const float* src, void* hi, void* lo, int64_t n, poet_stream_t stream);
+/* The same split for every weight matrix of a model in ONE launch (a step re-derives ~85 planes).
+ * table (device): n_tensors entries of 5 x 8 bytes {const float* src, void* hi, void* lo (may be 0),
+ * int64 n/4 (float4 count), int64 first_chunk}; tensor t owns chunks [first_chunk_t, first_chunk_{t+1}) of
+ * 1024 float4 each, entries sorted by first_chunk; total_chunks = sum_t ceil(n4_t / 1024). */
+int poet_split_bf16_multi(const void* table, int n_tensors, int64_t total_chunks, poet_stream_t stream);
 int poet_gemm_tc_eligible(int M, int N, int K, int64_t lda, int64_t ldb, int64_t ldc);
 int poet_gemm_bsplit(const float* A, int64_t lda, int a_kcontig, const float* Bm, const void* B_hi, const void* B_lo,
                      int64_t ldb, int b_kcontig, float* C, int64_t ldc, int M, int N, int K, float alpha,

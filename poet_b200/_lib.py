@@ -31,6 +31,7 @@ SIGNATURES = {
     "poet_gemm_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "poet_gemm": (_i, [_vp, _i64, _i, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp, _sz, _vp]),
     "poet_split_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "poet_split_bf16_multi": (_i, [_vp, _i, _i64, _vp]),
     "poet_gemm_tc_eligible": (_i, [_i, _i, _i, _i64, _i64, _i64]),
     "poet_gemm_bsplit": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp]),
     "poet_gemm_relu_bits_supported": (_i, [_i, _i, _i, _i]),

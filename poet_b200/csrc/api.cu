@@ -13,6 +13,7 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
 int poet_gemm_tc_bits_supported();
 bool poet_gemm_tc_supported(int M, int N, int K, int a_kcontig, int b_kcontig, int64_t lda, int64_t ldb, int64_t ldc);
 int poet_split_bf16_impl(const float* src, void* hi, void* lo, int64_t n, cudaStream_t s);
+int poet_split_bf16_multi_impl(const void* table_dev, int n_tensors, int64_t total_chunks, cudaStream_t s);
 #endif
 
 extern "C" int poet_version(void) { return 1; }
@@ -81,6 +82,15 @@ extern "C" int poet_split_bf16(const float* src, void* hi, void* lo, int64_t n, 
   return poet_split_bf16_impl(src, hi, lo, n, (cudaStream_t)stream);
 #else
   (void)src; (void)hi; (void)lo; (void)n; (void)stream;
+  return POET_ERR_UNSUPPORTED;
+#endif
+}
+
+extern "C" int poet_split_bf16_multi(const void* table, int n_tensors, int64_t total_chunks, poet_stream_t stream) {
+#ifdef POET_HAVE_TC_GEMM
+  return poet_split_bf16_multi_impl(table, n_tensors, total_chunks, (cudaStream_t)stream);
+#else
+  (void)table; (void)n_tensors; (void)total_chunks; (void)stream;
   return POET_ERR_UNSUPPORTED;
 #endif
 }

@@ -145,7 +145,8 @@ struct Args {
   int n_tiles, total_work;
   int epi_tma;            // 1: TMA-store epilogue, 0: smem-transpose + st.global epilogue
   int l2_prefetch;        // 1: L2 prefetch hints ahead of the register-prefetched operand loads
-  int debug;              // POET_GEMM_DEBUG bit flags (pipeline bisection only): 1 no A loads, 2 no A stores, 4 no TMA, 8 no epilogue stores
+  int debug;              // POET_GEMM_DEBUG bit flags (pipeline bisection only): 1 no A loads, 2 no A stores, 4 no TMA, 8 no epilogue stores,
+                          // 16 no epilogue math (TMA epilogue), 32 no MMA issue (barriers only)
 };
 
 // work item w -> (m0, n0, split, k-block range); n fastest so concurrent CTAs share A rows in L2
@@ -312,7 +313,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]);
   const uint32_t tfull0 = smem_u32(&bars[2 * STAGES]), tempty0 = smem_u32(&bars[2 * STAGES + 2]);
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, NT + (B_TMA ? 1 : 0)); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, PW + (B_TMA ? 1 : 0)); mbar_init(empty0 + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -354,8 +355,9 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
         TB::template store<X3>(b_hi, b_hi + B_BYTES, tid, vb);
       }
       fence_proxy_async();                                      // generic-proxy smem writes -> visible to the tensor core
-      mbar_arrive(full0 + 8 * s);
-      ++it;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full0 + 8 * s);                // one arrival per producer warp (256 arrivals on one
+      ++it;                                                     // mbarrier cost ~1000 cycles per k-block)
     };
     auto loadAB = [&](const Work& wk, int kb, float4 (&v)[TA::CH][2], float4 (&vbp)[BCH][2]) {
       if (p.debug & 1) {
@@ -459,6 +461,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
           const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + A_BYTES * PLANES, b_lo = b_hi + B_BYTES;
 #pragma unroll
           for (int j = 0; j < BK / 16; ++j) {
+            if (p.debug & 32) break;
             const uint64_t dah = make_desc(a_hi + j * A_STEP, A_LBO, 1024);
             const uint64_t dbh = make_desc(b_hi + j * B_STEP, B_LBO, 1024);
             const uint32_t first = (i | j) ? 1u : 0u;
@@ -540,6 +543,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
           }
           const int n0c = wk.n0 + col;
           if (mrow0 >= p.M || (p.debug & 8)) continue;               // warp-uniform
+          if (!(p.debug & 16)) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] *= alpha;
           if (p.bias != nullptr && wk.split == 0) {
@@ -577,6 +581,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
           if (dead) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
           }
           const uint32_t box = stage0 + (uint32_t)(nst & 1) * SP::EPI_BOX_BYTES;
           if (nst >= 2) {                                            // the store issued two boxes ago has read this buffer
@@ -692,6 +697,31 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float4* __restric
     const float h2 = __bfloat162float(__float2bfloat16_rn(x.z)), h3 = __bfloat162float(__float2bfloat16_rn(x.w));
     hi[i] = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
     if (lo) lo[i] = make_uint2(pack_bf16(x.x - h0, x.y - h1), pack_bf16(x.z - h2, x.w - h3));
+  }
+}
+
+// All weight matrices of a model in ONE launch: table[t] = {src, hi, lo, first_chunk}, chunk = 1024 float4.
+struct SplitEntry { const float4* src; uint2* hi; uint2* lo; int64_t n4; int64_t first_chunk; };
+__global__ void __launch_bounds__(256) split_bf16_multi_kernel(const SplitEntry* __restrict__ table, int n_tensors) {
+  // binary search of the chunk's tensor (n_tensors is ~100: 7 steps)
+  const int64_t chunk = blockIdx.x;
+  int lo_i = 0, hi_i = n_tensors - 1;
+  while (lo_i < hi_i) {
+    const int mid = (lo_i + hi_i + 1) >> 1;
+    if (table[mid].first_chunk <= chunk) lo_i = mid; else hi_i = mid - 1;
+  }
+  const SplitEntry e = table[lo_i];
+  const int64_t base = (chunk - e.first_chunk) * 1024;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t i = base + threadIdx.x + j * 256;
+    if (i < e.n4) {
+      const float4 x = e.src[i];
+      const float h0 = __bfloat162float(__float2bfloat16_rn(x.x)), h1 = __bfloat162float(__float2bfloat16_rn(x.y));
+      const float h2 = __bfloat162float(__float2bfloat16_rn(x.z)), h3 = __bfloat162float(__float2bfloat16_rn(x.w));
+      e.hi[i] = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
+      if (e.lo) e.lo[i] = make_uint2(pack_bf16(x.x - h0, x.y - h1), pack_bf16(x.z - h2, x.w - h3));
+    }
   }
 }
 
@@ -841,6 +871,14 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
   }
   if (bn == 256) return x3 ? tc::dispatch<256, true>(a, a_mn, b_mn, b_tma, m, s) : tc::dispatch<256, false>(a, a_mn, b_mn, b_tma, m, s);
   return x3 ? tc::dispatch<128, true>(a, a_mn, b_mn, b_tma, m, s) : tc::dispatch<128, false>(a, a_mn, b_mn, b_tma, m, s);
+}
+
+int poet_split_bf16_multi_impl(const void* table_dev, int n_tensors, int64_t total_chunks, cudaStream_t s) {
+  POET_REQUIRE(table_dev != nullptr, POET_ERR_NULL_POINTER);
+  POET_REQUIRE(n_tensors > 0 && total_chunks > 0 && total_chunks < ((int64_t)1 << 31), POET_ERR_BAD_SHAPE);
+  static_assert(sizeof(tc::SplitEntry) == 40, "table layout is part of the ABI (5 x 8 bytes)");
+  tc::split_bf16_multi_kernel<<<(unsigned)total_chunks, 256, 0, s>>>(reinterpret_cast<const tc::SplitEntry*>(table_dev), n_tensors);
+  return poet_launch_status();
 }
 
 int poet_split_bf16_impl(const float* src, void* hi, void* lo, int64_t n, cudaStream_t s) {

@@ -147,7 +147,8 @@ __device__ __forceinline__ float4 lds4(uint32_t saddr) {
 constexpr int kSlabBoxRows = 64;                 // TMA box: 64 rows x 16 floats = 4 KB
 constexpr int kSlabThreads = 256;
 constexpr int kSlabWarps = kSlabThreads / 32;
-constexpr int kRecBytesPerWarp = 2 * 16 * 32;    // 2 queries x 16 points x 4 corners x {offset, weight}
+constexpr int kRecCorner = 16 * 8 + 16;          // 16 points x {offset, weight} + 16 B pad: the 4 corners x 2 queries of a warp load hit distinct banks
+constexpr int kRecBytesPerWarp = 2 * 4 * kRecCorner;    // 2 queries x 4 corners x 16 points x {offset, weight}
 
 // Each warp walks pairs of queries of its CTA's chunk in two phases:
 //   A  one lane per (query, sampling point): softmax over the 16 logits (shuffles inside the 16-lane half),
@@ -191,8 +192,8 @@ msda_fwd_slab_kernel(const MsdaArgs p, const __grid_constant__ CUtensorMap tm_v,
   const float inv_W = p.lv.inv_W[lvl], inv_H = p.lv.inv_H[lvl];
   // phase B roles
   const int r = (lane >> 3) & 1, h = (lane >> 2) & 1, c4 = lane & 3;
-  const uint32_t rec_rd = rec + (uint32_t)(qa * 16 * 32 + (r * 2 + h) * 8);
-  const uint32_t rec_wr = rec + (uint32_t)((qa * 16 + pt) * 32);
+  const uint32_t rec_rd = rec + (uint32_t)((qa * 4 + r * 2 + h) * kRecCorner);
+  const uint32_t rec_wr = rec + (uint32_t)(qa * 4 * kRecCorner + pt * 8);
 
   // parameters of this lane's (query, point); prefetched one pair ahead
   auto load_params = [&](int pair, float& logit, float2& xy, float2& rf) {
@@ -203,9 +204,13 @@ msda_fwd_slab_kernel(const MsdaArgs p, const __grid_constant__ CUtensorMap tm_v,
     rf = make_float2(0.f, 0.f);
     if (FUSED) rf = __ldg(reinterpret_cast<const float2*>(p.ref + (bq * L + lvl) * 2));
   };
-  float logit, n_logit = 0.f;
-  float2 xy, rf, n_xy = make_float2(0.f, 0.f), n_rf = make_float2(0.f, 0.f);
-  if (warp < n_pairs) load_params(warp, logit, xy, rf);
+  // parameters are fetched a whole group of G pairs ahead (the loads miss L1 by construction: each line is
+  // used once), so their latency is covered by G pairs of work instead of one
+  constexpr int G = 4;
+  float lg[G], n_lg[G];
+  float2 xyv[G], rfv[G], n_xyv[G], n_rfv[G];
+#pragma unroll
+  for (int j = 0; j < G; ++j) load_params(warp + kSlabWarps * j, lg[j], xyv[j], rfv[j]);
 
   asm volatile(
       "{\n"
@@ -217,8 +222,15 @@ msda_fwd_slab_kernel(const MsdaArgs p, const __grid_constant__ CUtensorMap tm_v,
       "SLAB_DONE:\n"
       "}\n" ::"r"(bar_a) : "memory");
 
-  for (int pair = warp; pair < n_pairs; pair += kSlabWarps) {
-    if (pair + kSlabWarps < n_pairs) load_params(pair + kSlabWarps, n_logit, n_xy, n_rf);
+  for (int base = warp; base < n_pairs; base += kSlabWarps * G) {
+#pragma unroll
+    for (int j = 0; j < G; ++j) load_params(base + kSlabWarps * (G + j), n_lg[j], n_xyv[j], n_rfv[j]);
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+    const int pair = base + kSlabWarps * j;
+    if (pair >= n_pairs) break;                              // warp-uniform
+    const float logit = lg[j];
+    const float2 xy = xyv[j], rf = rfv[j];
     // ---- phase A ----
     float a = logit;
     if (FUSED) {
@@ -247,20 +259,21 @@ msda_fwd_slab_kernel(const MsdaArgs p, const __grid_constant__ CUtensorMap tm_v,
     const uint32_t o00 = (uint32_t)(start + yc0 * W + xc0) * (D * 4), o01 = (uint32_t)(start + yc0 * W + xc1) * (D * 4);
     const uint32_t o10 = (uint32_t)(start + yc1 * W + xc0) * (D * 4), o11 = (uint32_t)(start + yc1 * W + xc1) * (D * 4);
     __syncwarp();                                            // phase B of the previous pair has read its records
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rec_wr), "r"(o00), "r"(__float_as_uint(w00)), "r"(o01),
-                 "r"(__float_as_uint(w01)) : "memory");
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rec_wr + 16), "r"(o10), "r"(__float_as_uint(w10)), "r"(o11),
-                 "r"(__float_as_uint(w11)) : "memory");
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rec_wr), "r"(o00), "r"(__float_as_uint(w00)) : "memory");
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rec_wr + kRecCorner), "r"(o01), "r"(__float_as_uint(w01)) : "memory");
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rec_wr + 2 * kRecCorner), "r"(o10), "r"(__float_as_uint(w10)) : "memory");
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(rec_wr + 3 * kRecCorner), "r"(o11), "r"(__float_as_uint(w11)) : "memory");
     __syncwarp();
     // ---- phase B ----
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const uint32_t vbase = slab + (uint32_t)c4 * 16;
 #pragma unroll
-    for (int s = 0; s < LP; ++s) {
-      uint32_t off; float wgt;
-      asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(off), "=f"(wgt) : "r"(rec_rd + s * 32));
-      const float4 v = lds4(vbase + off);
-      acc.x += wgt * v.x; acc.y += wgt * v.y; acc.z += wgt * v.z; acc.w += wgt * v.w;
+    for (int s = 0; s < LP; s += 2) {                        // one 128-bit record load covers two sampling points
+      uint32_t off0, off1; float wgt0, wgt1;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(off0), "=f"(wgt0), "=r"(off1), "=f"(wgt1) : "r"(rec_rd + s * 8));
+      const float4 v0 = lds4(vbase + off0), v1 = lds4(vbase + off1);
+      acc.x += wgt0 * v0.x; acc.y += wgt0 * v0.y; acc.z += wgt0 * v0.z; acc.w += wgt0 * v0.w;
+      acc.x += wgt1 * v1.x; acc.y += wgt1 * v1.y; acc.z += wgt1 * v1.z; acc.w += wgt1 * v1.w;
     }
 #pragma unroll
     for (int o = 4; o <= 8; o <<= 1) {
@@ -271,7 +284,9 @@ msda_fwd_slab_kernel(const MsdaArgs p, const __grid_constant__ CUtensorMap tm_v,
     }
     const int q = q_beg + 2 * pair + qa;
     if (q < q_end && (lane & 12) == 0) st4(p.out + (((int64_t)b * p.Lq + q) * p.M + m) * D + c4 * 4, acc);
-    logit = n_logit; xy = n_xy; rf = n_rf;
+    }
+#pragma unroll
+    for (int j = 0; j < G; ++j) { lg[j] = n_lg[j]; xyv[j] = n_xyv[j]; rfv[j] = n_rfv[j]; }
   }
 }
 

@@ -245,6 +245,12 @@ class DeformableTransformer(nn.Module):
 
     def forward(self, srcs, masks, pos_embeds, query_embed=None, reference_points=None, pos_tokens=None,
                 layer_callback=None):
+        # all weight matrices -> bf16 hi/lo planes in one launch (no-op if an enclosing module already did it)
+        with ops.planes_scope(self):
+            return self._forward_impl(srcs, masks, pos_embeds, query_embed, reference_points, pos_tokens, layer_callback)
+
+    def _forward_impl(self, srcs, masks, pos_embeds, query_embed=None, reference_points=None, pos_tokens=None,
+                      layer_callback=None):
         """Reference signature (deformable_transformer.py:120).  `pos_tokens` (optional, ours):
         lvl_pos_embed_flatten [B,S,C] already in token layout with level_embed added."""
         if query_embed is None:

@@ -12,6 +12,16 @@ a tracing compiler.
 
 Inputs may be host (pinned) or device tensors; they are copied into the static buffers on the
 current stream.  Shapes (batch, pyramid, queries) are fixed at capture time.
+
+Input pipelining: `prefetch(...)` starts the host-to-device copy of the NEXT step's inputs on a
+dedicated copy stream into one of two landing buffer sets, so it overlaps the current step's replay;
+`run()` without arguments then consumes the oldest prefetched set (device-to-device into the static
+buffers, a few microseconds) before replaying:
+
+    step.prefetch(batch0)
+    for batch in batches[1:]:
+        step.prefetch(batch)              # H2D of step i+1 ...
+        loss, out = step.run()            # ... overlaps the replay of step i
 """
 from __future__ import annotations
 
@@ -35,6 +45,7 @@ class GraphedStep:
         self.s_classes = torch.empty((B, Q), dtype=torch.int64, device=dev)
         self.s_counts = torch.empty((B,), dtype=torch.int32, device=dev)
         self.counts_host = None
+        self._landing, self._pending, self._copy_stream, self._n_prefetched = None, [], None, 0
         self._copy_in(srcs, masks, boxes, labels)
 
         side = torch.cuda.Stream(device=dev)
@@ -73,11 +84,50 @@ class GraphedStep:
         self.s_counts.copy_(n_dev, non_blocking=True)
         self.counts_host = counts
 
+    # -- pipelined input copies ---------------------------------------------------------------
+    def _static_set(self):
+        return [*self.s_srcs, *self.s_masks, self.s_boxes, self.s_classes, self.s_counts]
+
+    def prefetch(self, srcs, masks, boxes, labels) -> None:
+        """Start copying the inputs of a FUTURE run() into a landing buffer set on the copy stream (at most two
+        prefetches may be outstanding).  Host tensors should be pinned for the copy to be asynchronous."""
+        dev = self.s_boxes.device
+        if self._landing is None:
+            self._landing = [[torch.empty_like(t) for t in self._static_set()] for _ in range(2)]
+            self._free_ev = [None, None]                       # landing set consumed (recorded on the compute stream)
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        if len(self._pending) >= 2:
+            raise RuntimeError("GraphedStep.prefetch: two prefetched input sets are already waiting for run()")
+        slot = self._n_prefetched % 2
+        self._n_prefetched += 1
+        pb, pc, counts, n_dev = self.model._pad_boxes(boxes, labels, boxes[0].device)
+        if not pb.is_cuda:
+            pb, pc, n_dev = pb.pin_memory(), pc.pin_memory(), n_dev.pin_memory()
+        src_set = [*srcs, *masks, pb, pc, n_dev]
+        with torch.cuda.stream(self._copy_stream):
+            if self._free_ev[slot] is not None:
+                self._copy_stream.wait_event(self._free_ev[slot])
+            for dst, src in zip(self._landing[slot], src_set):
+                dst.copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._pending.append((slot, ev, counts))
+
     def run(self, srcs=None, masks=None, boxes=None, labels=None):
-        """Copy new inputs (if given) into the static buffers and replay.  Returns (loss, out_dict);
-        both alias static graph memory: read them before the next run()."""
+        """Copy new inputs (if given; else the oldest prefetched set, if any) into the static buffers and replay.
+        Returns (loss, out_dict); both alias static graph memory: read them before the next run()."""
         if srcs is not None:
             self._copy_in(srcs, masks, boxes, labels)
+        elif self._pending:
+            slot, ev, counts = self._pending.pop(0)
+            main = torch.cuda.current_stream(self.s_boxes.device)
+            main.wait_event(ev)
+            for dst, src in zip(self._static_set(), self._landing[slot]):
+                dst.copy_(src, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            self._free_ev[slot] = done
+            self.counts_host = counts
         self.graph.replay()
         return self.loss, self.out
 

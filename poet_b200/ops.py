@@ -204,11 +204,128 @@ def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_kcontig
     return out
 
 
-# Weights are the B operand of the forward (NT) and of the dgrad (NN) GEMM of a layer: split them into
-# bf16 hi/lo planes once in forward, keep the planes on the autograd ctx for backward, and let both
-# GEMMs fetch them by TMA.  No cross-call cache: planes never outlive the forward/backward that made them.
+# Weights are the B operand of the forward (NT) and of the dgrad (NN) GEMM of a layer: they are split into
+# bf16 hi/lo planes once per step and both GEMMs fetch the planes by TMA.  `WeightPlanes` does that for ALL
+# weight matrices of a module tree in one launch into one arena (the per-layer autograd Functions then only
+# look their planes up); a weight that is not covered falls back to its own poet_split_bf16 launch.
+class WeightPlanes:
+    """bf16 hi/lo planes of every 2-D parameter of `module`, refreshed by one poet_split_bf16_multi launch.
+    Parameters keep their registration order in the arena, so row-blocks of one matrix and consecutive
+    matrices (sampling_offsets | attention_weights) are contiguous plane views as well."""
+
+    @staticmethod
+    def select(module: torch.nn.Module):
+        return [p for p in module.parameters() if p.dim() == 2 and p.dtype == torch.float32 and p.is_cuda
+                and p.is_contiguous() and p.numel() % 8 == 0]
+
+    def __init__(self, module: torch.nn.Module):
+        params = self.select(module)
+        self.params = params
+        self.device = params[0].device if params else None
+        total = sum(p.numel() for p in params)
+        self.hi = torch.empty(total, device=self.device, dtype=torch.bfloat16) if params else None
+        self.lo = torch.empty(total, device=self.device, dtype=torch.bfloat16) if params else None
+        self.ranges = []                      # (data_ptr, nbytes, element offset in the arena)
+        off = 0
+        for p in params:
+            self.ranges.append((p.data_ptr(), p.numel() * 4, off))
+            off += p.numel()
+        self._table_key, self._table, self._chunks = None, None, 0
+
+    def _build_table(self, with_lo: bool):
+        import struct
+        raw, chunk, off = bytearray(), 0, 0
+        for p in self.params:
+            n4 = p.numel() // 4
+            raw += struct.pack("<QQQqq", p.data_ptr(), self.hi.data_ptr() + 2 * off,
+                               (self.lo.data_ptr() + 2 * off) if with_lo else 0, n4, chunk)
+            chunk += (n4 + 1023) // 1024
+            off += p.numel()
+        self._table = torch.frombuffer(bytes(raw), dtype=torch.uint8).clone().to(self.device)
+        self._chunks = chunk
+
+    def refresh(self) -> None:
+        """Re-derive all planes from the current parameter values (call once per forward)."""
+        prec = _state["precision"]
+        if not self.params or prec == GEMM_FP32:
+            return
+        key = (tuple(p.data_ptr() for p in self.params), prec == GEMM_BF16X3)
+        if key != self._table_key:
+            self.ranges, off = [], 0
+            for p in self.params:
+                self.ranges.append((p.data_ptr(), p.numel() * 4, off))
+                off += p.numel()
+            self._build_table(prec == GEMM_BF16X3)
+            self._table_key = key
+        self.with_lo = prec == GEMM_BF16X3
+        _call("poet_split_bf16_multi", _p(self._table), len(self.params), self._chunks,
+              torch.cuda.current_stream(self.device).cuda_stream)
+
+    def lookup(self, ptr: int, numel: int):
+        """(hi, lo) flat plane views for the fp32 range [ptr, ptr + 4*numel) if it lies inside the arena's
+        parameters (a whole matrix, a row block, or consecutive matrices), else None."""
+        for base, nbytes, off in self.ranges:
+            if base <= ptr < base + nbytes:
+                e0 = off + (ptr - base) // 4
+                # consecutive parameters are consecutive in the arena only if they are consecutive in memory too
+                if ptr + 4 * numel > base + nbytes:
+                    return None
+                hi = self.hi[e0:e0 + numel]
+                lo = self.lo[e0:e0 + numel] if self.with_lo else None
+                return hi, lo
+        return None
+
+    def lookup_pair(self, W0: torch.Tensor, W1: torch.Tensor):
+        """Planes of cat(W0, W1) when the two matrices follow each other in the arena (no fp32 cat needed)."""
+        r0 = r1 = None
+        for base, nbytes, off in self.ranges:
+            if base == W0.data_ptr() and nbytes == W0.numel() * 4:
+                r0 = off
+            if base == W1.data_ptr() and nbytes == W1.numel() * 4:
+                r1 = off
+        if r0 is None or r1 is None or r1 != r0 + W0.numel():
+            return None
+        n = W0.numel() + W1.numel()
+        return self.hi[r0:r0 + n], (self.lo[r0:r0 + n] if self.with_lo else None)
+
+
+_active_planes: List[WeightPlanes] = []
+
+
+class planes_scope:
+    """with planes_scope(module): ... -- inside, split_weight() is served from the module's refreshed arena.
+    The arena object is cached on the module; nested scopes whose parameters are already covered are no-ops."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.module, self.pushed = module, False
+
+    def __enter__(self):
+        first = next((p for p in self.module.parameters() if p.dim() == 2), None)
+        if first is None or not first.is_cuda or _state["precision"] == GEMM_FP32:
+            return self
+        if any(pl.lookup(first.data_ptr(), first.numel()) is not None for pl in _active_planes):
+            return self                                   # an enclosing scope already covers this module
+        pl = getattr(self.module, "_poet_weight_planes", None)
+        if pl is None or [p.data_ptr() for p in pl.params] != [p.data_ptr() for p in WeightPlanes.select(self.module)]:
+            pl = WeightPlanes(self.module)
+            object.__setattr__(self.module, "_poet_weight_planes", pl)
+        pl.refresh()
+        _active_planes.append(pl)
+        self.pushed = True
+        return self
+
+    def __exit__(self, *exc):
+        if self.pushed:
+            _active_planes.pop()
+        return False
+
+
 def clear_weight_split_cache() -> None:
-    """Kept for API stability: planes are owned by the autograd graph, there is nothing to clear."""
+    """Kept for API stability: planes are owned by the autograd graph / the module arena, nothing to clear."""
+
+
+def _eligible(M_rows: int, N: int, K: int) -> bool:
+    return not (K % 8 or N % 8) and bool(_lib.lib().poet_gemm_tc_eligible(M_rows, N, K, K, K, N))
 
 
 def split_weight(W: torch.Tensor, M_rows: int):
@@ -217,12 +334,29 @@ def split_weight(W: torch.Tensor, M_rows: int):
     if prec == GEMM_FP32:
         return None
     N, K = W.shape
-    if K % 8 or N % 8 or not _lib.lib().poet_gemm_tc_eligible(M_rows, N, K, K, K, N):
+    if not _eligible(M_rows, N, K):
         return None
+    if W.is_contiguous():
+        for pl in reversed(_active_planes):
+            v = pl.lookup(W.data_ptr(), W.numel())
+            if v is not None:
+                return v[0].view(N, K), (v[1].view(N, K) if v[1] is not None else None)
     hi = torch.empty(W.shape, device=W.device, dtype=torch.bfloat16)
     lo = torch.empty(W.shape, device=W.device, dtype=torch.bfloat16) if prec == GEMM_BF16X3 else None
     _call("poet_split_bf16", _p(W), _p(hi), _p(lo), W.numel(), _stream(W))
     return hi, lo
+
+
+def split_weight_pair(W0: torch.Tensor, W1: torch.Tensor, M_rows: int):
+    """Planes of cat(W0, W1) [N0+N1, K] straight from the arena, or None (caller concatenates and splits)."""
+    if _state["precision"] == GEMM_FP32 or not _eligible(M_rows, W0.shape[0] + W1.shape[0], W0.shape[1]):
+        return None
+    for pl in reversed(_active_planes):
+        v = pl.lookup_pair(W0, W1)
+        if v is not None:
+            N, K = W0.shape[0] + W1.shape[0], W0.shape[1]
+            return v[0].view(N, K), (v[1].view(N, K) if v[1] is not None else None)
+    return None
 
 
 def relu_bits_buffer(R: int, N: int, K: int, device) -> Optional[torch.Tensor]:
@@ -437,9 +571,13 @@ class _ProjPair(torch.autograd.Function):
         if mode == "cat":
             N0, N1 = W0.shape[0], W1.shape[0]
             with torch.no_grad():
-                Wc = torch.cat((W0, W1), 0)
                 bc = torch.cat((b0, b1), 0)
-            ctx.w_split = split_weight(Wc, R)
+                ctx.w_split = split_weight_pair(W0, W1, R)
+                if ctx.w_split is not None:
+                    Wc = None                       # with planes the GEMMs never read the fp32 matrix
+                else:
+                    Wc = torch.cat((W0, W1), 0)
+                    ctx.w_split = split_weight(Wc, R)
             out = gemm(x0_2, Wc, R, N0 + N1, K, bias=bc, b_split=ctx.w_split)
             ctx.save_for_backward(x0_2, Wc)
             ctx.params = (W0, b0, W1, b1)

@@ -196,6 +196,10 @@ class PoET(nn.Module):
     def _run_with_heads(self, srcs, masks, pos, qe, ref, pred_classes, pos_tokens=None):
         """transformer + heads; with stream forking on, layer l's heads are issued on a side stream the moment
         decoder layer l is issued, so they (and their backward) overlap the rest of the decoder chain."""
+        with ops.planes_scope(self):          # transformer + head weights -> bf16 planes, one launch
+            return self._run_with_heads_impl(srcs, masks, pos, qe, ref, pred_classes, pos_tokens)
+
+    def _run_with_heads_impl(self, srcs, masks, pos, qe, ref, pred_classes, pos_tokens=None):
         if not (ops.parallel_streams_enabled() and srcs[0].is_cuda):
             hs = self.transformer(srcs, masks, pos, qe, ref, pos_tokens=pos_tokens)[0]
             return self._heads(hs, pred_classes)

@@ -278,7 +278,8 @@ struct SmemPlan {
   static constexpr int EPI_BOX_BYTES = 32 * 32 * 4;                           // one TMA store box (1024-byte aligned)
   static constexpr int EPI_WARP_BYTES = 2 * EPI_BOX_BYTES;                    // double-buffered per warp
   static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
-  static constexpr size_t TOTAL = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024;
+  static constexpr int BIAS_BYTES = BN * 4;                                    // this tile's bias slice, shared by the epilogue warps
+  static constexpr size_t TOTAL = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + BIAS_BYTES + 1024;
   static_assert(STAGE_BYTES % 1024 == 0, "stages must keep the 1024-byte swizzle alignment");
   static_assert(32 * 36 * 4 <= EPI_WARP_BYTES, "transpose tile of the st.global epilogue must fit the staging area");
 };
@@ -523,6 +524,10 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
       const bool reduce = accum || p.splits > 1;
       const int words = p.N >> 5;                                    // bitmask words per row
       int nst = 0;                                                   // boxes issued by this warp
+      // The tile's bias slice is staged in shared memory once per tile (a dependent global load per 32-column
+      // chunk costs ~500 cycles of epilogue latency, and the epilogue is what paces the accumulator hand-over).
+      const uint32_t bias_s = smem_u32(smem) + STAGES * STAGE_BYTES + SP::EPI_BYTES;
+      const int et = tid - (PW + 2) * 32;                            // 0..127 over the epilogue warps
       for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcnt) {
         const Work wk = decode<BK>(p, w, BN);
         const int ab = tcnt & 1;
@@ -530,6 +535,15 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
         const int row = mrow0 + lane;
         const bool row_ok = row < p.M;
         const bool dead = p.row_mask != nullptr && row_ok && p.row_mask[row] != 0;
+        const bool has_bias = p.bias != nullptr && wk.split == 0;
+        if (has_bias) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");             // every epilogue warp is done with the previous slice
+          if (et * 2 < BN) {
+            const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.bias + wk.n0 + et * 2));
+            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_s + et * 8), "f"(b2.x), "f"(b2.y) : "memory");
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         mbar_wait(tfull0 + 8 * ab, (tcnt >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
@@ -544,12 +558,14 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
           const int n0c = wk.n0 + col;
           if (mrow0 >= p.M || (p.debug & 8)) continue;               // warp-uniform
           if (!(p.debug & 16)) {
+          if (alpha != 1.f) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] *= alpha;
-          if (p.bias != nullptr && wk.split == 0) {
+            for (int i = 0; i < 32; ++i) v[i] *= alpha;
+          }
+          if (has_bias) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 b4 = ldg4(p.bias + n0c + 4 * j);          // warp-uniform address: one broadcast transaction
+              const float4 b4 = lds128(bias_s + (col + 4 * j) * 4);  // warp-uniform address: one broadcast wavefront
               v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
             }
           }
@@ -745,6 +761,11 @@ struct Maps {
   CUtensorMap hi, lo, c;
 };
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 template <int BN, int BK, bool A_MN, bool B_MN, bool X3, bool B_TMA, int STAGES>
 int launch(Args a, const Maps& m, cudaStream_t s) {
   constexpr int PW = 8;
@@ -766,6 +787,10 @@ int dispatch(const Args& a, bool a_mn, bool b_mn, bool b_tma, const Maps& m, cud
   constexpr int ST32 = (BN == 256) ? 4 : 6;
   if (b_tma) {                                      // B is a pre-split weight: A is k-contiguous (forward / dgrad)
     if (a_mn) return POET_ERR_UNSUPPORTED;
+    if constexpr (BN == 128) {
+      static const int st2 = env_int("POET_GEMM_STAGES128", 3) == 2;      // pipeline-depth experiment
+      if (st2) return b_mn ? launch<128, 64, false, true, X3, true, 2>(a, m, s) : launch<128, 64, false, false, X3, true, 2>(a, m, s);
+    }
     return b_mn ? launch<BN, 64, false, true, X3, true, ST64>(a, m, s) : launch<BN, 64, false, false, X3, true, ST64>(a, m, s);
   }
   if (a_mn && b_mn) return launch<BN, 32, true, true, X3, false, ST32>(a, m, s);   // weight gradient
@@ -775,11 +800,6 @@ int dispatch(const Args& a, bool a_mn, bool b_mn, bool b_tma, const Maps& m, cud
     return launch<128, 64, true, false, X3, false, 3>(a, m, s);
   }
   return POET_ERR_UNSUPPORTED;
-}
-
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
 }
 
 }  // namespace tc
@@ -832,9 +852,12 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
   // but convert every A tile twice as often, hence the 15 % handicap.
   int bn = 128;
   if (N % 256 == 0 && b_tma) {
-    const double c256 = (double)poet_ceil_div((int64_t)(N / 256) * m_tiles, POET_NUM_SMS) * 256.0;
-    const double c128 = (double)poet_ceil_div((int64_t)(N / 128) * m_tiles, POET_NUM_SMS) * 128.0 * 1.15;
-    if (c256 <= c128) bn = 256;
+    // 256-wide tiles convert each A tile once per 256 output columns; measured on the cfg2 shapes they are never
+    // slower than 128-wide ones once there is at least one tile per SM (K=1024: 63 vs 77 us), so the 128-wide
+    // tile is kept for small problems only (more CTAs in flight).
+    if ((int64_t)(N / 256) * m_tiles >= POET_NUM_SMS) bn = 256;
+    static const int force_bn = tc::env_int("POET_GEMM_FORCE_BN", 0);
+    if (force_bn == 128 || force_bn == 256) bn = force_bn;
   }
   // weight gradient: the wide tile halves the L2->SM operand traffic per flop; split-K fills the machine
   if (wgrad && N % 256 == 0 && wgrad_bn == 256 && total_kb >= 16) bn = 256;

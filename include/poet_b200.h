@@ -137,12 +137,15 @@ int poet_gemm_bsplit(const float* A, int64_t lda, int a_kcontig, const float* Bm
  * an fp32 re-read (words [M, N/32] row-major, bit c%32 of word [m, c/32]):
  *   relu_bits_out (with POET_GEMM_RELU): bit = (pre-activation > 0), written by the forward GEMM's epilogue;
  *   gate_bits: the dgrad GEMM keeps an element iff its bit is set (deformable_transformer.py:193-197 backward).
+ *   a_colsum (weight-gradient shape only: a_kcontig = b_kcontig = 0, no pre-split B): a_colsum[m] += sum_k A[k,m],
+ *   i.e. the bias gradient colsum(dY) accumulated while the dY tiles stream through the producers (caller
+ *   zero-fills or passes an existing gradient).
  * Returns POET_ERR_UNSUPPORTED when the shape is not tensor-core eligible (ask poet_gemm_relu_bits_supported()). */
 int poet_gemm_relu_bits_supported(int M, int N, int K, int precision);
 int poet_gemm_ex(const float* A, int64_t lda, int a_kcontig, const float* Bm, const void* B_hi, const void* B_lo,
                  int64_t ldb, int b_kcontig, float* C, int64_t ldc, int M, int N, int K, float alpha,
                  const float* bias, const uint8_t* row_mask, uint32_t* relu_bits_out, const uint32_t* gate_bits,
-                 int flags, int precision, poet_stream_t stream);
+                 float* a_colsum, int flags, int precision, poet_stream_t stream);
 /* out[N] (+)= sum_m X[m,n]  (bias gradients).  accumulate=0 overwrites. */
 int poet_colsum(const float* X, int64_t ldx, float* out, int M, int N, int accumulate, poet_stream_t stream);
 

@@ -139,6 +139,7 @@ struct Args {
   const float* bias; const float* gate; const uint8_t* row_mask;
   uint32_t* relu_bits;                    // [M, N/32] sign bitmask of the ReLU output (TMA epilogue only)
   const uint32_t* gate_bits;              // [M, N/32] keep-mask for the ReLU backward (TMA epilogue only)
+  float* a_colsum;                        // weight-gradient shape only: a_colsum[m] += sum_k A[k, m] (the bias gradient), or nullptr
   int flags;
   int kb_per_split;       // k-blocks (of BK) per split
   int splits;
@@ -335,6 +336,12 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
   if (warp < PW) {
     // ===================== producers =====================
     int it = 0;                                                    // k-blocks published so far (ring position)
+    const bool do_colsum = B_PREFETCH && p.a_colsum != nullptr;
+    float cs[B_PREFETCH ? TA::CH : 1][8];
+#pragma unroll
+    for (int i = 0; i < (B_PREFETCH ? TA::CH : 1); ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cs[i][j] = 0.f;
     auto publish = [&](const Work& wk, int kb, const float4 (&va)[TA::CH][2], const float4 (&vbp)[BCH][2]) {
       const int s = it % STAGES;
       const uint32_t a_hi = smem_u32(smem) + s * STAGE_BYTES;
@@ -343,9 +350,31 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
         if (it >= STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
         if (!(p.debug & 2)) TA::template store<X3>(a_hi, a_hi + A_BYTES, tid, va);
       } else if constexpr (B_PREFETCH) {
+        if (do_colsum && wk.n0 == 0) {                          // bias gradient: column sums of the dY tile, for free
+#pragma unroll
+          for (int i = 0; i < TA::CH; ++i) {
+            cs[i][0] += va[i][0].x; cs[i][1] += va[i][0].y; cs[i][2] += va[i][0].z; cs[i][3] += va[i][0].w;
+            cs[i][4] += va[i][1].x; cs[i][5] += va[i][1].y; cs[i][6] += va[i][1].z; cs[i][7] += va[i][1].w;
+          }
+        }
         if (it >= STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
         TA::template store<X3>(a_hi, a_hi + A_BYTES, tid, va);
         TB::template store<X3>(b_hi, b_hi + B_BYTES, tid, vbp);
+        if (do_colsum && wk.n0 == 0 && kb == wk.nkb - 1) {      // item finished: fold the 4 row groups of the warp, then atomics
+#pragma unroll
+          for (int i = 0; i < TA::CH; ++i) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float v = cs[i][j];
+              v += __shfl_xor_sync(0xffffffffu, v, 8);
+              v += __shfl_xor_sync(0xffffffffu, v, 16);
+              cs[i][j] = 0.f;
+              // chunk i of this thread: columns (seg = i) * 64 + (tid & 7) * 8 + j of the tile (Tile<> chunk map, ROWS = BK = 32)
+              const int gcol = wk.m0 + i * 64 + (tid & 7) * 8 + j;
+              if (lane < 8 && gcol < p.M) atomicAdd(p.a_colsum + gcol, v);
+            }
+          }
+        }
       } else {                                                  // fp32 activation B: loads issued before the stage wait
         float4 vb[TB::CH][2];
         const int k0 = (wk.kb0 + kb) * BK;
@@ -824,8 +853,8 @@ int poet_gemm_tc_bits_supported() {
 // b_hi / b_lo != nullptr: B was pre-split into bf16 planes (same logical layout / ldb as the fp32 B).
 int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, const void* b_hi, const void* b_lo,
                  int64_t ldb, int b_kcontig, float* C, int64_t ldc, int M, int N, int K, float alpha, const float* bias,
-                 const float* gate, const uint8_t* row_mask, uint32_t* relu_bits, const uint32_t* gate_bits, int flags,
-                 int precision, cudaStream_t s) {
+                 const float* gate, const uint8_t* row_mask, uint32_t* relu_bits, const uint32_t* gate_bits, float* a_colsum,
+                 int flags, int precision, cudaStream_t s) {
   POET_REQUIRE(poet_aligned16(A) && poet_aligned16(C), POET_ERR_BAD_ALIGNMENT);
   POET_REQUIRE(!bias || poet_aligned16(bias), POET_ERR_BAD_ALIGNMENT);
   POET_REQUIRE(!gate || poet_aligned16(gate), POET_ERR_BAD_ALIGNMENT);
@@ -840,10 +869,11 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
   POET_REQUIRE(b_tma || (Bm != nullptr && poet_aligned16(Bm)), POET_ERR_NULL_POINTER);
   const bool a_mn = !a_kcontig, b_mn = !b_kcontig;
   const bool wgrad = !b_tma && a_mn && b_mn;
+  POET_REQUIRE(a_colsum == nullptr || wgrad, POET_ERR_UNSUPPORTED);
   const int bk = wgrad ? 32 : 64;
   tc::Args a;
   a.A = A; a.lda = lda; a.B = b_tma ? nullptr : Bm; a.ldb = ldb; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
-  a.alpha = alpha; a.bias = bias; a.gate = gate; a.row_mask = row_mask; a.relu_bits = relu_bits; a.gate_bits = gate_bits;
+  a.alpha = alpha; a.bias = bias; a.gate = gate; a.row_mask = row_mask; a.relu_bits = relu_bits; a.gate_bits = gate_bits; a.a_colsum = a_colsum;
   a.flags = flags;
   a.epi_tma = epi_tma; a.l2_prefetch = l2pf; a.debug = dbg;
   const int m_tiles = poet_ceil_div(M, tc::BM);

@@ -171,7 +171,7 @@ def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_kcontig
          lda: Optional[int] = None, ldb: Optional[int] = None, bias=None, relu=False, gate=None, row_mask=None,
          out: Optional[torch.Tensor] = None, accumulate=False, alpha: float = 1.0,
          precision: Optional[int] = None, b_split=None, relu_bits: Optional[torch.Tensor] = None,
-         gate_bits: Optional[torch.Tensor] = None) -> torch.Tensor:
+         gate_bits: Optional[torch.Tensor] = None, a_colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = epi(alpha * op(A) @ op(B)); see include/poet_b200.h poet_gemm / poet_gemm_ex.
     relu_bits (out) / gate_bits (in): int32 [M, N/32] sign bitmask of a ReLU (tensor-core path only)."""
     if out is None:
@@ -187,12 +187,12 @@ def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_kcontig
     flags = (1 if relu else 0) | (2 if accumulate else 0)
     tag = (f"{M}x{N}x{K}" + ("" if a_kcontig else ",At") + ("" if b_kcontig else ",Bt")) if _timing["on"] else None
     work = (4 * (M * K + N * K + M * N), 2 * M * N * K)
-    if relu_bits is not None or gate_bits is not None:
+    if relu_bits is not None or gate_bits is not None or a_colsum is not None:
         assert gate is None and prec != GEMM_FP32
         bs = b_split if (b_split is not None and a_kcontig) else (None, None)
         _call("poet_gemm_ex", _p(A), lda, int(a_kcontig), _p(Bm), _p(bs[0]), _p(bs[1]), ldb, int(b_kcontig), _p(out),
-              out.stride(0), M, N, K, alpha, _p(bias), _p(row_mask), _p(relu_bits), _p(gate_bits), flags, prec,
-              _stream(A), tag=tag, work=work)
+              out.stride(0), M, N, K, alpha, _p(bias), _p(row_mask), _p(relu_bits), _p(gate_bits), _p(a_colsum), flags,
+              prec, _stream(A), tag=tag, work=work)
         return out
     if b_split is not None and prec != GEMM_FP32 and a_kcontig:
         _call("poet_gemm_bsplit", _p(A), lda, int(a_kcontig), _p(Bm), _p(b_split[0]), _p(b_split[1]), ldb,
@@ -370,6 +370,21 @@ def relu_bits_buffer(R: int, N: int, K: int, device) -> Optional[torch.Tensor]:
     return torch.empty((R, N // 32), device=device, dtype=torch.int32)
 
 
+def wgrad_bias(gy2: torch.Tensor, x2: torch.Tensor, N: int, K: int, R: int, w_out: torch.Tensor, b_out: Optional[torch.Tensor],
+               lda: Optional[int] = None) -> None:
+    """w_out[N,K] += gy2[R,N]^T x2[R,K] and, if given, b_out[N] += colsum(gy2): one launch when the weight-gradient GEMM
+    runs on the tensor-core path (the bias gradient is summed from the dY tiles as they stream through the
+    producers), else the GEMM plus a separate column-sum kernel.  gy2 may be a column block (lda = row stride)."""
+    lda = N if lda is None else lda
+    prec = _state["precision"]
+    fused = (b_out is not None and prec != GEMM_FP32 and
+             _lib.lib().poet_gemm_tc_eligible(N, K, R, lda, K, w_out.stride(0)))
+    gemm(gy2, x2, N, K, R, a_kcontig=False, b_kcontig=False, lda=lda, out=w_out, accumulate=True,
+         a_colsum=b_out if fused else None)
+    if b_out is not None and not fused:
+        _call("poet_colsum", _p(gy2), lda, _p(b_out), R, N, 1, _stream(gy2))
+
+
 def colsum(X: torch.Tensor, M: int, N: int, out: Optional[torch.Tensor] = None, accumulate=False) -> torch.Tensor:
     if out is None:
         out = torch.empty(N, device=X.device, dtype=torch.float32)
@@ -434,8 +449,8 @@ def _linear_bwd(gy2: torch.Tensor, x2: torch.Tensor, W: torch.Tensor, need_x: bo
         side.__enter__()
     try:
         if w_slot is not None:
-            gemm(gy2, x2, N, K, R, a_kcontig=False, b_kcontig=False, out=w_slot, accumulate=True)
-        if b_slot is not None:
+            wgrad_bias(gy2, x2, N, K, R, w_slot, b_slot)
+        elif b_slot is not None:
             colsum(gy2, R, N, out=b_slot, accumulate=True)
     finally:
         if side is not None:
@@ -610,8 +625,12 @@ class _ProjPair(torch.autograd.Function):
             for W, b, col, n in ((W0, b0, 0, N0), (W1, b1, N0, N1)):
                 gcols = g[:, col:col + n]                           # column block: pointer offset + ld = N0+N1
                 slot = _grad_slot(W)
-                dW = gemm(gcols, x2, n, K, R, a_kcontig=False, b_kcontig=False, lda=N0 + N1, out=slot, accumulate=slot is not None)
                 bslot = _grad_slot(b)
+                if slot is not None and bslot is not None:
+                    wgrad_bias(gcols, x2, n, K, R, slot, bslot, lda=N0 + N1)
+                    outs += [None, None]
+                    continue
+                dW = gemm(gcols, x2, n, K, R, a_kcontig=False, b_kcontig=False, lda=N0 + N1, out=slot, accumulate=slot is not None)
                 if bslot is not None:
                     _call("poet_colsum", _p(gcols), N0 + N1, _p(bslot), R, n, 1, _stream(g))
                     db = None
@@ -629,10 +648,8 @@ class _ProjPair(torch.autograd.Function):
         slot, bslot = _grad_slot(Wp), _grad_slot(bp)
         dW = slot if slot is not None else torch.zeros_like(W)
         db = bslot if bslot is not None else torch.zeros(3 * C, device=W.device, dtype=torch.float32)
-        gemm(gqk, x0_2, 2 * C, C, R, a_kcontig=False, b_kcontig=False, out=dW[: 2 * C], accumulate=True)
-        gemm(gv, x1_2, C, C, R, a_kcontig=False, b_kcontig=False, out=dW[2 * C:], accumulate=True)
-        _call("poet_colsum", _p(gqk), 2 * C, _p(db), R, 2 * C, 1, _stream(W))
-        _call("poet_colsum", _p(gv), C, _p(db[2 * C:]), R, C, 1, _stream(W))
+        wgrad_bias(gqk, x0_2, 2 * C, C, R, dW[: 2 * C], db[: 2 * C])
+        wgrad_bias(gv, x1_2, C, C, R, dW[2 * C:], db[2 * C:])
         return (None, dx0.view(ctx.xshape) if dx0 is not None else None, dx1.view(ctx.xshape) if dx1 is not None else None,
                 None if slot is not None else dW, None if bslot is not None else db, None, None)
 

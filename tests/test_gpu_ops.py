@@ -422,6 +422,16 @@ def test_gemm_tcgen05_wgrad_accumulate(Mo, No, R):
     acc = o.gemm(dY.to(DEV), X.to(DEV), Mo, No, R, a_kcontig=False, b_kcontig=False, out=base.to(DEV).clone(),
                  accumulate=True, precision=P)
     assert rel_err(acc, ref + base.double()) < 3e-5
+    # fused bias gradient: b += colsum(dY) summed from the dY tiles inside the weight-gradient GEMM
+    old = o.get_gemm_precision()
+    o.set_gemm_precision("bf16x3")
+    try:
+        w_acc, b_acc = base.to(DEV).clone(), torch.arange(Mo, dtype=torch.float32, device=DEV)
+        o.wgrad_bias(dY.to(DEV), X.to(DEV), Mo, No, R, w_acc, b_acc)
+        assert rel_err(w_acc, ref + base.double()) < 3e-5
+        assert rel_err(b_acc, dY.double().sum(0) + torch.arange(Mo, dtype=torch.float64)) < 1e-5
+    finally:
+        o.set_gemm_precision(old)
     # operands that are column blocks of wider activations (fused projection gradients): lda / ldb > extent
     wideY = torch.randn(R, Mo + 128, generator=g).to(DEV)
     out2 = o.gemm(wideY[:, 128:], X.to(DEV), Mo, No, R, a_kcontig=False, b_kcontig=False, lda=Mo + 128, precision=P)

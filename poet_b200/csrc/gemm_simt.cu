@@ -172,14 +172,18 @@ sgemm_kernel(const GemmArgs p) {
         if (dead) x = 0.f;
         v[j] = x;
       }
-      if (p.vecC && n + 3 < p.N) {
-        float4 o = make_float4(v[0], v[1], v[2], v[3]);
-        if (accum) { float4 old = ld4(cp); o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-        st4(cp, o);
+      if (accum) {
+        // beta = 1 goes through atomics: micro-batches on different streams accumulate into the same gradient
+        // (one writer per element inside a launch, so a lone launch stays bitwise deterministic)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (n + j < p.N) atomicAdd(cp + j, v[j]);
+      } else if (p.vecC && n + 3 < p.N) {
+        st4(cp, make_float4(v[0], v[1], v[2], v[3]));
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (n + j < p.N) cp[j] = accum ? cp[j] + v[j] : v[j];
+          if (n + j < p.N) cp[j] = v[j];
       }
     }
   }

@@ -39,6 +39,29 @@ def get_gemm_precision() -> str:
 # the stream of its forward, so the backward overlaps the same way.
 # ------------------------------------------------------------------------------------------
 _side_streams = {}
+_stream_ns = [0]          # namespace of the side streams: each micro-batch forks onto its own set
+
+
+class stream_namespace:
+    """Side streams requested inside the block are private to namespace `ns` (micro-batch index)."""
+
+    def __init__(self, ns: int):
+        self.ns = ns
+
+    def __enter__(self):
+        _stream_ns.append(self.ns)
+        return self
+
+    def __exit__(self, *exc):
+        _stream_ns.pop()
+        return False
+
+
+def side_stream(idx: int, device) -> "torch.cuda.Stream":
+    key = (str(device), _stream_ns[-1], idx)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
 
 
 def parallel_streams_enabled() -> bool:
@@ -54,10 +77,7 @@ class fork:
 
     def __init__(self, idx: int, device):
         self.main = torch.cuda.current_stream(device)
-        key = (str(device), idx)
-        if key not in _side_streams:
-            _side_streams[key] = torch.cuda.Stream(device=device)
-        self.side = _side_streams[key]
+        self.side = side_stream(idx, device)
         self._ctx = None
 
     def __enter__(self):
@@ -377,7 +397,9 @@ def wgrad_bias(gy2: torch.Tensor, x2: torch.Tensor, N: int, K: int, R: int, w_ou
     producers), else the GEMM plus a separate column-sum kernel.  gy2 may be a column block (lda = row stride)."""
     lda = N if lda is None else lda
     prec = _state["precision"]
-    fused = (b_out is not None and prec != GEMM_FP32 and
+    # Long reductions are split-K over ~148 CTAs whose per-warp partial sums would meet on the same N addresses
+    # (measured: +54 us of serialized L2 atomics on [256 x 256 x 25600]); those keep the streaming colsum kernel.
+    fused = (b_out is not None and prec != GEMM_FP32 and R <= 2048 and
              _lib.lib().poet_gemm_tc_eligible(N, K, R, lda, K, w_out.stride(0)))
     gemm(gy2, x2, N, K, R, a_kcontig=False, b_kcontig=False, lda=lda, out=w_out, accumulate=True,
          a_colsum=b_out if fused else None)
@@ -479,6 +501,37 @@ def _join_at_end_of_backward(f: "fork") -> None:
             torch.cuda.current_stream(side.device).wait_stream(side)
 
     torch.autograd.Variable._execution_engine.queue_callback(_cb)
+
+
+class _JoinAfterBackward(torch.autograd.Function):
+    """Identity whose backward (the first node of the slice's backward to run) asks the autograd engine to make the
+    stream that called backward() wait for `stream` when the pass is over: a micro-batch's backward runs on that
+    micro-batch's stream, and its tail (parameter gradients written straight into .grad) has no consumer the engine
+    would otherwise synchronise with."""
+
+    @staticmethod
+    def forward(ctx, x, stream):
+        ctx.stream = stream
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        side = ctx.stream
+        key = id(side)
+        if key not in _pending_joins:
+            _pending_joins[key] = side
+
+            def _cb():
+                st = _pending_joins.pop(key, None)
+                if st is not None:
+                    torch.cuda.current_stream(st.device).wait_stream(st)
+
+            torch.autograd.Variable._execution_engine.queue_callback(_cb)
+        return g, None
+
+
+def join_after_backward(x: torch.Tensor, stream) -> torch.Tensor:
+    return _JoinAfterBackward.apply(x, stream) if x.requires_grad else x
 
 
 class _Linear(torch.autograd.Function):

@@ -236,16 +236,53 @@ class PoET(nn.Module):
         pb, pc, counts, n_dev = self._pad_boxes(boxes, classes, srcs[0].device)
         return self.forward_padded(srcs, masks, pb, pc, n_dev), counts
 
+    # Images are independent, so the batch can be cut into `micro_batches` slices issued on different streams:
+    # the launch-latency-bound decoder / head chain of one slice (GPU mostly idle) then overlaps the
+    # throughput-bound encoder kernels of another.  Parameter gradients of all slices accumulate into the
+    # same .grad slots (atomic beta = 1 epilogues).  1 = off.
+    micro_batches = 1
+
     def forward_padded(self, srcs, masks, pred_boxes, pred_classes, n_boxes_dev):
         """Device-only part of the path (no host work, no syncs: capturable in a CUDA graph):
         padded boxes [B,Q,4] / classes [B,Q] int64 / counts [B] int32, all on the device."""
+        mb, B = int(self.micro_batches), srcs[0].shape[0]
+        if mb <= 1 or B % mb or not srcs[0].is_cuda:
+            return self._forward_padded_slice(srcs, masks, pred_boxes, pred_classes, n_boxes_dev)
+        dev, per = srcs[0].device, B // mb
+        main = torch.cuda.current_stream(dev)
+        with ops.planes_scope(self):                         # weight planes: one refresh for all slices
+            streams = [main] + [ops.side_stream(32 + i, dev) for i in range(1, mb)]
+            for st in streams[1:]:
+                st.wait_stream(main)                         # fork before any slice is enqueued
+            outs = []
+            for i, st in enumerate(streams):
+                sl = slice(i * per, (i + 1) * per)
+                with torch.cuda.stream(st), ops.stream_namespace(i):
+                    o = self._forward_padded_slice([s[sl] for s in srcs], [m[sl] for m in masks], pred_boxes[sl],
+                                                   pred_classes[sl], n_boxes_dev[sl], pack=False)
+                    if st is not main:                       # this slice's backward tail must rejoin the caller's stream
+                        o = ([ops.join_after_backward(t, st) for t in o[0]], [ops.join_after_backward(t, st) for t in o[1]])
+                if st is not main:
+                    for t in (*srcs, *masks, pred_boxes, pred_classes, n_boxes_dev):
+                        t.record_stream(st)
+                outs.append(o)
+            for st, o in zip(streams[1:], outs[1:]):
+                main.wait_stream(st)
+                for t in (*o[0], *o[1]):
+                    t.record_stream(main)
+        n_layers = len(outs[0][0])
+        t_all = [torch.cat([o[0][l] for o in outs], 0) for l in range(n_layers)]
+        R_all = [torch.cat([o[1][l] for o in outs], 0) for l in range(n_layers)]
+        return self._pack(t_all, R_all, pred_boxes, pred_classes)
+
+    def _forward_padded_slice(self, srcs, masks, pred_boxes, pred_classes, n_boxes_dev, pack=True):
         qe = ops.bbox_embed_pad(pred_boxes, n_boxes_dev, int(self.hidden_dim // 8))
         C = srcs[0].shape[1]
         S = sum(int(s.shape[2] * s.shape[3]) for s in srcs)
         pos_tokens = _PosTokens.apply(self.transformer.level_embed, C, S, *masks)
         t_all, R_all = self._run_with_heads(srcs, masks, None, qe, pred_boxes[:, :, :2].contiguous(), pred_classes,
                                             pos_tokens=pos_tokens)
-        return self._pack(t_all, R_all, pred_boxes, pred_classes)
+        return self._pack(t_all, R_all, pred_boxes, pred_classes) if pack else (t_all, R_all)
 
     def forward(self, samples, targets=None):
         samples = _as_nested(samples)

@@ -457,6 +457,166 @@ __global__ void __launch_bounds__(256, 3) msda_bwd_kernel(const MsdaArgs p) {
     if (j % G == c4) st4(gw + j * 4, make_float4(g_attn[j * 4], g_attn[j * 4 + 1], g_attn[j * 4 + 2], g_attn[j * 4 + 3]));
 }
 
+// ------------------------------------------------------------------------------------------
+// few queries (decoder: Lq = 10): one WARP per (b,q,m)
+// ------------------------------------------------------------------------------------------
+// The general kernels walk the L*P sampling points serially in each thread; with a handful of queries the
+// grid is a fraction of one wave and the launch is pure latency (43 us backward at cfg2).  Here the 32 lanes
+// of a warp split one (b,q,m): lane = (corner group cg, 4-channel group c4), cg owns PPL = L*P*G/32 sampling
+// points with all four corners, so every lane issues 4*PPL independent 128-bit loads at once and the points
+// are folded with log2(32/G) shuffle stages.
+template <int LP, int G>
+struct WarpMap {
+  static constexpr int NCG = 32 / G;          // corner groups per warp
+  static constexpr int PPL = LP / NCG;        // sampling points per lane
+  static_assert(LP % NCG == 0 && PPL >= 1, "points must divide over the corner groups");
+};
+
+template <int NCG, int G>
+__device__ __forceinline__ float cg_sum(float v) {      // sum over the corner groups (lanes with equal c4)
+#pragma unroll
+  for (int o = G; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int NCG, int G>
+__device__ __forceinline__ float cg_max(float v) {
+#pragma unroll
+  for (int o = G; o < 32; o <<= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+template <int L, int P, int G, bool FUSED, bool BWD>
+__global__ void __launch_bounds__(256) msda_warp_kernel(const MsdaArgs p) {
+  constexpr int LP = L * P, D = 4 * G;
+  using WM = WarpMap<LP, G>;
+  constexpr int PPL = WM::PPL, NCG = WM::NCG;
+  const int lane = threadIdx.x & 31;
+  const int64_t bqm = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (bqm >= (int64_t)p.B * p.Lq * p.M) return;                  // warp-uniform
+  const int c4 = lane % G, cg = lane / G;
+  const int m = (int)(bqm % p.M);
+  const int64_t bq = bqm / p.M;
+  const int b = (int)(bq / p.Lq);
+  const int vstride = p.M * D;
+  const int64_t voff = ((int64_t)b * p.S * p.M + m) * D + c4 * 4;
+
+  // this lane's sampling points: pt = cg * PPL + j
+  float a[PPL], lx[PPL], ly[PPL];
+#pragma unroll
+  for (int j = 0; j < PPL; ++j) {
+    const int pt = cg * PPL + j;
+    a[j] = __ldg(p.w + bq * p.ldw + m * LP + pt);
+    const float2 xy = __ldg(reinterpret_cast<const float2*>(p.a + bq * p.lda + (m * LP + pt) * 2));
+    lx[j] = xy.x; ly[j] = xy.y;
+  }
+  if (FUSED) {                                                   // softmax over the L*P logits of (b,q,m)
+    float mx = a[0];
+#pragma unroll
+    for (int j = 1; j < PPL; ++j) mx = fmaxf(mx, a[j]);
+    mx = cg_max<NCG, G>(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) { a[j] = __expf(a[j] - mx); sum += a[j]; }
+    sum = cg_sum<NCG, G>(sum);
+    const float inv = __fdividef(1.f, sum);
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) a[j] *= inv;
+  }
+  float4 go = make_float4(0.f, 0.f, 0.f, 0.f), acc = go;
+  if (BWD) go = ldg4(p.grad_out + bqm * D + c4 * 4);
+  float g_a[PPL], g_x[PPL], g_y[PPL];
+#pragma unroll
+  for (int j = 0; j < PPL; ++j) {
+    const int pt = cg * PPL + j, l = pt / P;
+    const int H = p.lv.H[l], W = p.lv.W[l];
+    float px = lx[j], py = ly[j];
+    if (FUSED) {
+      const float2 r = __ldg(reinterpret_cast<const float2*>(p.ref + (bq * L + l) * 2));
+      px = r.x + px * p.lv.inv_W[l]; py = r.y + py * p.lv.inv_H[l];
+    }
+    const float x = px * (float)W - 0.5f, y = py * (float)H - 0.5f;
+    g_a[j] = 0.f; g_x[j] = 0.f; g_y[j] = 0.f;
+    if (x > -1.f && y > -1.f && x < (float)W && y < (float)H) {
+      const float xf = floorf(x), yf = floorf(y);
+      const int x0 = (int)xf, y0 = (int)yf;
+      const float fx = x - xf, fy = y - yf;
+      const bool xl = x0 >= 0, xh = x0 + 1 < W, yl = y0 >= 0, yh = y0 + 1 < H;
+      const int64_t i00 = voff + ((int64_t)p.lv.start[l] + y0 * W + x0) * vstride;
+      float4 v00 = make_float4(0.f, 0.f, 0.f, 0.f), v01 = v00, v10 = v00, v11 = v00;
+      if (yl && xl) v00 = ldg4(p.value + i00);
+      if (yl && xh) v01 = ldg4(p.value + i00 + vstride);
+      if (yh && xl) v10 = ldg4(p.value + i00 + (int64_t)W * vstride);
+      if (yh && xh) v11 = ldg4(p.value + i00 + (int64_t)(W + 1) * vstride);
+      const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+      if (!BWD) {
+        const float aw = a[j];
+        acc.x += aw * (w00 * v00.x + w01 * v01.x + w10 * v10.x + w11 * v11.x);
+        acc.y += aw * (w00 * v00.y + w01 * v01.y + w10 * v10.y + w11 * v11.y);
+        acc.z += aw * (w00 * v00.z + w01 * v01.z + w10 * v10.z + w11 * v11.z);
+        acc.w += aw * (w00 * v00.w + w01 * v01.w + w10 * v10.w + w11 * v11.w);
+      } else {
+        const float aw = a[j];
+        if (yl && xl) red_add4(p.grad_value + i00, aw * w00, go);
+        if (yl && xh) red_add4(p.grad_value + i00 + vstride, aw * w01, go);
+        if (yh && xl) red_add4(p.grad_value + i00 + (int64_t)W * vstride, aw * w10, go);
+        if (yh && xh) red_add4(p.grad_value + i00 + (int64_t)(W + 1) * vstride, aw * w11, go);
+        const float d00 = dot4(go, v00), d01 = dot4(go, v01), d10 = dot4(go, v10), d11 = dot4(go, v11);
+        g_a[j] = w00 * d00 + w01 * d01 + w10 * d10 + w11 * d11;
+        g_x[j] = aw * ((1.f - fy) * (d01 - d00) + fy * (d11 - d10));
+        g_y[j] = aw * ((1.f - fx) * (d10 - d00) + fx * (d11 - d01));
+        if (!FUSED) { g_x[j] *= (float)W; g_y[j] *= (float)H; }
+      }
+    }
+  }
+  if (!BWD) {
+    acc.x = cg_sum<NCG, G>(acc.x); acc.y = cg_sum<NCG, G>(acc.y);
+    acc.z = cg_sum<NCG, G>(acc.z); acc.w = cg_sum<NCG, G>(acc.w);
+    if (cg == 0) st4(p.out + bqm * D + c4 * 4, acc);
+    return;
+  }
+  // backward: fold the channel groups (partial dot products), then the softmax backward over all points
+  float dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < PPL; ++j) {
+    g_a[j] = group_sum<G>(g_a[j]); g_x[j] = group_sum<G>(g_x[j]); g_y[j] = group_sum<G>(g_y[j]);
+    dot += a[j] * g_a[j];
+  }
+  if (FUSED) {
+    dot = cg_sum<NCG, G>(dot);
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) g_a[j] = a[j] * (g_a[j] - dot);
+  }
+  if (c4 == 0) {
+#pragma unroll
+    for (int j = 0; j < PPL; ++j) {
+      const int pt = cg * PPL + j;
+      p.grad_w[bq * p.ldw + m * LP + pt] = g_a[j];
+      *reinterpret_cast<float2*>(p.grad_a + bq * p.lda + (m * LP + pt) * 2) = make_float2(g_x[j], g_y[j]);
+    }
+  }
+}
+
+template <bool BWD>
+static int try_warp_kernel(const MsdaArgs& a, int mode, cudaStream_t s) {
+  static const int enabled = []() { const char* e = getenv("POET_MSDA_WARP"); return e ? atoi(e) : 1; }();
+  const int64_t warps = (int64_t)a.B * a.Lq * a.M;
+  if (!enabled || a.L != 4 || a.P != 4 || warps * 32 > (int64_t)POET_NUM_SMS * 2048) return POET_ERR_UNSUPPORTED;
+  const int grid = poet_ceil_div(warps * 32, 256);
+#define POET_WARP_LAUNCH(GG)                                                                  \
+  do {                                                                                        \
+    if (mode) msda_warp_kernel<4, 4, GG, true, BWD><<<grid, 256, 0, s>>>(a);                  \
+    else msda_warp_kernel<4, 4, GG, false, BWD><<<grid, 256, 0, s>>>(a);                      \
+    return poet_launch_status();                                                              \
+  } while (0)
+  switch (a.D) {
+    case 8: POET_WARP_LAUNCH(2);
+    case 16: POET_WARP_LAUNCH(4);
+    case 32: POET_WARP_LAUNCH(8);
+    default: return POET_ERR_UNSUPPORTED;
+  }
+#undef POET_WARP_LAUNCH
+}
+
 int fill_args(MsdaArgs& a, const int32_t* shapes_host, int B, int S, int Lq, int M, int D, int L, int P,
               const float* value, const float* aa, int64_t lda, const float* w, int64_t ldw, const float* ref, int mode) {
   POET_REQUIRE(value && aa && w && shapes_host, POET_ERR_NULL_POINTER);
@@ -528,6 +688,8 @@ extern "C" int poet_msda_fwd(const float* value, const float* a, int64_t lda, co
   POET_REQUIRE(out != nullptr, POET_ERR_NULL_POINTER);
   POET_REQUIRE(poet_aligned16(out), POET_ERR_BAD_ALIGNMENT);
   args.out = out;
+  const int rc_warp = try_warp_kernel<false>(args, mode, (cudaStream_t)stream);
+  if (rc_warp != POET_ERR_UNSUPPORTED) return rc_warp;
   const int rc_slab = try_slab_fwd(args, mode, (cudaStream_t)stream);
   if (rc_slab != POET_ERR_UNSUPPORTED) return rc_slab;
   return dispatch<false>(args, mode, (cudaStream_t)stream);
@@ -544,5 +706,7 @@ extern "C" int poet_msda_bwd(const float* value, const float* a, int64_t lda, co
   POET_REQUIRE(poet_aligned16(grad_out) && poet_aligned16(grad_value) && poet_aligned16(grad_a) &&
                poet_aligned16(grad_w), POET_ERR_BAD_ALIGNMENT);
   args.grad_out = grad_out; args.grad_value = grad_value; args.grad_a = grad_a; args.grad_w = grad_w;
+  const int rc_warp = try_warp_kernel<true>(args, mode, (cudaStream_t)stream);
+  if (rc_warp != POET_ERR_UNSUPPORTED) return rc_warp;
   return dispatch<true>(args, mode, (cudaStream_t)stream);
 }

@@ -117,10 +117,11 @@ def _msda_inputs(B, M, D, Lq, P, shapes, seed):
 
 @pytest.mark.parametrize("B,M,D,Lq,P,shapes", [
     (1, 2, 8, 2, 2, [(6, 4), (3, 2)]),                                   # upstream test.py shapes (D rounded to 8)
-    (2, 16, 16, 37, 4, [(30, 40), (15, 20), (8, 10), (4, 5)]),           # YCB-V head geometry on the REF pyramid
+    (2, 16, 16, 37, 4, [(30, 40), (15, 20), (8, 10), (4, 5)]),           # YCB-V head geometry on the REF pyramid (few queries: warp-per-(q,m) kernels)
     (2, 8, 32, 50, 4, [(30, 40), (15, 20), (8, 10), (4, 5)]),            # cfg1 head geometry
     (1, 4, 64, 9, 4, [(6, 8), (3, 4), (2, 2), (1, 1)]),
-    (2, 3, 16, 40, 4, [(6, 8), (3, 4), (2, 2), (1, 1)]),                 # smem-slab forward: S=65 (TMA box tail, OOB fill)
+    (2, 3, 16, 1700, 4, [(6, 8), (3, 4), (2, 2), (1, 1)]),               # smem-slab forward: S=65 (TMA box tail, OOB fill)
+    (3, 8, 8, 21, 4, [(6, 8), (3, 4), (2, 2), (1, 1)]),                  # warp-per-(q,m) kernels, D=8
     (2, 16, 16, 500, 4, [(30, 40), (15, 20), (8, 10), (4, 5)]),          # smem-slab forward on the REF pyramid
 ])
 def test_msda_core_fwd_bwd(B, M, D, Lq, P, shapes):

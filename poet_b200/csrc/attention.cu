@@ -10,6 +10,21 @@ namespace {
 
 constexpr int kWarps = 4;
 
+// D floats of a row with 128-bit loads (head slices start at multiples of D >= 8 floats: 16-byte aligned)
+template <int D>
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, float (&x)[D]) {
+#pragma unroll
+  for (int d = 0; d < D; d += 4) {
+    const float4 t = ldg4(p + d);
+    x[d] = t.x; x[d + 1] = t.y; x[d + 2] = t.z; x[d + 3] = t.w;
+  }
+}
+template <int D>
+__device__ __forceinline__ void store_vec(float* __restrict__ p, const float (&x)[D], float s) {
+#pragma unroll
+  for (int d = 0; d < D; d += 4) st4(p + d, make_float4(x[d] * s, x[d + 1] * s, x[d + 2] * s, x[d + 3] * s));
+}
+
 template <int D>
 __global__ void __launch_bounds__(kWarps * 32) mha_fwd_kernel(const float* __restrict__ q, int64_t ldq,
                                                               const float* __restrict__ k, int64_t ldk,
@@ -21,18 +36,20 @@ __global__ void __launch_bounds__(kWarps * 32) mha_fwd_kernel(const float* __res
   const int b = warp / M, m = warp % M;
   const bool row = lane < Q;
   float qi[D];
+  load_vec<D>(q + ((int64_t)b * Q + (row ? lane : 0)) * ldq + m * D, qi);
 #pragma unroll
-  for (int d = 0; d < D; ++d) qi[d] = row ? __ldg(q + ((int64_t)b * Q + lane) * ldq + m * D + d) * scale : 0.f;
+  for (int d = 0; d < D; ++d) qi[d] *= scale;
   float sc[32];
   float mx = -INFINITY;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     sc[j] = -INFINITY;
     if (j < Q) {
-      const float* kj = k + ((int64_t)b * Q + j) * ldk + m * D;
+      float kj[D];
+      load_vec<D>(k + ((int64_t)b * Q + j) * ldk + m * D, kj);
       float s = 0.f;
 #pragma unroll
-      for (int d = 0; d < D; ++d) s = fmaf(qi[d], __ldg(kj + d), s);
+      for (int d = 0; d < D; ++d) s = fmaf(qi[d], kj[d], s);
       sc[j] = s;
       mx = fmaxf(mx, s);
     }
@@ -50,9 +67,10 @@ __global__ void __launch_bounds__(kWarps * 32) mha_fwd_kernel(const float* __res
     if (j < Q) {
       const float pj = sc[j] * inv;
       if (row && probs) probs[(((int64_t)b * M + m) * Q + lane) * Q + j] = pj;
-      const float* vj = v + ((int64_t)b * Q + j) * ldv + m * D;
+      float vj[D];
+      load_vec<D>(v + ((int64_t)b * Q + j) * ldv + m * D, vj);
 #pragma unroll
-      for (int d = 0; d < D; ++d) o[d] = fmaf(pj, __ldg(vj + d), o[d]);
+      for (int d = 0; d < D; ++d) o[d] = fmaf(pj, vj[d], o[d]);
     }
   if (row) {
     float* op = out + ((int64_t)b * Q + lane) * (M * D) + m * D;
@@ -77,8 +95,7 @@ __global__ void __launch_bounds__(kWarps * 32) mha_bwd_kernel(const float* __res
   const int b = warp / M, m = warp % M;
   const bool row = lane < Q;
   float gi[D];
-#pragma unroll
-  for (int d = 0; d < D; ++d) gi[d] = row ? __ldg(go + ((int64_t)b * Q + lane) * (M * D) + m * D + d) : 0.f;
+  load_vec<D>(go + ((int64_t)b * Q + (row ? lane : 0)) * (M * D) + m * D, gi);
   // dp_ij = <go_i, v_j>;  ds_ij = p_ij (dp_ij - sum_j p_ij dp_ij)
   float dp[32], pr[32];
   float dsum = 0.f;
@@ -86,10 +103,11 @@ __global__ void __launch_bounds__(kWarps * 32) mha_bwd_kernel(const float* __res
   for (int j = 0; j < 32; ++j) {
     dp[j] = 0.f; pr[j] = 0.f;
     if (j < Q) {
-      const float* vj = v + ((int64_t)b * Q + j) * ldv + m * D;
+      float vj[D];
+      load_vec<D>(v + ((int64_t)b * Q + j) * ldv + m * D, vj);
       float s = 0.f;
 #pragma unroll
-      for (int d = 0; d < D; ++d) s = fmaf(gi[d], __ldg(vj + d), s);
+      for (int d = 0; d < D; ++d) s = fmaf(gi[d], vj[d], s);
       dp[j] = s;
       pr[j] = row ? __ldg(probs + (((int64_t)b * M + m) * Q + lane) * Q + j) : 0.f;
       dsum = fmaf(pr[j], s, dsum);
@@ -104,15 +122,12 @@ __global__ void __launch_bounds__(kWarps * 32) mha_bwd_kernel(const float* __res
       const float ds = pr[j] * (dp[j] - dsum);
       s_p[w][lane][j] = pr[j];
       s_ds[w][lane][j] = ds;
-      const float* kj = k + ((int64_t)b * Q + j) * ldk + m * D;
+      float kj[D];
+      load_vec<D>(k + ((int64_t)b * Q + j) * ldk + m * D, kj);
 #pragma unroll
-      for (int d = 0; d < D; ++d) dq[d] = fmaf(ds, __ldg(kj + d), dq[d]);
+      for (int d = 0; d < D; ++d) dq[d] = fmaf(ds, kj[d], dq[d]);
     }
-  if (row) {
-    float* p = gq + ((int64_t)b * Q + lane) * ldgq + m * D;
-#pragma unroll
-    for (int d = 0; d < D; ++d) p[d] = dq[d] * scale;
-  }
+  if (row) store_vec<D>(gq + ((int64_t)b * Q + lane) * ldgq + m * D, dq, scale);
   __syncwarp();
   // lane j: dk_j = scale * sum_i ds_ij q_i ; dv_j = sum_i p_ij go_i
   float dk[D], dv[D];
@@ -120,16 +135,15 @@ __global__ void __launch_bounds__(kWarps * 32) mha_bwd_kernel(const float* __res
   for (int d = 0; d < D; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
   for (int i = 0; i < Q; ++i) {
     const float ds = row ? s_ds[w][i][lane] : 0.f, pp = row ? s_p[w][i][lane] : 0.f;
-    const float* qi = q + ((int64_t)b * Q + i) * ldq + m * D;
-    const float* gp = go + ((int64_t)b * Q + i) * (M * D) + m * D;
+    float qi[D], gp[D];
+    load_vec<D>(q + ((int64_t)b * Q + i) * ldq + m * D, qi);
+    load_vec<D>(go + ((int64_t)b * Q + i) * (M * D) + m * D, gp);
 #pragma unroll
-    for (int d = 0; d < D; ++d) { dk[d] = fmaf(ds, __ldg(qi + d), dk[d]); dv[d] = fmaf(pp, __ldg(gp + d), dv[d]); }
+    for (int d = 0; d < D; ++d) { dk[d] = fmaf(ds, qi[d], dk[d]); dv[d] = fmaf(pp, gp[d], dv[d]); }
   }
   if (row) {
-    float* pk = gk + ((int64_t)b * Q + lane) * ldgk + m * D;
-    float* pv = gv + ((int64_t)b * Q + lane) * ldgv + m * D;
-#pragma unroll
-    for (int d = 0; d < D; ++d) { pk[d] = dk[d] * scale; pv[d] = dv[d]; }
+    store_vec<D>(gk + ((int64_t)b * Q + lane) * ldgk + m * D, dk, scale);
+    store_vec<D>(gv + ((int64_t)b * Q + lane) * ldgv + m * D, dv, 1.f);
   }
 }
 
@@ -139,7 +153,8 @@ extern "C" int poet_mha_smallq_fwd(const float* q, int64_t ldq, const float* k, 
                                    float* out, float* probs, int B, int Q, int M, int D, float scale, poet_stream_t stream) {
   POET_REQUIRE(q && k && v && out, POET_ERR_NULL_POINTER);
   POET_REQUIRE(B > 0 && M > 0 && Q >= 1 && Q <= 32, POET_ERR_BAD_SHAPE);
-  POET_REQUIRE(poet_aligned16(out), POET_ERR_BAD_ALIGNMENT);
+  POET_REQUIRE(poet_aligned16(out) && poet_aligned16(q) && poet_aligned16(k) && poet_aligned16(v) &&
+               ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, POET_ERR_BAD_ALIGNMENT);
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = poet_ceil_div(B * M, kWarps);
   switch (D) {
@@ -158,6 +173,9 @@ extern "C" int poet_mha_smallq_bwd(const float* q, int64_t ldq, const float* k, 
                                    poet_stream_t stream) {
   POET_REQUIRE(q && k && v && probs && grad_out && gq && gk && gv, POET_ERR_NULL_POINTER);
   POET_REQUIRE(B > 0 && M > 0 && Q >= 1 && Q <= 32, POET_ERR_BAD_SHAPE);
+  POET_REQUIRE(poet_aligned16(q) && poet_aligned16(k) && poet_aligned16(v) && poet_aligned16(grad_out) && poet_aligned16(gq) &&
+               poet_aligned16(gk) && poet_aligned16(gv) && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldgq % 4 == 0 &&
+               ldgk % 4 == 0 && ldgv % 4 == 0, POET_ERR_BAD_ALIGNMENT);
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = poet_ceil_div(B * M, kWarps);
 #define POET_MHA_BWD(DD) mha_bwd_kernel<DD><<<grid, kWarps * 32, 0, s>>>(q, ldq, k, ldk, v, ldv, probs, grad_out, gq, ldgq, gk, ldgk, gv, ldgv, B, Q, M, scale)

@@ -276,6 +276,8 @@ def run_gpu(args):
     h2d = sum(t.numel() * t.element_size() for t in h_srcs + h_masks) + sum(b.numel() * 4 + l.numel() * 8 for b, l in zip(inp["boxes"], inp["labels"]))
     d2h = 0
 
+    d2h_pinned = torch.empty(1 + B * cfg["num_queries"] * 12, dtype=torch.float32).pin_memory()
+
     def e2e_loop(pipelined: bool) -> float:
         """Wall-clock ms of args.steps end-to-end steps (one untimed pass first).  pipelined: the H2D copy of
         step i+1's inputs is issued on the copy stream before step i is replayed (GraphedStep.prefetch), so every
@@ -290,16 +292,19 @@ def run_gpu(args):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             if pipelined:
-                graphed.prefetch(h_srcs, h_masks, inp["boxes"], inp["labels"])     # inputs of the NEXT step
                 loss, out = step()                                                   # consumes the oldest prefetched set
+                graphed.prefetch(h_srcs, h_masks, inp["boxes"], inp["labels"])     # inputs of the NEXT step, during this replay
             elif graphed is not None:
                 loss, out = step(h_srcs, h_masks, inp["boxes"], inp["labels"])     # H2D into the graph's static buffers
             else:
                 srcs = [s.to(dev, non_blocking=True) for s in h_srcs]
                 masks = [m.to(dev, non_blocking=True) for m in h_masks]
                 loss, out = step(srcs, masks, inp["boxes"], inp["labels"])          # host box lists: padded on host, one H2D
-            host = [loss.detach().cpu(), out["pred_translation"].detach().cpu(), out["pred_rotation"].detach().cpu()]
+            res = torch.cat((loss.detach().reshape(1), out["pred_translation"].detach().reshape(-1),
+                             out["pred_rotation"].detach().reshape(-1)))
+            d2h_pinned.copy_(res, non_blocking=True)                            # one read-back of loss + final predictions
             torch.cuda.synchronize()
+            host = [d2h_pinned]
             if it > 0:                                                         # first pass warms the pinned path
                 total += 1e3 * (time.perf_counter() - t0)
             d2h = sum(t.numel() * t.element_size() for t in host)

@@ -96,13 +96,22 @@ class GraphedStep:
             self._landing = [[torch.empty_like(t) for t in self._static_set()] for _ in range(2)]
             self._free_ev = [None, None]                       # landing set consumed (recorded on the compute stream)
             self._copy_stream = torch.cuda.Stream(device=dev)
+            # persistent pinned staging for the padded boxes / classes / counts (allocating pinned memory per call
+            # costs more than the copies themselves)
+            self._pinned = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in
+                             (self.s_boxes, self.s_classes, self.s_counts)] for _ in range(2)]
+            self._h2d_ev = [None, None]
         if len(self._pending) >= 2:
             raise RuntimeError("GraphedStep.prefetch: two prefetched input sets are already waiting for run()")
         slot = self._n_prefetched % 2
         self._n_prefetched += 1
-        pb, pc, counts, n_dev = self.model._pad_boxes(boxes, labels, boxes[0].device)
+        pb, pc, counts, n_dev = self.model._pad_boxes(boxes, labels, boxes[0].device, pin=False)
         if not pb.is_cuda:
-            pb, pc, n_dev = pb.pin_memory(), pc.pin_memory(), n_dev.pin_memory()
+            if self._h2d_ev[slot] is not None:
+                self._h2d_ev[slot].synchronize()               # the previous copy out of this pinned set has finished
+            for dst, src in zip(self._pinned[slot], (pb, pc, n_dev)):
+                dst.copy_(src)
+            pb, pc, n_dev = self._pinned[slot]
         src_set = [*srcs, *masks, pb, pc, n_dev]
         with torch.cuda.stream(self._copy_stream):
             if self._free_ev[slot] is not None:
@@ -111,6 +120,7 @@ class GraphedStep:
                 dst.copy_(src, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
+        self._h2d_ev[slot] = ev
         self._pending.append((slot, ev, counts))
 
     def run(self, srcs=None, masks=None, boxes=None, labels=None):

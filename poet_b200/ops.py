@@ -261,7 +261,7 @@ class WeightPlanes:
                                (self.lo.data_ptr() + 2 * off) if with_lo else 0, n4, chunk)
             chunk += (n4 + 1023) // 1024
             off += p.numel()
-        self._table = torch.frombuffer(bytes(raw), dtype=torch.uint8).clone().to(self.device)
+        self._table = torch.frombuffer(raw, dtype=torch.uint8).clone().to(self.device)
         self._chunks = chunk
 
     def refresh(self) -> None:

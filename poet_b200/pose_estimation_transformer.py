@@ -123,7 +123,7 @@ class PoET(nn.Module):
         self.bbox_embedding = BoundingBoxEmbeddingSine(num_pos_feats=hidden_dim / 8)
 
     # ------------------------------------------------------------------ queries (A1)
-    def _pad_boxes(self, boxes: Sequence[torch.Tensor], classes: Sequence[torch.Tensor], device):
+    def _pad_boxes(self, boxes: Sequence[torch.Tensor], classes: Sequence[torch.Tensor], device, pin: bool = True):
         """Lists of per-image boxes [n_i,4] / classes [n_i] -> padded [B,Q,4] (-1), [B,Q] int64 (-1), counts."""
         B, Q = len(boxes), self.n_queries
         counts = [min(int(b.shape[0]), Q) for b in boxes]
@@ -137,7 +137,7 @@ class PoET(nn.Module):
             pb[idx] = torch.cat([b[:n].to(torch.float32) for b, n in zip(boxes, counts)], 0)
             pc[idx] = torch.cat([c[:n].to(torch.int64) for c, n in zip(classes, counts)], 0)
         n_dev = torch.tensor(counts, dtype=torch.int32)
-        if src_dev.type == "cpu" and torch.device(device).type == "cuda":
+        if pin and src_dev.type == "cpu" and torch.device(device).type == "cuda":
             pb, pc, n_dev = pb.pin_memory(), pc.pin_memory(), n_dev.pin_memory()
         pb = pb.view(B, Q, 4).to(device, non_blocking=True)
         pc = pc.view(B, Q).to(device, non_blocking=True)

@@ -184,6 +184,20 @@ int poet_heads_select_rot6d_bwd(const float* rot6d, const int64_t* classes, cons
                                 const float* grad_rotmat, float* grad_rot_all, float* grad_trans_all,
                                 int R, int n_slots, poet_stream_t stream);
 
+/* ---- optimizer step (next: SURVEY.md section 8f N3; reference engine.py:77-81, main.py:253-277) ------------ */
+/* out[0] = sum_i x[i]^2 (double, on the device; overwritten).  n % 4 == 0. */
+int poet_sumsq(const float* x, int64_t n, double* out, poet_stream_t stream);
+/* clip_grad_norm_(max_norm) + AdamW.step() over every parameter tensor in one launch.
+ * table (device): n_tensors entries of 7 x 8 bytes {float* param, int64 arena offset / 4, void* hi, void* lo,
+ * int64 numel, int64 first_chunk, int32 lr group, int32 0}; tensor t owns ceil(ceil(numel/4)/1024) chunks of
+ * 1024 float4, entries sorted by first_chunk (as in poet_split_bf16_multi); planes need numel % 8 == 0.  grad / m / v: flat fp32 arenas sharing the offsets.  sumsq: poet_sumsq of the gradient
+ * arena (read on the device; ignored when max_norm <= 0).  lr_host[n_groups]: learning rate per group (host).
+ * step: 1-based step count (bias correction).  hi / lo (nullable per tensor): bf16 planes of the UPDATED weights. */
+int poet_adamw_clip_multi(const void* table, int n_tensors, int64_t total_chunks, const float* grad, float* m,
+                          float* v, const double* sumsq, float max_norm, const float* lr_host, int n_groups,
+                          float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                          poet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

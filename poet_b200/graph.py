@@ -34,9 +34,13 @@ from .data_parallel import FlatGradReducer
 
 class GraphedStep:
     def __init__(self, model, loss_fn: Callable, srcs: Sequence[torch.Tensor], masks: Sequence[torch.Tensor],
-                 boxes, labels, reducer: Optional[FlatGradReducer] = None, warmup: int = 3, backward: bool = True):
+                 boxes, labels, reducer: Optional[FlatGradReducer] = None, warmup: int = 3, backward: bool = True,
+                 optimizer=None):
+        """optimizer (poet_b200.optim.FusedClipAdamW, optional): its step() writes the bf16 planes of the updated
+        weights, so the captured step contains no split pass; call optimizer.step() after every run()."""
         dev = next(model.parameters()).device
         self.model, self.loss_fn, self.backward = model, loss_fn, backward
+        self.external_planes = optimizer is not None and getattr(optimizer, "planes", None) is not None
         self.reducer = reducer if reducer is not None else (FlatGradReducer(model.parameters()) if backward else None)
         self.s_srcs = [torch.empty(s.shape, dtype=torch.float32, device=dev) for s in srcs]
         self.s_masks = [torch.empty(m.shape, dtype=torch.bool, device=dev) for m in masks]
@@ -67,7 +71,8 @@ class GraphedStep:
         ops.clear_weight_split_cache()          # the bf16 weight planes must be re-derived inside the graph
         if self.reducer is not None:
             self.reducer.zero()
-        out = self.model.forward_padded(self.s_srcs, self.s_masks, self.s_boxes, self.s_classes, self.s_counts)
+        with ops.planes_scope(self.model, refresh=not self.external_planes):
+            out = self.model.forward_padded(self.s_srcs, self.s_masks, self.s_boxes, self.s_classes, self.s_counts)
         loss = self.loss_fn(out)
         if self.backward:
             loss.backward()

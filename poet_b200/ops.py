@@ -251,6 +251,8 @@ class WeightPlanes:
             self.ranges.append((p.data_ptr(), p.numel() * 4, off))
             off += p.numel()
         self._table_key, self._table, self._chunks = None, None, 0
+        self.with_lo = True
+        self._fresh_versions = None           # parameter versions for which the planes are known to be current
 
     def _build_table(self, with_lo: bool):
         import struct
@@ -264,10 +266,18 @@ class WeightPlanes:
         self._table = torch.frombuffer(raw, dtype=torch.uint8).clone().to(self.device)
         self._chunks = chunk
 
+    def mark_fresh(self) -> None:
+        """The planes were just written from the current parameter values by someone else (the fused optimizer
+        step): the next refresh() is a no-op unless a parameter is modified in between."""
+        self._fresh_versions = [p._version for p in self.params]
+
     def refresh(self) -> None:
         """Re-derive all planes from the current parameter values (call once per forward)."""
         prec = _state["precision"]
         if not self.params or prec == GEMM_FP32:
+            return
+        if (self._fresh_versions is not None and self.with_lo == (prec == GEMM_BF16X3) and
+                self._fresh_versions == [p._version for p in self.params]):
             return
         key = (tuple(p.data_ptr() for p in self.params), prec == GEMM_BF16X3)
         if key != self._table_key:
@@ -316,8 +326,10 @@ class planes_scope:
     """with planes_scope(module): ... -- inside, split_weight() is served from the module's refreshed arena.
     The arena object is cached on the module; nested scopes whose parameters are already covered are no-ops."""
 
-    def __init__(self, module: torch.nn.Module):
-        self.module, self.pushed = module, False
+    def __init__(self, module: torch.nn.Module, refresh: bool = True):
+        """refresh=False: trust the arena as it is (the fused optimizer step wrote the planes of the new weights;
+        used when the forward is replayed from a CUDA graph that must not contain the split pass)."""
+        self.module, self.pushed, self.do_refresh = module, False, refresh
 
     def __enter__(self):
         first = next((p for p in self.module.parameters() if p.dim() == 2), None)
@@ -327,9 +339,12 @@ class planes_scope:
             return self                                   # an enclosing scope already covers this module
         pl = getattr(self.module, "_poet_weight_planes", None)
         if pl is None or [p.data_ptr() for p in pl.params] != [p.data_ptr() for p in WeightPlanes.select(self.module)]:
+            if not self.do_refresh:
+                raise RuntimeError("planes_scope(refresh=False) needs planes written by FusedClipAdamW for this module")
             pl = WeightPlanes(self.module)
             object.__setattr__(self.module, "_poet_weight_planes", pl)
-        pl.refresh()
+        if self.do_refresh:
+            pl.refresh()
         _active_planes.append(pl)
         self.pushed = True
         return self

@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(kWarps * 32) mha_fwd_kernel(const float* __res
                                                               const float* __restrict__ v, int64_t ldv,
                                                               float* __restrict__ out, float* __restrict__ probs,
                                                               int B, int Q, int M, float scale) {
+  poet_pdl_entry();
   const int warp = blockIdx.x * kWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (warp >= B * M) return;
   const int b = warp / M, m = warp % M;
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(kWarps * 32) mha_bwd_kernel(const float* __res
                                                               float* __restrict__ gq, int64_t ldgq, float* __restrict__ gk,
                                                               int64_t ldgk, float* __restrict__ gv, int64_t ldgv,
                                                               int B, int Q, int M, float scale) {
+  poet_pdl_entry();
   __shared__ float s_p[kWarps][32][33];
   __shared__ float s_ds[kWarps][32][33];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -158,10 +160,10 @@ extern "C" int poet_mha_smallq_fwd(const float* q, int64_t ldq, const float* k, 
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = poet_ceil_div(B * M, kWarps);
   switch (D) {
-    case 8: mha_fwd_kernel<8><<<grid, kWarps * 32, 0, s>>>(q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale); break;
-    case 16: mha_fwd_kernel<16><<<grid, kWarps * 32, 0, s>>>(q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale); break;
-    case 32: mha_fwd_kernel<32><<<grid, kWarps * 32, 0, s>>>(q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale); break;
-    case 64: mha_fwd_kernel<64><<<grid, kWarps * 32, 0, s>>>(q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale); break;
+    case 8: poet_launch(mha_fwd_kernel<8>, dim3(grid), dim3(kWarps * 32), 0, s, q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale); break;
+    case 16: poet_launch(mha_fwd_kernel<16>, dim3(grid), dim3(kWarps * 32), 0, s, q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale); break;
+    case 32: poet_launch(mha_fwd_kernel<32>, dim3(grid), dim3(kWarps * 32), 0, s, q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale); break;
+    case 64: poet_launch(mha_fwd_kernel<64>, dim3(grid), dim3(kWarps * 32), 0, s, q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale); break;
     default: return POET_ERR_UNSUPPORTED;
   }
   return poet_launch_status();
@@ -178,7 +180,7 @@ extern "C" int poet_mha_smallq_bwd(const float* q, int64_t ldq, const float* k, 
                ldgk % 4 == 0 && ldgv % 4 == 0, POET_ERR_BAD_ALIGNMENT);
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = poet_ceil_div(B * M, kWarps);
-#define POET_MHA_BWD(DD) mha_bwd_kernel<DD><<<grid, kWarps * 32, 0, s>>>(q, ldq, k, ldk, v, ldv, probs, grad_out, gq, ldgq, gk, ldgk, gv, ldgv, B, Q, M, scale)
+#define POET_MHA_BWD(DD) poet_launch(mha_bwd_kernel<DD>, dim3(grid), dim3(kWarps * 32), 0, s, q, ldq, k, ldk, v, ldv, probs, grad_out, gq, ldgq, gk, ldgk, gv, ldgv, B, Q, M, scale)
   switch (D) {
     case 8: POET_MHA_BWD(8); break;
     case 16: POET_MHA_BWD(16); break;

@@ -79,6 +79,7 @@ __device__ __forceinline__ void tile_store(float (*sm)[ROWS + 4], const float4 (
 template <int BM, int BN, int BK, int TM, int TN, bool AK, bool BKC>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 sgemm_kernel(const GemmArgs p) {
+  poet_pdl_entry();
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int TX = BN / TN;
   __shared__ __align__(16) float As[2][BK][BM + 4];
@@ -193,10 +194,10 @@ template <int BM, int BN, int BK, int TM, int TN>
 void launch_cfg(const GemmArgs& a, int a_k, int b_k, cudaStream_t s) {
   dim3 grid(poet_ceil_div(a.N, BN), poet_ceil_div(a.M, BM), a.splits);
   dim3 block((BM / TM) * (BN / TN));
-  if (a_k && b_k) sgemm_kernel<BM, BN, BK, TM, TN, true, true><<<grid, block, 0, s>>>(a);
-  else if (a_k && !b_k) sgemm_kernel<BM, BN, BK, TM, TN, true, false><<<grid, block, 0, s>>>(a);
-  else if (!a_k && b_k) sgemm_kernel<BM, BN, BK, TM, TN, false, true><<<grid, block, 0, s>>>(a);
-  else sgemm_kernel<BM, BN, BK, TM, TN, false, false><<<grid, block, 0, s>>>(a);
+  if (a_k && b_k) poet_launch(sgemm_kernel<BM, BN, BK, TM, TN, true, true>, dim3(grid), dim3(block), 0, s, a);
+  else if (a_k && !b_k) poet_launch(sgemm_kernel<BM, BN, BK, TM, TN, true, false>, dim3(grid), dim3(block), 0, s, a);
+  else if (!a_k && b_k) poet_launch(sgemm_kernel<BM, BN, BK, TM, TN, false, true>, dim3(grid), dim3(block), 0, s, a);
+  else poet_launch(sgemm_kernel<BM, BN, BK, TM, TN, false, false>, dim3(grid), dim3(block), 0, s, a);
 }
 
 }  // namespace

@@ -297,6 +297,7 @@ template <int BN, int BK, bool A_MN, bool B_MN, bool X3, bool B_TMA, int PW, int
 __global__ void __launch_bounds__(BLOCK_THREADS, 1)
 gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                const __grid_constant__ CUtensorMap tm_c) {
+  poet_pdl_launch_dependents();                  // dependents may be scheduled; they wait for our completion themselves
   using SP = SmemPlan<BN, BK, X3, STAGES>;
   constexpr int NT = PW * 32;                                        // producer threads
   constexpr int PLANES = SP::PLANES, A_BYTES = SP::A_BYTES, B_BYTES = SP::B_BYTES, STAGE_BYTES = SP::STAGE_BYTES;
@@ -331,6 +332,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
+  poet_pdl_wait();                                                // prologue done; from here on we touch global memory
   if (warp < PW) regs_inc(); else regs_dec();                     // warpgroup-uniform
 
   if (warp < PW) {
@@ -736,6 +738,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
 // ---- fp32 -> bf16 hi/lo planes (weights, once per step) --------------------------------------
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ hi,
                                                          uint2* __restrict__ lo, int64_t n4) {
+  poet_pdl_entry();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 x = src[i];
     const float h0 = __bfloat162float(__float2bfloat16_rn(x.x)), h1 = __bfloat162float(__float2bfloat16_rn(x.y));
@@ -748,6 +751,7 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float4* __restric
 // All weight matrices of a model in ONE launch: table[t] = {src, hi, lo, first_chunk}, chunk = 1024 float4.
 struct SplitEntry { const float4* src; uint2* hi; uint2* lo; int64_t n4; int64_t first_chunk; };
 __global__ void __launch_bounds__(256) split_bf16_multi_kernel(const SplitEntry* __restrict__ table, int n_tensors) {
+  poet_pdl_entry();
   // binary search of the chunk's tensor (n_tensors is ~100: 7 steps)
   const int64_t chunk = blockIdx.x;
   int lo_i = 0, hi_i = n_tensors - 1;
@@ -804,7 +808,7 @@ int launch(Args a, const Maps& m, cudaStream_t s) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int grid = a.total_work < POET_NUM_SMS ? a.total_work : POET_NUM_SMS;       // persistent: one CTA per SM
-  kern<<<grid, BLOCK_THREADS, smem, s>>>(a, m.hi, m.lo, m.c);
+  poet_launch(kern, dim3(grid), dim3(BLOCK_THREADS), smem, s, a, m.hi, m.lo, m.c);
   return poet_launch_status();
 }
 
@@ -930,7 +934,7 @@ int poet_split_bf16_multi_impl(const void* table_dev, int n_tensors, int64_t tot
   POET_REQUIRE(table_dev != nullptr, POET_ERR_NULL_POINTER);
   POET_REQUIRE(n_tensors > 0 && total_chunks > 0 && total_chunks < ((int64_t)1 << 31), POET_ERR_BAD_SHAPE);
   static_assert(sizeof(tc::SplitEntry) == 40, "table layout is part of the ABI (5 x 8 bytes)");
-  tc::split_bf16_multi_kernel<<<(unsigned)total_chunks, 256, 0, s>>>(reinterpret_cast<const tc::SplitEntry*>(table_dev), n_tensors);
+  poet_launch(tc::split_bf16_multi_kernel, dim3((unsigned)total_chunks), dim3(256), 0, s, reinterpret_cast<const tc::SplitEntry*>(table_dev), n_tensors);
   return poet_launch_status();
 }
 
@@ -941,7 +945,7 @@ int poet_split_bf16_impl(const float* src, void* hi, void* lo, int64_t n, cudaSt
                (!lo || reinterpret_cast<uintptr_t>(lo) % 8 == 0), POET_ERR_BAD_ALIGNMENT);
   int grid = poet_ceil_div(n / 4, 256);
   if (grid > POET_NUM_SMS * 8) grid = POET_NUM_SMS * 8;
-  tc::split_bf16_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(hi),
+  poet_launch(tc::split_bf16_kernel, dim3(grid), dim3(256), 0, s, reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(hi),
                                              reinterpret_cast<uint2*>(lo), n / 4);
   return poet_launch_status();
 }

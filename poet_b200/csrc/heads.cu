@@ -18,6 +18,7 @@ constexpr float kNormEps = 1e-12f;
 __global__ void __launch_bounds__(128) heads_fwd_kernel(const float* __restrict__ rot_all, const float* __restrict__ trans_all,
                                                         const int64_t* __restrict__ classes, float* __restrict__ trans,
                                                         float* __restrict__ rot6d, float* __restrict__ rotmat, int R, int n_slots) {
+  poet_pdl_entry();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   int slot = 0;
@@ -48,6 +49,7 @@ __global__ void __launch_bounds__(128) heads_bwd_kernel(const float* __restrict_
                                                         const float* __restrict__ g_trans, const float* __restrict__ g_rotmat,
                                                         float* __restrict__ g_rot_all, float* __restrict__ g_trans_all,
                                                         int R, int n_slots) {
+  poet_pdl_entry();
   __shared__ float s_g[9];
   __shared__ int s_slot;
   const int r = blockIdx.x;
@@ -120,7 +122,7 @@ extern "C" int poet_heads_select_rot6d_fwd(const float* rot_all, const float* tr
   POET_REQUIRE(rot_all && trans_all && trans && rot6d && rotmat, POET_ERR_NULL_POINTER);
   POET_REQUIRE(n_slots == 1 || classes != nullptr, POET_ERR_NULL_POINTER);
   POET_REQUIRE(R > 0 && n_slots >= 1, POET_ERR_BAD_SHAPE);
-  heads_fwd_kernel<<<poet_ceil_div(R, 128), 128, 0, (cudaStream_t)stream>>>(rot_all, trans_all, classes, trans, rot6d,
+  poet_launch(heads_fwd_kernel, dim3(poet_ceil_div(R, 128)), dim3(128), 0, (cudaStream_t)stream, rot_all, trans_all, classes, trans, rot6d,
                                                                             rotmat, R, n_slots);
   return poet_launch_status();
 }
@@ -131,7 +133,7 @@ extern "C" int poet_heads_select_rot6d_bwd(const float* rot6d, const int64_t* cl
   POET_REQUIRE(rot6d && grad_trans && grad_rotmat && grad_rot_all && grad_trans_all, POET_ERR_NULL_POINTER);
   POET_REQUIRE(n_slots == 1 || classes != nullptr, POET_ERR_NULL_POINTER);
   POET_REQUIRE(R > 0 && n_slots >= 1, POET_ERR_BAD_SHAPE);
-  heads_bwd_kernel<<<R, 128, 0, (cudaStream_t)stream>>>(rot6d, classes, grad_trans, grad_rotmat, grad_rot_all,
+  poet_launch(heads_bwd_kernel, dim3(R), dim3(128), 0, (cudaStream_t)stream, rot6d, classes, grad_trans, grad_rotmat, grad_rot_all,
                                                         grad_trans_all, R, n_slots);
   return poet_launch_status();
 }

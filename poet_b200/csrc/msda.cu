@@ -73,6 +73,7 @@ __device__ __forceinline__ void softmax_inplace(float (&x)[LP]) {
 // ------------------------------------------------------------------------------------------
 template <int L, int P, int G, bool FUSED>
 __global__ void __launch_bounds__(256) msda_fwd_kernel(const MsdaArgs p) {
+  poet_pdl_entry();
   constexpr int LP = L * P, D = 4 * G;                       // G lanes per (b,q,m)
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)p.B * p.Lq * p.M * G;
@@ -161,6 +162,7 @@ constexpr int kRecBytesPerWarp = 2 * 4 * kRecCorner;    // 2 queries x 4 corners
 template <int L, int P, bool FUSED>
 __global__ void __launch_bounds__(kSlabThreads, 2)
 msda_fwd_slab_kernel(const MsdaArgs p, const __grid_constant__ CUtensorMap tm_v, int nsplit, int q_per_cta, int n_boxes) {
+  poet_pdl_entry();
   constexpr int LP = L * P, D = 16;
   static_assert(LP == 16, "one lane per sampling point in a 16-lane half-warp");
   extern __shared__ uint8_t slab_raw[];
@@ -327,7 +329,7 @@ static int try_slab_fwd(const MsdaArgs& a, int mode, cudaStream_t s) {
   auto launch = [&](auto kern) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)slab_bytes);
     if (e != cudaSuccess) return (int)e;
-    kern<<<grid, kSlabThreads, slab_bytes, s>>>(a, tm, nsplit, q_per_cta, n_boxes);
+    poet_launch(kern, dim3(grid), dim3(kSlabThreads), slab_bytes, s, a, tm, nsplit, q_per_cta, n_boxes);
     return poet_launch_status();
   };
   return mode ? launch(msda_fwd_slab_kernel<4, 4, true>) : launch(msda_fwd_slab_kernel<4, 4, false>);
@@ -356,6 +358,7 @@ __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a
 // the L*P attention gradients stay live until the softmax backward at the end.
 template <int L, int P, int G, bool FUSED>
 __global__ void __launch_bounds__(256, 3) msda_bwd_kernel(const MsdaArgs p) {
+  poet_pdl_entry();
   constexpr int LP = L * P, D = 4 * G;
   static_assert(P % 2 == 0, "points per level must be even (float4 location stores)");
   const int64_t total = (int64_t)p.B * p.Lq * p.M * G;
@@ -487,6 +490,7 @@ __device__ __forceinline__ float cg_max(float v) {
 
 template <int L, int P, int G, bool FUSED, bool BWD>
 __global__ void __launch_bounds__(256) msda_warp_kernel(const MsdaArgs p) {
+  poet_pdl_entry();
   constexpr int LP = L * P, D = 4 * G;
   using WM = WarpMap<LP, G>;
   constexpr int PPL = WM::PPL, NCG = WM::NCG;
@@ -604,8 +608,8 @@ static int try_warp_kernel(const MsdaArgs& a, int mode, cudaStream_t s) {
   const int grid = poet_ceil_div(warps * 32, 256);
 #define POET_WARP_LAUNCH(GG)                                                                  \
   do {                                                                                        \
-    if (mode) msda_warp_kernel<4, 4, GG, true, BWD><<<grid, 256, 0, s>>>(a);                  \
-    else msda_warp_kernel<4, 4, GG, false, BWD><<<grid, 256, 0, s>>>(a);                      \
+    if (mode) poet_launch(msda_warp_kernel<4, 4, GG, true, BWD>, dim3(grid), dim3(256), 0, s, a);                  \
+    else poet_launch(msda_warp_kernel<4, 4, GG, false, BWD>, dim3(grid), dim3(256), 0, s, a);                      \
     return poet_launch_status();                                                              \
   } while (0)
   switch (a.D) {
@@ -645,11 +649,11 @@ int fill_args(MsdaArgs& a, const int32_t* shapes_host, int B, int S, int Lq, int
 template <bool BWD, int LL, int PP, int GG>
 void launch_one(const MsdaArgs& a, int mode, int grid, cudaStream_t s) {
   if (BWD) {
-    if (mode) msda_bwd_kernel<LL, PP, GG, true><<<grid, 256, 0, s>>>(a);
-    else msda_bwd_kernel<LL, PP, GG, false><<<grid, 256, 0, s>>>(a);
+    if (mode) poet_launch(msda_bwd_kernel<LL, PP, GG, true>, dim3(grid), dim3(256), 0, s, a);
+    else poet_launch(msda_bwd_kernel<LL, PP, GG, false>, dim3(grid), dim3(256), 0, s, a);
   } else {
-    if (mode) msda_fwd_kernel<LL, PP, GG, true><<<grid, 256, 0, s>>>(a);
-    else msda_fwd_kernel<LL, PP, GG, false><<<grid, 256, 0, s>>>(a);
+    if (mode) poet_launch(msda_fwd_kernel<LL, PP, GG, true>, dim3(grid), dim3(256), 0, s, a);
+    else poet_launch(msda_fwd_kernel<LL, PP, GG, false>, dim3(grid), dim3(256), 0, s, a);
   }
 }
 

@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float* __restrict
                                                          const float* __restrict__ pos, float* __restrict__ y,
                                                          float* __restrict__ y2, float* __restrict__ xhat,
                                                          float* __restrict__ rstd_out, int R, float eps) {
+  poet_pdl_entry();
   constexpr int C = NV * 128;
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                                      const float* __restrict__ xhat, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, float* __restrict__ dz,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int R) {
+  poet_pdl_entry();
   constexpr int C = NV * 128;
   __shared__ float s_dg[C], s_db[C];
   const int lane = threadIdx.x & 31;
@@ -109,6 +111,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 // are combined in smem and leave as one atomic per column.  Tail columns (N % 4 != 0) use the scalar path.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int64_t ldx, float* __restrict__ out,
                                                      int M, int N, int rows_per_block, int vec) {
+  poet_pdl_entry();
   __shared__ float part[8][128];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 128 + lane * 4;
@@ -144,6 +147,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
 
 __global__ void __launch_bounds__(256) add_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
                                                   float4* __restrict__ out, int64_t n4) {
+  poet_pdl_entry();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 v = a[i];
     if (b) { float4 w = b[i]; v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
@@ -152,6 +156,7 @@ __global__ void __launch_bounds__(256) add_kernel(const float4* __restrict__ a, 
 }
 
 __global__ void __launch_bounds__(256) mask_rows_kernel(float* __restrict__ x, const uint8_t* __restrict__ mask, int R, int C) {
+  poet_pdl_entry();
   const int64_t total = (int64_t)R * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
     if (mask[i / C]) x[i] = 0.f;
@@ -177,10 +182,10 @@ extern "C" int poet_add_layernorm_fwd(const float* x, const float* r, const floa
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = row_grid(R);
   switch (C / 128) {
-    case 1: add_ln_fwd_kernel<1><<<grid, 256, 0, s>>>(x, r, gamma, beta, pos, y, y2, xhat, rstd, R, eps); break;
-    case 2: add_ln_fwd_kernel<2><<<grid, 256, 0, s>>>(x, r, gamma, beta, pos, y, y2, xhat, rstd, R, eps); break;
-    case 4: add_ln_fwd_kernel<4><<<grid, 256, 0, s>>>(x, r, gamma, beta, pos, y, y2, xhat, rstd, R, eps); break;
-    case 8: add_ln_fwd_kernel<8><<<grid, 256, 0, s>>>(x, r, gamma, beta, pos, y, y2, xhat, rstd, R, eps); break;
+    case 1: poet_launch(add_ln_fwd_kernel<1>, dim3(grid), dim3(256), 0, s, x, r, gamma, beta, pos, y, y2, xhat, rstd, R, eps); break;
+    case 2: poet_launch(add_ln_fwd_kernel<2>, dim3(grid), dim3(256), 0, s, x, r, gamma, beta, pos, y, y2, xhat, rstd, R, eps); break;
+    case 4: poet_launch(add_ln_fwd_kernel<4>, dim3(grid), dim3(256), 0, s, x, r, gamma, beta, pos, y, y2, xhat, rstd, R, eps); break;
+    case 8: poet_launch(add_ln_fwd_kernel<8>, dim3(grid), dim3(256), 0, s, x, r, gamma, beta, pos, y, y2, xhat, rstd, R, eps); break;
     default: return POET_ERR_UNSUPPORTED;
   }
   return poet_launch_status();
@@ -197,10 +202,10 @@ extern "C" int poet_layernorm_bwd(const float* dy, const float* dy2, const float
   int grid = row_grid(R);
   if (grid > POET_NUM_SMS * 2) grid = POET_NUM_SMS * 2;   // fewer blocks -> fewer global atomics on dgamma/dbeta
   switch (C / 128) {
-    case 1: ln_bwd_kernel<1><<<grid, 256, 0, s>>>(dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R); break;
-    case 2: ln_bwd_kernel<2><<<grid, 256, 0, s>>>(dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R); break;
-    case 4: ln_bwd_kernel<4><<<grid, 256, 0, s>>>(dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R); break;
-    case 8: ln_bwd_kernel<8><<<grid, 256, 0, s>>>(dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R); break;
+    case 1: poet_launch(ln_bwd_kernel<1>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R); break;
+    case 2: poet_launch(ln_bwd_kernel<2>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R); break;
+    case 4: poet_launch(ln_bwd_kernel<4>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R); break;
+    case 8: poet_launch(ln_bwd_kernel<8>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R); break;
     default: return POET_ERR_UNSUPPORTED;
   }
   return poet_launch_status();
@@ -219,7 +224,7 @@ extern "C" int poet_colsum(const float* X, int64_t ldx, float* out, int M, int N
   while ((int64_t)poet_ceil_div(M, rows_per_block) * col_tiles > 8 * POET_NUM_SMS) rows_per_block *= 2;
   const int row_chunks = poet_ceil_div(M, rows_per_block);
   const int vec = poet_aligned16(X) && (ldx % 4 == 0);
-  colsum_kernel<<<dim3(col_tiles, row_chunks), 256, 0, s>>>(X, ldx, out, M, N, rows_per_block, vec);
+  poet_launch(colsum_kernel, dim3(col_tiles, row_chunks), dim3(256), 0, s, X, ldx, out, M, N, rows_per_block, vec);
   return poet_launch_status();
 }
 
@@ -230,7 +235,7 @@ extern "C" int poet_add(const float* a, const float* b, float* out, int64_t n, p
   int64_t n4 = n / 4;
   int grid = poet_ceil_div(n4, 256);
   if (grid > POET_NUM_SMS * 8) grid = POET_NUM_SMS * 8;
-  add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
+  poet_launch(add_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
                                                      reinterpret_cast<float4*>(out), n4);
   return poet_launch_status();
 }
@@ -240,6 +245,6 @@ extern "C" int poet_mask_rows(float* x, const uint8_t* mask, int R, int C, poet_
   POET_REQUIRE(R > 0 && C > 0, POET_ERR_BAD_SHAPE);
   int grid = poet_ceil_div((int64_t)R * C, 256);
   if (grid > POET_NUM_SMS * 8) grid = POET_NUM_SMS * 8;
-  mask_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, mask, R, C);
+  poet_launch(mask_rows_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, mask, R, C);
   return poet_launch_status();
 }

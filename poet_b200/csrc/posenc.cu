@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256) posenc_kernel(const uint8_t* __restrict__
                                                      const float* __restrict__ level_embed, float* __restrict__ out,
                                                      int B, int H, int W, int F, float scale, int normalize, int layout,
                                                      int S_total, int row_offset) {
+  poet_pdl_entry();
   __shared__ float s_ey[kPix], s_ex[kPix];
   const int HW = H * W;
   const int64_t pix0 = (int64_t)blockIdx.x * kPix;           // over B*HW
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(256) posenc_kernel(const uint8_t* __restrict__
 
 __global__ void __launch_bounds__(256) bbox_embed_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ n_boxes,
                                                          float* __restrict__ out, int B, int Q, int F) {
+  poet_pdl_entry();
   const int C = 8 * F;
   const int64_t total = (int64_t)B * Q * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -94,6 +96,7 @@ __global__ void __launch_bounds__(256) bbox_embed_kernel(const float* __restrict
 // 32x32 smem transpose tiles: src [B][C][HW]  <->  tokens [B][S_total][C] rows row_offset..row_offset+HW
 __global__ void __launch_bounds__(256) nchw_to_tokens_kernel(const float* __restrict__ src, const float* __restrict__ add_vec,
                                                              float* __restrict__ tokens, int C, int HW, int S_total, int row_offset) {
+  poet_pdl_entry();
   __shared__ float tile[32][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += 8) {
@@ -113,6 +116,7 @@ __global__ void __launch_bounds__(256) nchw_to_tokens_kernel(const float* __rest
 
 __global__ void __launch_bounds__(256) tokens_to_nchw_kernel(const float* __restrict__ gtok, float* __restrict__ gsrc,
                                                              float* __restrict__ gvec, int C, int HW, int S_total, int row_offset) {
+  poet_pdl_entry();
   __shared__ float tile[32][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += 8) {
@@ -136,6 +140,7 @@ __global__ void __launch_bounds__(256) tokens_to_nchw_kernel(const float* __rest
 struct RefLevels { int H[4]; int W[4]; int start[4]; int L; int S; };
 
 __global__ void __launch_bounds__(256) enc_ref_kernel(const float* __restrict__ vr, float* __restrict__ out, RefLevels lv, int B) {
+  poet_pdl_entry();
   const int64_t total = (int64_t)B * lv.S;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(i / lv.S), s = (int)(i % lv.S);
@@ -165,7 +170,7 @@ extern "C" int poet_posenc_sine(const uint8_t* mask, const float* dim_t, const f
     POET_REQUIRE(poet_aligned16(out) && (!level_embed || poet_aligned16(level_embed)), POET_ERR_BAD_ALIGNMENT);
   }
   const int grid = poet_ceil_div((int64_t)B * H * W, kPix);
-  posenc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mask, dim_t, level_embed, out, B, H, W, F, scale, normalize,
+  poet_launch(posenc_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, mask, dim_t, level_embed, out, B, H, W, F, scale, normalize,
                                                         layout, S_total, row_offset);
   return poet_launch_status();
 }
@@ -177,7 +182,7 @@ extern "C" int poet_bbox_embed_pad(const float* boxes, const int32_t* n_boxes, f
   const int64_t total = (int64_t)B * Q * 8 * F;
   int grid = poet_ceil_div(total, 256);
   if (grid > POET_NUM_SMS * 8) grid = POET_NUM_SMS * 8;
-  bbox_embed_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(boxes, n_boxes, query_embeds, B, Q, F);
+  poet_launch(bbox_embed_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, boxes, n_boxes, query_embeds, B, Q, F);
   return poet_launch_status();
 }
 
@@ -186,7 +191,7 @@ extern "C" int poet_nchw_to_tokens(const float* src, const float* add_vec, float
   POET_REQUIRE(src && tokens, POET_ERR_NULL_POINTER);
   POET_REQUIRE(B > 0 && C > 0 && HW > 0 && row_offset >= 0 && row_offset + HW <= S_total, POET_ERR_BAD_SHAPE);
   dim3 grid(poet_ceil_div(HW, 32), poet_ceil_div(C, 32), B);
-  nchw_to_tokens_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, add_vec, tokens, C, HW, S_total, row_offset);
+  poet_launch(nchw_to_tokens_kernel, dim3(grid), dim3(32, 8), 0, (cudaStream_t)stream, src, add_vec, tokens, C, HW, S_total, row_offset);
   return poet_launch_status();
 }
 
@@ -195,7 +200,7 @@ extern "C" int poet_tokens_to_nchw(const float* grad_tokens, float* grad_src, fl
   POET_REQUIRE(grad_tokens && (grad_src || grad_vec), POET_ERR_NULL_POINTER);
   POET_REQUIRE(B > 0 && C > 0 && HW > 0 && row_offset >= 0 && row_offset + HW <= S_total, POET_ERR_BAD_SHAPE);
   dim3 grid(poet_ceil_div(HW, 32), poet_ceil_div(C, 32), B);
-  tokens_to_nchw_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(grad_tokens, grad_src, grad_vec, C, HW, S_total,
+  poet_launch(tokens_to_nchw_kernel, dim3(grid), dim3(32, 8), 0, (cudaStream_t)stream, grad_tokens, grad_src, grad_vec, C, HW, S_total,
                                                                         row_offset);
   return poet_launch_status();
 }
@@ -215,6 +220,6 @@ extern "C" int poet_enc_reference_points(const float* valid_ratios, float* out, 
   lv.S = start;
   int grid = poet_ceil_div((int64_t)B * start, 256);
   if (grid > POET_NUM_SMS * 8) grid = POET_NUM_SMS * 8;
-  enc_ref_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(valid_ratios, out, lv, B);
+  poet_launch(enc_ref_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, valid_ratios, out, lv, B);
   return poet_launch_status();
 }

@@ -78,6 +78,13 @@ int poet_nchw_to_tokens(const float* src, const float* add_vec, float* tokens, i
 int poet_tokens_to_nchw(const float* grad_tokens, float* grad_src, float* grad_vec, int B, int C, int HW,
                         int S_total, int row_offset, poet_stream_t stream);
 
+/* ---- A6: padding-mask tokens and valid ratios ------------------------------------------------------- */
+/* masks_host: L device pointers (on the HOST) to uint8/bool masks [B,H_l,W_l] (1 = padded).  pad [B,S] = the levels'
+ * masks flattened and concatenated; valid_ratios [B,L,2] = (unpadded columns of row 0 / W, unpadded rows of
+ * column 0 / H): deformable_transformer.py:111-118, 126-141 in one launch. */
+int poet_mask_prep(const uint8_t* const* masks_host, const int32_t* shapes_host, uint8_t* pad, float* valid_ratios,
+                   int B, int L, poet_stream_t stream);
+
 /* ---- A5: encoder reference points -------------------------------------------------------- */
 /* valid_ratios [B,L,2] (w,h).  out [B,S,L,2].  shapes_host [L*2] = (H_l, W_l). */
 int poet_enc_reference_points(const float* valid_ratios, float* out, const int32_t* shapes_host,

@@ -25,6 +25,7 @@ SIGNATURES = {
     "poet_bbox_embed_pad": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "poet_nchw_to_tokens": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "poet_tokens_to_nchw": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "poet_mask_prep": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "poet_enc_reference_points": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "poet_msda_fwd": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "poet_msda_bwd": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -205,6 +205,52 @@ extern "C" int poet_tokens_to_nchw(const float* grad_tokens, float* grad_src, fl
   return poet_launch_status();
 }
 
+// ---- A6: padding mask tokens + valid ratios in one launch ------------------------------------------------
+// Replaces torch.cat([m.flatten(1) ...]) and the per-level get_valid_ratio of deformable_transformer.py:111-118,
+// 126-141 (about 45 tiny ATen launches per forward).  One block per (image, level).
+struct MaskPrepArgs { const uint8_t* mask[4]; int H[4], W[4], start[4]; };
+__global__ void __launch_bounds__(256) mask_prep_kernel(const MaskPrepArgs a, uint8_t* __restrict__ pad,
+                                                        float* __restrict__ valid_ratios, int L, int S) {
+  poet_pdl_entry();
+  const int b = blockIdx.x / L, l = blockIdx.x % L;
+  const int H = a.H[l], W = a.W[l];
+  const uint8_t* m = a.mask[l] + (int64_t)b * H * W;
+  uint8_t* dst = pad + (int64_t)b * S + a.start[l];
+  int cnt_h = 0, cnt_w = 0;                                   // unpadded rows of column 0 / unpadded columns of row 0
+  for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+    const uint8_t v = m[i];
+    dst[i] = v;
+    if (v == 0) { cnt_h += (i % W) == 0; cnt_w += i < W; }
+  }
+  __shared__ int s_h, s_w;
+  if (threadIdx.x == 0) { s_h = 0; s_w = 0; }
+  __syncthreads();
+  if (cnt_h) atomicAdd(&s_h, cnt_h);
+  if (cnt_w) atomicAdd(&s_w, cnt_w);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float* vr = valid_ratios + ((int64_t)b * L + l) * 2;
+    vr[0] = (float)s_w / (float)W;                             // (w, h) order: deformable_transformer.py:117
+    vr[1] = (float)s_h / (float)H;
+  }
+}
+
+extern "C" int poet_mask_prep(const uint8_t* const* masks_host, const int32_t* shapes_host, uint8_t* pad,
+                              float* valid_ratios, int B, int L, poet_stream_t stream) {
+  POET_REQUIRE(masks_host && shapes_host && pad && valid_ratios, POET_ERR_NULL_POINTER);
+  POET_REQUIRE(B > 0 && L >= 1 && L <= 4, POET_ERR_BAD_SHAPE);
+  MaskPrepArgs a;
+  int S = 0;
+  for (int l = 0; l < L; ++l) {
+    POET_REQUIRE(masks_host[l] != nullptr, POET_ERR_NULL_POINTER);
+    a.mask[l] = masks_host[l]; a.H[l] = shapes_host[2 * l]; a.W[l] = shapes_host[2 * l + 1]; a.start[l] = S;
+    POET_REQUIRE(a.H[l] > 0 && a.W[l] > 0, POET_ERR_BAD_SHAPE);
+    S += a.H[l] * a.W[l];
+  }
+  poet_launch(mask_prep_kernel, dim3(B * L), dim3(256), 0, (cudaStream_t)stream, a, pad, valid_ratios, L, S);
+  return poet_launch_status();
+}
+
 extern "C" int poet_enc_reference_points(const float* valid_ratios, float* out, const int32_t* shapes_host, int B, int L,
                                          poet_stream_t stream) {
   POET_REQUIRE(valid_ratios && out && shapes_host, POET_ERR_NULL_POINTER);

@@ -261,10 +261,13 @@ class DeformableTransformer(nn.Module):
         shapes = tuple((int(s.shape[2]), int(s.shape[3])) for s in srcs)
         src = ops.flatten_levels(list(srcs))
         pos = pos_tokens if pos_tokens is not None else ops.flatten_levels(list(pos_embeds), self.level_embed)
-        mask = torch.cat([m.flatten(1) for m in masks], 1)
         spatial_shapes, level_start = _shape_tensors(shapes, src.device)
-        valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
-        pad = mask.to(torch.uint8)              # converted once; every MSDeformAttn layer reuses it
+        if src.is_cuda and len(masks) <= 4:
+            pad, valid_ratios = ops.mask_prep(masks)          # flattened padding mask + valid ratios: one launch
+        else:
+            mask = torch.cat([m.flatten(1) for m in masks], 1)
+            valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
+            pad = mask.to(torch.uint8)          # converted once; every MSDeformAttn layer reuses it
 
         memory = self.encoder(src, spatial_shapes, level_start, valid_ratios, pos, pad)
 

@@ -971,7 +971,7 @@ def posenc_sine_nchw(mask: torch.Tensor, F: int = 128, temperature: float = 1000
                      scale: float = 2 * math.pi) -> torch.Tensor:
     """mask [B,H,W] bool -> [B,2F,H,W] (reference layout, position_encoding.py:40-60)."""
     B, H, W = mask.shape
-    m8 = _chk(mask.to(torch.uint8), torch.uint8)
+    m8 = _chk(as_u8(mask), torch.uint8)
     out = torch.empty((B, 2 * F, H, W), device=mask.device, dtype=torch.float32)
     _call("poet_posenc_sine", _p(m8), _p(_dim_t(F, temperature, mask.device)), None, _p(out), B, H, W, F, scale,
           int(normalize), 0, 0, 0, _stream(out))
@@ -983,7 +983,7 @@ def posenc_sine_tokens_(out: torch.Tensor, mask: torch.Tensor, level_embed_row: 
                         scale: float = 2 * math.pi) -> None:
     """Writes pos (+level_embed) for one level straight into the token-major [B,S,2F] buffer."""
     B, H, W = mask.shape
-    m8 = _chk(mask.to(torch.uint8), torch.uint8)
+    m8 = _chk(as_u8(mask), torch.uint8)
     _call("poet_posenc_sine", _p(m8), _p(_dim_t(F, temperature, mask.device)), _p(level_embed_row), _p(out), B, H, W, F,
           scale, int(normalize), 1, out.shape[1], row_offset, _stream(out))
 
@@ -994,6 +994,26 @@ def bbox_embed_pad(boxes_padded: torch.Tensor, n_boxes: torch.Tensor, F: int) ->
     out = torch.empty((B, Q, 16 * F), device=boxes_padded.device, dtype=torch.float32)
     _call("poet_bbox_embed_pad", _p(_chk(boxes_padded)), _p(_chk(n_boxes, torch.int32)), _p(out), B, Q, F, _stream(out))
     return out
+
+
+def as_u8(mask: torch.Tensor) -> torch.Tensor:
+    """bool -> uint8 without a copy (same bytes)."""
+    if mask.dtype == torch.uint8:
+        return mask
+    return mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8)
+
+
+def mask_prep(masks: Sequence[torch.Tensor]):
+    """Per-level masks [B,H_l,W_l] -> (pad [B,S] uint8, valid_ratios [B,L,2] fp32) in one launch."""
+    m8 = [_chk(as_u8(m), torch.uint8) for m in masks]
+    B, L = m8[0].shape[0], len(m8)
+    shapes = [(int(m.shape[1]), int(m.shape[2])) for m in m8]
+    S = sum(h * w for h, w in shapes)
+    pad = torch.empty((B, S), device=m8[0].device, dtype=torch.uint8)
+    vr = torch.empty((B, L, 2), device=m8[0].device, dtype=torch.float32)
+    ptrs = (C.c_void_p * L)(*[m.data_ptr() for m in m8])
+    _call("poet_mask_prep", ptrs, shapes_array(shapes), _p(pad), _p(vr), B, L, _stream(pad))
+    return pad, vr
 
 
 def enc_reference_points(valid_ratios: torch.Tensor, shapes) -> torch.Tensor:

@@ -214,10 +214,27 @@ def run_gpu(args):
     d_labels = [l.to(dev) for l in inp["labels"]]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def loss_fn(out):
+    def synthetic_loss(out):
         t = torch.stack([a["pred_translation"] for a in out["aux_outputs"]] + [out["pred_translation"]])
         R = torch.stack([a["pred_rotation"] for a in out["aux_outputs"]] + [out["pred_rotation"]])
         return (t * g_t).sum() + (R * g_R).sum()
+
+    loss_fn = synthetic_loss
+    if args.criterion:
+        from poet_b200.criterion import PoseCriterion
+        Q = cfg["num_queries"]
+        gen = torch.Generator().manual_seed(777 + rank)
+        tgt_t = torch.randn(B, Q, 3, generator=gen).to(dev)
+        q4 = torch.nn.functional.normalize(torch.randn(B, Q, 4, generator=gen), dim=-1)      # random unit quaternions -> SO(3)
+        w, x, y, z = q4.unbind(-1)
+        tgt_R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                             2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                             2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], -1).view(B, Q, 3, 3).to(dev)
+        n_boxes_dev = torch.tensor([min(int(b.shape[0]), Q) for b in inp["boxes"]], dtype=torch.int32, device=dev)
+        crit = PoseCriterion({"loss_trans": 1.0, "loss_rot": 1.0})                            # reference defaults (main.py:121-122)
+
+        def loss_fn(out):
+            return crit(out, tgt_t, tgt_R, n_boxes_dev)[1]
 
     def eager_step(srcs, masks, boxes, labels):
         reducer.zero()
@@ -373,6 +390,8 @@ def run_gpu(args):
                                             "gemm_precision": args.precision,
                                             "launch": "one CUDA graph per step" if args.graph else "eager",
                                             "micro_batches": args.micro_batches,
+                                            "loss": ("on-device PoseCriterion (SetCriterion + 'gt' matcher), synthetic targets" if args.criterion
+                                                     else "fixed-cotangent loss (SURVEY.md section 8d)"),
                                             "optimizer": "fused clip_grad_norm_(0.1) + AdamW inside every step" if opt is not None else "none (forward + backward [+ all-reduce])",
                                             "kernel_table": "eager single-stream pass, CUDA events around every library call"}),
                 "e2e": {"value": B * world * args.steps / (e2e_ms / 1e3), "unit": "images/s",
@@ -451,6 +470,9 @@ def main():
     ap.add_argument("--no-kernel-table", dest="kernel_table", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false")
+    ap.add_argument("--criterion", action="store_true",
+                    help="back-propagate the on-device PoseCriterion (reference SetCriterion + 'gt' matcher) instead of the "
+                         "fixed-cotangent loss of SURVEY.md section 8d")
     ap.add_argument("--optimizer", action="store_true",
                     help="include the fused clip_grad_norm_(0.1) + AdamW step in every step (training step of cfg4)")
     ap.add_argument("--micro-batches", type=int, default=int(os.environ.get("POET_MICRO_BATCHES", "1")),

@@ -191,6 +191,16 @@ int poet_heads_select_rot6d_bwd(const float* rot6d, const int64_t* classes, cons
                                 const float* grad_rotmat, float* grad_rot_all, float* grad_trans_all,
                                 int R, int n_slots, poet_stream_t stream);
 
+/* ---- pose loss (next: SURVEY.md section 8f N2; reference pose_estimation_transformer.py:478-494, 519-537, 635-662) -- */
+/* pred_t [L,B,Q,3], pred_R [L,B,Q,9] (row-major 3x3) for the L decoder layers; tgt_t [B,T,3], tgt_R [B,T,9] padded
+ * targets; assign [B,Q] int32 = target index of each query or -1 (PoseMatcher result; 'gt' mode: j for j < n_i);
+ * n_obj [1] int32 on the device = number of matched pairs (clamped to >= 1).
+ * losses [L,2] = (sum ||t - t*||_2 / n_obj, sum acos(clamp((tr(R R*^T) - 1)/2, -1+1e-6, 1-1e-6)) / n_obj) per layer;
+ * grad_t / grad_R = gradient of  sum_l (w_trans * losses[l,0] + w_rot * losses[l,1])  w.r.t. the predictions. */
+int poet_pose_loss(const float* pred_t, const float* pred_R, const float* tgt_t, const float* tgt_R,
+                   const int32_t* assign, const int32_t* n_obj, float* losses, float* grad_t, float* grad_R,
+                   int L, int B, int Q, int T, float w_trans, float w_rot, poet_stream_t stream);
+
 /* ---- optimizer step (next: SURVEY.md section 8f N3; reference engine.py:77-81, main.py:253-277) ------------ */
 /* out[0] = sum_i x[i]^2 (double, on the device; overwritten).  n % 4 == 0. */
 int poet_sumsq(const float* x, int64_t n, double* out, poet_stream_t stream);

@@ -189,18 +189,69 @@ def golden_poet(cfg_name: str, pad: bool):
                 fp_inputs=S.fingerprint(inp["srcs"][:3]))
 
 
+def criterion_case(seed=99, L=3, B=4, Q=6, n_boxes=(6, 3, 1, 4)):
+    """Seeded inputs of the criterion fixture (shared with the tests through poet_b200.synthetic-style seeding)."""
+    g = torch.Generator().manual_seed(seed)
+    t_all = torch.randn(L, B, Q, 3, generator=g)
+    R_all = O.rotation_6d_to_matrix(torch.randn(L, B, Q, 6, generator=g))
+    boxes, labels, tgt_t, tgt_R = [], [], [], []
+    for n in n_boxes:
+        boxes.append(torch.rand(n, 4, generator=g) * 0.5 + 0.2)
+        labels.append(torch.randint(1, 22, (n,), generator=g))
+        tgt_t.append(torch.randn(n, 3, generator=g))
+        tgt_R.append(O.rotation_6d_to_matrix(torch.randn(n, 6, generator=g)))
+    return t_all, R_all, boxes, labels, tgt_t, tgt_R, list(n_boxes)
+
+
+def golden_criterion():
+    """Reference SetCriterion + PoseMatcher(bbox_mode='gt') on seeded predictions / targets: loss dict and the
+    gradients of the weighted total w.r.t. every layer's predictions."""
+    from models.matcher import PoseMatcher
+    from models.pose_estimation_transformer import SetCriterion
+    t_all, R_all, boxes, labels, tgt_t, tgt_R, n_boxes = criterion_case()
+    L, B, Q = t_all.shape[:3]
+    t_all.requires_grad_(True)
+    R_all.requires_grad_(True)
+    pb = torch.full((B, Q, 4), -1.0)
+    pc = torch.full((B, Q), -1, dtype=torch.int64)
+    for b, n in enumerate(n_boxes):
+        pb[b, :n], pc[b, :n] = boxes[b], labels[b]
+    targets = [dict(boxes=boxes[b], labels=labels[b], relative_position=tgt_t[b], relative_rotation=tgt_R[b]) for b in range(B)]
+    w = {"loss_trans": 2.0, "loss_rot": 0.5}
+    weight_dict = dict(w)
+    for i in range(L - 1):
+        weight_dict.update({k + f"_{i}": v for k, v in w.items()})
+    crit = SetCriterion(PoseMatcher(cost_bbox=1, cost_class=1, bbox_mode="gt", class_mode="specific"), weight_dict,
+                        ["translation", "rotation"])
+    mk = lambda l: {"pred_translation": t_all[l], "pred_rotation": R_all[l], "pred_boxes": pb, "pred_classes": pc}
+    outputs = mk(L - 1)
+    outputs["aux_outputs"] = [mk(l) for l in range(L - 1)]
+    losses = crit(outputs, targets, n_boxes)
+    total = sum(losses[k] * weight_dict[k] for k in losses if k in weight_dict)          # engine.py:60-61
+    total.backward()
+    return dict(losses={k: float(v) for k, v in losses.items()}, total=float(total), weights=w,
+                grad_t=t_all.grad.clone(), grad_R=R_all.grad.clone())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden"))
+    ap.add_argument("--only", default=None, help="regenerate only the fixtures whose key starts with this prefix")
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
     install_shim()
     torch.set_num_threads(os.cpu_count() or 1)
-    gold = {"posenc": golden_posenc()}
+    gold = {}
+    if args.only is None or "posenc".startswith(args.only):
+        gold["posenc"] = golden_posenc()
     for name, pad in (("tiny", False), ("tiny", True), ("tiny16", True), ("cfg1", False)):
-        gold[f"transformer/{name}/pad{int(pad)}"] = golden_transformer(name, pad)
+        if args.only is None or f"transformer/{name}".startswith(args.only):
+            gold[f"transformer/{name}/pad{int(pad)}"] = golden_transformer(name, pad)
     for name, pad in (("tiny", True), ("tiny16", False), ("cfg1", False), ("cfg2_b2", True)):
-        gold[f"poet/{name}/pad{int(pad)}"] = golden_poet(name, pad)
+        if args.only is None or f"poet/{name}".startswith(args.only):
+            gold[f"poet/{name}/pad{int(pad)}"] = golden_poet(name, pad)
+    if args.only is None or "criterion/gt".startswith(args.only):
+        gold["criterion/gt"] = golden_criterion()
     meta = dict(torch=torch.__version__, reference=REF, note="generated by oracle/make_golden.py")
     for key, val in gold.items():
         fn = os.path.join(args.out, key.replace("/", "__") + ".pt")

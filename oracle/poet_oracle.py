@@ -395,3 +395,35 @@ def synthetic_loss(capture_or_tR, g_t: Tensor, g_R: Tensor) -> Tensor:
     """sum_l <translation_l, g_t[l]> + <rotation_l, g_R[l]> (fixed cotangents)."""
     t, R = capture_or_tR
     return (t * g_t).sum() + (R * g_R).sum()
+
+
+# --------------------------------------------------------------------------------------
+# N2: SetCriterion + PoseMatcher in 'gt' bbox mode (SURVEY.md §8f)
+# --------------------------------------------------------------------------------------
+def pose_criterion_gt(t_all, R_all, tgt_t, tgt_R, n_boxes, w_trans=1.0, w_rot=1.0):
+    """Restatement of reference models/pose_estimation_transformer.py SetCriterion.forward (:635-662) with
+    losses ['translation', 'rotation'] (:478-494, :519-537) and models/matcher.py PoseMatcher in bbox_mode 'gt'
+    (:158-173, :192-195): the predicted boxes of the first n_boxes[i] queries ARE the target boxes, so the L1
+    cost matrix has a zero diagonal and the Hungarian assignment is query j <-> target j.
+
+    t_all [L,B,Q,3], R_all [L,B,Q,3,3] (decoder layers, last = final output); tgt_t / tgt_R: lists (len B) of
+    [n_i,3] / [n_i,3,3]; n_boxes: list of ints.  Returns (dict with the reference's keys: 'loss_trans',
+    'loss_rot' for the last layer and '<k>_<i>' for aux layer i, weighted total as in engine.py:60-61)."""
+    L = t_all.shape[0]
+    n_obj = sum(int(n) for n in n_boxes)
+    losses = {}
+    for l in range(L):
+        src_t = torch.cat([t_all[l, b, :n] for b, n in enumerate(n_boxes)], 0)
+        src_R = torch.cat([R_all[l, b, :n] for b, n in enumerate(n_boxes)], 0)
+        gt_t = torch.cat([t[:n] for t, n in zip(tgt_t, n_boxes)], 0)
+        gt_R = torch.cat([r[:n] for r, n in zip(tgt_R, n_boxes)], 0)
+        lt = torch.sqrt(((src_t - gt_t) ** 2).sum(1)).sum() / n_obj                       # :486-490
+        prod = torch.bmm(src_R, gt_R.transpose(1, 2))                                     # :531
+        trace = prod.diagonal(dim1=1, dim2=2).sum(1)
+        theta = torch.clamp(0.5 * (trace - 1), -1 + 1e-6, 1 - 1e-6)                       # :533
+        lr = torch.acos(theta).sum() / n_obj
+        suffix = "" if l == L - 1 else f"_{l}"
+        losses["loss_trans" + suffix] = lt
+        losses["loss_rot" + suffix] = lr
+    total = sum(v * (w_trans if k.startswith("loss_trans") else w_rot) for k, v in losses.items())
+    return losses, total

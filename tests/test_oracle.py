@@ -126,3 +126,23 @@ def test_fp32_noise_floor_vs_fp64():
     _, _, _, _, _, _, _, cap64 = oracle_poet_from_feats(cfg, True, torch.float64, need_grad=False)
     assert (cap32["translation_all"].double() - cap64["translation_all"]).abs().max() < 1e-5
     assert (cap32["rot6d"].double() - cap64["rot6d"]).abs().max() < 1e-5
+
+
+def test_pose_criterion_oracle_matches_reference_golden():
+    """oracle.pose_criterion_gt == the unmodified reference SetCriterion + PoseMatcher('gt') (fixture generated by
+    oracle/make_golden.py): every loss term and the gradient of the weighted total."""
+    from helpers import load_golden
+    from oracle.make_golden import criterion_case
+    from oracle import poet_oracle as O
+    g = load_golden("criterion/gt")
+    t_all, R_all, _boxes, _labels, tgt_t, tgt_R, n_boxes = criterion_case()
+    t_all, R_all = t_all.double().requires_grad_(True), R_all.double().requires_grad_(True)
+    losses, total = O.pose_criterion_gt(t_all, R_all, [t.double() for t in tgt_t], [r.double() for r in tgt_R], n_boxes,
+                                        g["weights"]["loss_trans"], g["weights"]["loss_rot"])
+    assert set(losses) == set(g["losses"])
+    for k, v in g["losses"].items():
+        assert abs(float(losses[k]) - v) <= 2e-6 * max(1.0, abs(v)), k
+    assert abs(float(total) - g["total"]) <= 2e-6 * abs(g["total"])
+    total.backward()
+    assert float((t_all.grad - g["grad_t"].double()).abs().max()) < 1e-6
+    assert float((R_all.grad - g["grad_R"].double()).abs().max()) < 2e-4      # fp32 acos' near the clamp in the fixture

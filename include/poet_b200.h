@@ -191,6 +191,20 @@ int poet_heads_select_rot6d_bwd(const float* rot6d, const int64_t* classes, cons
                                 const float* grad_rotmat, float* grad_rot_all, float* grad_trans_all,
                                 int R, int n_slots, poet_stream_t stream);
 
+/* ---- input_proj (next: SURVEY.md section 8f N1; reference pose_estimation_transformer.py:100-135, 313-335) ------ */
+/* The 1x1 / 3x3-stride-2 convolutions are poet_gemm calls on token rows; these are the pieces around them.
+ * col[(b*Ho + oy)*Wo + ox, c*9 + ky*3 + kx] = x[b, c, 2*oy-1+ky, 2*ox-1+kx] (0 outside), Ho = (H-1)/2+1. */
+int poet_im2col_3x3s2(const float* x, float* col, int B, int C, int H, int W, poet_stream_t stream);
+/* GroupNorm(G, C) of the conv output y [B*HW, C] (token rows of one level), written into rows
+ * (b*S_total + row_offset + hw) of the transformer's token matrix.  stats [B,G,2] doubles (sum, sum of squares)
+ * is written here and read by the backward; C % 32 == 0, C/G a power of two <= 32. */
+int poet_groupnorm_tokens_fwd(const float* y, const float* gamma, const float* beta, float* tokens, double* stats,
+                              int B, int HW, int C, int G, int S_total, int row_offset, float eps, poet_stream_t stream);
+/* grad_y [B*HW, C] overwritten; dgamma / dbeta [C] ACCUMULATED into; workspace [B,G,2] doubles. */
+int poet_groupnorm_tokens_bwd(const float* grad_tokens, const float* y, const double* stats, const float* gamma,
+                              float* grad_y, float* dgamma, float* dbeta, double* workspace, int B, int HW, int C, int G,
+                              int S_total, int row_offset, float eps, poet_stream_t stream);
+
 /* ---- pose loss (next: SURVEY.md section 8f N2; reference pose_estimation_transformer.py:478-494, 519-537, 635-662) -- */
 /* pred_t [L,B,Q,3], pred_R [L,B,Q,9] (row-major 3x3) for the L decoder layers; tgt_t [B,T,3], tgt_R [B,T,9] padded
  * targets; assign [B,Q] int32 = target index of each query or -1 (PoseMatcher result; 'gt' mode: j for j < n_i);

@@ -244,13 +244,14 @@ class DeformableTransformer(nn.Module):
         return torch.stack((vw, vh), -1)
 
     def forward(self, srcs, masks, pos_embeds, query_embed=None, reference_points=None, pos_tokens=None,
-                layer_callback=None):
+                layer_callback=None, src_tokens=None):
         # all weight matrices -> bf16 hi/lo planes in one launch (no-op if an enclosing module already did it)
         with ops.planes_scope(self):
-            return self._forward_impl(srcs, masks, pos_embeds, query_embed, reference_points, pos_tokens, layer_callback)
+            return self._forward_impl(srcs, masks, pos_embeds, query_embed, reference_points, pos_tokens, layer_callback,
+                                      src_tokens)
 
     def _forward_impl(self, srcs, masks, pos_embeds, query_embed=None, reference_points=None, pos_tokens=None,
-                      layer_callback=None):
+                      layer_callback=None, src_tokens=None):
         """Reference signature (deformable_transformer.py:120).  `pos_tokens` (optional, ours):
         lvl_pos_embed_flatten [B,S,C] already in token layout with level_embed added."""
         if query_embed is None:
@@ -258,8 +259,12 @@ class DeformableTransformer(nn.Module):
         ops.clear_weight_split_cache()          # bf16 weight planes live for one forward + its backward
         if reference_points is None:
             raise NotImplementedError("learned reference points are not used by PoET ('bbox' mode only)")
-        shapes = tuple((int(s.shape[2]), int(s.shape[3])) for s in srcs)
-        src = ops.flatten_levels(list(srcs))
+        if src_tokens is not None:               # ours: the pyramid already in token layout (ops.input_proj_tokens)
+            shapes = tuple((int(m.shape[1]), int(m.shape[2])) for m in masks)
+            src = src_tokens
+        else:
+            shapes = tuple((int(s.shape[2]), int(s.shape[3])) for s in srcs)
+            src = ops.flatten_levels(list(srcs))
         pos = pos_tokens if pos_tokens is not None else ops.flatten_levels(list(pos_embeds), self.level_embed)
         spatial_shapes, level_start = _shape_tensors(shapes, src.device)
         if src.is_cuda and len(masks) <= 4:

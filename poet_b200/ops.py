@@ -235,7 +235,8 @@ class WeightPlanes:
 
     @staticmethod
     def select(module: torch.nn.Module):
-        return [p for p in module.parameters() if p.dim() == 2 and p.dtype == torch.float32 and p.is_cuda
+        # matrices and conv kernels (input_proj: [out, in, kh, kw] is the GEMM weight [out, in*kh*kw])
+        return [p for p in module.parameters() if p.dim() in (2, 4) and p.dtype == torch.float32 and p.is_cuda
                 and p.is_contiguous() and p.numel() % 8 == 0]
 
     def __init__(self, module: torch.nn.Module):
@@ -332,7 +333,7 @@ class planes_scope:
         self.module, self.pushed, self.do_refresh = module, False, refresh
 
     def __enter__(self):
-        first = next((p for p in self.module.parameters() if p.dim() == 2), None)
+        first = next((p for p in self.module.parameters() if p.dim() in (2, 4)), None)
         if first is None or not first.is_cuda or _state["precision"] == GEMM_FP32:
             return self
         if any(pl.lookup(first.data_ptr(), first.numel()) is not None for pl in _active_planes):
@@ -1067,3 +1068,90 @@ class _FlattenLevels(torch.autograd.Function):
 
 def flatten_levels(maps: Sequence[torch.Tensor], level_embed: Optional[torch.Tensor] = None) -> torch.Tensor:
     return _FlattenLevels.apply(level_embed, *maps)
+
+
+# ------------------------------------------------------------------------------------------
+# autograd: input_proj
+# ------------------------------------------------------------------------------------------
+class _InputProj(torch.autograd.Function):
+    """Backbone feature maps -> the transformer's token matrix [B, S, C]: per level Conv2d(1x1) + GroupNorm(32), and
+    for the extra level Conv2d(3x3, stride 2, padding 1) + GroupNorm(32) on the last feature map (reference
+    models/pose_estimation_transformer.py:100-135, 313-335).  The convolutions are tensor-core GEMMs on token rows
+    (NCHW -> rows by poet_nchw_to_tokens / poet_im2col_3x3s2), GroupNorm writes each level straight into its
+    slice of the token matrix, so the NCHW projections and their flatten / transpose / cat copies never exist.
+    Gradients: conv weights / biases and GroupNorm affine parameters (the backbone is frozen: no input gradient)."""
+
+    @staticmethod
+    def forward(ctx, n_feats, groups, eps, *tensors):
+        feats = [_chk(t) for t in tensors[:n_feats]]
+        params = tensors[n_feats:]                           # per level: conv weight, conv bias, gn weight, gn bias
+        L = len(params) // 4
+        if L > n_feats + 1:
+            raise NotImplementedError("more than one extra feature level")
+        B = feats[0].shape[0]
+        C = params[0].shape[0]
+        dims = []                                            # (H, W) per level
+        for f in feats:
+            dims.append((int(f.shape[2]), int(f.shape[3])))
+        if L == n_feats + 1:
+            H, W = dims[-1]
+            dims.append(((H - 1) // 2 + 1, (W - 1) // 2 + 1))
+        S = sum(h * w for h, w in dims)
+        tokens = torch.empty((B, S, C), device=feats[0].device, dtype=torch.float32)
+        saved, off = [], 0
+        for l in range(L):
+            Wc, bc, gw, gb = params[4 * l: 4 * l + 4]
+            HW = dims[l][0] * dims[l][1]
+            if l < n_feats:
+                Cin = feats[l].shape[1]
+                x2 = torch.empty((B * HW, Cin), device=tokens.device, dtype=torch.float32)
+                _call("poet_nchw_to_tokens", _p(feats[l]), None, _p(x2), B, Cin, HW, HW, 0, _stream(x2))
+            else:
+                f = feats[-1]
+                Cin = f.shape[1] * 9
+                x2 = torch.empty((B * HW, Cin), device=tokens.device, dtype=torch.float32)
+                _call("poet_im2col_3x3s2", _p(f), _p(x2), B, f.shape[1], f.shape[2], f.shape[3], _stream(x2))
+            W2 = _chk(Wc).view(C, Cin)
+            y = gemm(x2, W2, B * HW, C, Cin, bias=bc, b_split=split_weight(W2, B * HW))
+            stats = torch.empty((B, groups, 2), device=tokens.device, dtype=torch.float64)
+            _call("poet_groupnorm_tokens_fwd", _p(y), _p(gw), _p(gb), _p(tokens), _p(stats), B, HW, C, groups, S, off,
+                  float(eps), _stream(y))
+            saved += [x2, y, stats]
+            off += HW
+        ctx.save_for_backward(*saved)
+        ctx.params, ctx.meta = params, (n_feats, groups, eps, B, C, S, dims)
+        return tokens
+
+    @staticmethod
+    def backward(ctx, g):
+        n_feats, groups, eps, B, C, S, dims = ctx.meta
+        g = _chk(g)
+        saved, params = ctx.saved_tensors, ctx.params
+        grads, off = [], 0
+        for l in range(len(params) // 4):
+            Wc, bc, gw, gb = params[4 * l: 4 * l + 4]
+            x2, y, stats = saved[3 * l: 3 * l + 3]
+            HW = dims[l][0] * dims[l][1]
+            Cin = x2.shape[1]
+            gw_slot, gb_slot = _grad_slot(gw), _grad_slot(gb)
+            dgw = gw_slot if gw_slot is not None else torch.zeros(C, device=g.device, dtype=torch.float32)
+            dgb = gb_slot if gb_slot is not None else torch.zeros(C, device=g.device, dtype=torch.float32)
+            dy = torch.empty_like(y)
+            ws = torch.empty((B, groups, 2), device=g.device, dtype=torch.float64)
+            _call("poet_groupnorm_tokens_bwd", _p(g), _p(y), _p(stats), _p(gw), _p(dy), _p(dgw), _p(dgb), _p(ws), B, HW, C,
+                  groups, S, off, float(eps), _stream(g))
+            w_slot, b_slot = _grad_slot(Wc), _grad_slot(bc)
+            dW = w_slot.view(C, Cin) if w_slot is not None else torch.zeros((C, Cin), device=g.device, dtype=torch.float32)
+            db = b_slot if b_slot is not None else torch.zeros(C, device=g.device, dtype=torch.float32)
+            wgrad_bias(dy, x2, C, Cin, B * HW, dW, db)
+            grads += [None if w_slot is not None else dW.view_as(Wc), None if b_slot is not None else db,
+                      None if gw_slot is not None else dgw, None if gb_slot is not None else dgb]
+            off += HW
+        return (None, None, None, *([None] * n_feats), *grads)
+
+
+def input_proj_tokens(feats: Sequence[torch.Tensor], levels: Sequence[Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]],
+                      groups: int = 32, eps: float = 1e-5) -> torch.Tensor:
+    """levels[l] = (conv weight, conv bias, GroupNorm weight, GroupNorm bias); returns the token matrix [B, S, C]."""
+    flat = [t for lv in levels for t in lv]
+    return _InputProj.apply(len(feats), groups, eps, *feats, *flat)

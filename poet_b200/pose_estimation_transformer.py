@@ -193,17 +193,17 @@ class PoET(nn.Module):
             R_all.append(R)
         return t_all, R_all
 
-    def _run_with_heads(self, srcs, masks, pos, qe, ref, pred_classes, pos_tokens=None):
+    def _run_with_heads(self, srcs, masks, pos, qe, ref, pred_classes, pos_tokens=None, src_tokens=None):
         """transformer + heads; with stream forking on, layer l's heads are issued on a side stream the moment
         decoder layer l is issued, so they (and their backward) overlap the rest of the decoder chain."""
         with ops.planes_scope(self):          # transformer + head weights -> bf16 planes, one launch
-            return self._run_with_heads_impl(srcs, masks, pos, qe, ref, pred_classes, pos_tokens)
+            return self._run_with_heads_impl(srcs, masks, pos, qe, ref, pred_classes, pos_tokens, src_tokens)
 
-    def _run_with_heads_impl(self, srcs, masks, pos, qe, ref, pred_classes, pos_tokens=None):
-        if not (ops.parallel_streams_enabled() and srcs[0].is_cuda):
-            hs = self.transformer(srcs, masks, pos, qe, ref, pos_tokens=pos_tokens)[0]
+    def _run_with_heads_impl(self, srcs, masks, pos, qe, ref, pred_classes, pos_tokens=None, src_tokens=None):
+        if not (ops.parallel_streams_enabled() and masks[0].is_cuda):
+            hs = self.transformer(srcs, masks, pos, qe, ref, pos_tokens=pos_tokens, src_tokens=src_tokens)[0]
             return self._heads(hs, pred_classes)
-        dev = srcs[0].device
+        dev = masks[0].device
         pending = []
 
         def on_layer(l, out):
@@ -213,7 +213,7 @@ class PoET(nn.Module):
                 t, R = self._head_layer(l, out, pred_classes)
                 pending.append((f, f.checkpoint(), t, R))
 
-        self.transformer(srcs, masks, pos, qe, ref, pos_tokens=pos_tokens, layer_callback=on_layer)
+        self.transformer(srcs, masks, pos, qe, ref, pos_tokens=pos_tokens, layer_callback=on_layer, src_tokens=src_tokens)
         t_all, R_all = [], []
         for f, ev, t, R in pending:
             f.wait(ev, t, R)
@@ -284,6 +284,33 @@ class PoET(nn.Module):
                                             pos_tokens=pos_tokens)
         return self._pack(t_all, R_all, pred_boxes, pred_classes) if pack else (t_all, R_all)
 
+    def forward_features(self, feats: Sequence[torch.Tensor], feat_masks: Sequence[torch.Tensor], image_mask: torch.Tensor,
+                         boxes, classes):
+        """Backbone feature maps -> output dict: input_proj + the hot path, all on our kernels.
+        feats[l] [B,Cin,H_l,W_l] with masks feat_masks[l] [B,H_l,W_l]; image_mask [B,H,W] is the padded-image mask the
+        extra level's mask is interpolated from (reference :326-334).  The projections are written token-major."""
+        if len(self.input_proj) == 0:
+            raise RuntimeError("this PoET was built without a backbone: no input_proj parameters")
+        pb, pc, counts, n_dev = self._pad_boxes(boxes, classes, feats[0].device)
+        qe = ops.bbox_embed_pad(pb, n_dev, int(self.hidden_dim // 8))
+        return self._features_to_outputs(feats, feat_masks, image_mask, qe, pb, pc), counts
+
+    def _features_to_outputs(self, feats, feat_masks, image_mask, qe, pb, pc):
+        masks = list(feat_masks)
+        h, w = int(feats[-1].shape[2]), int(feats[-1].shape[3])
+        for _ in range(len(feats), self.num_feature_levels):
+            h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+            masks.append(F.interpolate(image_mask[None].float(), size=(h, w)).to(torch.bool)[0])
+        with ops.planes_scope(self):
+            levels = [(ip[0].weight, ip[0].bias, ip[1].weight, ip[1].bias) for ip in self.input_proj]
+            src_tokens = ops.input_proj_tokens(list(feats), levels, groups=self.input_proj[0][1].num_groups,
+                                               eps=self.input_proj[0][1].eps)
+            C, S = src_tokens.shape[2], src_tokens.shape[1]
+            pos_tokens = _PosTokens.apply(self.transformer.level_embed, C, S, *masks)
+            t_all, R_all = self._run_with_heads(None, masks, None, qe, pb[:, :, :2].contiguous(), pc,
+                                                pos_tokens=pos_tokens, src_tokens=src_tokens)
+        return self._pack(t_all, R_all, pb, pc)
+
     def forward(self, samples, targets=None):
         samples = _as_nested(samples)
         image_hw = (int(samples.tensors.shape[-2]), int(samples.tensors.shape[-1]))
@@ -295,6 +322,14 @@ class PoET(nn.Module):
             qe, pb, pc, counts = self._queries_from_backbone(pred_objects, image_hw, dev)
         else:
             raise NotImplementedError("PoET Bounding Box Mode not implemented!")
+
+        if (dev.type == "cuda" and self.num_feature_levels > 1 and len(self.input_proj) == self.num_feature_levels
+                and self.num_feature_levels - len(features) in (0, 1)):
+            # input_proj + path on our kernels; position encodings are rebuilt from the masks in token layout
+            fm = [feat.decompose() for feat in features]
+            if any(m is None for _, m in fm):
+                raise ValueError("backbone features need padding masks")
+            return self._features_to_outputs([f for f, _ in fm], [m for _, m in fm], samples.mask, qe, pb, pc), counts
 
         srcs, masks, pos = [], [], list(pos)
         for lvl, feat in enumerate(features):

@@ -319,3 +319,76 @@ def test_edge_cases_vs_oracle(case):
         assert len(bad) <= max(1, len(loose) // 20), f"gradients off by more than 10 %: {bad[:8]}"
     finally:
         ops.set_gemm_precision(old)
+
+
+class _StubBackbone(torch.nn.Module):
+    """What PoET reads from a backbone: strides / num_channels to size input_proj, and a forward that returns
+    (feature maps with masks, position encodings, predictions); the maps are fixed seeded tensors (the detector
+    itself is outside the path)."""
+
+    def __init__(self, channels, feats=None, masks=None):
+        super().__init__()
+        self.strides, self.num_channels = [8, 16, 32], [channels] * 3
+        self.feats, self.masks = feats, masks
+
+    def forward(self, samples):
+        from poet_b200.pose_estimation_transformer import _Nested
+        return [_Nested(f, m) for f, m in zip(self.feats, self.masks)], [None] * len(self.feats), None
+
+
+@pytest.mark.parametrize("key", ["poet/tiny/pad1", "poet/tiny16/pad0", "poet/cfg1/pad0", "poet/cfg2_b2/pad1"])
+def test_input_proj_and_path_vs_reference_golden(key, precision):
+    """backbone feature maps -> input_proj (1x1 conv + GroupNorm, 3x3/s2 conv + GroupNorm) -> hot path,
+    all on our kernels, against the fixture produced by the unmodified reference PoET.forward on the same stub
+    feature maps: projected tokens vs the oracle, every decoder layer's pose, and the gradients of the input_proj
+    parameters."""
+    from poet_b200 import ops
+    from poet_b200.deformable_transformer import DeformableTransformer
+    from poet_b200.pose_estimation_transformer import PoET
+    from helpers import image_mask_for
+    g = load_golden(key)
+    cfg = S.CONFIGS[g["cfg"]]
+    P, feats, srcs, masks, inp, _, _, _ = oracle_poet_from_feats(cfg, g["pad"], need_grad=False)
+    tr = DeformableTransformer(cfg["d_model"], cfg["nheads"], cfg["enc_layers"], cfg["dec_layers"], cfg["dim_ff"], 0.0,
+                               "relu", True, cfg["n_levels"], cfg["n_points"], cfg["n_points"])
+    model = PoET(_StubBackbone(cfg["d_model"]), tr, cfg["num_queries"], cfg["n_levels"], cfg["n_classes"],
+                 class_mode=cfg["class_mode"])
+    model.load_state_dict({k: v.detach() for k, v in P.items()}, strict=True)
+    model = model.to(DEV).train()
+    d_feats = [f.detach().to(DEV) for f in feats]
+    levels = [(ip[0].weight, ip[0].bias, ip[1].weight, ip[1].bias) for ip in model.input_proj]
+    tokens = ops.input_proj_tokens(d_feats, levels)
+    ref_tokens = torch.cat([s.detach().flatten(2).transpose(1, 2) for s in srcs], 1)
+    tol = 2e-5 if precision == "fp32" else 1e-4
+    assert float((tokens.detach().cpu() - ref_tokens).abs().max()) < tol * max(1.0, float(ref_tokens.abs().max()))
+    out, n_boxes = model.forward_features(d_feats, [m.to(DEV) for m in inp["masks"][:3]],
+                                          image_mask_for(cfg, g["pad"]).to(DEV), inp["boxes"], inp["labels"])
+    assert n_boxes == g["n_boxes"]
+    t, R = stack_outputs(out)
+    assert float((t.detach().cpu() - g["translation"]).abs().max()) < TOL_T
+    assert float((R.detach().cpu() - g["rotation"]).abs().max()) < TOL_R
+    g_t, g_R = S.make_cotangents(cfg)
+    ((t * g_t.to(DEV)).sum() + (R * g_R.to(DEV)).sum()).backward()
+    checked, bad = 0, []
+    for name, p in model.named_parameters():
+        if not name.startswith("input_proj"):
+            continue
+        rec = g["grads"].get(name)
+        assert rec is not None and p.grad is not None, name
+        flat = p.grad.detach().cpu().flatten()
+        norm_err = abs(float(flat.double().norm()) - rec["norm"]) / max(rec["norm"], 1e-6)
+        scale = max(rec["norm"] / math.sqrt(flat.numel()), 1e-6)
+        err = float((flat[sample_indices(flat.numel())] - rec["samples"]).abs().max())
+        checked += 1
+        if norm_err > 0.1 or err > 3.0 * scale + 1e-5:
+            bad.append((name, norm_err, err / scale))
+    assert checked == 4 * cfg["n_levels"] and not bad, bad
+    # the reference-facing entry point model(samples, targets) takes the same route
+    from poet_b200.pose_estimation_transformer import _Nested
+    model.backbone.feats, model.backbone.masks = d_feats, [m.to(DEV) for m in inp["masks"][:3]]
+    img_mask = image_mask_for(cfg, g["pad"]).to(DEV)
+    samples = _Nested(torch.zeros(img_mask.shape[0], 3, *img_mask.shape[1:], device=DEV), img_mask)
+    targets = [{"boxes": b.to(DEV), "labels": l.to(DEV)} for b, l in zip(inp["boxes"], inp["labels"])]
+    out2, n2 = model(samples, targets)
+    assert n2 == n_boxes
+    assert torch.equal(out2["pred_translation"], out["pred_translation"]) and torch.equal(out2["pred_rotation"], out["pred_rotation"])

@@ -173,14 +173,23 @@ class ClockSampler:
         return out
 
 
-def build_gpu_model(cfg, dev):
+class _FeatureBackbone(torch.nn.Module):
+    """Sizes PoET.input_proj like the reference's Mask R-CNN FPN backbone (three 256-channel maps, backbone_maskrcnn.py:41-42)."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.strides, self.num_channels = [8, 16, 32], [channels] * 3
+
+
+def build_gpu_model(cfg, dev, with_input_proj=False):
     from poet_b200 import synthetic as S
     from poet_b200.deformable_transformer import DeformableTransformer
     from poet_b200.pose_estimation_transformer import PoET
     tr = DeformableTransformer(cfg["d_model"], cfg["nheads"], cfg["enc_layers"], cfg["dec_layers"], cfg["dim_ff"], 0.0,
                                "relu", True, cfg["n_levels"], cfg["n_points"], cfg["n_points"])
-    model = PoET(None, tr, cfg["num_queries"], cfg["n_levels"], cfg["n_classes"], class_mode=cfg["class_mode"])
-    model.load_state_dict(S.make_params(cfg), strict=True)
+    backbone = _FeatureBackbone(cfg["d_model"]) if with_input_proj else None
+    model = PoET(backbone, tr, cfg["num_queries"], cfg["n_levels"], cfg["n_classes"], class_mode=cfg["class_mode"])
+    model.load_state_dict(S.make_params(cfg, with_input_proj=with_input_proj), strict=True)
     return model.to(dev).train()
 
 
@@ -203,11 +212,15 @@ def run_gpu(args):
 
     cfg = S.CONFIGS[WORKLOAD]
     B = cfg["batch"]
-    model = build_gpu_model(cfg, dev)
+    model = build_gpu_model(cfg, dev, with_input_proj=args.from_features)
     model.micro_batches = args.micro_batches
     reducer = FlatGradReducer(model.parameters())
     inp = S.make_inputs(cfg, seed=1234 + rank)           # each rank owns a different image shard (weak scaling)
     g_t, g_R = (t.to(dev) for t in S.make_cotangents(cfg))
+    if args.from_features:                                  # three feature maps + their masks + the padded-image mask
+        H0, W0 = S.pyramid_of(cfg)[0]
+        inp["srcs"] = inp["srcs"][:3]
+        inp["masks"] = inp["masks"][:3] + [torch.zeros(B, H0 * 16, W0 * 16, dtype=torch.bool)]
     d_srcs = [s.to(dev) for s in inp["srcs"]]
     d_masks = [m.to(dev) for m in inp["masks"]]
     d_boxes = [b.to(dev) for b in inp["boxes"]]
@@ -236,9 +249,14 @@ def run_gpu(args):
         def loss_fn(out):
             return crit(out, tgt_t, tgt_R, n_boxes_dev)[1]
 
+    def fwd(srcs, masks, boxes, labels):
+        if args.from_features:
+            return model.forward_features(srcs, masks[:-1], masks[-1], boxes, labels)
+        return model.forward_pyramid(srcs, masks, boxes, labels)
+
     def eager_step(srcs, masks, boxes, labels):
         reducer.zero()
-        out, _ = model.forward_pyramid(srcs, masks, boxes, labels)
+        out, _ = fwd(srcs, masks, boxes, labels)
         loss = loss_fn(out)
         loss.backward()
         reducer.all_reduce()
@@ -257,7 +275,8 @@ def run_gpu(args):
     graphed = None
     if args.graph:
         from poet_b200.graph import GraphedStep
-        graphed = GraphedStep(model, loss_fn, d_srcs, d_masks, d_boxes, d_labels, reducer=reducer, optimizer=opt)
+        graphed = GraphedStep(model, loss_fn, d_srcs, d_masks, d_boxes, d_labels, reducer=reducer, optimizer=opt,
+                              entry="features" if args.from_features else "pyramid")
 
         def step(srcs=None, masks=None, boxes=None, labels=None):
             loss, out = graphed.run(srcs, masks, boxes, labels)
@@ -354,7 +373,7 @@ def run_gpu(args):
 
     def local_step():                                   # no collective: only rank 0 runs the table pass
         reducer.zero()
-        out, _ = model.forward_pyramid(d_srcs, d_masks, d_boxes, d_labels)
+        out, _ = fwd(d_srcs, d_masks, d_boxes, d_labels)
         loss_fn(out).backward()
 
     l0 = ops.launch_count()
@@ -390,6 +409,8 @@ def run_gpu(args):
                                             "gemm_precision": args.precision,
                                             "launch": "one CUDA graph per step" if args.graph else "eager",
                                             "micro_batches": args.micro_batches,
+                                            "entry": ("backbone feature maps (input_proj inside the step)" if args.from_features
+                                                      else "post-input_proj pyramid"),
                                             "loss": ("on-device PoseCriterion (SetCriterion + 'gt' matcher), synthetic targets" if args.criterion
                                                      else "fixed-cotangent loss (SURVEY.md section 8d)"),
                                             "optimizer": "fused clip_grad_norm_(0.1) + AdamW inside every step" if opt is not None else "none (forward + backward [+ all-reduce])",
@@ -470,6 +491,8 @@ def main():
     ap.add_argument("--no-kernel-table", dest="kernel_table", action="store_false")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", dest="graph", action="store_false")
+    ap.add_argument("--from-features", action="store_true",
+                    help="start from three backbone feature maps [B,256,H_l,W_l]: input_proj (SURVEY.md 8f N1) is part of the step")
     ap.add_argument("--criterion", action="store_true",
                     help="back-propagate the on-device PoseCriterion (reference SetCriterion + 'gt' matcher) instead of the "
                          "fixed-cotangent loss of SURVEY.md section 8d")

@@ -35,10 +35,13 @@ from .data_parallel import FlatGradReducer
 class GraphedStep:
     def __init__(self, model, loss_fn: Callable, srcs: Sequence[torch.Tensor], masks: Sequence[torch.Tensor],
                  boxes, labels, reducer: Optional[FlatGradReducer] = None, warmup: int = 3, backward: bool = True,
-                 optimizer=None):
+                 optimizer=None, entry: str = "pyramid"):
         """optimizer (poet_b200.optim.FusedClipAdamW, optional): its step() writes the bf16 planes of the updated
         weights, so the captured step contains no split pass; call optimizer.step() after every run()."""
         dev = next(model.parameters()).device
+        # entry "pyramid": srcs = post-input_proj maps, masks = their masks (the benchmarked path);
+        # entry "features": srcs = backbone feature maps, masks = their masks + [padded-image mask] (input_proj included)
+        self.entry = entry
         self.model, self.loss_fn, self.backward = model, loss_fn, backward
         self.external_planes = optimizer is not None and getattr(optimizer, "planes", None) is not None
         self.reducer = reducer if reducer is not None else (FlatGradReducer(model.parameters()) if backward else None)
@@ -72,7 +75,11 @@ class GraphedStep:
         if self.reducer is not None:
             self.reducer.zero()
         with ops.planes_scope(self.model, refresh=not self.external_planes):
-            out = self.model.forward_padded(self.s_srcs, self.s_masks, self.s_boxes, self.s_classes, self.s_counts)
+            if self.entry == "features":
+                out = self.model.forward_features_padded(self.s_srcs, self.s_masks[:-1], self.s_masks[-1], self.s_boxes,
+                                                         self.s_classes, self.s_counts)
+            else:
+                out = self.model.forward_padded(self.s_srcs, self.s_masks, self.s_boxes, self.s_classes, self.s_counts)
         loss = self.loss_fn(out)
         if self.backward:
             loss.backward()

@@ -295,6 +295,11 @@ class PoET(nn.Module):
         qe = ops.bbox_embed_pad(pb, n_dev, int(self.hidden_dim // 8))
         return self._features_to_outputs(feats, feat_masks, image_mask, qe, pb, pc), counts
 
+    def forward_features_padded(self, feats, feat_masks, image_mask, pred_boxes, pred_classes, n_boxes_dev):
+        """Device-only form of forward_features (padded boxes / classes / counts already on the device): capturable."""
+        qe = ops.bbox_embed_pad(pred_boxes, n_boxes_dev, int(self.hidden_dim // 8))
+        return self._features_to_outputs(feats, feat_masks, image_mask, qe, pred_boxes, pred_classes)
+
     def _features_to_outputs(self, feats, feat_masks, image_mask, qe, pb, pc):
         masks = list(feat_masks)
         h, w = int(feats[-1].shape[2]), int(feats[-1].shape[3])

@@ -147,14 +147,20 @@ int poet_gemm_bsplit(const float* A, int64_t lda, int a_kcontig, const float* Bm
  *   a_colsum (weight-gradient shape only: a_kcontig = b_kcontig = 0, no pre-split B): a_colsum[m] += sum_k A[k,m],
  *   i.e. the bias gradient colsum(dY) accumulated while the dY tiles stream through the producers (caller
  *   zero-fills or passes an existing gradient).
+ *   a_row_mask (nullable): uint8 per STORED row of A (a token in every GEMM of this path, whether A is [M,K] or
+ *   [K,M]); rows with a non-zero entry are read as zeros: the backward of MSDeformAttn's value masked_fill applied
+ *   while the gradient streams through the producers instead of by poet_mask_rows.
  * Returns POET_ERR_UNSUPPORTED when the shape is not tensor-core eligible (ask poet_gemm_relu_bits_supported()). */
 int poet_gemm_relu_bits_supported(int M, int N, int K, int precision);
 int poet_gemm_ex(const float* A, int64_t lda, int a_kcontig, const float* Bm, const void* B_hi, const void* B_lo,
                  int64_t ldb, int b_kcontig, float* C, int64_t ldc, int M, int N, int K, float alpha,
                  const float* bias, const uint8_t* row_mask, uint32_t* relu_bits_out, const uint32_t* gate_bits,
-                 float* a_colsum, int flags, int precision, poet_stream_t stream);
+                 float* a_colsum, const uint8_t* a_row_mask, int flags, int precision, poet_stream_t stream);
 /* out[N] (+)= sum_m X[m,n]  (bias gradients).  accumulate=0 overwrites. */
 int poet_colsum(const float* X, int64_t ldx, float* out, int M, int N, int accumulate, poet_stream_t stream);
+/* the same, skipping rows with row_mask[m] != 0 (row_mask nullable) */
+int poet_colsum_masked(const float* X, int64_t ldx, const uint8_t* row_mask, float* out, int M, int N, int accumulate,
+                       poet_stream_t stream);
 
 /* ---- residual + LayerNorm ---------------------------------------------------------------- */
 /* z = x + r (r nullable); y = LN(z)*gamma + beta; y2 = y + pos (if y2 != NULL);

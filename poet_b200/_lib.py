@@ -36,7 +36,8 @@ SIGNATURES = {
     "poet_gemm_tc_eligible": (_i, [_i, _i, _i, _i64, _i64, _i64]),
     "poet_gemm_bsplit": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp]),
     "poet_gemm_relu_bits_supported": (_i, [_i, _i, _i, _i]),
-    "poet_gemm_ex": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "poet_gemm_ex": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "poet_colsum_masked": (_i, [_vp, _i64, _vp, _vp, _i, _i, _i, _vp]),
     "poet_colsum": (_i, [_vp, _i64, _vp, _i, _i, _i, _vp]),
     "poet_mask_rows": (_i, [_vp, _vp, _i, _i, _vp]),
     "poet_add_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),

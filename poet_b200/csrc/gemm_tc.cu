@@ -139,6 +139,7 @@ struct Args {
   const float* bias; const float* gate; const uint8_t* row_mask;
   uint32_t* relu_bits;                    // [M, N/32] sign bitmask of the ReLU output (TMA epilogue only)
   const uint32_t* gate_bits;              // [M, N/32] keep-mask for the ReLU backward (TMA epilogue only)
+  const uint8_t* a_row_mask;              // rows of the stored A operand (tokens) to read as zeros, or nullptr
   float* a_colsum;                        // weight-gradient shape only: a_colsum[m] += sum_k A[k, m] (the bias gradient), or nullptr
   int flags;
   int kb_per_split;       // k-blocks (of BK) per split
@@ -213,8 +214,10 @@ struct Tile {
   static constexpr int CH = CHUNKS / NT;
   static_assert(CHUNKS % NT == 0, "tile / thread mismatch");
 
+  // row_mask (nullable): stored rows of the operand with row_mask[row] != 0 are read as zeros (the masked_fill
+  // backward of MSDeformAttn.value_proj, applied on the fly instead of by a separate pass over the gradient)
   __device__ static __forceinline__ void load(const float* __restrict__ G, int64_t ld, int row0, int row_end, int col0,
-                                              int col_end, int tid, float4 (&v)[CH][2]) {
+                                              int col_end, int tid, float4 (&v)[CH][2], const uint8_t* __restrict__ row_mask = nullptr) {
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
       const int ch = tid + i * NT;
@@ -223,7 +226,7 @@ struct Tile {
       const int grow = row0 + row, gcol = col0 + seg * 64 + c * 8;
       v[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
       v[i][1] = v[i][0];
-      if (grow < row_end && gcol < col_end) {                    // col_end % 8 == 0 (checked on the host)
+      if (grow < row_end && gcol < col_end && !(row_mask != nullptr && row_mask[grow] != 0)) {   // col_end % 8 == 0 (host)
         const float* p = G + (int64_t)grow * ld + gcol;
         v[i][0] = ldg4(p);
         v[i][1] = ldg4(p + 4);
@@ -397,8 +400,8 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
         for (int i = 0; i < TA::CH; ++i) { v[i][0] = make_float4(1.f, 1.f, 1.f, 1.f); v[i][1] = v[i][0]; }
       } else {
         const int k0 = (wk.kb0 + kb) * BK;
-        if (A_MN) TA::load(p.A, p.lda, k0, p.K, wk.m0, p.M, tid, v);
-        else      TA::load(p.A, p.lda, wk.m0, p.M, k0, p.K, tid, v);
+        if (A_MN) TA::load(p.A, p.lda, k0, p.K, wk.m0, p.M, tid, v, p.a_row_mask);
+        else      TA::load(p.A, p.lda, wk.m0, p.M, k0, p.K, tid, v, p.a_row_mask);
       }
       if constexpr (B_PREFETCH) {
         const int k0 = (wk.kb0 + kb) * BK;
@@ -858,7 +861,7 @@ int poet_gemm_tc_bits_supported() {
 int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, const void* b_hi, const void* b_lo,
                  int64_t ldb, int b_kcontig, float* C, int64_t ldc, int M, int N, int K, float alpha, const float* bias,
                  const float* gate, const uint8_t* row_mask, uint32_t* relu_bits, const uint32_t* gate_bits, float* a_colsum,
-                 int flags, int precision, cudaStream_t s) {
+                 const uint8_t* a_row_mask, int flags, int precision, cudaStream_t s) {
   POET_REQUIRE(poet_aligned16(A) && poet_aligned16(C), POET_ERR_BAD_ALIGNMENT);
   POET_REQUIRE(!bias || poet_aligned16(bias), POET_ERR_BAD_ALIGNMENT);
   POET_REQUIRE(!gate || poet_aligned16(gate), POET_ERR_BAD_ALIGNMENT);
@@ -877,7 +880,7 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
   const int bk = wgrad ? 32 : 64;
   tc::Args a;
   a.A = A; a.lda = lda; a.B = b_tma ? nullptr : Bm; a.ldb = ldb; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
-  a.alpha = alpha; a.bias = bias; a.gate = gate; a.row_mask = row_mask; a.relu_bits = relu_bits; a.gate_bits = gate_bits; a.a_colsum = a_colsum;
+  a.alpha = alpha; a.bias = bias; a.gate = gate; a.row_mask = row_mask; a.relu_bits = relu_bits; a.gate_bits = gate_bits; a.a_colsum = a_colsum; a.a_row_mask = a_row_mask;
   a.flags = flags;
   a.epi_tma = epi_tma; a.l2_prefetch = l2pf; a.debug = dbg;
   const int m_tiles = poet_ceil_div(M, tc::BM);

@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 // alternate rows of a 64-row chunk (8 independent 128-bit loads in flight per thread); per-block partials
 // are combined in smem and leave as one atomic per column.  Tail columns (N % 4 != 0) use the scalar path.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int64_t ldx, float* __restrict__ out,
-                                                     int M, int N, int rows_per_block, int vec) {
+                                                     int M, int N, int rows_per_block, int vec,
+                                                     const uint8_t* __restrict__ row_mask) {
   poet_pdl_entry();
   __shared__ float part[8][128];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -120,11 +121,13 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
   if (vec && c0 + 3 < N) {
 #pragma unroll 4
     for (int r = r0 + w; r < r1; r += 8) {
+      if (row_mask != nullptr && row_mask[r] != 0) continue;
       const float4 v = ldg4(X + (int64_t)r * ldx + c0);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
   } else {
     for (int r = r0 + w; r < r1; r += 8) {
+      if (row_mask != nullptr && row_mask[r] != 0) continue;
       const float* p = X + (int64_t)r * ldx + c0;
       if (c0 + 0 < N) acc.x += __ldg(p + 0);
       if (c0 + 1 < N) acc.y += __ldg(p + 1);
@@ -212,6 +215,11 @@ extern "C" int poet_layernorm_bwd(const float* dy, const float* dy2, const float
 }
 
 extern "C" int poet_colsum(const float* X, int64_t ldx, float* out, int M, int N, int accumulate, poet_stream_t stream) {
+  return poet_colsum_masked(X, ldx, nullptr, out, M, N, accumulate, stream);
+}
+
+extern "C" int poet_colsum_masked(const float* X, int64_t ldx, const uint8_t* row_mask, float* out, int M, int N,
+                                  int accumulate, poet_stream_t stream) {
   POET_REQUIRE(X && out, POET_ERR_NULL_POINTER);
   POET_REQUIRE(M > 0 && N > 0 && ldx >= N, POET_ERR_BAD_SHAPE);
   cudaStream_t s = (cudaStream_t)stream;
@@ -224,7 +232,7 @@ extern "C" int poet_colsum(const float* X, int64_t ldx, float* out, int M, int N
   while ((int64_t)poet_ceil_div(M, rows_per_block) * col_tiles > 8 * POET_NUM_SMS) rows_per_block *= 2;
   const int row_chunks = poet_ceil_div(M, rows_per_block);
   const int vec = poet_aligned16(X) && (ldx % 4 == 0);
-  poet_launch(colsum_kernel, dim3(col_tiles, row_chunks), dim3(256), 0, s, X, ldx, out, M, N, rows_per_block, vec);
+  poet_launch(colsum_kernel, dim3(col_tiles, row_chunks), dim3(256), 0, s, X, ldx, out, M, N, rows_per_block, vec, row_mask);
   return poet_launch_status();
 }
 

@@ -191,7 +191,8 @@ def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_kcontig
          lda: Optional[int] = None, ldb: Optional[int] = None, bias=None, relu=False, gate=None, row_mask=None,
          out: Optional[torch.Tensor] = None, accumulate=False, alpha: float = 1.0,
          precision: Optional[int] = None, b_split=None, relu_bits: Optional[torch.Tensor] = None,
-         gate_bits: Optional[torch.Tensor] = None, a_colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+         gate_bits: Optional[torch.Tensor] = None, a_colsum: Optional[torch.Tensor] = None,
+         a_row_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[M,N] = epi(alpha * op(A) @ op(B)); see include/poet_b200.h poet_gemm / poet_gemm_ex.
     relu_bits (out) / gate_bits (in): int32 [M, N/32] sign bitmask of a ReLU (tensor-core path only)."""
     if out is None:
@@ -207,12 +208,12 @@ def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_kcontig
     flags = (1 if relu else 0) | (2 if accumulate else 0)
     tag = (f"{M}x{N}x{K}" + ("" if a_kcontig else ",At") + ("" if b_kcontig else ",Bt")) if _timing["on"] else None
     work = (4 * (M * K + N * K + M * N), 2 * M * N * K)
-    if relu_bits is not None or gate_bits is not None or a_colsum is not None:
+    if relu_bits is not None or gate_bits is not None or a_colsum is not None or a_row_mask is not None:
         assert gate is None and prec != GEMM_FP32
         bs = b_split if (b_split is not None and a_kcontig) else (None, None)
         _call("poet_gemm_ex", _p(A), lda, int(a_kcontig), _p(Bm), _p(bs[0]), _p(bs[1]), ldb, int(b_kcontig), _p(out),
-              out.stride(0), M, N, K, alpha, _p(bias), _p(row_mask), _p(relu_bits), _p(gate_bits), _p(a_colsum), flags,
-              prec, _stream(A), tag=tag, work=work)
+              out.stride(0), M, N, K, alpha, _p(bias), _p(row_mask), _p(relu_bits), _p(gate_bits), _p(a_colsum),
+              _p(a_row_mask), flags, prec, _stream(A), tag=tag, work=work)
         return out
     if b_split is not None and prec != GEMM_FP32 and a_kcontig:
         _call("poet_gemm_bsplit", _p(A), lda, int(a_kcontig), _p(Bm), _p(b_split[0]), _p(b_split[1]), ldb,
@@ -407,7 +408,7 @@ def relu_bits_buffer(R: int, N: int, K: int, device) -> Optional[torch.Tensor]:
 
 
 def wgrad_bias(gy2: torch.Tensor, x2: torch.Tensor, N: int, K: int, R: int, w_out: torch.Tensor, b_out: Optional[torch.Tensor],
-               lda: Optional[int] = None) -> None:
+               lda: Optional[int] = None, row_mask: Optional[torch.Tensor] = None) -> None:
     """w_out[N,K] += gy2[R,N]^T x2[R,K] and, if given, b_out[N] += colsum(gy2): one launch when the weight-gradient GEMM
     runs on the tensor-core path (the bias gradient is summed from the dY tiles as they stream through the
     producers), else the GEMM plus a separate column-sum kernel.  gy2 may be a column block (lda = row stride)."""
@@ -418,9 +419,9 @@ def wgrad_bias(gy2: torch.Tensor, x2: torch.Tensor, N: int, K: int, R: int, w_ou
     fused = (b_out is not None and prec != GEMM_FP32 and R <= 2048 and
              _lib.lib().poet_gemm_tc_eligible(N, K, R, lda, K, w_out.stride(0)))
     gemm(gy2, x2, N, K, R, a_kcontig=False, b_kcontig=False, lda=lda, out=w_out, accumulate=True,
-         a_colsum=b_out if fused else None)
+         a_colsum=b_out if fused else None, a_row_mask=row_mask)
     if b_out is not None and not fused:
-        _call("poet_colsum", _p(gy2), lda, _p(b_out), R, N, 1, _stream(gy2))
+        _call("poet_colsum_masked", _p(gy2), lda, _p(row_mask), _p(b_out), R, N, 1, _stream(gy2))
 
 
 def colsum(X: torch.Tensor, M: int, N: int, out: Optional[torch.Tensor] = None, accumulate=False) -> torch.Tensor:
@@ -464,15 +465,17 @@ def set_direct_param_grads(on: bool) -> None:
 
 def _linear_bwd(gy2: torch.Tensor, x2: torch.Tensor, W: torch.Tensor, need_x: bool, need_w: bool, need_b: bool,
                 gate: Optional[torch.Tensor] = None, w_split=None, w_param=None, b_param=None,
-                gate_bits: Optional[torch.Tensor] = None):
+                gate_bits: Optional[torch.Tensor] = None, gy_row_mask: Optional[torch.Tensor] = None):
     """gy2 [R,N], x2 [R,K], W [N,K] -> (dx [R,K] (gated by `gate`>0 if given), dW [N,K], db [N]).
     dW / db come back as None when they were accumulated directly into the parameters' .grad."""
     R, N = gy2.shape
     K = x2.shape[1]
     if gate_bits is not None:
         gate = None
+    # gy_row_mask: rows of gy2 to treat as zero (value masked_fill backward).  Zero rows of dY give zero rows of dX,
+    # so the dgrad applies it as an output row mask; the weight / bias gradients read dY through the masked producer.
     dx = gemm(gy2, W, R, K, N, a_kcontig=True, b_kcontig=False, gate=gate, b_split=w_split,
-              gate_bits=gate_bits) if need_x else None
+              gate_bits=gate_bits, row_mask=gy_row_mask) if need_x else None
     dW = db = None
     w_slot = _grad_slot(w_param) if need_w else None
     b_slot = _grad_slot(b_param) if need_b else None
@@ -487,16 +490,17 @@ def _linear_bwd(gy2: torch.Tensor, x2: torch.Tensor, W: torch.Tensor, need_x: bo
         side.__enter__()
     try:
         if w_slot is not None:
-            wgrad_bias(gy2, x2, N, K, R, w_slot, b_slot)
+            wgrad_bias(gy2, x2, N, K, R, w_slot, b_slot, row_mask=gy_row_mask)
         elif b_slot is not None:
-            colsum(gy2, R, N, out=b_slot, accumulate=True)
+            _call("poet_colsum_masked", _p(gy2), N, _p(gy_row_mask), _p(b_slot), R, N, 1, _stream(gy2))
     finally:
         if side is not None:
             side.__exit__(None, None, None)
     if need_w and w_slot is None:
-        dW = gemm(gy2, x2, N, K, R, a_kcontig=False, b_kcontig=False)
+        dW = gemm(gy2, x2, N, K, R, a_kcontig=False, b_kcontig=False, a_row_mask=gy_row_mask)
     if need_b and b_slot is None:
-        db = colsum(gy2, R, N)
+        db = torch.zeros(N, device=gy2.device, dtype=torch.float32)
+        _call("poet_colsum_masked", _p(gy2), N, _p(gy_row_mask), _p(db), R, N, 1, _stream(gy2))
     return dx, dW, db
 
 
@@ -573,11 +577,17 @@ class _Linear(torch.autograd.Function):
     def backward(ctx, gy):
         x2, W = ctx.saved_tensors
         gy2 = _chk(gy).view(-1, gy.shape[-1])
+        gy_mask = None
         if ctx.row_mask is not None:
-            gy2 = mask_rows_(gy2 if ctx.mask_grad_inplace else gy2.clone(), ctx.row_mask)
+            R, N, K = gy2.shape[0], gy2.shape[1], x2.shape[1]
+            if (_state["precision"] != GEMM_FP32 and _os.environ.get("POET_FUSE_ROW_MASK", "1") != "0" and
+                    _lib.lib().poet_gemm_tc_eligible(N, K, R, N, K, K)):
+                gy_mask = ctx.row_mask            # applied inside the dgrad epilogue / wgrad producers / masked colsum
+            else:
+                gy2 = mask_rows_(gy2 if ctx.mask_grad_inplace else gy2.clone(), ctx.row_mask)
         dx, dW, db = _linear_bwd(gy2, x2, W, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
                                  ctx.has_bias and ctx.needs_input_grad[2], w_split=ctx.w_split,
-                                 w_param=ctx.w_param, b_param=ctx.b_param)
+                                 w_param=ctx.w_param, b_param=ctx.b_param, gy_row_mask=gy_mask)
         return (dx.view(ctx.xshape) if dx is not None else None), dW, db, None, None
 
 

@@ -226,10 +226,18 @@ struct Tile {
       const int grow = row0 + row, gcol = col0 + seg * 64 + c * 8;
       v[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
       v[i][1] = v[i][0];
-      if (grow < row_end && gcol < col_end && !(row_mask != nullptr && row_mask[grow] != 0)) {   // col_end % 8 == 0 (host)
+      if (grow < row_end && gcol < col_end) {                    // col_end % 8 == 0 (checked on the host)
         const float* p = G + (int64_t)grow * ld + gcol;
         v[i][0] = ldg4(p);
         v[i][1] = ldg4(p + 4);
+      }
+    }
+    if (row_mask != nullptr) {                                   // after the data loads are in flight: no added latency
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const int rs = (tid + i * NT) >> 3;
+        const int grow = row0 + rs % ROWS;
+        if (grow < row_end && __ldg(row_mask + grow) != 0) { v[i][0] = make_float4(0.f, 0.f, 0.f, 0.f); v[i][1] = v[i][0]; }
       }
     }
   }

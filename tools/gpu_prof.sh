@@ -1,11 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 O=gpurun_out
-T0=$(date +%s)
-which compute-sanitizer || ls /usr/local/cuda/bin | grep -i sanit
-timeout 420 compute-sanitizer --tool memcheck --error-exitcode 3 --print-limit 20 python -m pytest tests/test_gpu_ops.py -m gpu -x -q -k "msda_block or relu_bitmask or mha or layernorm or heads or wgrad_accumulate or posenc or flatten" > $O/sanitizer_memcheck.log 2>&1; echo "memcheck rc=$?" >> $O/sanitizer_memcheck.log
-tail -15 $O/sanitizer_memcheck.log
-echo "memcheck done $(( $(date +%s) - T0 )) s"
-timeout 300 compute-sanitizer --tool racecheck --error-exitcode 3 --print-limit 20 python -m pytest tests/test_gpu_ops.py -m gpu -x -q -k "msda_block or relu_bitmask" > $O/sanitizer_racecheck.log 2>&1; echo "racecheck rc=$?" >> $O/sanitizer_racecheck.log
-tail -15 $O/sanitizer_racecheck.log
-echo "all done $(( $(date +%s) - T0 )) s"
+timeout 300 python -m pytest tests/test_gpu_model.py -m gpu -x -q -k "oracle_all_grads or golden" > $O/t_mask.log 2>&1; echo "rc=$?" >> $O/t_mask.log; tail -3 $O/t_mask.log
+for fm in 1 0 1 0; do
+POET_FUSE_ROW_MASK=$fm timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-kernel-table > $O/bench_fm$fm.json 2> $O/bench_fm$fm.err
+python -c "import json; d=json.loads([l for l in open('$O/bench_fm$fm.json') if l.startswith('{')][-1]); print('fuse_mask=$fm', round(d['value'],1), round(d['ms_per_step'],3), round(d['e2e']['value'],1))"
+done

@@ -145,6 +145,7 @@ struct Args {
   int kb_per_split;       // k-blocks (of BK) per split
   int splits;
   int n_tiles, total_work;
+  int tail_start, tail_slices;   // work ids >= tail_start are column slices of the last round's tiles (tail_start = total_work: none)
   int epi_tma;            // 1: TMA-store epilogue, 0: smem-transpose + st.global epilogue
   int l2_prefetch;        // 1: L2 prefetch hints ahead of the register-prefetched operand loads
   int debug;              // POET_GEMM_DEBUG bit flags (pipeline bisection only): 1 no A loads, 2 no A stores, 4 no TMA, 8 no epilogue stores,
@@ -152,17 +153,31 @@ struct Args {
 };
 
 // work item w -> (m0, n0, split, k-block range); n fastest so concurrent CTAs share A rows in L2
+// Tail splitting: with T tiles on G = 148 persistent CTAs the last, partial round leaves most SMs idle for a whole
+// tile time ([25600 x 256] outputs: 200 tiles = 1.35 rounds).  The T % G tiles of that round are therefore cut
+// into tail_slices column slices of bn / tail_slices columns each (work ids >= tail_start), so the last round is a
+// full one of a fraction of the duration.  A slice is the same work item with a narrower MMA N / epilogue width.
 struct Work {
-  int m0, n0, split, kb0, nkb;
+  int m0, n0, split, kb0, nkb, bn;
 };
 template <int BK>
 __device__ __forceinline__ Work decode(const Args& p, int w, int bn) {
   Work k;
+  const int total_kb = (p.K + BK - 1) / BK;
+  if (w >= p.tail_start) {                                   // only set up when splits == 1
+    const int t = w - p.tail_start;
+    const int tile = p.tail_start + t / p.tail_slices, sl = t % p.tail_slices;
+    k.bn = bn / p.tail_slices;
+    k.n0 = (tile % p.n_tiles) * bn + sl * k.bn;
+    k.m0 = (tile / p.n_tiles) * BM;
+    k.split = 0; k.kb0 = 0; k.nkb = total_kb;
+    return k;
+  }
   k.split = w % p.splits;
   const int tile = w / p.splits;
+  k.bn = bn;
   k.n0 = (tile % p.n_tiles) * bn;
   k.m0 = (tile / p.n_tiles) * BM;
-  const int total_kb = (p.K + BK - 1) / BK;
   k.kb0 = k.split * p.kb_per_split;
   k.nkb = min(total_kb, k.kb0 + p.kb_per_split) - k.kb0;
   return k;
@@ -483,7 +498,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
   } else if (warp == PW) {
     if (lane == 0) {
       // ===================== MMA issuer (one thread) =====================
-      constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+
       // K-major: 8-row groups 1024 B apart, a 16-wide k-step is 32 B inside the 128 B swizzle row.
       // MN-major: 64-element m/n groups BK*128 B apart (LBO), 8-row k groups 1024 B apart (SBO),
       //           a 16-wide k-step is two k groups = 2048 B.
@@ -496,6 +511,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
         if (tcnt >= 2) mbar_wait(tempty0 + 8 * ab, ((tcnt >> 1) - 1) & 1);    // epilogue drained this buffer
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(ab * BN);
+        const uint32_t idesc = make_idesc(wk.bn, A_MN, B_MN);      // MMA N = this item's width (BN, or a tail slice)
         for (int i = 0; i < wk.nkb; ++i, ++it) {
           const int s = it % STAGES;
           mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
@@ -580,7 +596,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
         const bool has_bias = p.bias != nullptr && wk.split == 0;
         if (has_bias) {
           asm volatile("bar.sync 1, 128;" ::: "memory");             // every epilogue warp is done with the previous slice
-          if (et * 2 < BN) {
+          if (et * 2 < wk.bn) {
             const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.bias + wk.n0 + et * 2));
             asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_s + et * 8), "f"(b2.x), "f"(b2.y) : "memory");
           }
@@ -589,10 +605,10 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
         mbar_wait(tfull0 + 8 * ab, (tcnt >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int col = 0; col < BN; col += 32) {
+        for (int col = 0; col < wk.bn; col += 32) {
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN + col), v);
-          if (col + 32 >= BN) {                                      // last read of this accumulator: release it
+          if (col + 32 >= wk.bn) {                                      // last read of this accumulator: release it
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * ab);
@@ -678,10 +694,10 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
         mbar_wait(tfull0 + 8 * ab, (tcnt >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int col = 0; col < BN; col += 32) {
+        for (int col = 0; col < wk.bn; col += 32) {
           float v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN + col), v);
-          if (col + 32 >= BN) {                                        // last read of this accumulator: release it
+          if (col + 32 >= wk.bn) {                                        // last read of this accumulator: release it
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * ab);
@@ -919,6 +935,18 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
   a.splits = poet_ceil_div(total_kb, a.kb_per_split);
   a.n_tiles = N / bn;
   a.total_work = a.n_tiles * m_tiles * a.splits;
+  a.tail_start = a.total_work; a.tail_slices = 1;
+  static const int tail_split = tc::env_int("POET_GEMM_TAIL_SPLIT", 1);
+  if (tail_split && a.splits == 1 && !wgrad && a.total_work > POET_NUM_SMS) {
+    const int rem = a.total_work % POET_NUM_SMS;
+    int sl = 1;
+    while (rem > 0 && sl * 2 <= bn / 64 && rem * sl * 2 <= POET_NUM_SMS + POET_NUM_SMS / 4) sl *= 2;
+    if (sl > 1) {
+      a.tail_start = a.total_work - rem;
+      a.tail_slices = sl;
+      a.total_work = a.tail_start + rem * sl;
+    }
+  }
   if (a.splits > 1 && !(flags & POET_GEMM_ACCUMULATE)) {
     cudaError_t e = cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s);
     if (e != cudaSuccess) return (int)e;

@@ -136,16 +136,16 @@ def golden_transformer(cfg_name: str, pad: bool):
 
 class _StubDetector(nn.Module):
     """Stands in for MaskRCNNBackbone: returns seeded feature maps as NestedTensors."""
-    def __init__(self, feats, masks):
+    def __init__(self, feats, masks, predictions=None):
         super().__init__()
-        self.feats, self.masks = feats, masks
+        self.feats, self.masks, self.predictions = feats, masks, predictions
         self.train_backbone = False
         self.strides = [8, 16, 32]
         self.num_channels = [feats[0].shape[1]] * 3
 
     def forward(self, samples):
         from util.misc import NestedTensor
-        return None, {str(i): NestedTensor(f, m) for i, (f, m) in enumerate(zip(self.feats, self.masks))}
+        return self.predictions, {str(i): NestedTensor(f, m) for i, (f, m) in enumerate(zip(self.feats, self.masks))}
 
 
 def golden_poet(cfg_name: str, pad: bool):
@@ -187,6 +187,55 @@ def golden_poet(cfg_name: str, pad: bool):
                 pred_boxes=out["pred_boxes"].detach(), pred_classes=out["pred_classes"].detach(),
                 n_boxes=n_boxes, loss=float(loss), grads=grad_digest(named), image_mask_shape=tuple(image_mask.shape),
                 fp_inputs=S.fingerprint(inp["srcs"][:3]))
+
+
+def backbone_predictions(cfg, image_hw, seed=321):
+    """Detector output per image for the 'backbone' bbox mode: [n, 6] = (x1, y1, x2, y2, score, class) in pixels, or None.
+    Image 0: nothing detected; image 1: fewer than Q boxes; image 2: more than Q (top-Q by score is taken)."""
+    g = torch.Generator().manual_seed(seed)
+    Q, (H, W) = cfg["num_queries"], image_hw
+    preds = [None]
+    for n in (max(1, Q - 2), Q + 3):
+        cxy = torch.rand(n, 2, generator=g) * 0.5 + 0.25
+        wh = torch.rand(n, 2, generator=g) * 0.25 + 0.05
+        x1y1, x2y2 = (cxy - wh / 2) * torch.tensor([W, H]), (cxy + wh / 2) * torch.tensor([W, H])
+        score = torch.rand(n, 1, generator=g)
+        cls = torch.randint(1, cfg["n_classes"] + 1, (n, 1), generator=g).float()
+        preds.append(torch.cat((x1y1, x2y2, score, cls), 1))
+    return preds
+
+
+def golden_poet_backbone_mode(cfg_name: str = "tiny16"):
+    """Reference PoET.forward in inference mode (bbox_mode='backbone', targets=None): query construction from detector
+    output (pose_estimation_transformer.py:240-305: xyxy -> normalised cxcywh, top-Q by score, the `predictions is None`
+    branch) + the path.  SURVEY.md section 8f N4."""
+    from models.backbone import Joiner
+    from models.position_encoding import PositionEmbeddingSine
+    from models.deformable_transformer import build_deforamble_transformer
+    from models.pose_estimation_transformer import PoET
+    from util.misc import NestedTensor
+    cfg = dict(S.CONFIGS[cfg_name], batch=3)
+    inp = S.make_inputs(cfg, pad_columns=False)
+    feats, fmasks = inp["srcs"][:3], inp["masks"][:3]
+    H0, W0 = feats[0].shape[-2:]
+    image_mask = torch.zeros(cfg["batch"], H0 * 16, W0 * 16, dtype=torch.bool)
+    preds = backbone_predictions(cfg, (H0 * 16, W0 * 16))
+    torch.manual_seed(0)
+    joiner = Joiner(_StubDetector(feats, fmasks, preds), PositionEmbeddingSine(cfg["d_model"] // 2, normalize=True))
+    model = PoET(joiner, build_deforamble_transformer(ref_args(cfg)), num_queries=cfg["num_queries"],
+                 num_feature_levels=cfg["n_levels"], n_classes=cfg["n_classes"], bbox_mode="backbone",
+                 ref_points_mode="bbox", query_embedding_mode="bbox", rotation_mode="6d",
+                 class_mode=cfg["class_mode"], aleatoric=False, aux_loss=True, backbone_type="maskrcnn").eval()
+    P = S.make_params(cfg, with_input_proj=True)
+    missing, unexpected = model.load_state_dict(P, strict=False)
+    assert not unexpected and all(k.startswith("backbone.") for k in missing), (missing, unexpected)
+    samples = NestedTensor(torch.zeros(cfg["batch"], 3, image_mask.shape[1], image_mask.shape[2]), image_mask)
+    with torch.no_grad():
+        out, n_boxes = model(samples, None)
+    t_all = torch.stack([a["pred_translation"] for a in out["aux_outputs"]] + [out["pred_translation"]])
+    R_all = torch.stack([a["pred_rotation"] for a in out["aux_outputs"]] + [out["pred_rotation"]])
+    return dict(cfg=cfg_name, batch=3, translation=t_all, rotation=R_all, pred_boxes=out["pred_boxes"],
+                pred_classes=out["pred_classes"], n_boxes=n_boxes)
 
 
 def criterion_case(seed=99, L=3, B=4, Q=6, n_boxes=(6, 3, 1, 4)):
@@ -250,6 +299,8 @@ def main():
     for name, pad in (("tiny", True), ("tiny16", False), ("cfg1", False), ("cfg2_b2", True)):
         if args.only is None or f"poet/{name}".startswith(args.only):
             gold[f"poet/{name}/pad{int(pad)}"] = golden_poet(name, pad)
+    if args.only is None or "poet_backbone_mode/tiny16".startswith(args.only):
+        gold["poet_backbone_mode/tiny16"] = golden_poet_backbone_mode("tiny16")
     if args.only is None or "criterion/gt".startswith(args.only):
         gold["criterion/gt"] = golden_criterion()
     meta = dict(torch=torch.__version__, reference=REF, note="generated by oracle/make_golden.py")

@@ -392,3 +392,42 @@ def test_input_proj_and_path_vs_reference_golden(key, precision):
     out2, n2 = model(samples, targets)
     assert n2 == n_boxes
     assert torch.equal(out2["pred_translation"], out["pred_translation"]) and torch.equal(out2["pred_rotation"], out["pred_rotation"])
+
+
+def test_backbone_mode_inference_vs_reference_golden():
+    """SURVEY.md section 8f N4 (inference mode): queries built from detector output (xyxy -> normalised cxcywh, top-Q by score,
+    an image with no detections) + input_proj + path, model(samples, None) in eval mode, against the reference run."""
+    from poet_b200 import ops
+    from poet_b200.deformable_transformer import DeformableTransformer
+    from poet_b200.pose_estimation_transformer import PoET, _Nested
+    from oracle.make_golden import backbone_predictions
+    g = load_golden("poet_backbone_mode/tiny16")
+    cfg = dict(S.CONFIGS[g["cfg"]], batch=g["batch"])
+    P = S.make_params(cfg, with_input_proj=True)
+    inp = S.make_inputs(cfg, pad_columns=False)
+    H0, W0 = inp["srcs"][0].shape[-2:]
+    preds = backbone_predictions(cfg, (H0 * 16, W0 * 16))
+    old = ops.get_gemm_precision()
+    ops.set_gemm_precision("bf16x3")
+    try:
+        tr = DeformableTransformer(cfg["d_model"], cfg["nheads"], cfg["enc_layers"], cfg["dec_layers"], cfg["dim_ff"], 0.0,
+                                   "relu", True, cfg["n_levels"], cfg["n_points"], cfg["n_points"])
+        bb = _StubBackbone(cfg["d_model"], [f.to(DEV) for f in inp["srcs"][:3]], [m.to(DEV) for m in inp["masks"][:3]])
+        bb.forward = lambda samples: ([_Nested(f, m) for f, m in zip(bb.feats, bb.masks)], [None] * 3,
+                                      [None if p is None else p.to(DEV) for p in preds])
+        model = PoET(bb, tr, cfg["num_queries"], cfg["n_levels"], cfg["n_classes"], bbox_mode="backbone",
+                     class_mode=cfg["class_mode"])
+        model.load_state_dict(P, strict=True)
+        model = model.to(DEV).eval()
+        img_mask = torch.zeros(cfg["batch"], H0 * 16, W0 * 16, dtype=torch.bool, device=DEV)
+        samples = _Nested(torch.zeros(cfg["batch"], 3, H0 * 16, W0 * 16, device=DEV), img_mask)
+        with torch.no_grad():
+            out, n_boxes = model(samples, None)
+    finally:
+        ops.set_gemm_precision(old)
+    assert n_boxes == g["n_boxes"]
+    assert torch.equal(out["pred_classes"].cpu(), g["pred_classes"])
+    assert float((out["pred_boxes"].cpu() - g["pred_boxes"]).abs().max()) < 1e-6
+    t, R = stack_outputs(out)
+    assert float((t.cpu() - g["translation"]).abs().max()) < TOL_T
+    assert float((R.cpu() - g["rotation"]).abs().max()) < TOL_R

@@ -253,6 +253,14 @@ class WeightPlanes:
             self.ranges.append((p.data_ptr(), p.numel() * 4, off))
             off += p.numel()
         self._table_key, self._table, self._chunks = None, None, 0
+        # all 1-D parameters (biases, norm affine) in registration order: refresh() concatenates them with ONE launch, so
+        # [sampling_offsets.bias | attention_weights.bias] of the fused projection is a view instead of a cat per layer
+        self.vec_params = [p for p in module.parameters() if p.dim() == 1 and p.dtype == torch.float32 and p.is_cuda]
+        self.vec_flat, self.vec_off = None, {}
+        o = 0
+        for p in self.vec_params:
+            self.vec_off[p.data_ptr()] = (o, p.numel())
+            o += p.numel()
         self.with_lo = True
         self._fresh_versions = None           # parameter versions for which the planes are known to be current
 
@@ -273,11 +281,23 @@ class WeightPlanes:
         step): the next refresh() is a no-op unless a parameter is modified in between."""
         self._fresh_versions = [p._version for p in self.params]
 
+    def bias_pair(self, b0: torch.Tensor, b1: torch.Tensor):
+        """cat(b0, b1) as a view of the per-step flat copy of the 1-D parameters, or None."""
+        if self.vec_flat is None:
+            return None
+        r0, r1 = self.vec_off.get(b0.data_ptr()), self.vec_off.get(b1.data_ptr())
+        if r0 is None or r1 is None or r1[0] != r0[0] + r0[1] or r0[1] != b0.numel() or r1[1] != b1.numel() or r0[0] % 4:
+            return None
+        return self.vec_flat[r0[0]: r0[0] + r0[1] + r1[1]]
+
     def refresh(self) -> None:
         """Re-derive all planes from the current parameter values (call once per forward)."""
         prec = _state["precision"]
         if not self.params or prec == GEMM_FP32:
             return
+        if self.vec_params:
+            with torch.no_grad():
+                self.vec_flat = torch.cat([p.detach().reshape(-1) for p in self.vec_params])
         if (self._fresh_versions is not None and self.with_lo == (prec == GEMM_BF16X3) and
                 self._fresh_versions == [p._version for p in self.params]):
             return
@@ -665,7 +685,13 @@ class _ProjPair(torch.autograd.Function):
         if mode == "cat":
             N0, N1 = W0.shape[0], W1.shape[0]
             with torch.no_grad():
-                bc = torch.cat((b0, b1), 0)
+                bc = None
+                for pl in reversed(_active_planes):
+                    bc = pl.bias_pair(b0, b1)
+                    if bc is not None:
+                        break
+                if bc is None:
+                    bc = torch.cat((b0, b1), 0)
                 ctx.w_split = split_weight_pair(W0, W1, R)
                 if ctx.w_split is not None:
                     Wc = None                       # with planes the GEMMs never read the fp32 matrix

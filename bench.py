@@ -11,6 +11,14 @@ batch (N>1: plus the flat-buffer gradient all-reduce).  Metric: images/s.
 
 Timing: per-step CUDA events on the launching stream, an L2 flush (256 MiB write) between timed
 steps outside the events, barrier + synchronize on both sides, MAX over ranks.
+
+Keys beyond the driver contract: `e2e` (pinned host inputs -> GraphedStep.prefetch on a copy stream -> replay ->
+read-back of loss + final predictions every step; `serial_value` = without the copy pipeline), `roofline`
+(+ `alt`: the reduction-issue bound of the MSDA backward), `kernels` (per-kernel table; GEMM rows carry
+`issued_tflops` / `tensor_pipe_frac`), `cpu_baseline`, `clocks`.
+Optional rows, each stated in `config`: `--from-features` (input_proj inside the step),
+`--criterion` (on-device SetCriterion + 'gt' matcher instead of the fixed-cotangent loss), `--optimizer`
+(clip_grad_norm_ + AdamW inside the step); `--micro-batches`, `--no-graph`, `--precision` are A/B knobs.
 """
 from __future__ import annotations
 

@@ -316,6 +316,13 @@ class WeightPlanes:
     def lookup(self, ptr: int, numel: int):
         """(hi, lo) flat plane views for the fp32 range [ptr, ptr + 4*numel) if it lies inside the arena's
         parameters (a whole matrix, a row block, or consecutive matrices), else None."""
+        if getattr(self, "_by_base_src", None) is not self.ranges:       # rebuilt whenever the ranges list is replaced
+            self._by_base = {base: (nbytes, off) for base, nbytes, off in self.ranges}
+            self._by_base_src = self.ranges
+        hit = self._by_base.get(ptr)
+        if hit is not None and 4 * numel <= hit[0]:
+            off = hit[1]
+            return self.hi[off:off + numel], (self.lo[off:off + numel] if self.with_lo else None)
         for base, nbytes, off in self.ranges:
             if base <= ptr < base + nbytes:
                 e0 = off + (ptr - base) // 4
@@ -354,6 +361,8 @@ class planes_scope:
         self.module, self.pushed, self.do_refresh = module, False, refresh
 
     def __enter__(self):
+        if not _active_planes:
+            _pending_joins.clear()                        # a backward that raised must not suppress the next one's joins
         first = next((p for p in self.module.parameters() if p.dim() in (2, 4)), None)
         if first is None or not first.is_cuda or _state["precision"] == GEMM_FP32:
             return self

@@ -281,16 +281,20 @@ struct Tile {
       const uint32_t off = (uint32_t)seg * (ROWS * 128) + (uint32_t)(row >> 3) * 1024 + (uint32_t)(row & 7) * 128 +
                            (uint32_t)((c ^ (row & 7)) << 4);
       const float x[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
-      float h[8];
+      // hi = bf16(x) by the packed convert (F2FP.BF16.F32.PACK_AB, two elements per instruction); the fp32 value of
+      // hi needed for lo = bf16(x - hi) is the same 16 bits shifted back up, so no single-element F2F is issued
+      uint32_t hp[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) h[j] = __bfloat162float(__float2bfloat16_rn(x[j]));
-      uint4 hi;
-      hi.x = pack_bf16(h[0], h[1]); hi.y = pack_bf16(h[2], h[3]); hi.z = pack_bf16(h[4], h[5]); hi.w = pack_bf16(h[6], h[7]);
-      sts128(s_hi + off, hi);
+      for (int j = 0; j < 4; ++j) hp[j] = pack_bf16(x[2 * j], x[2 * j + 1]);
+      sts128(s_hi + off, make_uint4(hp[0], hp[1], hp[2], hp[3]));
       if (WITH_LO) {
-        uint4 lo;
-        lo.x = pack_bf16(x[0] - h[0], x[1] - h[1]); lo.y = pack_bf16(x[2] - h[2], x[3] - h[3]);
-        lo.z = pack_bf16(x[4] - h[4], x[5] - h[5]); lo.w = pack_bf16(x[6] - h[6], x[7] - h[7]);
+        uint32_t lp[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float h0 = __uint_as_float(hp[j] << 16), h1 = __uint_as_float(hp[j] & 0xffff0000u);
+          lp[j] = pack_bf16(x[2 * j] - h0, x[2 * j + 1] - h1);
+        }
+        uint4 lo = make_uint4(lp[0], lp[1], lp[2], lp[3]);
         sts128(s_lo + off, lo);
       }
     }

@@ -37,9 +37,31 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-WORKLOAD = "cfg2"
+WORKLOAD = "cfg2"            # default; --workload selects another BASELINE.json config (module-level so helpers see it)
 POET_SMS = 148
-METRIC = "images/sec, PoET deformable enc/dec fwd+bwd (5enc/5dec/16h, 640x480 REF pyramid, batch 16/GPU)"
+
+# BASELINE.json `configs` -> (synthetic config, what a step is, description)
+WORKLOADS = {
+    "cfg1": dict(cfg="cfg1", backward=False,
+                 text="cfg1: 1x640x480, 2enc/2dec/8h d256 Q5 (reference CPU eval case), eval forward only"),
+    "cfg2": dict(cfg="cfg2", backward=True,
+                 text="cfg2: YCB-V 5enc/5dec/16h d256 Q10 22 class slots, fwd+bwd, synthetic cotangent loss"),
+    "cfg3": dict(cfg="cfg3", backward=True,
+                 text="cfg3: LM-O 5enc/5dec/16h d256 Q10 9 class slots (heads 27/54), fwd+bwd, synthetic cotangent loss"),
+    "cfg4": dict(cfg="cfg4", backward=True,
+                 text="cfg4: YCB-V training step in the bf16 throughput mode (single-pass bf16 MMAs in the encoder, bf16x3 "
+                      "elsewhere), fwd+bwd + gradient all-reduce + fused clip+AdamW"),
+    "cfg5": dict(cfg="cfg5", backward=True,
+                 text="cfg5: 1280x960 REF pyramid (S=6380), 6enc/6dec/8h d256 Q25, fwd+bwd, global batch 32 (strong scaling)"),
+}
+
+
+def metric_name(workload, cfg, per_gpu_batch):
+    from poet_b200 import synthetic as S
+    res = "1280x960" if cfg["pyramid"] == "REF1280" else "640x480"
+    what = "fwd+bwd" if WORKLOADS[workload]["backward"] else "eval fwd"
+    return (f"images/sec, PoET deformable enc/dec {what} ({cfg['enc_layers']}enc/{cfg['dec_layers']}dec/{cfg['nheads']}h, "
+            f"{res} REF pyramid, batch {per_gpu_batch}/GPU)")
 
 
 def load_peaks():
@@ -54,7 +76,7 @@ def load_peaks():
 
 def config_dict(cfg, extra=None):
     from poet_b200 import synthetic as S
-    d = {"workload": f"{WORKLOAD}: YCB-V 5enc/5dec/16h d256 Q10 22 class slots, fwd+bwd, synthetic cotangent loss",
+    d = {"workload": WORKLOADS[WORKLOAD]["text"],
          "batch_per_gpu": cfg["batch"], "pyramid": S.pyramid_of(cfg), "tokens": S.n_tokens(cfg),
          "dropout": 0.0, "l2": "flushed between timed steps (256 MiB write, outside the events)"}
     if extra:
@@ -65,10 +87,20 @@ def config_dict(cfg, extra=None):
 # ------------------------------------------------------------------------------------------
 # CPU legs (the only places bench.py executes oracle/)
 # ------------------------------------------------------------------------------------------
-def cpu_step_fn(cfg, batch):
+def default_batch(workload, cfg, world):
+    """Per-GPU batch: BASELINE.json quotes cfg5 at a GLOBAL batch of 32 swept over 1/2/4/8 GPUs (strong scaling);
+    every other config keeps its per-GPU batch as GPUs are added (weak scaling)."""
+    return max(1, 32 // world) if workload == "cfg5" else cfg["batch"]
+
+
+def scaling_of(workload):
+    return "strong" if workload == "cfg5" else "weak"
+
+
+def cpu_step_fn(cfg, batch, backward=True):
     from oracle import poet_oracle as O
     from poet_b200 import synthetic as S
-    P = {k: v.requires_grad_(True) for k, v in S.make_params(cfg).items()}
+    P = {k: v.requires_grad_(backward) for k, v in S.make_params(cfg).items()}
     inp = S.make_inputs(cfg, batch=batch)
     g_t, g_R = S.make_cotangents(cfg, batch=batch)
 
@@ -76,25 +108,50 @@ def cpu_step_fn(cfg, batch):
         for v in P.values():
             v.grad = None
         cap = {}
-        O.poet_path_forward(P, cfg, inp["srcs"], inp["masks"], inp["boxes"], inp["labels"], capture=cap)
-        loss = O.synthetic_loss((cap["translation_all"], cap["rotation_all"]), g_t, g_R)
-        loss.backward()
+        with torch.set_grad_enabled(backward):
+            O.poet_path_forward(P, cfg, inp["srcs"], inp["masks"], inp["boxes"], inp["labels"], capture=cap)
+            loss = O.synthetic_loss((cap["translation_all"], cap["rotation_all"]), g_t, g_R)
+        if backward:
+            loss.backward()
         return float(loss.detach())
     return step
 
 
-def cpu_baseline(cfg, batch=4, reps=2):
+def cpu_baseline(cfg, batch=4, reps=2, backward=True):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = cpu_step_fn(cfg, batch)
+    if cfg["pyramid"] == "REF1280":
+        batch, reps = 1, 1
+    batch = min(batch, cfg["batch"])
+    step = cpu_step_fn(cfg, batch, backward=backward)
     step()                                             # warm-up
     t0 = time.perf_counter()
     for _ in range(reps):
         step()
     dt = (time.perf_counter() - t0) / reps
     return {"value": batch / dt, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": f"{reps} fwd+bwd steps of {batch} images of the same workload (oracle/poet_oracle.py, torch CPU fp32, "
-                      f"{cores} threads) after 1 warm-up"}
+            "sample": f"{reps} {'fwd+bwd' if backward else 'eval fwd'} steps of {batch} images of the same workload "
+                      f"(oracle/poet_oracle.py, torch CPU fp32, {cores} threads) after 1 warm-up"}
+
+
+def parity_check(cfg, inp, out, n_images=4):
+    """The benchmarked path against the CPU oracle on the first images of the benchmarked batch (images are
+    independent): max |translation|, |rotation| error over ALL decoder layers; tolerances of BASELINE.json."""
+    from oracle import poet_oracle as O
+    from poet_b200 import synthetic as S
+    n = min(n_images, len(inp["boxes"]))
+    P = S.make_params(cfg)
+    cap = {}
+    with torch.no_grad():
+        O.poet_path_forward(P, cfg, [s[:n] for s in inp["srcs"]], [m[:n] for m in inp["masks"]], inp["boxes"][:n],
+                            inp["labels"][:n], capture=cap)
+    t = torch.stack([a["pred_translation"] for a in out["aux_outputs"]] + [out["pred_translation"]]).detach().cpu()
+    R = torch.stack([a["pred_rotation"] for a in out["aux_outputs"]] + [out["pred_rotation"]]).detach().cpu()
+    dt = float((t[:, :n] - cap["translation_all"]).abs().max())
+    dR = float((R[:, :n] - cap["rotation_all"]).abs().max())
+    return {"checked": f"first {n} images of the benchmarked batch, all {t.shape[0]} decoder layers, vs oracle/poet_oracle.py (fp32 CPU)",
+            "max_abs_translation": dt, "max_abs_rotation": dR, "tol_translation": 1e-4, "tol_rotation": 1e-3,
+            "ok": bool(dt <= 1e-4 and dR <= 1e-3)}
 
 
 def run_reference(args):
@@ -104,11 +161,12 @@ def run_reference(args):
     if rank != 0:
         return
     from poet_b200 import synthetic as S
-    cfg = S.CONFIGS[WORKLOAD]
+    wl = WORKLOADS[WORKLOAD]
+    cfg = dict(S.CONFIGS[wl["cfg"]])
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    batch = 2                                           # bounded sample per step
-    step = cpu_step_fn(cfg, batch)
+    batch = 1 if cfg["pyramid"] == "REF1280" or cfg["batch"] == 1 else 2      # bounded sample per step
+    step = cpu_step_fn(cfg, batch, backward=wl["backward"])
     for _ in range(max(1, min(args.warmup, 2))):
         step()
     times = []
@@ -118,11 +176,13 @@ def run_reference(args):
         times.append(time.perf_counter() - t0)
     total = sum(times)
     value = batch * args.steps / total
-    sample = f"each step = fwd+bwd of {batch} images of {WORKLOAD} (bounded sample), oracle port, {cores} threads"
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+    what = "fwd+bwd" if wl["backward"] else "eval fwd"
+    sample = f"each step = {what} of {batch} images of {WORKLOAD} (bounded sample), oracle port, {cores} threads"
+    per_gpu = args.batch or default_batch(WORKLOAD, cfg, max(1, args.gpus))
+    line = {"impl": "reference", "metric": metric_name(WORKLOAD, cfg, per_gpu), "value": value, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": config_dict(cfg, {"batch_per_step": batch}),
+            "higher_is_better": True, "scaling": scaling_of(WORKLOAD), "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": config_dict(dict(cfg, batch=per_gpu), {"batch_per_step": batch}),
             "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -218,9 +278,13 @@ def run_gpu(args):
     dev = torch.device(f"cuda:{local}")
     ops.set_gemm_precision(args.precision)
 
-    cfg = S.CONFIGS[WORKLOAD]
-    B = cfg["batch"]
+    wl = WORKLOADS[WORKLOAD]
+    cfg = dict(S.CONFIGS[wl["cfg"]])
+    cfg["batch"] = B = args.batch or default_batch(WORKLOAD, cfg, world)
+    do_backward = wl["backward"]
     model = build_gpu_model(cfg, dev, with_input_proj=args.from_features)
+    if not do_backward:
+        model.eval()
     model.micro_batches = args.micro_batches
     reducer = FlatGradReducer(model.parameters())
     inp = S.make_inputs(cfg, seed=1234 + rank)           # each rank owns a different image shard (weak scaling)
@@ -263,6 +327,10 @@ def run_gpu(args):
         return model.forward_pyramid(srcs, masks, boxes, labels)
 
     def eager_step(srcs, masks, boxes, labels):
+        if not do_backward:
+            with torch.no_grad():
+                out, _ = fwd(srcs, masks, boxes, labels)
+                return loss_fn(out), out
         reducer.zero()
         out, _ = fwd(srcs, masks, boxes, labels)
         loss = loss_fn(out)
@@ -284,11 +352,12 @@ def run_gpu(args):
     if args.graph:
         from poet_b200.graph import GraphedStep
         graphed = GraphedStep(model, loss_fn, d_srcs, d_masks, d_boxes, d_labels, reducer=reducer, optimizer=opt,
-                              entry="features" if args.from_features else "pyramid")
+                              entry="features" if args.from_features else "pyramid", backward=do_backward)
 
         def step(srcs=None, masks=None, boxes=None, labels=None):
             loss, out = graphed.run(srcs, masks, boxes, labels)
-            reducer.all_reduce()
+            if do_backward:
+                reducer.all_reduce()
             if opt is not None:
                 opt.step()
             return loss, out
@@ -302,8 +371,14 @@ def run_gpu(args):
             return r
 
     for _ in range(max(args.warmup, 3)):
-        step()
+        loss0, out0 = step()
     sync_all()
+    # parity of the benchmarked path itself (same model, same inputs, same graph replay) against the CPU oracle
+    parity = None
+    if rank == 0 and not args.no_parity and not args.from_features and opt is None:
+        parity = parity_check(cfg, inp, out0)
+        if not parity["ok"]:
+            print(f"bench.py: PARITY FAILED on the benchmarked path: {parity}", file=sys.stderr, flush=True)
 
     # ---- device-resident timed region -------------------------------------------------------
     sampler = ClockSampler(local)
@@ -380,6 +455,10 @@ def run_gpu(args):
     ktimes, ksteps = {}, min(args.steps, 5)
 
     def local_step():                                   # no collective: only rank 0 runs the table pass
+        if not do_backward:
+            with torch.no_grad():
+                fwd(d_srcs, d_masks, d_boxes, d_labels)
+            return
         reducer.zero()
         out, _ = fwd(d_srcs, d_masks, d_boxes, d_labels)
         loss_fn(out).backward()
@@ -408,8 +487,8 @@ def run_gpu(args):
         peaks = load_peaks()
         ms_per_step = total_ms / args.steps
         value = B * world * args.steps / (total_ms / 1e3)
-        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        line = {"metric": metric_name(WORKLOAD, cfg, B), "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling_of(WORKLOAD),
                 "vs_baseline": None, "dtype": "fp32" if args.precision == "fp32" else f"fp32 ({args.precision} tensor-core GEMMs)",
                 "data": "synthetic",
                 "config": config_dict(cfg, {"global_batch": B * world, "parallelism": f"dp{world}",
@@ -422,18 +501,22 @@ def run_gpu(args):
                                             "loss": ("on-device PoseCriterion (SetCriterion + 'gt' matcher), synthetic targets" if args.criterion
                                                      else "fixed-cotangent loss (SURVEY.md section 8d)"),
                                             "optimizer": "fused clip_grad_norm_(0.1) + AdamW inside every step" if opt is not None else "none (forward + backward [+ all-reduce])",
-                                            "kernel_table": "eager single-stream pass, CUDA events around every library call"}),
+                                            "kernel_table": ("eager single-stream pass, CUDA events around every library call; `share` is "
+                                                             "of the table's own sum (the replayed graph overlaps branches on "
+                                                             "side streams: kernel_table_ms / ms_per_step = serial-to-graph ratio)")}),
                 "e2e": {"value": B * world * args.steps / (e2e_ms / 1e3), "unit": "images/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "pipeline": ("pinned host inputs of step i+1 copied on a copy stream while step i replays "
                                      "(GraphedStep.prefetch); result read back every step") if graphed is not None else "serial",
                         "serial_value": B * world * args.steps / (e2e_serial_ms / 1e3)},
                 "gpu_launches": launches, "clocks": clocks}
+        if parity is not None:
+            line["parity"] = parity
         if ktimes:
             line["roofline"], line["kernels"] = roofline_from(ktimes, peaks, ksteps, ms_per_step,
                                                               mma_passes=3 if args.precision == "bf16x3" else 1)
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(cfg)
+            line["cpu_baseline"] = cpu_baseline(cfg, backward=do_backward)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -444,6 +527,7 @@ def roofline_from(ktimes, peaks, steps, ms_per_step, mma_passes=1):
     GEMMs are judged against the tensor pipe (sustained bf16 peak: the kernel is timed inside a long step),
     everything else against HBM.  Algorithmic bytes/flops per launch are the figures of DESIGN.md."""
     rows = []
+    table_ms = sum(ms for ms, _n, _b, _f in ktimes.values()) / steps          # serialised library time per step
     for name, (ms, n, nbytes, flops) in ktimes.items():
         if ms <= 0:
             continue
@@ -453,7 +537,7 @@ def roofline_from(ktimes, peaks, steps, ms_per_step, mma_passes=1):
         else:
             ach, peak, unit, bound = nbytes / (ms * 1e-3) / 1e9, peaks["hbm"], "GB/s", "hbm"
         row = {"kernel": name, "launches_per_step": n / steps, "ms_per_step": ms / steps,
-               "share": ms / steps / ms_per_step, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
+               "share": ms / steps / table_ms, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
                "frac": ach / peak if nbytes or flops else None,
                "hbm_gbs": nbytes / (ms * 1e-3) / 1e9 if nbytes else None}
         if is_gemm and flops:
@@ -466,17 +550,20 @@ def roofline_from(ktimes, peaks, steps, ms_per_step, mma_passes=1):
     # group GEMM shapes into one dominant-kernel line as well
     gemm = [r for r in rows if r["kernel"].startswith("poet_gemm")]
     top = rows[0]
-    traffic = None
+    traffic, traffic_src = None, None
     try:                                        # measured DRAM bytes per launch of that kernel (ncu --set full)
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            traffic = json.load(fh).get(top["kernel"])
+            tj = json.load(fh)
+        traffic = tj.get(top["kernel"])
+        traffic_src = tj.get("_source")
     except Exception:
         pass
     roof = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
-            "unit": top["unit"], "frac": top["frac"], "traffic": traffic, "peak_source": peaks["source"],
-            "share_of_step": top["share"]}
+            "unit": top["unit"], "frac": top["frac"], "traffic": traffic, "traffic_source": traffic_src,
+            "peak_source": peaks["source"], "share_of_table": top["share"],
+            "kernel_table_ms": table_ms, "serial_to_graph_ratio": table_ms / ms_per_step}
     if gemm:
-        roof["all_gemm_share_of_step"] = sum(r["share"] for r in gemm)
+        roof["all_gemm_share_of_table"] = sum(r["share"] for r in gemm)
     if top["kernel"].startswith("poet_msda_bwd"):
         # What actually bounds this kernel: every bilinear corner of every sampling point is one
         # 16-byte red.global.add.v4.f32 per 4 channels = B*Lq*M*L*P*D reduction lane-ops per launch (flops field / 30),
@@ -506,9 +593,15 @@ def main():
                          "fixed-cotangent loss of SURVEY.md section 8d")
     ap.add_argument("--optimizer", action="store_true",
                     help="include the fused clip_grad_norm_(0.1) + AdamW step in every step (training step of cfg4)")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
+                    help="BASELINE.json config to run (default cfg2, the configuration the metric is quoted on)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the workload's)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity check of the benchmarked path")
     ap.add_argument("--micro-batches", type=int, default=int(os.environ.get("POET_MICRO_BATCHES", "1")),
                     help="slices of the per-GPU batch issued on separate streams (decoder chain of one overlaps the encoder of another)")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
     if args.impl == "reference":
         run_reference(args)
         return

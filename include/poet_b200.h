@@ -224,16 +224,26 @@ int poet_pose_loss(const float* pred_t, const float* pred_R, const float* tgt_t,
 /* ---- optimizer step (next: SURVEY.md section 8f N3; reference engine.py:77-81, main.py:253-277) ------------ */
 /* out[0] = sum_i x[i]^2 (double, on the device; overwritten).  n % 4 == 0. */
 int poet_sumsq(const float* x, int64_t n, double* out, poet_stream_t stream);
+/* Per-tensor squared gradient norms over the same pointer table as poet_adamw_clip_multi: tensor_sumsq[t] (device,
+ * n_tensors floats, overwritten) = sum of squares of tensor t's slice of the gradient arena.  Their sum is the global
+ * norm of torch.nn.utils.clip_grad_norm_ (engine.py:77-78); a tensor whose norm is exactly 0 received no gradient in
+ * this step (torch leaves its .grad at None and torch.optim.AdamW does not touch it). */
+int poet_grad_sumsq_multi(const void* table, int n_tensors, int64_t total_chunks, const float* grad,
+                          float* tensor_sumsq, poet_stream_t stream);
 /* clip_grad_norm_(max_norm) + AdamW.step() over every parameter tensor in one launch.
  * table (device): n_tensors entries of 7 x 8 bytes {float* param, int64 arena offset / 4, void* hi, void* lo,
  * int64 numel, int64 first_chunk, int32 lr group, int32 0}; tensor t owns ceil(ceil(numel/4)/1024) chunks of
- * 1024 float4, entries sorted by first_chunk (as in poet_split_bf16_multi); planes need numel % 8 == 0.  grad / m / v: flat fp32 arenas sharing the offsets.  sumsq: poet_sumsq of the gradient
- * arena (read on the device; ignored when max_norm <= 0).  lr_host[n_groups]: learning rate per group (host).
- * step: 1-based step count (bias correction).  hi / lo (nullable per tensor): bf16 planes of the UPDATED weights. */
+ * 1024 float4, entries sorted by first_chunk (as in poet_split_bf16_multi); planes need numel % 8 == 0.  grad / m / v:
+ * flat fp32 arenas sharing the offsets.  Gradient norm, one of: tensor_sumsq (poet_grad_sumsq_multi; tensors with a
+ * zero norm are skipped like torch skips grad-None parameters, the total is written to sumsq if non-null, and
+ * touched[t] (nullable, device floats) accumulates the norms so the host can tell which tensors own optimizer state),
+ * or sumsq alone (poet_sumsq of the arena, read on the device; every tensor is updated).  Ignored when max_norm <= 0
+ * and tensor_sumsq is null.  lr_host[n_groups]: learning rate per group (host).  step: 1-based step count (bias
+ * correction).  hi / lo (nullable per tensor): bf16 planes of the UPDATED weights. */
 int poet_adamw_clip_multi(const void* table, int n_tensors, int64_t total_chunks, const float* grad, float* m,
-                          float* v, const double* sumsq, float max_norm, const float* lr_host, int n_groups,
-                          float beta1, float beta2, float eps, float weight_decay, int64_t step,
-                          poet_stream_t stream);
+                          float* v, double* sumsq, const float* tensor_sumsq, float* touched, float max_norm,
+                          const float* lr_host, int n_groups, float beta1, float beta2, float eps, float weight_decay,
+                          int64_t step, poet_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -52,7 +52,8 @@ SIGNATURES = {
     "poet_groupnorm_tokens_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "poet_pose_loss": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp]),
     "poet_sumsq": (_i, [_vp, _i64, _vp, _vp]),
-    "poet_adamw_clip_multi": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp, _f, _vp, _i, _f, _f, _f, _f, _i64, _vp]),
+    "poet_grad_sumsq_multi": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
+    "poet_adamw_clip_multi": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _f, _f, _f, _f, _i64, _vp]),
     "poet_heads_select_rot6d_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
 }
 

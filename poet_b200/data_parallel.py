@@ -36,15 +36,33 @@ class FlatGradReducer:
         self.bind()
 
     def bind(self) -> None:
-        """(Re-)point every p.grad at its slice of the arena."""
+        """(Re-)point every p.grad at its slice of the arena and register the slices as direct-accumulation slots:
+        the backward kernels of poet_b200.ops add parameter gradients straight into them (no AccumulateGrad node, hence
+        no gradient hooks: this reducer replaces DistributedDataParallel, it does not combine with it)."""
         for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
+        if self.flat.is_cuda:
+            from . import ops
+            ops.register_direct_grad_slots([p.grad for p in self.params])
 
     def zero(self) -> None:
         self.flat.zero_()
+        rebound = []
         for p, off in zip(self.params, self.offsets):
             if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + off * self.flat.element_size():
                 p.grad = self.flat[off:off + p.numel()].view_as(p)
+                rebound.append(p.grad)
+        if rebound and self.flat.is_cuda:
+            from . import ops
+            ops.register_direct_grad_slots(rebound)
+
+    def __del__(self):
+        try:
+            if self.flat.is_cuda:
+                from . import ops
+                ops.unregister_direct_grad_slots([self.flat[off:off + p.numel()] for p, off in zip(self.params, self.offsets)])
+        except Exception:
+            pass
 
     def world_size(self) -> int:
         return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1

@@ -256,7 +256,6 @@ class DeformableTransformer(nn.Module):
         lvl_pos_embed_flatten [B,S,C] already in token layout with level_embed added."""
         if query_embed is None:
             raise ValueError("query_embed is required")
-        ops.clear_weight_split_cache()          # bf16 weight planes live for one forward + its backward
         if reference_points is None:
             raise NotImplementedError("learned reference points are not used by PoET ('bbox' mode only)")
         if src_tokens is not None:               # ours: the pyramid already in token layout (ops.input_proj_tokens)

@@ -71,7 +71,6 @@ class GraphedStep:
     # -- the captured region ----------------------------------------------------------------
     def _body(self):
         from . import ops
-        ops.clear_weight_split_cache()          # the bf16 weight planes must be re-derived inside the graph
         if self.reducer is not None:
             self.reducer.zero()
         with ops.planes_scope(self.model, refresh=not self.external_planes):

@@ -290,14 +290,25 @@ class WeightPlanes:
             return None
         return self.vec_flat[r0[0]: r0[0] + r0[1] + r1[1]]
 
+    def refresh_vectors(self) -> None:
+        """Re-copy the 1-D parameters into the flat buffer, IN PLACE: the buffer's address is baked into captured
+        CUDA graphs (bias_pair views), and this copy is part of every forward -- also of one replayed from a graph
+        whose planes are written by the fused optimizer -- so a bias updated by optimizer.step() or load_state_dict
+        is what the next forward reads."""
+        if not self.vec_params:
+            return
+        with torch.no_grad():
+            srcs = [p.detach().reshape(-1) for p in self.vec_params]
+            if self.vec_flat is None or self.vec_flat.numel() != sum(t.numel() for t in srcs):
+                self.vec_flat = torch.empty(sum(t.numel() for t in srcs), device=self.device, dtype=torch.float32)
+            torch.cat(srcs, out=self.vec_flat)
+
     def refresh(self) -> None:
         """Re-derive all planes from the current parameter values (call once per forward)."""
         prec = _state["precision"]
         if not self.params or prec == GEMM_FP32:
             return
-        if self.vec_params:
-            with torch.no_grad():
-                self.vec_flat = torch.cat([p.detach().reshape(-1) for p in self.vec_params])
+        self.refresh_vectors()
         if (self._fresh_versions is not None and self.with_lo == (prec == GEMM_BF16X3) and
                 self._fresh_versions == [p._version for p in self.params]):
             return
@@ -376,6 +387,8 @@ class planes_scope:
             object.__setattr__(self.module, "_poet_weight_planes", pl)
         if self.do_refresh:
             pl.refresh()
+        else:
+            pl.refresh_vectors()                          # the optimizer writes the matrix planes, not the bias copy
         _active_planes.append(pl)
         self.pushed = True
         return self
@@ -384,10 +397,6 @@ class planes_scope:
         if self.pushed:
             _active_planes.pop()
         return False
-
-
-def clear_weight_split_cache() -> None:
-    """Kept for API stability: planes are owned by the autograd graph / the module arena, nothing to clear."""
 
 
 def _eligible(M_rows: int, N: int, K: int) -> bool:
@@ -415,7 +424,10 @@ def split_weight(W: torch.Tensor, M_rows: int):
 
 def split_weight_pair(W0: torch.Tensor, W1: torch.Tensor, M_rows: int):
     """Planes of cat(W0, W1) [N0+N1, K] straight from the arena, or None (caller concatenates and splits)."""
-    if _state["precision"] == GEMM_FP32 or not _eligible(M_rows, W0.shape[0] + W1.shape[0], W0.shape[1]):
+    N, K = W0.shape[0] + W1.shape[0], W0.shape[1]
+    # the planes serve the forward [R,N,K] AND the dgrad [R,K,N] GEMM (the fp32 matrix is then never built): both
+    # must be tensor-core eligible, else the caller concatenates and keeps the fp32 copy for the SIMT path
+    if _state["precision"] == GEMM_FP32 or not _eligible(M_rows, N, K) or not _eligible(M_rows, K, N):
         return None
     for pl in reversed(_active_planes):
         v = pl.lookup_pair(W0, W1)
@@ -450,7 +462,7 @@ def wgrad_bias(gy2: torch.Tensor, x2: torch.Tensor, N: int, K: int, R: int, w_ou
     gemm(gy2, x2, N, K, R, a_kcontig=False, b_kcontig=False, lda=lda, out=w_out, accumulate=True,
          a_colsum=b_out if fused else None, a_row_mask=row_mask)
     if b_out is not None and not fused:
-        _call("poet_colsum_masked", _p(gy2), lda, _p(row_mask), _p(b_out), R, N, 1, _stream(gy2))
+        _call("poet_colsum_masked", _p(gy2), lda, _p(row_mask), _p(b_out), R, N, 1, _stream(gy2), work=(4 * R * N, R * N))
 
 
 def colsum(X: torch.Tensor, M: int, N: int, out: Optional[torch.Tensor] = None, accumulate=False) -> torch.Tensor:
@@ -474,16 +486,39 @@ def add(a: torch.Tensor, b: Optional[torch.Tensor]) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------
 # autograd: Linear / FFN / MLP
 # ------------------------------------------------------------------------------------------
+_direct_slots = {}          # data_ptr of a registered gradient slot -> numel
+
+
+def register_direct_grad_slots(grads) -> None:
+    """Opt in: backward kernels may accumulate straight into these tensors (FlatGradReducer registers the views of
+    its arena).  A .grad that was not registered is left to autograd's AccumulateGrad, so tensor hooks,
+    post-accumulate hooks and DistributedDataParallel's reducer hooks keep firing for it."""
+    for g in grads:
+        _direct_slots[g.data_ptr()] = g.numel()
+
+
+def unregister_direct_grad_slots(grads=None) -> None:
+    if grads is None:
+        _direct_slots.clear()
+        return
+    for g in grads:
+        _direct_slots.pop(g.data_ptr(), None)
+
+
 def _grad_slot(param) -> Optional[torch.Tensor]:
-    """The pre-allocated .grad of a leaf parameter (e.g. a view of FlatGradReducer's arena), if any.
+    """The .grad of a leaf parameter if it is a registered arena slot (FlatGradReducer), else None.
     Backward kernels then accumulate straight into it (beta = 1 epilogue) and hand autograd `None`,
-    which removes one zero-fill and one add kernel per parameter per step."""
-    if not _state["direct_grads"] or param is None or not isinstance(param, torch.Tensor):
+    which removes one zero-fill and one add kernel per parameter per step.  Direct accumulation bypasses
+    AccumulateGrad (no hooks, torch.autograd.grad() sees None): it is therefore opt-in per tensor, and
+    incompatible with DistributedDataParallel -- FlatGradReducer is the data-parallel path that goes with it."""
+    if not _state["direct_grads"] or not _direct_slots or param is None or not isinstance(param, torch.Tensor):
         return None
     if not (param.is_leaf and param.requires_grad):
         return None
     g = param.grad
-    if g is None or not g.is_contiguous() or g.dtype != torch.float32 or g.shape != param.shape:
+    if g is None or _direct_slots.get(g.data_ptr()) != g.numel():
+        return None
+    if not g.is_contiguous() or g.dtype != torch.float32 or g.shape != param.shape:
         return None
     return g
 
@@ -521,7 +556,7 @@ def _linear_bwd(gy2: torch.Tensor, x2: torch.Tensor, W: torch.Tensor, need_x: bo
         if w_slot is not None:
             wgrad_bias(gy2, x2, N, K, R, w_slot, b_slot, row_mask=gy_row_mask)
         elif b_slot is not None:
-            _call("poet_colsum_masked", _p(gy2), N, _p(gy_row_mask), _p(b_slot), R, N, 1, _stream(gy2))
+            _call("poet_colsum_masked", _p(gy2), N, _p(gy_row_mask), _p(b_slot), R, N, 1, _stream(gy2), work=(4 * R * N, R * N))
     finally:
         if side is not None:
             side.__exit__(None, None, None)
@@ -529,7 +564,7 @@ def _linear_bwd(gy2: torch.Tensor, x2: torch.Tensor, W: torch.Tensor, need_x: bo
         dW = gemm(gy2, x2, N, K, R, a_kcontig=False, b_kcontig=False, a_row_mask=gy_row_mask)
     if need_b and b_slot is None:
         db = torch.zeros(N, device=gy2.device, dtype=torch.float32)
-        _call("poet_colsum_masked", _p(gy2), N, _p(gy_row_mask), _p(db), R, N, 1, _stream(gy2))
+        _call("poet_colsum_masked", _p(gy2), N, _p(gy_row_mask), _p(db), R, N, 1, _stream(gy2), work=(4 * R * N, R * N))
     return dx, dW, db
 
 
@@ -795,8 +830,9 @@ class _AddLayerNorm(torch.autograd.Function):
         rstd = torch.empty(R, device=x.device, dtype=torch.float32) if need_grad else None
         p2 = None if pos is None else _chk(pos).view(-1, Cc)
         y2 = torch.empty_like(x2) if pos is not None else None
+        n_streams = 2 + (r is not None) + 2 * (pos is not None) + (1 if need_grad else 0)     # x, y [, r] [, pos, y2] [, xhat]
         _call("poet_add_layernorm_fwd", _p(x2), _p(r2), _p(gamma), _p(beta), _p(p2), _p(y), _p(y2), _p(xhat), _p(rstd),
-              R, Cc, eps, _stream(x))
+              R, Cc, eps, _stream(x), work=(4 * R * Cc * n_streams + 4 * R, 8 * R * Cc))
         ctx.gb_params = (gamma, beta)
         if need_grad:
             ctx.save_for_backward(xhat, rstd, gamma)
@@ -822,7 +858,7 @@ class _AddLayerNorm(torch.autograd.Function):
             dgb = torch.zeros(2, Cc, device=xhat.device, dtype=torch.float32)
             dg_ptr, db_ptr = _p(dgb[0]), _p(dgb[1])
         _call("poet_layernorm_bwd", _p(gy), _p(gy2), _p(xhat), _p(rstd), _p(gamma), _p(dz), dg_ptr, db_ptr,
-              R, Cc, _stream(xhat))
+              R, Cc, _stream(xhat), work=(4 * R * Cc * (3 + (gy2 is not None)) + 4 * R, 10 * R * Cc))   # gy [, gy2], xhat -> dz
         dz = dz.view(ctx.shape)
         gpos = None
         if ctx.has_pos and ctx.needs_input_grad[4]:

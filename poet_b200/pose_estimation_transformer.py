@@ -316,6 +316,19 @@ class PoET(nn.Module):
                                                 pos_tokens=pos_tokens, src_tokens=src_tokens)
         return self._pack(t_all, R_all, pb, pc)
 
+    def _default_sine_posenc(self) -> bool:
+        """True when backbone[1] is the sine position encoding every PoET config builds (position_encoding.py:87-99:
+        hidden_dim/2 features, temperature 1e4, normalize, scale 2*pi): only then may the token-layout kernel rebuild
+        the encodings from the masks instead of using the `pos` tensors the backbone returned."""
+        import math
+        try:
+            pe = self.backbone[1]
+        except (TypeError, IndexError, KeyError):
+            return False
+        return (type(pe).__name__ == "PositionEmbeddingSine" and int(getattr(pe, "num_pos_feats", -1)) * 2 == self.hidden_dim
+                and float(getattr(pe, "temperature", 0)) == 10000.0 and bool(getattr(pe, "normalize", False))
+                and abs(float(getattr(pe, "scale", 0.0)) - 2 * math.pi) < 1e-12)
+
     def forward(self, samples, targets=None):
         samples = _as_nested(samples)
         image_hw = (int(samples.tensors.shape[-2]), int(samples.tensors.shape[-1]))
@@ -329,7 +342,8 @@ class PoET(nn.Module):
             raise NotImplementedError("PoET Bounding Box Mode not implemented!")
 
         if (dev.type == "cuda" and self.num_feature_levels > 1 and len(self.input_proj) == self.num_feature_levels
-                and self.num_feature_levels - len(features) in (0, 1)):
+                and self.num_feature_levels - len(features) in (0, 1)
+                and (all(pe is None for pe in pos) or self._default_sine_posenc())):
             # input_proj + path on our kernels; position encodings are rebuilt from the masks in token layout
             fm = [feat.decompose() for feat in features]
             if any(m is None for _, m in fm):

@@ -150,12 +150,16 @@ int poet_gemm_bsplit(const float* A, int64_t lda, int a_kcontig, const float* Bm
  *   a_row_mask (nullable): uint8 per STORED row of A (a token in every GEMM of this path, whether A is [M,K] or
  *   [K,M]); rows with a non-zero entry are read as zeros: the backward of MSDeformAttn's value masked_fill applied
  *   while the gradient streams through the producers instead of by poet_mask_rows.
+ *   drop_* (drop_p > 0): nn.Dropout on the epilogue's output, after the ReLU (deformable_transformer.py:194,268:
+ *   dropout2 / dropout3 on relu(linear1(x))), pair scheme of poet_dropout; the keep mask is ANDed into relu_bits_out,
+ *   so the backward is gate_bits + alpha = poet_dropout_scale(p, 1) on the dgrad and needs no second mask.
  * Returns POET_ERR_UNSUPPORTED when the shape is not tensor-core eligible (ask poet_gemm_relu_bits_supported()). */
 int poet_gemm_relu_bits_supported(int M, int N, int K, int precision);
 int poet_gemm_ex(const float* A, int64_t lda, int a_kcontig, const float* Bm, const void* B_hi, const void* B_lo,
                  int64_t ldb, int b_kcontig, float* C, int64_t ldc, int M, int N, int K, float alpha,
                  const float* bias, const uint8_t* row_mask, uint32_t* relu_bits_out, const uint32_t* gate_bits,
-                 float* a_colsum, const uint8_t* a_row_mask, int flags, int precision, poet_stream_t stream);
+                 float* a_colsum, const uint8_t* a_row_mask, int flags, int precision, const void* drop_seed,
+                 uint32_t drop_site, float drop_p, poet_stream_t stream);
 /* out[N] (+)= sum_m X[m,n]  (bias gradients).  accumulate=0 overwrites. */
 int poet_colsum(const float* X, int64_t ldx, float* out, int M, int N, int accumulate, poet_stream_t stream);
 /* the same, skipping rows with row_mask[m] != 0 (row_mask nullable) */
@@ -163,15 +167,31 @@ int poet_colsum_masked(const float* X, int64_t ldx, const uint8_t* row_mask, flo
                        poet_stream_t stream);
 
 /* ---- residual + LayerNorm ---------------------------------------------------------------- */
-/* z = x + r (r nullable); y = LN(z)*gamma + beta; y2 = y + pos (if y2 != NULL);
+/* Train-mode dropout (reference nn.Dropout sites deformable_transformer.py:178-286, default p 0.1 main.py:94) is
+ * counter-based everywhere in this library: element idx of site `drop_site` is kept iff hash(*drop_seed, drop_site,
+ * idx) >= drop_p * 2^32 and scaled by 1/(1 - drop_p).  drop_seed: DEVICE pointer to one uint64, read when the kernel
+ * runs (a replayed CUDA graph draws a new mask whenever the value changed); backward entry points regenerate the
+ * forward's mask from the same triple.  drop_p = 0 (eval / parity path): no dropout, drop_seed may be NULL. */
+
+/* z = x + dropout(r) (r nullable); y = LN(z)*gamma + beta; y2 = y + pos (if y2 != NULL);
  * xhat [R,C] and rstd [R] are saved for backward when non-NULL. C % 128 == 0, C <= 1024. */
 int poet_add_layernorm_fwd(const float* x, const float* r, const float* gamma, const float* beta,
                            const float* pos, float* y, float* y2, float* xhat, float* rstd,
-                           int R, int C, float eps, poet_stream_t stream);
-/* dz = LN backward of (dy [+ dy2]); dgamma/dbeta [C] are ACCUMULATED into (caller zero-fills). */
+                           int R, int C, float eps, const void* drop_seed, uint32_t drop_site, float drop_p,
+                           poet_stream_t stream);
+/* dz = LN backward of (dy [+ dy2]) = gradient of x; dgamma/dbeta [C] are ACCUMULATED into (caller zero-fills).
+ * With drop_p > 0 the gradient of the dropped branch r is written to dr [R,C] (= dz * mask / (1-p)); without
+ * dropout it equals dz and dr may be NULL. */
 int poet_layernorm_bwd(const float* dy, const float* dy2, const float* xhat, const float* rstd,
                        const float* gamma, float* dz, float* dgamma, float* dbeta,
-                       int R, int C, poet_stream_t stream);
+                       int R, int C, float* dr, const void* drop_seed, uint32_t drop_site, float drop_p,
+                       poet_stream_t stream);
+/* x <- dropout(x) in place over n floats (n % 4 == 0) with the PAIR scheme the GEMM epilogue uses for the FFN hidden
+ * activation (elements 2j, 2j+1 <- low / high half of hash(j), p quantised to 1/65536): fallback for a hidden
+ * activation whose producing GEMM is not tensor-core eligible; same mask as poet_gemm_ex for the same triple. */
+int poet_dropout(float* x, int64_t n, const void* drop_seed, uint32_t drop_site, float drop_p, poet_stream_t stream);
+/* 1 / (1 - p) as the kernels apply it (pair_scheme != 0: with p quantised to 1/65536): the alpha of the dgrad GEMM. */
+float poet_dropout_scale(float drop_p, int pair_scheme);
 /* x[r,:] = 0 where mask[r] != 0 (in place; MSDeformAttn value masked_fill and its backward). */
 int poet_mask_rows(float* x, const uint8_t* mask, int R, int C, poet_stream_t stream);
 /* out = a + b (nullable b -> copy); elementwise over n floats, n % 4 == 0. */
@@ -179,12 +199,15 @@ int poet_add(const float* a, const float* b, float* out, int64_t n, poet_stream_
 
 /* ---- decoder self-attention core (Q <= 32) ---------------------------------------------- */
 /* q,k,v: [B,Q,*] with row strides ldq/ldk/ldv (so they may be slices of one projection output);
- * head m uses channels [m*D,(m+1)*D).  probs [B,M,Q,Q] saved.  out [B,Q,M*D]. */
+ * head m uses channels [m*D,(m+1)*D).  probs [B,M,Q,Q] saved (before dropout).  out [B,Q,M*D].
+ * drop_*: nn.MultiheadAttention's attention-probability dropout (deformable_transformer.py:253), see above. */
 int poet_mha_smallq_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
-                        float* out, float* probs, int B, int Q, int M, int D, float scale, poet_stream_t stream);
+                        float* out, float* probs, int B, int Q, int M, int D, float scale, const void* drop_seed,
+                        uint32_t drop_site, float drop_p, poet_stream_t stream);
 int poet_mha_smallq_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                         const float* probs, const float* grad_out, float* gq, int64_t ldgq, float* gk, int64_t ldgk,
-                        float* gv, int64_t ldgv, int B, int Q, int M, int D, float scale, poet_stream_t stream);
+                        float* gv, int64_t ldgv, int B, int Q, int M, int D, float scale, const void* drop_seed,
+                        uint32_t drop_site, float drop_p, poet_stream_t stream);
 
 /* ---- heads: class-specific select + 6D -> SO(3) ------------------------------------------ */
 /* rot_all [R, n_slots*6], trans_all [R, n_slots*3], classes [R] int64 (slot = max(cls,0); n_slots = 1 => slot 0).

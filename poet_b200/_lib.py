@@ -13,7 +13,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libpoet_b200.so")
 
-_vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+_vp, _i, _i64, _f, _sz, _u32 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t, C.c_uint32
 
 # name -> (restype, argtypes); mirrors include/poet_b200.h exactly (tests/test_abi.py parses the header)
 SIGNATURES = {
@@ -36,16 +36,19 @@ SIGNATURES = {
     "poet_gemm_tc_eligible": (_i, [_i, _i, _i, _i64, _i64, _i64]),
     "poet_gemm_bsplit": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _i, _i, _vp]),
     "poet_gemm_relu_bits_supported": (_i, [_i, _i, _i, _i]),
-    "poet_gemm_ex": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "poet_gemm_ex": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i64, _i, _vp, _i64, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i,
+                          _vp, _u32, _f, _vp]),
+    "poet_dropout": (_i, [_vp, _i64, _vp, _u32, _f, _vp]),
+    "poet_dropout_scale": (_f, [_f, _i]),
     "poet_colsum_masked": (_i, [_vp, _i64, _vp, _vp, _i, _i, _i, _vp]),
     "poet_colsum": (_i, [_vp, _i64, _vp, _i, _i, _i, _vp]),
     "poet_mask_rows": (_i, [_vp, _vp, _i, _i, _vp]),
-    "poet_add_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
-    "poet_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "poet_add_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _u32, _f, _vp]),
+    "poet_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _u32, _f, _vp]),
     "poet_add": (_i, [_vp, _vp, _vp, _i64, _vp]),
-    "poet_mha_smallq_fwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    "poet_mha_smallq_fwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _f, _vp, _u32, _f, _vp]),
     "poet_mha_smallq_bwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64,
-                                 _i, _i, _i, _i, _f, _vp]),
+                                 _i, _i, _i, _i, _f, _vp, _u32, _f, _vp]),
     "poet_heads_select_rot6d_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "poet_im2col_3x3s2": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "poet_groupnorm_tokens_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),

@@ -9,7 +9,7 @@ size_t poet_gemm_tc_workspace_bytes(int M, int N, int K, int a_kcontig, int b_kc
 int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, const void* b_hi, const void* b_lo,
                  int64_t ldb, int b_kcontig, float* C, int64_t ldc, int M, int N, int K, float alpha, const float* bias,
                  const float* gate, const uint8_t* row_mask, uint32_t* relu_bits, const uint32_t* gate_bits, float* a_colsum,
-                 const uint8_t* a_row_mask, int flags, int precision, cudaStream_t s);
+                 const uint8_t* a_row_mask, int flags, int precision, cudaStream_t s, const PoetDropout* drop = nullptr);
 int poet_gemm_tc_bits_supported();
 bool poet_gemm_tc_supported(int M, int N, int K, int a_kcontig, int b_kcontig, int64_t lda, int64_t ldb, int64_t ldc);
 int poet_split_bf16_impl(const float* src, void* hi, void* lo, int64_t n, cudaStream_t s);
@@ -108,8 +108,9 @@ extern "C" int poet_gemm_ex(const float* A, int64_t lda, int a_kcontig, const fl
                             const void* B_lo, int64_t ldb, int b_kcontig, float* C, int64_t ldc, int M, int N, int K,
                             float alpha, const float* bias, const uint8_t* row_mask, uint32_t* relu_bits_out,
                             const uint32_t* gate_bits, float* a_colsum, const uint8_t* a_row_mask, int flags, int precision,
-                            poet_stream_t stream) {
+                            const void* drop_seed, uint32_t drop_site, float drop_p, poet_stream_t stream) {
   POET_REQUIRE(A && C && (Bm || B_hi), POET_ERR_NULL_POINTER);
+  POET_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || drop_seed != nullptr), POET_ERR_BAD_SHAPE);
   POET_REQUIRE(M > 0 && N > 0 && K > 0, POET_ERR_BAD_SHAPE);
   POET_REQUIRE(lda >= (a_kcontig ? K : M) && ldb >= (b_kcontig ? K : N) && ldc >= N, POET_ERR_BAD_SHAPE);
   POET_REQUIRE(!relu_bits_out || (flags & POET_GEMM_RELU), POET_ERR_UNSUPPORTED);
@@ -117,10 +118,12 @@ extern "C" int poet_gemm_ex(const float* A, int64_t lda, int a_kcontig, const fl
   POET_REQUIRE(precision == POET_GEMM_BF16X3 || precision == POET_GEMM_BF16, POET_ERR_UNSUPPORTED);
   POET_REQUIRE(poet_gemm_tc_supported(M, N, K, a_kcontig, b_kcontig, lda, ldb, ldc), POET_ERR_UNSUPPORTED);
   POET_REQUIRE(!a_colsum || (!a_kcontig && !b_kcontig && !B_hi), POET_ERR_UNSUPPORTED);
+  const PoetDropout drop = poet_make_dropout(drop_seed, drop_site, drop_p);
   return poet_gemm_tc(A, lda, a_kcontig, Bm, B_hi, B_lo, ldb, b_kcontig, C, ldc, M, N, K, alpha, bias, nullptr, row_mask,
-                      relu_bits_out, gate_bits, a_colsum, a_row_mask, flags, precision, (cudaStream_t)stream);
+                      relu_bits_out, gate_bits, a_colsum, a_row_mask, flags, precision, (cudaStream_t)stream, &drop);
 #else
   (void)alpha; (void)bias; (void)row_mask; (void)gate_bits; (void)a_colsum; (void)a_row_mask; (void)precision; (void)stream;
+  (void)drop_seed; (void)drop_site;
   return POET_ERR_UNSUPPORTED;
 #endif
 }

@@ -30,12 +30,17 @@ __global__ void __launch_bounds__(kWarps * 32) mha_fwd_kernel(const float* __res
                                                               const float* __restrict__ k, int64_t ldk,
                                                               const float* __restrict__ v, int64_t ldv,
                                                               float* __restrict__ out, float* __restrict__ probs,
-                                                              int B, int Q, int M, float scale) {
+                                                              int B, int Q, int M, float scale, const PoetDropout drop) {
   poet_pdl_entry();
   const int warp = blockIdx.x * kWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (warp >= B * M) return;
   const int b = warp / M, m = warp % M;
   const bool row = lane < Q;
+  // attention-probability dropout of nn.MultiheadAttention(dropout=p) (reference deformable_transformer.py:253,277):
+  // out = (P * mask / (1-p)) V; `probs` keeps the un-dropped P, the backward regenerates the mask
+  const bool dropping = drop.seed != nullptr;
+  PoetDropKey key{0u, 0u};
+  if (dropping) key = poet_drop_key(drop);
   float qi[D];
   load_vec<D>(q + ((int64_t)b * Q + (row ? lane : 0)) * ldq + m * D, qi);
 #pragma unroll
@@ -66,8 +71,10 @@ __global__ void __launch_bounds__(kWarps * 32) mha_fwd_kernel(const float* __res
 #pragma unroll
   for (int j = 0; j < 32; ++j)
     if (j < Q) {
-      const float pj = sc[j] * inv;
-      if (row && probs) probs[(((int64_t)b * M + m) * Q + lane) * Q + j] = pj;
+      float pj = sc[j] * inv;
+      const int64_t pidx = (((int64_t)b * M + m) * Q + lane) * Q + j;
+      if (row && probs) probs[pidx] = pj;
+      if (dropping) pj *= poet_drop_mult(key, (uint64_t)pidx, drop.threshold, drop.scale);
       float vj[D];
       load_vec<D>(v + ((int64_t)b * Q + j) * ldv + m * D, vj);
 #pragma unroll
@@ -87,8 +94,11 @@ __global__ void __launch_bounds__(kWarps * 32) mha_bwd_kernel(const float* __res
                                                               const float* __restrict__ probs, const float* __restrict__ go,
                                                               float* __restrict__ gq, int64_t ldgq, float* __restrict__ gk,
                                                               int64_t ldgk, float* __restrict__ gv, int64_t ldgv,
-                                                              int B, int Q, int M, float scale) {
+                                                              int B, int Q, int M, float scale, const PoetDropout drop) {
   poet_pdl_entry();
+  const bool dropping = drop.seed != nullptr;
+  PoetDropKey key{0u, 0u};
+  if (dropping) key = poet_drop_key(drop);
   __shared__ float s_p[kWarps][32][33];
   __shared__ float s_ds[kWarps][32][33];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -99,19 +109,22 @@ __global__ void __launch_bounds__(kWarps * 32) mha_bwd_kernel(const float* __res
   float gi[D];
   load_vec<D>(go + ((int64_t)b * Q + (row ? lane : 0)) * (M * D) + m * D, gi);
   // dp_ij = <go_i, v_j>;  ds_ij = p_ij (dp_ij - sum_j p_ij dp_ij)
-  float dp[32], pr[32];
+  // with dropout: out = (P o Mk) V, Mk = mask / (1-p): dP = (dO V^T) o Mk, dV = (P o Mk)^T dO, softmax backward on P
+  float dp[32], pr[32], mk[32];
   float dsum = 0.f;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    dp[j] = 0.f; pr[j] = 0.f;
+    dp[j] = 0.f; pr[j] = 0.f; mk[j] = 1.f;
     if (j < Q) {
       float vj[D];
       load_vec<D>(v + ((int64_t)b * Q + j) * ldv + m * D, vj);
       float s = 0.f;
 #pragma unroll
       for (int d = 0; d < D; ++d) s = fmaf(gi[d], vj[d], s);
+      const int64_t pidx = (((int64_t)b * M + m) * Q + (row ? lane : 0)) * Q + j;
+      if (dropping) { mk[j] = poet_drop_mult(key, (uint64_t)pidx, drop.threshold, drop.scale); s *= mk[j]; }
       dp[j] = s;
-      pr[j] = row ? __ldg(probs + (((int64_t)b * M + m) * Q + lane) * Q + j) : 0.f;
+      pr[j] = row ? __ldg(probs + pidx) : 0.f;
       dsum = fmaf(pr[j], s, dsum);
     }
   }
@@ -122,7 +135,7 @@ __global__ void __launch_bounds__(kWarps * 32) mha_bwd_kernel(const float* __res
   for (int j = 0; j < 32; ++j)
     if (j < Q) {
       const float ds = pr[j] * (dp[j] - dsum);
-      s_p[w][lane][j] = pr[j];
+      s_p[w][lane][j] = pr[j] * mk[j];
       s_ds[w][lane][j] = ds;
       float kj[D];
       load_vec<D>(k + ((int64_t)b * Q + j) * ldk + m * D, kj);
@@ -152,18 +165,21 @@ __global__ void __launch_bounds__(kWarps * 32) mha_bwd_kernel(const float* __res
 }  // namespace
 
 extern "C" int poet_mha_smallq_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
-                                   float* out, float* probs, int B, int Q, int M, int D, float scale, poet_stream_t stream) {
+                                   float* out, float* probs, int B, int Q, int M, int D, float scale, const void* drop_seed,
+                                   uint32_t drop_site, float drop_p, poet_stream_t stream) {
   POET_REQUIRE(q && k && v && out, POET_ERR_NULL_POINTER);
+  POET_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || drop_seed != nullptr), POET_ERR_BAD_SHAPE);
+  const PoetDropout drop = poet_make_dropout(drop_seed, drop_site, drop_p);
   POET_REQUIRE(B > 0 && M > 0 && Q >= 1 && Q <= 32, POET_ERR_BAD_SHAPE);
   POET_REQUIRE(poet_aligned16(out) && poet_aligned16(q) && poet_aligned16(k) && poet_aligned16(v) &&
                ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0, POET_ERR_BAD_ALIGNMENT);
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = poet_ceil_div(B * M, kWarps);
   switch (D) {
-    case 8: poet_launch(mha_fwd_kernel<8>, dim3(grid), dim3(kWarps * 32), 0, s, q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale); break;
-    case 16: poet_launch(mha_fwd_kernel<16>, dim3(grid), dim3(kWarps * 32), 0, s, q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale); break;
-    case 32: poet_launch(mha_fwd_kernel<32>, dim3(grid), dim3(kWarps * 32), 0, s, q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale); break;
-    case 64: poet_launch(mha_fwd_kernel<64>, dim3(grid), dim3(kWarps * 32), 0, s, q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale); break;
+    case 8: poet_launch(mha_fwd_kernel<8>, dim3(grid), dim3(kWarps * 32), 0, s, q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale, drop); break;
+    case 16: poet_launch(mha_fwd_kernel<16>, dim3(grid), dim3(kWarps * 32), 0, s, q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale, drop); break;
+    case 32: poet_launch(mha_fwd_kernel<32>, dim3(grid), dim3(kWarps * 32), 0, s, q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale, drop); break;
+    case 64: poet_launch(mha_fwd_kernel<64>, dim3(grid), dim3(kWarps * 32), 0, s, q, ldq, k, ldk, v, ldv, out, probs, B, Q, M, scale, drop); break;
     default: return POET_ERR_UNSUPPORTED;
   }
   return poet_launch_status();
@@ -172,15 +188,17 @@ extern "C" int poet_mha_smallq_fwd(const float* q, int64_t ldq, const float* k, 
 extern "C" int poet_mha_smallq_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                                    const float* probs, const float* grad_out, float* gq, int64_t ldgq, float* gk,
                                    int64_t ldgk, float* gv, int64_t ldgv, int B, int Q, int M, int D, float scale,
-                                   poet_stream_t stream) {
+                                   const void* drop_seed, uint32_t drop_site, float drop_p, poet_stream_t stream) {
   POET_REQUIRE(q && k && v && probs && grad_out && gq && gk && gv, POET_ERR_NULL_POINTER);
+  POET_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || drop_seed != nullptr), POET_ERR_BAD_SHAPE);
+  const PoetDropout drop = poet_make_dropout(drop_seed, drop_site, drop_p);
   POET_REQUIRE(B > 0 && M > 0 && Q >= 1 && Q <= 32, POET_ERR_BAD_SHAPE);
   POET_REQUIRE(poet_aligned16(q) && poet_aligned16(k) && poet_aligned16(v) && poet_aligned16(grad_out) && poet_aligned16(gq) &&
                poet_aligned16(gk) && poet_aligned16(gv) && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldgq % 4 == 0 &&
                ldgk % 4 == 0 && ldgv % 4 == 0, POET_ERR_BAD_ALIGNMENT);
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = poet_ceil_div(B * M, kWarps);
-#define POET_MHA_BWD(DD) poet_launch(mha_bwd_kernel<DD>, dim3(grid), dim3(kWarps * 32), 0, s, q, ldq, k, ldk, v, ldv, probs, grad_out, gq, ldgq, gk, ldgk, gv, ldgv, B, Q, M, scale)
+#define POET_MHA_BWD(DD) poet_launch(mha_bwd_kernel<DD>, dim3(grid), dim3(kWarps * 32), 0, s, q, ldq, k, ldk, v, ldv, probs, grad_out, gq, ldgq, gk, ldgk, gv, ldgv, B, Q, M, scale, drop)
   switch (D) {
     case 8: POET_MHA_BWD(8); break;
     case 16: POET_MHA_BWD(16); break;

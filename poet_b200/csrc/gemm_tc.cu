@@ -141,6 +141,7 @@ struct Args {
   const uint32_t* gate_bits;              // [M, N/32] keep-mask for the ReLU backward (TMA epilogue only)
   const uint8_t* a_row_mask;              // rows of the stored A operand (tokens) to read as zeros, or nullptr
   float* a_colsum;                        // weight-gradient shape only: a_colsum[m] += sum_k A[k, m] (the bias gradient), or nullptr
+  PoetDropout drop;                       // train-mode dropout of the (activated) output, TMA epilogue only; seed == nullptr: off
   int flags;
   int kb_per_split;       // k-blocks (of BK) per split
   int splits;
@@ -631,15 +632,30 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
               v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
             }
           }
+          // nn.Dropout on the epilogue's output (reference: dropout2 / dropout3 on relu(linear1(x)),
+          // deformable_transformer.py:194,268).  The keep mask is folded into the ReLU sign bitmask, so the backward
+          // needs no second mask: the dgrad gates on (pre-activation > 0 AND kept) and scales by 1/(1-p) through alpha.
+          uint32_t keep = 0xffffffffu;
+          if (p.drop.seed != nullptr) {
+            const PoetDropKey key = poet_drop_key(p.drop);
+            const uint64_t pair0 = ((uint64_t)row * (uint64_t)p.N + (uint64_t)n0c) >> 1;      // N and n0c are even
+            keep = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) keep |= poet_drop_keep2(key, pair0 + j, p.drop.threshold16) << (2 * j);
+          }
           if (relu) {
             if (p.relu_bits != nullptr) {
               uint32_t bits = 0;
 #pragma unroll
               for (int i = 0; i < 32; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
-              if (row_ok) p.relu_bits[(int64_t)row * words + (n0c >> 5)] = dead ? 0u : bits;
+              if (row_ok) p.relu_bits[(int64_t)row * words + (n0c >> 5)] = dead ? 0u : (bits & keep);
             }
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (p.drop.seed != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * p.drop.scale16 : 0.f;
           }
           if (p.gate_bits != nullptr) {                              // ReLU backward from the saved sign bitmask
             const uint32_t bits = row_ok ? __ldg(p.gate_bits + (int64_t)row * words + (n0c >> 5)) : 0u;
@@ -889,7 +905,7 @@ int poet_gemm_tc_bits_supported() {
 int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, const void* b_hi, const void* b_lo,
                  int64_t ldb, int b_kcontig, float* C, int64_t ldc, int M, int N, int K, float alpha, const float* bias,
                  const float* gate, const uint8_t* row_mask, uint32_t* relu_bits, const uint32_t* gate_bits, float* a_colsum,
-                 const uint8_t* a_row_mask, int flags, int precision, cudaStream_t s) {
+                 const uint8_t* a_row_mask, int flags, int precision, cudaStream_t s, const PoetDropout* drop) {
   POET_REQUIRE(poet_aligned16(A) && poet_aligned16(C), POET_ERR_BAD_ALIGNMENT);
   POET_REQUIRE(!bias || poet_aligned16(bias), POET_ERR_BAD_ALIGNMENT);
   POET_REQUIRE(!gate || poet_aligned16(gate), POET_ERR_BAD_ALIGNMENT);
@@ -898,6 +914,8 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
   static const int l2pf = tc::env_int("POET_GEMM_L2_PREFETCH", 1);
   static const int wgrad_bn = tc::env_int("POET_GEMM_WGRAD_BN", 256);
   POET_REQUIRE(epi_tma || (relu_bits == nullptr && gate_bits == nullptr), POET_ERR_UNSUPPORTED);
+  const bool dropping = drop != nullptr && drop->seed != nullptr;
+  POET_REQUIRE(!dropping || (epi_tma && N % 32 == 0), POET_ERR_UNSUPPORTED);
   const bool x3 = precision == POET_GEMM_BF16X3;
   const bool b_tma = b_hi != nullptr && (!x3 || b_lo != nullptr) && a_kcontig && (ldb % 8 == 0) &&
                      poet_aligned16(b_hi) && (!x3 || poet_aligned16(b_lo));
@@ -910,6 +928,8 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
   a.A = A; a.lda = lda; a.B = b_tma ? nullptr : Bm; a.ldb = ldb; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
   a.alpha = alpha; a.bias = bias; a.gate = gate; a.row_mask = row_mask; a.relu_bits = relu_bits; a.gate_bits = gate_bits; a.a_colsum = a_colsum; a.a_row_mask = a_row_mask;
   a.flags = flags;
+  memset(&a.drop, 0, sizeof(a.drop));
+  if (dropping) a.drop = *drop;
   a.epi_tma = epi_tma; a.l2_prefetch = l2pf; a.debug = dbg;
   const int m_tiles = poet_ceil_div(M, tc::BM);
   const int total_kb = poet_ceil_div(K, bk);

@@ -1,7 +1,8 @@
 // Residual + LayerNorm (forward/backward), column sums (bias gradients), elementwise add.
 // Replaces the `src = norm(src + dropout(src2))` pairs of the reference
-// (models/deformable_transformer.py:196-197, 202-203, 270-271, 279-280, 286-287); dropout is the
-// identity on the parity path (eval / --dropout 0).
+// (models/deformable_transformer.py:196-197, 202-203, 270-271, 279-280, 286-287).  Train-mode dropout of the
+// residual branch is counter-based (common.cuh PoetDropout): applied to r on the fly in the forward, and the
+// backward writes the branch gradient dr = dz * mask / (1-p) next to dz; p = 0 / eval is the parity path.
 // All of these are HBM-bound streaming kernels: one warp per row, 128-bit accesses, grid sized in
 // multiples of the SM count with a grid-stride loop.
 #include "common.cuh"
@@ -13,11 +14,14 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float* __restrict
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
                                                          const float* __restrict__ pos, float* __restrict__ y,
                                                          float* __restrict__ y2, float* __restrict__ xhat,
-                                                         float* __restrict__ rstd_out, int R, float eps) {
+                                                         float* __restrict__ rstd_out, int R, float eps, const PoetDropout drop) {
   poet_pdl_entry();
   constexpr int C = NV * 128;
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
+  const bool dropping = drop.seed != nullptr && r != nullptr;      // y = LN(x + dropout(r))
+  PoetDropKey key{0u, 0u};
+  if (dropping) key = poet_drop_key(drop);
   float4 g[NV], bt[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) { g[i] = ldg4(gamma + i * 128 + lane * 4); bt[i] = ldg4(beta + i * 128 + lane * 4); }
@@ -28,7 +32,15 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float* __restrict
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       z[i] = ld4(x + base + i * 128);
-      if (r) { float4 t = ld4(r + base + i * 128); z[i].x += t.x; z[i].y += t.y; z[i].z += t.z; z[i].w += t.w; }
+      if (r) {
+        float4 t = ld4(r + base + i * 128);
+        if (dropping) {
+          const uint64_t e = (uint64_t)(base + i * 128);
+          t.x *= poet_drop_mult(key, e, drop.threshold, drop.scale); t.y *= poet_drop_mult(key, e + 1, drop.threshold, drop.scale);
+          t.z *= poet_drop_mult(key, e + 2, drop.threshold, drop.scale); t.w *= poet_drop_mult(key, e + 3, drop.threshold, drop.scale);
+        }
+        z[i].x += t.x; z[i].y += t.y; z[i].z += t.z; z[i].w += t.w;
+      }
       sum += z[i].x + z[i].y + z[i].z + z[i].w;
     }
     const float mean = warp_sum(sum) * (1.f / C);
@@ -60,10 +72,14 @@ template <int NV>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2,
                                                      const float* __restrict__ xhat, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, float* __restrict__ dz,
-                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int R) {
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int R,
+                                                     float* __restrict__ dr, const PoetDropout drop) {
   poet_pdl_entry();
   constexpr int C = NV * 128;
   __shared__ float s_dg[C], s_db[C];
+  const bool dropping = drop.seed != nullptr && dr != nullptr;     // dr = dz * mask / (1 - p): gradient of the dropped branch
+  PoetDropKey key{0u, 0u};
+  if (dropping) key = poet_drop_key(drop);
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   for (int i = threadIdx.x; i < C; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
@@ -92,9 +108,18 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
     const float m1 = warp_sum(s1) * (1.f / C), m2 = warp_sum(s2) * (1.f / C);
     const float rs = __ldg(rstd + row);
 #pragma unroll
-    for (int i = 0; i < NV; ++i)
-      st4(dz + base + i * 128, make_float4(rs * (d[i].x - m1 - h[i].x * m2), rs * (d[i].y - m1 - h[i].y * m2),
-                                           rs * (d[i].z - m1 - h[i].z * m2), rs * (d[i].w - m1 - h[i].w * m2)));
+    for (int i = 0; i < NV; ++i) {
+      const float4 o = make_float4(rs * (d[i].x - m1 - h[i].x * m2), rs * (d[i].y - m1 - h[i].y * m2),
+                                   rs * (d[i].z - m1 - h[i].z * m2), rs * (d[i].w - m1 - h[i].w * m2));
+      st4(dz + base + i * 128, o);
+      if (dropping) {
+        const uint64_t e = (uint64_t)(base + i * 128);
+        st4(dr + base + i * 128, make_float4(o.x * poet_drop_mult(key, e, drop.threshold, drop.scale),
+                                             o.y * poet_drop_mult(key, e + 1, drop.threshold, drop.scale),
+                                             o.z * poet_drop_mult(key, e + 2, drop.threshold, drop.scale),
+                                             o.w * poet_drop_mult(key, e + 3, drop.threshold, drop.scale)));
+      }
+    }
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -165,6 +190,21 @@ __global__ void __launch_bounds__(256) mask_rows_kernel(float* __restrict__ x, c
     if (mask[i / C]) x[i] = 0.f;
 }
 
+// x <- dropout(x) in place with the pair scheme of the GEMM epilogue (same mask for the same (seed, site, index)):
+// the fallback for an FFN hidden activation whose producing GEMM is not on the tensor-core epilogue path.
+__global__ void __launch_bounds__(256) dropout_pairs_kernel(float4* __restrict__ x, int64_t n4, const PoetDropout drop) {
+  poet_pdl_entry();
+  const PoetDropKey key = poet_drop_key(drop);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = x[i];
+    const uint32_t k0 = poet_drop_keep2(key, (uint64_t)(2 * i), drop.threshold16);
+    const uint32_t k1 = poet_drop_keep2(key, (uint64_t)(2 * i + 1), drop.threshold16);
+    v.x = (k0 & 1u) ? v.x * drop.scale16 : 0.f; v.y = (k0 & 2u) ? v.y * drop.scale16 : 0.f;
+    v.z = (k1 & 1u) ? v.z * drop.scale16 : 0.f; v.w = (k1 & 2u) ? v.w * drop.scale16 : 0.f;
+    x[i] = v;
+  }
+}
+
 inline int row_grid(int R) {
   int blocks = poet_ceil_div(R, 8);                       // 8 warps (rows) per block
   int cap = POET_NUM_SMS * 8;
@@ -175,8 +215,11 @@ inline int row_grid(int R) {
 
 extern "C" int poet_add_layernorm_fwd(const float* x, const float* r, const float* gamma, const float* beta,
                                       const float* pos, float* y, float* y2, float* xhat, float* rstd, int R, int C,
-                                      float eps, poet_stream_t stream) {
+                                      float eps, const void* drop_seed, uint32_t drop_site, float drop_p,
+                                      poet_stream_t stream) {
   POET_REQUIRE(x && gamma && beta && y, POET_ERR_NULL_POINTER);
+  POET_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || drop_seed != nullptr), POET_ERR_BAD_SHAPE);
+  const PoetDropout drop = poet_make_dropout(drop_seed, drop_site, drop_p);
   POET_REQUIRE((y2 == nullptr) == (pos == nullptr), POET_ERR_NULL_POINTER);
   POET_REQUIRE(R > 0 && C % 128 == 0 && C <= 1024, POET_ERR_BAD_SHAPE);
   POET_REQUIRE(poet_aligned16(x) && poet_aligned16(y) && poet_aligned16(gamma) && poet_aligned16(beta) &&
@@ -185,10 +228,10 @@ extern "C" int poet_add_layernorm_fwd(const float* x, const float* r, const floa
   cudaStream_t s = (cudaStream_t)stream;
   const int grid = row_grid(R);
   switch (C / 128) {
-    case 1: poet_launch(add_ln_fwd_kernel<1>, dim3(grid), dim3(256), 0, s, x, r, gamma, beta, pos, y, y2, xhat, rstd, R, eps); break;
-    case 2: poet_launch(add_ln_fwd_kernel<2>, dim3(grid), dim3(256), 0, s, x, r, gamma, beta, pos, y, y2, xhat, rstd, R, eps); break;
-    case 4: poet_launch(add_ln_fwd_kernel<4>, dim3(grid), dim3(256), 0, s, x, r, gamma, beta, pos, y, y2, xhat, rstd, R, eps); break;
-    case 8: poet_launch(add_ln_fwd_kernel<8>, dim3(grid), dim3(256), 0, s, x, r, gamma, beta, pos, y, y2, xhat, rstd, R, eps); break;
+    case 1: poet_launch(add_ln_fwd_kernel<1>, dim3(grid), dim3(256), 0, s, x, r, gamma, beta, pos, y, y2, xhat, rstd, R, eps, drop); break;
+    case 2: poet_launch(add_ln_fwd_kernel<2>, dim3(grid), dim3(256), 0, s, x, r, gamma, beta, pos, y, y2, xhat, rstd, R, eps, drop); break;
+    case 4: poet_launch(add_ln_fwd_kernel<4>, dim3(grid), dim3(256), 0, s, x, r, gamma, beta, pos, y, y2, xhat, rstd, R, eps, drop); break;
+    case 8: poet_launch(add_ln_fwd_kernel<8>, dim3(grid), dim3(256), 0, s, x, r, gamma, beta, pos, y, y2, xhat, rstd, R, eps, drop); break;
     default: return POET_ERR_UNSUPPORTED;
   }
   return poet_launch_status();
@@ -196,8 +239,12 @@ extern "C" int poet_add_layernorm_fwd(const float* x, const float* r, const floa
 
 extern "C" int poet_layernorm_bwd(const float* dy, const float* dy2, const float* xhat, const float* rstd,
                                   const float* gamma, float* dz, float* dgamma, float* dbeta, int R, int C,
+                                  float* dr, const void* drop_seed, uint32_t drop_site, float drop_p,
                                   poet_stream_t stream) {
   POET_REQUIRE(dy && xhat && rstd && gamma && dz && dgamma && dbeta, POET_ERR_NULL_POINTER);
+  POET_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || (drop_seed != nullptr && dr != nullptr)), POET_ERR_BAD_SHAPE);
+  POET_REQUIRE(!dr || poet_aligned16(dr), POET_ERR_BAD_ALIGNMENT);
+  const PoetDropout drop = poet_make_dropout(drop_seed, drop_site, drop_p);
   POET_REQUIRE(R > 0 && C % 128 == 0 && C <= 1024, POET_ERR_BAD_SHAPE);
   POET_REQUIRE(poet_aligned16(dy) && poet_aligned16(xhat) && poet_aligned16(dz) && poet_aligned16(gamma) &&
                (!dy2 || poet_aligned16(dy2)), POET_ERR_BAD_ALIGNMENT);
@@ -205,10 +252,10 @@ extern "C" int poet_layernorm_bwd(const float* dy, const float* dy2, const float
   int grid = row_grid(R);
   if (grid > POET_NUM_SMS * 2) grid = POET_NUM_SMS * 2;   // fewer blocks -> fewer global atomics on dgamma/dbeta
   switch (C / 128) {
-    case 1: poet_launch(ln_bwd_kernel<1>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R); break;
-    case 2: poet_launch(ln_bwd_kernel<2>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R); break;
-    case 4: poet_launch(ln_bwd_kernel<4>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R); break;
-    case 8: poet_launch(ln_bwd_kernel<8>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R); break;
+    case 1: poet_launch(ln_bwd_kernel<1>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, drop); break;
+    case 2: poet_launch(ln_bwd_kernel<2>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, drop); break;
+    case 4: poet_launch(ln_bwd_kernel<4>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, drop); break;
+    case 8: poet_launch(ln_bwd_kernel<8>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, drop); break;
     default: return POET_ERR_UNSUPPORTED;
   }
   return poet_launch_status();
@@ -246,6 +293,24 @@ extern "C" int poet_add(const float* a, const float* b, float* out, int64_t n, p
   poet_launch(add_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
                                                      reinterpret_cast<float4*>(out), n4);
   return poet_launch_status();
+}
+
+extern "C" int poet_dropout(float* x, int64_t n, const void* drop_seed, uint32_t drop_site, float drop_p,
+                            poet_stream_t stream) {
+  POET_REQUIRE(x && drop_seed, POET_ERR_NULL_POINTER);
+  POET_REQUIRE(n > 0 && n % 4 == 0 && drop_p > 0.f && drop_p < 1.f, POET_ERR_BAD_SHAPE);
+  POET_REQUIRE(poet_aligned16(x), POET_ERR_BAD_ALIGNMENT);
+  const PoetDropout drop = poet_make_dropout(drop_seed, drop_site, drop_p);
+  const int64_t n4 = n / 4;
+  int grid = poet_ceil_div(n4, 256);
+  if (grid > POET_NUM_SMS * 8) grid = POET_NUM_SMS * 8;
+  poet_launch(dropout_pairs_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<float4*>(x), n4, drop);
+  return poet_launch_status();
+}
+
+extern "C" float poet_dropout_scale(float drop_p, int pair_scheme) {
+  const PoetDropout d = poet_make_dropout(reinterpret_cast<const void*>(1), 0, drop_p);
+  return drop_p > 0.f ? (pair_scheme ? d.scale16 : d.scale) : 1.f;
 }
 
 extern "C" int poet_mask_rows(float* x, const uint8_t* mask, int R, int C, poet_stream_t stream) {

@@ -11,8 +11,12 @@ libpoet_b200 kernel via ``poet_b200.ops``:
   decoder layer                :275-292  -> in_proj GEMMs + ops.mha_smallq + MSDeformAttn + LN + FFN
   next-layer query (x + pos)             -> second output of the LayerNorm kernel (fused)
 
-Dropout is the identity on the parity path (eval() or dropout=0); training with
-dropout > 0 uses the counter-based dropout of ops when available and raises otherwise.
+Dropout (reference :178,184,186,249,253-254,260,262 and the attention-probability dropout inside
+nn.MultiheadAttention; default 0.1, main.py:94) is counter-based and fused into the kernels that own the
+dropped tensors (the LayerNorm kernels for the residual branches, the FFN1 GEMM epilogue for the hidden
+activation, the attention kernel for the probabilities): active in train() with dropout > 0, the identity in
+eval() or with dropout = 0 -- the parity path (PyTorch's Philox stream cannot be reproduced, so
+train-mode checks are statistical).
 """
 from __future__ import annotations
 
@@ -46,10 +50,13 @@ def _shape_tensors(shapes, device):
     return _shape_cache[key]
 
 
-def _check_dropout(mod: nn.Module, p: float) -> None:
-    if mod.training and p > 0.0:
-        raise NotImplementedError("poet_b200: dropout > 0 in train mode is not implemented yet; build the model "
-                                  "with dropout=0 (the parity / benchmark configuration) or call eval()")
+def _p_drop(mod: nn.Module) -> float:
+    """Dropout probability in effect: the layer's `dropout` in train(), 0 in eval()."""
+    return float(mod.p_drop) if mod.training else 0.0
+
+
+# dropout site ids: (layer base) + (site within the layer); bases are assigned by DeformableTransformer.__init__
+_SITE_ATTN_PROB, _SITE_D1, _SITE_D2, _SITE_HIDDEN, _SITE_D4 = 0, 1, 2, 3, 5
 
 
 class _SelfAttentionParams(nn.Module):
@@ -65,11 +72,11 @@ class _SelfAttentionParams(nn.Module):
         nn.init.xavier_uniform_(self.in_proj_weight)
         nn.init.zeros_(self.out_proj.bias)
 
-    def forward(self, qk_in: torch.Tensor, v_in: torch.Tensor) -> torch.Tensor:
+    def forward(self, qk_in: torch.Tensor, v_in: torch.Tensor, drop_site: int = 0) -> torch.Tensor:
         """qk_in = tgt + query_pos, v_in = tgt, both [B,Q,C] (batch-first) -> attention output [B,Q,C]."""
         C = self.embed_dim
         qk, v = ops.in_proj_qk_v(qk_in, v_in, self.in_proj_weight, self.in_proj_bias)
-        o = ops.mha_smallq(qk, v, self.num_heads)
+        o = ops.mha_smallq(qk, v, self.num_heads, drop_p=float(self.dropout) if self.training else 0.0, drop_site=drop_site)
         return ops.linear(o, self.out_proj.weight, self.out_proj.bias)
 
 
@@ -79,6 +86,7 @@ class DeformableTransformerEncoderLayer(nn.Module):
         if activation != "relu":
             raise NotImplementedError("poet_b200 implements the 'relu' FFN used by every PoET config")
         self.p_drop = dropout
+        self.site_base = 0x100                     # re-assigned per layer by DeformableTransformer
         self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
         self.dropout1 = nn.Dropout(dropout)
         self.norm1 = nn.LayerNorm(d_model)
@@ -92,15 +100,19 @@ class DeformableTransformerEncoderLayer(nn.Module):
                 query=None, emit_next_query=False):
         """Reference signature plus two optional arguments used by our encoder stack: `query`
         (= src + pos, produced by the previous layer's LayerNorm kernel) and `emit_next_query`."""
-        _check_dropout(self, self.p_drop)
+        p, sb = _p_drop(self), self.site_base
         if query is None:
             query = src if pos is None else ops.add_tensors(src, pos)
         attn = self.self_attn(query, reference_points, src, spatial_shapes, level_start_index, padding_mask)
-        src = ops.add_layernorm(src, attn, self.norm1.weight, self.norm1.bias, eps=self.norm1.eps)
-        ffn = ops.mlp(src, ((self.linear1.weight, self.linear1.bias), (self.linear2.weight, self.linear2.bias)))
+        src = ops.add_layernorm(src, attn, self.norm1.weight, self.norm1.bias, eps=self.norm1.eps,
+                                drop_p=p, drop_site=sb + _SITE_D1)                                   # dropout1
+        ffn = ops.mlp(src, ((self.linear1.weight, self.linear1.bias), (self.linear2.weight, self.linear2.bias)),
+                      drop_p=p, drop_site=sb + _SITE_HIDDEN)                                         # dropout2
         if emit_next_query and pos is not None:
-            return ops.add_layernorm(src, ffn, self.norm2.weight, self.norm2.bias, pos=pos, eps=self.norm2.eps)
-        return ops.add_layernorm(src, ffn, self.norm2.weight, self.norm2.bias, eps=self.norm2.eps)
+            return ops.add_layernorm(src, ffn, self.norm2.weight, self.norm2.bias, pos=pos, eps=self.norm2.eps,
+                                     drop_p=p, drop_site=sb + _SITE_D2)                              # dropout3
+        return ops.add_layernorm(src, ffn, self.norm2.weight, self.norm2.bias, eps=self.norm2.eps,
+                                 drop_p=p, drop_site=sb + _SITE_D2)
 
 
 class DeformableTransformerEncoder(nn.Module):
@@ -131,6 +143,7 @@ class DeformableTransformerDecoderLayer(nn.Module):
         if activation != "relu":
             raise NotImplementedError("poet_b200 implements the 'relu' FFN used by every PoET config")
         self.p_drop = dropout
+        self.site_base = 0x10100                   # re-assigned per layer by DeformableTransformer
         self.cross_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
         self.dropout1 = nn.Dropout(dropout)
         self.norm1 = nn.LayerNorm(d_model)
@@ -145,21 +158,26 @@ class DeformableTransformerDecoderLayer(nn.Module):
 
     def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index,
                 src_padding_mask=None, value=None):
-        _check_dropout(self, self.p_drop)
+        p, sb = _p_drop(self), self.site_base
         if tgt.shape[1] > 32:
             raise NotImplementedError("decoder self-attention kernel supports at most 32 object queries")
         q = tgt if query_pos is None else ops.add_tensors(tgt, query_pos)
-        sa = self.self_attn(q, tgt)
+        sa = self.self_attn(q, tgt, drop_site=sb + _SITE_ATTN_PROB)                                  # MHA(dropout=p)
         if query_pos is not None:
-            tgt, q2 = ops.add_layernorm(tgt, sa, self.norm2.weight, self.norm2.bias, pos=query_pos, eps=self.norm2.eps)
+            tgt, q2 = ops.add_layernorm(tgt, sa, self.norm2.weight, self.norm2.bias, pos=query_pos, eps=self.norm2.eps,
+                                        drop_p=p, drop_site=sb + _SITE_D2)                           # dropout2
         else:
-            tgt = ops.add_layernorm(tgt, sa, self.norm2.weight, self.norm2.bias, eps=self.norm2.eps)
+            tgt = ops.add_layernorm(tgt, sa, self.norm2.weight, self.norm2.bias, eps=self.norm2.eps,
+                                    drop_p=p, drop_site=sb + _SITE_D2)
             q2 = tgt
         ca = self.cross_attn(q2, reference_points, src, src_spatial_shapes, level_start_index, src_padding_mask,
                              value=value)
-        tgt = ops.add_layernorm(tgt, ca, self.norm1.weight, self.norm1.bias, eps=self.norm1.eps)
-        ffn = ops.mlp(tgt, ((self.linear1.weight, self.linear1.bias), (self.linear2.weight, self.linear2.bias)))
-        return ops.add_layernorm(tgt, ffn, self.norm3.weight, self.norm3.bias, eps=self.norm3.eps)
+        tgt = ops.add_layernorm(tgt, ca, self.norm1.weight, self.norm1.bias, eps=self.norm1.eps,
+                                drop_p=p, drop_site=sb + _SITE_D1)                                   # dropout1
+        ffn = ops.mlp(tgt, ((self.linear1.weight, self.linear1.bias), (self.linear2.weight, self.linear2.bias)),
+                      drop_p=p, drop_site=sb + _SITE_HIDDEN)                                         # dropout3
+        return ops.add_layernorm(tgt, ffn, self.norm3.weight, self.norm3.bias, eps=self.norm3.eps,
+                                 drop_p=p, drop_site=sb + _SITE_D4)                                  # dropout4
 
 
 class DeformableTransformerDecoder(nn.Module):
@@ -223,6 +241,11 @@ class DeformableTransformer(nn.Module):
         self.level_embed = nn.Parameter(torch.empty(num_feature_levels, d_model))
         # unused when reference points come from boxes (reference :157-158) but part of the checkpoint format
         self.reference_points = nn.Linear(d_model, 2)
+        self.dropout = dropout
+        for i, layer in enumerate(self.encoder.layers):            # distinct dropout sites per layer (ops: counter-based masks)
+            layer.site_base = 0x100 * (i + 1)
+        for i, layer in enumerate(self.decoder.layers):
+            layer.site_base = 0x10000 + 0x100 * (i + 1)
         self._reset_parameters()
 
     def _reset_parameters(self):
@@ -256,6 +279,8 @@ class DeformableTransformer(nn.Module):
         lvl_pos_embed_flatten [B,S,C] already in token layout with level_embed added."""
         if query_embed is None:
             raise ValueError("query_embed is required")
+        if self.training and self.dropout > 0.0 and masks[0].is_cuda:
+            ops.begin_dropout_forward(masks[0].device)       # this forward's dropout seed (bumped in place: graph-safe)
         if reference_points is None:
             raise NotImplementedError("learned reference points are not used by PoET ('bbox' mode only)")
         if src_tokens is not None:               # ours: the pyramid already in token layout (ops.input_proj_tokens)

@@ -123,6 +123,53 @@ def launch_count() -> int:
 
 
 # ------------------------------------------------------------------------------------------
+# train-mode dropout: counter-based, no mask tensors (include/poet_b200.h "Train-mode dropout")
+# ------------------------------------------------------------------------------------------
+# One int64 counter per device.  Every training forward bumps it IN PLACE (so the bump is a node of a captured CUDA
+# graph and every replay draws new masks) and takes a private snapshot; all dropout sites of that forward -- and
+# their backward kernels, which regenerate the masks -- read the snapshot through its device pointer.
+_drop_counters = {}
+
+
+def set_dropout_seed(seed: int, device=None) -> None:
+    """Deterministic mask sequence from here on (the analogue of torch.manual_seed for the dropout of this library)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    c = _drop_counters.get(str(dev))
+    if c is None:
+        _drop_counters[str(dev)] = torch.full((1,), int(seed), dtype=torch.int64, device=dev)
+    else:
+        c.fill_(int(seed))
+
+
+def begin_dropout_forward(device) -> torch.Tensor:
+    """Called once per training forward with dropout > 0: returns this forward's seed tensor (int64 [1], device)."""
+    key = str(torch.device(device))
+    c = _drop_counters.get(key)
+    if c is None:
+        c = _drop_counters[key] = torch.full((1,), int(torch.initial_seed()) & 0x7FFFFFFFFFFF, dtype=torch.int64, device=device)
+    c.add_(1)
+    cur = c.clone()
+    _state["drop_seed"] = cur
+    return cur
+
+
+def _drop_args(p: float):
+    """(seed tensor, p) for an op called with dropout probability p; the seed must have been set by the model."""
+    if p <= 0.0:
+        return None, 0.0
+    if not 0.0 < p < 1.0:
+        raise ValueError(f"dropout probability must be in [0, 1), got {p}")
+    seed = _state.get("drop_seed")
+    if seed is None:
+        raise RuntimeError("dropout > 0 needs ops.begin_dropout_forward() at the start of the forward pass")
+    return seed, float(p)
+
+
+def dropout_scale(p: float, pair_scheme: bool = False) -> float:
+    return float(_lib.lib().poet_dropout_scale(float(p), int(pair_scheme))) if p > 0.0 else 1.0
+
+
+# ------------------------------------------------------------------------------------------
 # helpers
 # ------------------------------------------------------------------------------------------
 def _p(t: Optional[torch.Tensor]):
@@ -192,7 +239,7 @@ def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_kcontig
          out: Optional[torch.Tensor] = None, accumulate=False, alpha: float = 1.0,
          precision: Optional[int] = None, b_split=None, relu_bits: Optional[torch.Tensor] = None,
          gate_bits: Optional[torch.Tensor] = None, a_colsum: Optional[torch.Tensor] = None,
-         a_row_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+         a_row_mask: Optional[torch.Tensor] = None, drop=None) -> torch.Tensor:
     """out[M,N] = epi(alpha * op(A) @ op(B)); see include/poet_b200.h poet_gemm / poet_gemm_ex.
     relu_bits (out) / gate_bits (in): int32 [M, N/32] sign bitmask of a ReLU (tensor-core path only)."""
     if out is None:
@@ -208,12 +255,13 @@ def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_kcontig
     flags = (1 if relu else 0) | (2 if accumulate else 0)
     tag = (f"{M}x{N}x{K}" + ("" if a_kcontig else ",At") + ("" if b_kcontig else ",Bt")) if _timing["on"] else None
     work = (4 * (M * K + N * K + M * N), 2 * M * N * K)
-    if relu_bits is not None or gate_bits is not None or a_colsum is not None or a_row_mask is not None:
+    if relu_bits is not None or gate_bits is not None or a_colsum is not None or a_row_mask is not None or drop is not None:
         assert gate is None and prec != GEMM_FP32
         bs = b_split if (b_split is not None and a_kcontig) else (None, None)
+        d_seed, d_site, d_p = drop if drop is not None else (None, 0, 0.0)        # (seed tensor, site, p): epilogue dropout
         _call("poet_gemm_ex", _p(A), lda, int(a_kcontig), _p(Bm), _p(bs[0]), _p(bs[1]), ldb, int(b_kcontig), _p(out),
               out.stride(0), M, N, K, alpha, _p(bias), _p(row_mask), _p(relu_bits), _p(gate_bits), _p(a_colsum),
-              _p(a_row_mask), flags, prec, _stream(A), tag=tag, work=work)
+              _p(a_row_mask), flags, prec, _p(d_seed), int(d_site), float(d_p), _stream(A), tag=tag, work=work)
         return out
     if b_split is not None and prec != GEMM_FP32 and a_kcontig:
         _call("poet_gemm_bsplit", _p(A), lda, int(a_kcontig), _p(Bm), _p(b_split[0]), _p(b_split[1]), ldb,
@@ -529,7 +577,7 @@ def set_direct_param_grads(on: bool) -> None:
 
 def _linear_bwd(gy2: torch.Tensor, x2: torch.Tensor, W: torch.Tensor, need_x: bool, need_w: bool, need_b: bool,
                 gate: Optional[torch.Tensor] = None, w_split=None, w_param=None, b_param=None,
-                gate_bits: Optional[torch.Tensor] = None, gy_row_mask: Optional[torch.Tensor] = None):
+                gate_bits: Optional[torch.Tensor] = None, gy_row_mask: Optional[torch.Tensor] = None, alpha: float = 1.0):
     """gy2 [R,N], x2 [R,K], W [N,K] -> (dx [R,K] (gated by `gate`>0 if given), dW [N,K], db [N]).
     dW / db come back as None when they were accumulated directly into the parameters' .grad."""
     R, N = gy2.shape
@@ -539,7 +587,7 @@ def _linear_bwd(gy2: torch.Tensor, x2: torch.Tensor, W: torch.Tensor, need_x: bo
     # gy_row_mask: rows of gy2 to treat as zero (value masked_fill backward).  Zero rows of dY give zero rows of dX,
     # so the dgrad applies it as an output row mask; the weight / bias gradients read dY through the masked producer.
     dx = gemm(gy2, W, R, K, N, a_kcontig=True, b_kcontig=False, gate=gate, b_split=w_split,
-              gate_bits=gate_bits, row_mask=gy_row_mask) if need_x else None
+              gate_bits=gate_bits, row_mask=gy_row_mask, alpha=alpha) if need_x else None
     dW = db = None
     w_slot = _grad_slot(w_param) if need_w else None
     b_slot = _grad_slot(b_param) if need_b else None
@@ -665,21 +713,35 @@ class _MLP(torch.autograd.Function):
     producing GEMM's epilogue; its backward is the `gate` epilogue of the dgrad GEMM."""
 
     @staticmethod
-    def forward(ctx, x, *wb):
+    def forward(ctx, x, drop_p, drop_site, *wb):
         n = len(wb) // 2
         x2 = _chk(x).view(-1, x.shape[-1])
         acts = [x2]
         ctx.params = wb
         ctx.w_splits = []
         ctx.relu_bits = []                       # sign bitmask of layer i's ReLU output (None: gate on the fp32 activation)
+        # nn.Dropout after every ReLU (reference FFN: dropout2 / dropout3 on relu(linear1(x))).  On the tensor-core
+        # epilogue path the mask is folded into the ReLU bitmask; otherwise the activation is dropped in place and the
+        # backward gates on it.  Either way the dgrad of the next layer is scaled by 1/(1-p) through its alpha.
+        seed, drop_p = _drop_args(drop_p)
+        ctx.drop_alpha = dropout_scale(drop_p, pair_scheme=True)
         for i in range(n):
             W, b = _chk(wb[2 * i]), wb[2 * i + 1]
             h = acts[-1]
             ctx.w_splits.append(split_weight(W, h.shape[0]))
             bits = relu_bits_buffer(h.shape[0], W.shape[0], W.shape[1], h.device) if i < n - 1 else None
             ctx.relu_bits.append(bits)
+            dropping = drop_p > 0.0 and i < n - 1
+            fused = dropping and bits is not None and W.shape[0] % 32 == 0
             acts.append(gemm(h, W, h.shape[0], W.shape[0], W.shape[1], bias=b, relu=(i < n - 1),
-                             b_split=ctx.w_splits[-1], relu_bits=bits))
+                             b_split=ctx.w_splits[-1], relu_bits=bits,
+                             drop=(seed, drop_site + i, drop_p) if fused else None))
+            if dropping and not fused:
+                if acts[-1].numel() % 4:
+                    raise NotImplementedError("dropout needs hidden activations with a multiple of 4 elements")
+                _call("poet_dropout", _p(acts[-1]), acts[-1].numel(), _p(seed), int(drop_site + i), float(drop_p), _stream(h))
+                if bits is not None:             # the sign bitmask does not know the mask: gate on the dropped activation
+                    ctx.relu_bits[-1] = None
         ctx.save_for_backward(*acts[:-1], *[wb[2 * i] for i in range(n)])
         ctx.n = n
         ctx.xshape = x.shape
@@ -693,20 +755,22 @@ class _MLP(torch.autograd.Function):
         grads = [None] * (2 * n)
         for i in range(n - 1, -1, -1):
             need_x = i > 0 or ctx.needs_input_grad[0]
-            dx, dW, db = _linear_bwd(g, acts[i], Ws[i], need_x, ctx.needs_input_grad[1 + 2 * i],
-                                     ctx.needs_input_grad[2 + 2 * i], gate=acts[i] if i > 0 else None,
+            dx, dW, db = _linear_bwd(g, acts[i], Ws[i], need_x, ctx.needs_input_grad[3 + 2 * i],
+                                     ctx.needs_input_grad[4 + 2 * i], gate=acts[i] if i > 0 else None,
                                      w_split=ctx.w_splits[i], w_param=ctx.params[2 * i], b_param=ctx.params[2 * i + 1],
-                                     gate_bits=ctx.relu_bits[i - 1] if i > 0 else None)
+                                     gate_bits=ctx.relu_bits[i - 1] if i > 0 else None,
+                                     alpha=ctx.drop_alpha if i > 0 else 1.0)
             grads[2 * i], grads[2 * i + 1] = dW, db
             g = dx
-        return (g.view(ctx.xshape) if g is not None else None, *grads)
+        return (g.view(ctx.xshape) if g is not None else None, None, None, *grads)
 
 
-def mlp(x, layers: Sequence[Tuple[torch.Tensor, torch.Tensor]]):
+def mlp(x, layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], drop_p: float = 0.0, drop_site: int = 0):
+    """Linear/ReLU chain; drop_p > 0: nn.Dropout after every ReLU (sites drop_site, drop_site + 1, ...)."""
     flat = []
     for W, b in layers:
         flat += [W, b]
-    return _MLP.apply(x, *flat)
+    return _MLP.apply(x, float(drop_p), int(drop_site), *flat)
 
 
 class _ProjPair(torch.autograd.Function):
@@ -817,10 +881,10 @@ def in_proj_qk_v(qk_in, v_in, in_proj_weight, in_proj_bias):
 # autograd: residual + LayerNorm
 # ------------------------------------------------------------------------------------------
 class _AddLayerNorm(torch.autograd.Function):
-    """y = LN(x + r); optionally also y2 = y + pos (the next layer's query), one pass over HBM."""
+    """y = LN(x + dropout(r)); optionally also y2 = y + pos (the next layer's query), one pass over HBM."""
 
     @staticmethod
-    def forward(ctx, x, r, gamma, beta, pos, eps):
+    def forward(ctx, x, r, gamma, beta, pos, eps, drop_p=0.0, drop_site=0):
         x2 = _chk(x).view(-1, x.shape[-1])
         r2 = None if r is None else _chk(r).view(-1, x.shape[-1])
         R, Cc = x2.shape
@@ -831,8 +895,10 @@ class _AddLayerNorm(torch.autograd.Function):
         p2 = None if pos is None else _chk(pos).view(-1, Cc)
         y2 = torch.empty_like(x2) if pos is not None else None
         n_streams = 2 + (r is not None) + 2 * (pos is not None) + (1 if need_grad else 0)     # x, y [, r] [, pos, y2] [, xhat]
+        seed, drop_p = _drop_args(drop_p if r is not None else 0.0)
+        ctx.drop = (seed, int(drop_site), drop_p)
         _call("poet_add_layernorm_fwd", _p(x2), _p(r2), _p(gamma), _p(beta), _p(p2), _p(y), _p(y2), _p(xhat), _p(rstd),
-              R, Cc, eps, _stream(x), work=(4 * R * Cc * n_streams + 4 * R, 8 * R * Cc))
+              R, Cc, eps, _p(seed), int(drop_site), drop_p, _stream(x), work=(4 * R * Cc * n_streams + 4 * R, 8 * R * Cc))
         ctx.gb_params = (gamma, beta)
         if need_grad:
             ctx.save_for_backward(xhat, rstd, gamma)
@@ -857,17 +923,22 @@ class _AddLayerNorm(torch.autograd.Function):
         else:
             dgb = torch.zeros(2, Cc, device=xhat.device, dtype=torch.float32)
             dg_ptr, db_ptr = _p(dgb[0]), _p(dgb[1])
+        seed, site, drop_p = ctx.drop
+        dr = torch.empty_like(xhat) if (drop_p > 0.0 and ctx.has_r) else None     # gradient of the dropped branch
         _call("poet_layernorm_bwd", _p(gy), _p(gy2), _p(xhat), _p(rstd), _p(gamma), _p(dz), dg_ptr, db_ptr,
-              R, Cc, _stream(xhat), work=(4 * R * Cc * (3 + (gy2 is not None)) + 4 * R, 10 * R * Cc))   # gy [, gy2], xhat -> dz
+              R, Cc, _p(dr), _p(seed), site, drop_p if dr is not None else 0.0, _stream(xhat),
+              work=(4 * R * Cc * (3 + (gy2 is not None) + (dr is not None)) + 4 * R, 10 * R * Cc))   # gy [, gy2], xhat -> dz [, dr]
         dz = dz.view(ctx.shape)
         gpos = None
         if ctx.has_pos and ctx.needs_input_grad[4]:
             gpos = gy2.view(ctx.shape) if gy2 is not None else None
-        return dz, (dz if ctx.has_r else None), dgb[0], dgb[1], gpos, None
+        g_r = None if not ctx.has_r else (dr.view(ctx.shape) if dr is not None else dz)
+        return dz, g_r, dgb[0], dgb[1], gpos, None, None, None
 
 
-def add_layernorm(x, r, gamma, beta, pos=None, eps: float = 1e-5):
-    return _AddLayerNorm.apply(x, r, gamma, beta, pos, eps)
+def add_layernorm(x, r, gamma, beta, pos=None, eps: float = 1e-5, drop_p: float = 0.0, drop_site: int = 0):
+    """LN(x + dropout_p(r)) [, + pos]; drop_p > 0 only in training (the residual branch's nn.Dropout)."""
+    return _AddLayerNorm.apply(x, r, gamma, beta, pos, eps, float(drop_p), int(drop_site))
 
 
 class _Add(torch.autograd.Function):
@@ -966,7 +1037,7 @@ class _MhaSmallQ(torch.autograd.Function):
     """qk [B,Q,2C] (q | k projections of tgt+pos), v [B,Q,C] -> softmax(q k^T / sqrt(D)) v  [B,Q,C]."""
 
     @staticmethod
-    def forward(ctx, qk, v, M):
+    def forward(ctx, qk, v, M, drop_p=0.0, drop_site=0):
         qk, v = _chk(qk), _chk(v)
         B, Q, C2 = qk.shape
         Cc = C2 // 2
@@ -974,8 +1045,10 @@ class _MhaSmallQ(torch.autograd.Function):
         out = torch.empty((B, Q, Cc), device=qk.device, dtype=torch.float32)
         probs = torch.empty((B, M, Q, Q), device=qk.device, dtype=torch.float32)
         scale = 1.0 / math.sqrt(D)
+        seed, drop_p = _drop_args(drop_p)
+        ctx.drop = (seed, int(drop_site), drop_p)
         _call("poet_mha_smallq_fwd", _p(qk), C2, _p(qk.view(-1)[Cc:]), C2, _p(v), Cc, _p(out), _p(probs), B, Q, M, D,
-              scale, _stream(qk))
+              scale, _p(seed), int(drop_site), drop_p, _stream(qk))
         ctx.save_for_backward(qk, v, probs)
         ctx.dims = (B, Q, M, D, Cc, scale)
         return out
@@ -986,13 +1059,15 @@ class _MhaSmallQ(torch.autograd.Function):
         B, Q, M, D, Cc, scale = ctx.dims
         go = _chk(go)
         gqk, gv = torch.empty_like(qk), torch.empty_like(v)
+        seed, site, drop_p = ctx.drop
         _call("poet_mha_smallq_bwd", _p(qk), 2 * Cc, _p(qk.view(-1)[Cc:]), 2 * Cc, _p(v), Cc, _p(probs), _p(go),
-              _p(gqk), 2 * Cc, _p(gqk.view(-1)[Cc:]), 2 * Cc, _p(gv), Cc, B, Q, M, D, scale, _stream(qk))
-        return gqk, gv, None
+              _p(gqk), 2 * Cc, _p(gqk.view(-1)[Cc:]), 2 * Cc, _p(gv), Cc, B, Q, M, D, scale, _p(seed), site, drop_p, _stream(qk))
+        return gqk, gv, None, None, None
 
 
-def mha_smallq(qk, v, M):
-    return _MhaSmallQ.apply(qk, v, M)
+def mha_smallq(qk, v, M, drop_p: float = 0.0, drop_site: int = 0):
+    """softmax(q k^T / sqrt(D)) v; drop_p > 0: nn.MultiheadAttention's dropout on the attention probabilities."""
+    return _MhaSmallQ.apply(qk, v, M, float(drop_p), int(drop_site))
 
 
 # ------------------------------------------------------------------------------------------

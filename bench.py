@@ -249,11 +249,11 @@ class _FeatureBackbone(torch.nn.Module):
         self.strides, self.num_channels = [8, 16, 32], [channels] * 3
 
 
-def build_gpu_model(cfg, dev, with_input_proj=False):
+def build_gpu_model(cfg, dev, with_input_proj=False, dropout=0.0):
     from poet_b200 import synthetic as S
     from poet_b200.deformable_transformer import DeformableTransformer
     from poet_b200.pose_estimation_transformer import PoET
-    tr = DeformableTransformer(cfg["d_model"], cfg["nheads"], cfg["enc_layers"], cfg["dec_layers"], cfg["dim_ff"], 0.0,
+    tr = DeformableTransformer(cfg["d_model"], cfg["nheads"], cfg["enc_layers"], cfg["dec_layers"], cfg["dim_ff"], dropout,
                                "relu", True, cfg["n_levels"], cfg["n_points"], cfg["n_points"])
     backbone = _FeatureBackbone(cfg["d_model"]) if with_input_proj else None
     model = PoET(backbone, tr, cfg["num_queries"], cfg["n_levels"], cfg["n_classes"], class_mode=cfg["class_mode"])
@@ -282,7 +282,7 @@ def run_gpu(args):
     cfg = dict(S.CONFIGS[wl["cfg"]])
     cfg["batch"] = B = args.batch or default_batch(WORKLOAD, cfg, world)
     do_backward = wl["backward"]
-    model = build_gpu_model(cfg, dev, with_input_proj=args.from_features)
+    model = build_gpu_model(cfg, dev, with_input_proj=args.from_features, dropout=args.dropout)
     if not do_backward:
         model.eval()
     model.micro_batches = args.micro_batches
@@ -375,7 +375,7 @@ def run_gpu(args):
     sync_all()
     # parity of the benchmarked path itself (same model, same inputs, same graph replay) against the CPU oracle
     parity = None
-    if rank == 0 and not args.no_parity and not args.from_features and opt is None:
+    if rank == 0 and not args.no_parity and not args.from_features and opt is None and args.dropout == 0.0:
         parity = parity_check(cfg, inp, out0)
         if not parity["ok"]:
             print(f"bench.py: PARITY FAILED on the benchmarked path: {parity}", file=sys.stderr, flush=True)
@@ -494,6 +494,7 @@ def run_gpu(args):
                 "config": config_dict(cfg, {"global_batch": B * world, "parallelism": f"dp{world}",
                                             "grad_allreduce_bytes": reducer.nbytes() if world > 1 else 0,
                                             "gemm_precision": args.precision,
+                                            "dropout": args.dropout,
                                             "launch": "one CUDA graph per step" if args.graph else "eager",
                                             "micro_batches": args.micro_batches,
                                             "entry": ("backbone feature maps (input_proj inside the step)" if args.from_features
@@ -596,6 +597,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
                     help="BASELINE.json config to run (default cfg2, the configuration the metric is quoted on)")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the workload's)")
+    ap.add_argument("--dropout", type=float, default=0.0,
+                    help="train-mode dropout probability (reference default 0.1, main.py:94); 0 = the parity configuration")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity check of the benchmarked path")
     ap.add_argument("--micro-batches", type=int, default=int(os.environ.get("POET_MICRO_BATCHES", "1")),
                     help="slices of the per-GPU batch issued on separate streams (decoder chain of one overlaps the encoder of another)")

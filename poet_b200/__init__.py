@@ -17,3 +17,9 @@ def install_into_reference() -> None:
     (`from deformable_attention import MSDeformAttn`, reference models/deformable_transformer.py:24)."""
     from . import deformable_attention
     _sys.modules["deformable_attention"] = deformable_attention
+
+
+def build_model(args):
+    """Seam B-py2: drop-in for the reference's `models.build_model(args)` -> (model, criterion, matcher)."""
+    from .pose_estimation_transformer import build
+    return build(args)

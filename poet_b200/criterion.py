@@ -1,27 +1,36 @@
 """Pose loss on the device: the reference's SetCriterion (translation L2 + rotation geodesic,
 final + auxiliary decoder layers; models/pose_estimation_transformer.py:455-674) under the PoseMatcher assignment
-(models/matcher.py:104-229), as ONE kernel launch with no host synchronisation.
+(models/matcher.py:104-229), as ONE kernel launch for all decoder layers.
 
-In bbox_mode 'gt' / 'jitter' the first n_i queries of image i carry the target boxes in target order, so the
-Hungarian assignment is the identity on them (matcher.py:169-183: zero-cost diagonal) and is built on the device
-from the box counts.  For other modes pass an explicit `assign` tensor computed by any matcher.
+Two surfaces over the same kernel (`poet_pose_loss`):
 
-    crit = PoseCriterion(weight_dict={'loss_trans': 1.0, 'loss_rot': 1.0})
-    losses, total = crit(outputs, tgt_t, tgt_R, n_boxes_dev)        # same keys as the reference's loss dict
-    total.backward()
+  SetCriterion(matcher, weight_dict, losses)(outputs, targets, n_boxes) -> loss dict
+      the reference's class, constructor and call signature (engine.py:56 calls it exactly like this), every entry
+      of the dict differentiable (engine.py:57-58 forms the weighted sum itself);
+  PoseCriterion(weight_dict)(outputs, tgt_t, tgt_R, n_boxes_dev) -> (loss dict, weighted total)
+      padded device tensors in, no host work at all: the form a captured CUDA graph uses (bench.py --criterion).
+
+PoseMatcher mirrors matcher.py:104-229.  In bbox_mode 'gt' the first n_i queries of image i carry the target boxes
+in target order, so the Hungarian solution is the identity on them (zero-cost diagonal, matcher.py:169-173) and is
+built without leaving the device; 'jitter' queries are built from the jittered target boxes in target order
+(pose_estimation_transformer.py:207-214), so the intended one-to-one match is the identity as well; 'backbone' runs
+the reference's procedure (L1 centre + class cost, linear_sum_assignment, class / GIoU filter, matcher.py:186-229) on
+the host -- detector boxes are not part of the hot path.
 """
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Dict, List, Optional, Sequence
 
 import torch
 
 from . import ops
 
 
-class _PoseLoss(torch.autograd.Function):
+class _PoseLossTerms(torch.autograd.Function):
+    """losses [L,2] = (translation, rotation) per decoder layer, differentiable entry by entry."""
+
     @staticmethod
-    def forward(ctx, t_all, R_all, tgt_t, tgt_R, assign, n_obj, w_trans, w_rot):
+    def forward(ctx, t_all, R_all, tgt_t, tgt_R, assign, n_obj):
         t_all, R_all = ops._chk(t_all), ops._chk(R_all)
         L, B, Q = t_all.shape[:3]
         T = tgt_t.shape[1]
@@ -29,16 +38,32 @@ class _PoseLoss(torch.autograd.Function):
         gt, gR = torch.empty_like(t_all), torch.empty_like(R_all)
         ops._call("poet_pose_loss", t_all.data_ptr(), R_all.data_ptr(), ops._chk(tgt_t).data_ptr(), ops._chk(tgt_R).data_ptr(),
                   ops._chk(assign, torch.int32).data_ptr(), ops._chk(n_obj, torch.int32).data_ptr(), losses.data_ptr(),
-                  gt.data_ptr(), gR.data_ptr(), L, B, Q, T, float(w_trans), float(w_rot), ops._stream(t_all))
+                  gt.data_ptr(), gR.data_ptr(), L, B, Q, T, 1.0, 1.0, ops._stream(t_all))
         ctx.save_for_backward(gt, gR)
-        total = (losses[:, 0] * w_trans + losses[:, 1] * w_rot).sum()
-        ctx.mark_non_differentiable(losses)
-        return total, losses
+        return losses
 
     @staticmethod
-    def backward(ctx, g_total, _g_losses):
-        gt, gR = ctx.saved_tensors
-        return gt * g_total, gR * g_total, None, None, None, None, None, None
+    def backward(ctx, g):
+        gt, gR = ctx.saved_tensors                       # d loss_trans_l / d t_l and d loss_rot_l / d R_l
+        L = gt.shape[0]
+        return gt * g[:, 0].reshape(L, 1, 1, 1), gR * g[:, 1].reshape(L, 1, 1, 1), None, None, None, None
+
+
+def _stack_layers(outputs: dict):
+    layers = list(outputs.get("aux_outputs", [])) + [outputs]
+    t_all = torch.stack([o["pred_translation"] for o in layers])
+    R_all = torch.stack([o["pred_rotation"] for o in layers])
+    return t_all, R_all
+
+
+def _loss_dict(losses: torch.Tensor) -> Dict[str, torch.Tensor]:
+    L = losses.shape[0]
+    out = {}
+    for l in range(L):
+        suffix = "" if l == L - 1 else f"_{l}"           # reference: final layer unsuffixed, aux layer i -> '_i'
+        out["loss_trans" + suffix] = losses[l, 0]
+        out["loss_rot" + suffix] = losses[l, 1]
+    return out
 
 
 class PoseCriterion(torch.nn.Module):
@@ -58,18 +83,142 @@ class PoseCriterion(torch.nn.Module):
         """outputs: the model's dict (pred_translation [B,Q,3], pred_rotation [B,Q,3,3], aux_outputs);
         tgt_t [B,T,3] / tgt_R [B,T,3,3]: padded targets; n_boxes_dev [B] int32.  Returns (loss dict with the
         reference's keys, weighted total)."""
-        layers = list(outputs.get("aux_outputs", [])) + [outputs]
-        t_all = torch.stack([o["pred_translation"] for o in layers])
-        R_all = torch.stack([o["pred_rotation"] for o in layers])
+        t_all, R_all = _stack_layers(outputs)
         L, B, Q = t_all.shape[:3]
         if assign is None:
             assign = self.identity_assignment(n_boxes_dev, Q)
         n_obj = (assign >= 0).sum().to(torch.int32).reshape(1)
-        total, losses = _PoseLoss.apply(t_all, R_all.reshape(L, B, Q, 9), tgt_t, tgt_R.reshape(B, -1, 9), assign, n_obj,
-                                        self.w_trans, self.w_rot)
-        out = {}
-        for l in range(L):
-            suffix = "" if l == L - 1 else f"_{l}"
-            out["loss_trans" + suffix] = losses[l, 0]
-            out["loss_rot" + suffix] = losses[l, 1]
-        return out, total
+        losses = _PoseLossTerms.apply(t_all, R_all.reshape(L, B, Q, 9), tgt_t, tgt_R.reshape(B, -1, 9), assign, n_obj)
+        total = (losses[:, 0] * self.w_trans + losses[:, 1] * self.w_rot).sum()
+        return _loss_dict(losses), total
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference-signature surface (engine.py:55-58, models/__init__.py:10)
+# ------------------------------------------------------------------------------------------------------
+def _cxcywh_to_xyxy(b):
+    cx, cy, w, h = b.unbind(-1)
+    return torch.stack((cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h), -1)
+
+
+def _generalized_box_iou(a, b):
+    """util/box_ops.py:generalized_box_iou on xyxy boxes: [n,4] x [m,4] -> [n,m]."""
+    area_a = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1])
+    area_b = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    lt = torch.max(a[:, None, :2], b[None, :, :2])
+    rb = torch.min(a[:, None, 2:], b[None, :, 2:])
+    wh = (rb - lt).clamp(min=0)
+    inter = wh[..., 0] * wh[..., 1]
+    union = area_a[:, None] + area_b[None, :] - inter
+    iou = inter / union
+    lt_c = torch.min(a[:, None, :2], b[None, :, :2])
+    rb_c = torch.max(a[:, None, 2:], b[None, :, 2:])
+    wh_c = (rb_c - lt_c).clamp(min=0)
+    area_c = wh_c[..., 0] * wh_c[..., 1]
+    return iou - (area_c - union) / area_c
+
+
+class PoseMatcher(torch.nn.Module):
+    """models/matcher.py:104-229: same constructor, same forward(outputs, targets, n_boxes, giou_thresh) ->
+    list of (prediction indices, target indices) int64 tensor pairs, one per image."""
+
+    def __init__(self, cost_bbox: float = 1, cost_class: float = 1, bbox_mode: str = "gt", class_mode: str = "specific"):
+        super().__init__()
+        self.cost_bbox, self.cost_class = cost_bbox, cost_class
+        self.bbox_mode, self.class_mode = bbox_mode, class_mode
+
+    @torch.no_grad()
+    def forward(self, outputs, targets, n_boxes, giou_thresh: float = 0.5):
+        if self.bbox_mode in ("gt", "jitter"):
+            out = []
+            for t, n in zip(targets, n_boxes):
+                k = min(int(n), int(t["boxes"].shape[0]))
+                idx = torch.arange(k, dtype=torch.int64)
+                out.append((idx, idx.clone()))
+            return out
+        if self.bbox_mode != "backbone":
+            raise NotImplementedError(f"bbox_mode '{self.bbox_mode}'")
+        from scipy.optimize import linear_sum_assignment
+        boxes = outputs["pred_boxes"].detach().float().cpu()
+        classes = outputs["pred_classes"].detach().cpu()
+        result = []
+        for b, (t, n) in enumerate(zip(targets, n_boxes)):
+            n = int(n)
+            tb, tc = t["boxes"].detach().float().cpu(), t["labels"].detach().cpu()
+            pb, pc = boxes[b, :n], classes[b, :n]
+            if n == 0 or tb.shape[0] == 0:
+                result.append((torch.zeros(0, dtype=torch.int64), torch.zeros(0, dtype=torch.int64)))
+                continue
+            cost = self.cost_bbox * torch.cdist(pb[:, :2], tb[:, :2], p=1) + \
+                self.cost_class * (pc[:, None].float() != tc[None, :].float()).float()
+            rows, cols = linear_sum_assignment(cost.numpy())
+            giou = _generalized_box_iou(_cxcywh_to_xyxy(pb), _cxcywh_to_xyxy(tb))
+            keep_i, keep_j = [], []
+            for i, j in zip(rows.tolist(), cols.tolist()):
+                if self.class_mode == "specific" and int(pc[i]) != int(tc[j]):
+                    continue
+                if float(giou[i, j]) < giou_thresh:
+                    continue
+                keep_i.append(i)
+                keep_j.append(j)
+            result.append((torch.as_tensor(keep_i, dtype=torch.int64), torch.as_tensor(keep_j, dtype=torch.int64)))
+        return result
+
+
+class SetCriterion(torch.nn.Module):
+    """models/pose_estimation_transformer.py:455-674 for the '6d' losses ['translation', 'rotation']: same
+    constructor, `weight_dict` attribute and forward(outputs, targets, n_boxes) -> loss dict (keys loss_trans, loss_rot,
+    loss_trans_i, loss_rot_i).  targets: list of dicts with 'relative_position' [n,3], 'relative_rotation' [n,3,3],
+    'boxes', 'labels'.  The matching is computed once: pred_boxes / pred_classes are the same tensors for every decoder
+    layer (pose_estimation_transformer.py:398-418), so the per-layer matcher calls of the reference return the same
+    indices."""
+
+    def __init__(self, matcher, weight_dict, losses: Sequence[str] = ("translation", "rotation")):
+        super().__init__()
+        if sorted(losses) != ["rotation", "translation"]:
+            raise NotImplementedError(f"losses {list(losses)}: poet_b200 implements the '6d' pair ['translation', 'rotation']")
+        self.matcher, self.weight_dict, self.losses = matcher, weight_dict, list(losses)
+
+    def forward(self, outputs, targets, n_boxes):
+        head = {k: v for k, v in outputs.items() if k not in ("aux_outputs", "enc_outputs")}
+        indices = self.matcher(head, targets, n_boxes)
+        t_all, R_all = _stack_layers(outputs)
+        L, B, Q = t_all.shape[:3]
+        dev = t_all.device
+        T = max(1, max(int(t["relative_position"].shape[0]) for t in targets))
+        tgt_t = torch.zeros((B, T, 3), dtype=torch.float32)
+        tgt_R = torch.zeros((B, T, 9), dtype=torch.float32)
+        assign = torch.full((B, Q), -1, dtype=torch.int32)
+        on_host = all(not t["relative_position"].is_cuda for t in targets)
+        if not on_host:
+            tgt_t, tgt_R = tgt_t.to(dev), tgt_R.to(dev)
+        for b, (t, (src, tgt)) in enumerate(zip(targets, indices)):
+            n = int(t["relative_position"].shape[0])
+            if n:
+                tgt_t[b, :n] = t["relative_position"].to(tgt_t.device, torch.float32)
+                tgt_R[b, :n] = t["relative_rotation"].reshape(n, 9).to(tgt_R.device, torch.float32)
+            if src.numel():
+                assign[b, src.long().cpu()] = tgt.to(torch.int32).cpu()
+        n_obj = torch.tensor([int((assign >= 0).sum())], dtype=torch.int32)
+        losses = _PoseLossTerms.apply(t_all, R_all.reshape(L, B, Q, 9), tgt_t.to(dev, non_blocking=True),
+                                      tgt_R.to(dev, non_blocking=True), assign.to(dev, non_blocking=True),
+                                      n_obj.to(dev, non_blocking=True))
+        return _loss_dict(losses)
+
+
+def build_criterion(args):
+    """(criterion, matcher) as reference build() makes them (pose_estimation_transformer.py:714-739)."""
+    if getattr(args, "matcher_type", "pose") != "pose":
+        raise NotImplementedError("Matcher type not implemented!")
+    if args.rotation_representation != "6d" or getattr(args, "aleatoric", False):
+        raise NotImplementedError("poet_b200 implements the '6d' losses ['translation', 'rotation']")
+    matcher = PoseMatcher(cost_bbox=getattr(args, "set_cost_bbox", 1), cost_class=getattr(args, "set_cost_class", 1),
+                          bbox_mode=args.bbox_mode, class_mode=args.class_mode)
+    weight_dict = {"loss_trans": args.translation_loss_coef, "loss_rot": args.rotation_loss_coef}
+    if args.aux_loss:
+        aux = {}
+        for i in range(args.dec_layers - 1):
+            aux.update({k + f"_{i}": v for k, v in weight_dict.items()})
+        aux.update({k + "_enc": v for k, v in weight_dict.items()})
+        weight_dict.update(aux)
+    return SetCriterion(matcher, weight_dict, ["translation", "rotation"]), matcher

@@ -95,8 +95,10 @@ class PoET(nn.Module):
             raise NotImplementedError("Class mode is not supported.")
         self.t_dim, self.rot_dim = 3, 6
         slots = self.n_classes if class_mode == "specific" else 1
-        t_head = MLP(hidden_dim, hidden_dim, self.t_dim * slots, 3)
-        r_head = MLP(hidden_dim, hidden_dim, self.rot_dim * slots, 3)
+        # registration (= optimizer parameter numbering, an on-disk format: main.py:302) and RNG order of the reference
+        # (:86-96): the two prototype heads first, input_proj next, then the per-layer copies replace the prototypes
+        self.translation_head = MLP(hidden_dim, hidden_dim, self.t_dim * slots, 3)
+        self.rotation_head = MLP(hidden_dim, hidden_dim, self.rot_dim * slots, 3)
 
         self.num_feature_levels = num_feature_levels
         if backbone is not None:
@@ -118,8 +120,8 @@ class PoET(nn.Module):
             self.input_proj = nn.ModuleList()             # pyramid-only use (forward_pyramid)
 
         n_pred = transformer.decoder.num_layers
-        self.translation_head = nn.ModuleList(copy.deepcopy(t_head) for _ in range(n_pred))
-        self.rotation_head = nn.ModuleList(copy.deepcopy(r_head) for _ in range(n_pred))
+        self.translation_head = nn.ModuleList(copy.deepcopy(self.translation_head) for _ in range(n_pred))
+        self.rotation_head = nn.ModuleList(copy.deepcopy(self.rotation_head) for _ in range(n_pred))
         self.bbox_embedding = BoundingBoxEmbeddingSine(num_pos_feats=hidden_dim / 8)
 
     # ------------------------------------------------------------------ queries (A1)
@@ -398,13 +400,39 @@ class _PosTokens(torch.autograd.Function):
         return (None if slot is not None else gle, None, None, *([None] * len(hws)))
 
 
-def build(args):
-    """reference :692-739 minus the detector: returns the model only; criterion / matcher are the
-    reference's own (see INTEGRATION.md for plugging this into models.build_model)."""
-    backbone = getattr(args, "backbone_module", None)
+def build_poet(args, backbone=None):
+    """The model of reference build() (:692-712).  The detector backbone is outside the hot path: pass the
+    reference's own (`models.backbone.build_backbone(args)`) or any module with the same contract as `backbone`
+    / `args.backbone_module`."""
+    backbone = backbone if backbone is not None else getattr(args, "backbone_module", None)
     transformer = build_deforamble_transformer(args)
     return PoET(backbone, transformer, num_queries=args.num_queries, num_feature_levels=args.num_feature_levels,
                 n_classes=args.n_classes, bbox_mode=args.bbox_mode, ref_points_mode=args.reference_points,
                 query_embedding_mode=args.query_embedding, rotation_mode=args.rotation_representation,
                 class_mode=args.class_mode, aleatoric=args.aleatoric, aux_loss=args.aux_loss,
                 backbone_type=getattr(args, "backbone", "maskrcnn"))
+
+
+def build(args):
+    """reference :692-739: `models.build_model(args)` -> (model, criterion, matcher) (models/__init__.py:10, called at
+    main.py:205 and inference_tools/inference_engine.py:31).  The backbone comes from `args.backbone_module` when set,
+    else from the reference's `models.backbone.build_backbone` if that package is importable."""
+    from .criterion import build_criterion
+    backbone = getattr(args, "backbone_module", None)
+    if backbone is None:
+        try:
+            from models.backbone import build_backbone           # the reference's detector, unmodified
+            backbone = build_backbone(args)
+        except ImportError:
+            backbone = None
+    model = build_poet(args, backbone)
+    criterion, matcher = build_criterion(args)
+    dev = getattr(args, "device", None)
+    if dev is not None:
+        criterion.to(torch.device(dev))
+    return model, criterion, matcher
+
+
+def build_model(args):
+    """models/__init__.py:10."""
+    return build(args)

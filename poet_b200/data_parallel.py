@@ -72,6 +72,9 @@ class FlatGradReducer:
         ws = self.world_size()
         if ws == 1:
             return None
+        if self.average and dist.get_backend(self.group) == "nccl":
+            # ncclAvg: the 1/world scaling happens inside the collective, no extra pass over the arena
+            return dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group, async_op=async_op)
         if self.average:
             self.flat.mul_(1.0 / ws)
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)

@@ -1,0 +1,110 @@
+"""SURVEY.md §4 'distributed' tier on real GPUs: N ranks (one per GPU, NCCL), each running the CUDA path on its image
+shard; after FlatGradReducer.all_reduce() the gradient arena of every rank must equal the single-process gradients of
+the concatenated batch (divided by N: the reducer averages, like DDP).  Needs >= 2 GPUs (gpurun --gpus 2); skipped on
+one GPU.  Also covers the whole-step CUDA graph with the all-reduce of the arena after the replay, the way bench.py
+runs it."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from poet_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _build(cfg, P, dev):
+    from poet_b200.deformable_transformer import DeformableTransformer
+    from poet_b200.pose_estimation_transformer import PoET
+    tr = DeformableTransformer(cfg["d_model"], cfg["nheads"], cfg["enc_layers"], cfg["dec_layers"], cfg["dim_ff"], 0.0,
+                               "relu", True, cfg["n_levels"], cfg["n_points"], cfg["n_points"])
+    model = PoET(None, tr, cfg["num_queries"], cfg["n_levels"], cfg["n_classes"], class_mode=cfg["class_mode"])
+    model.load_state_dict(P, strict=True)
+    return model.to(dev).train()
+
+
+def _step(model, red, cfg, inp, g_t, g_R, lo, hi, dev, graphed):
+    from poet_b200.graph import GraphedStep
+    srcs = [s[lo:hi].to(dev) for s in inp["srcs"]]
+    masks = [m[lo:hi].to(dev) for m in inp["masks"]]
+    gt, gR = g_t[:, lo:hi].to(dev), g_R[:, lo:hi].to(dev)
+
+    def loss_fn(out):
+        t = torch.stack([a["pred_translation"] for a in out["aux_outputs"]] + [out["pred_translation"]])
+        R = torch.stack([a["pred_rotation"] for a in out["aux_outputs"]] + [out["pred_rotation"]])
+        return (t * gt).sum() + (R * gR).sum()
+
+    if graphed:
+        step = GraphedStep(model, loss_fn, srcs, masks, inp["boxes"][lo:hi], inp["labels"][lo:hi], reducer=red, warmup=1)
+        step.run()
+    else:
+        red.zero()
+        out, _ = model.forward_pyramid(srcs, masks, inp["boxes"][lo:hi], inp["labels"][lo:hi])
+        loss_fn(out).backward()
+    torch.cuda.synchronize(dev)
+
+
+def _worker(rank, world, port, out_dir, graphed):
+    from poet_b200 import ops
+    from poet_b200.data_parallel import FlatGradReducer, shard_range
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    ops.set_gemm_precision("bf16x3")
+    cfg = dict(S.CONFIGS["cfg2_b2"], batch=2 * world)
+    P = S.make_params(cfg)
+    inp = S.make_inputs(cfg, pad_columns=True)
+    g_t, g_R = S.make_cotangents(cfg)
+    model = _build(cfg, P, dev)
+    red = FlatGradReducer(model.parameters())
+    lo, hi = shard_range(cfg["batch"], rank, world)
+    _step(model, red, cfg, inp, g_t, g_R, lo, hi, dev, graphed)
+    red.all_reduce()
+    torch.cuda.synchronize(dev)
+    mine = red.flat.detach().clone()
+    # every rank holds the same reduced arena
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    for g in gathered:
+        assert torch.equal(g, mine)
+    if rank == 0:
+        full = _build(cfg, P, dev)
+        red_full = FlatGradReducer(full.parameters())
+        _step(full, red_full, cfg, inp, g_t, g_R, 0, cfg["batch"], dev, False)
+        torch.save({"reduced": mine.cpu(), "full": red_full.flat.detach().cpu(), "world": world,
+                    "offsets": red.offsets, "names": [n for n, _ in model.named_parameters()]}, os.path.join(out_dir, "grads.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("graphed", [False, True])
+def test_nccl_allreduced_gradients_equal_single_process(tmp_path, graphed):
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least two GPUs")
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), graphed), nprocs=world, join=True)
+    rec = torch.load(os.path.join(tmp_path, "grads.pt"))
+    reduced, ref = rec["reduced"], rec["full"] / rec["world"]
+    bounds = list(rec["offsets"]) + [reduced.numel()]
+    worst = 0.0
+    for name, a, b in zip(rec["names"], bounds[:-1], bounds[1:]):
+        r, f = reduced[a:b], ref[a:b]
+        scale = float(f.abs().max())
+        if scale == 0.0:
+            assert float(r.abs().max()) == 0.0, name
+            continue
+        err = float((r - f).abs().max()) / scale
+        worst = max(worst, err)
+        # fp32 summation order differs (B*S rows reduced per rank, then across ranks): a few ulps of the largest entry
+        assert err <= 2e-5, (name, err)
+    assert worst > 0.0 or world == 1

@@ -22,6 +22,7 @@
 // one shuffle at the end.
 #include <cstdlib>
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "tma_host.cuh"
 
@@ -43,6 +44,8 @@ struct MsdaArgs {
   float* out;
   const float* grad_out; float* grad_value; float* grad_a; float* grad_w;
   int B, S, Lq, M, D, L, P;
+  int red_levels;            // backward: levels [0, red_levels) scatter grad_value with global reductions; the rest is
+                             // produced by msda_bwd_dense_kernel (L = all levels: the classic path)
   Levels lv;
 };
 
@@ -409,21 +412,22 @@ __global__ void __launch_bounds__(256, 3) msda_bwd_kernel(const MsdaArgs p) {
         const bool xl = x0 >= 0, xh = x0 + 1 < W, yl = y0 >= 0, yh = y0 + 1 < H;
         const int i00 = (y0 * W + x0) * vstride;
         float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;      // <grad_out, corner value>
+        const bool scatter = live && l < p.red_levels;        // the dense kernel owns the other levels' grad_value
         if (yl && xl) {
           d00 = dot4(go, ldg4(vl + i00));
-          if (live) red_add4(gl + i00, a * (1.f - fy) * (1.f - fx), go);
+          if (scatter) red_add4(gl + i00, a * (1.f - fy) * (1.f - fx), go);
         }
         if (yl && xh) {
           d01 = dot4(go, ldg4(vl + i00 + vstride));
-          if (live) red_add4(gl + i00 + vstride, a * (1.f - fy) * fx, go);
+          if (scatter) red_add4(gl + i00 + vstride, a * (1.f - fy) * fx, go);
         }
         if (yh && xl) {
           d10 = dot4(go, ldg4(vl + i00 + W * vstride));
-          if (live) red_add4(gl + i00 + W * vstride, a * fy * (1.f - fx), go);
+          if (scatter) red_add4(gl + i00 + W * vstride, a * fy * (1.f - fx), go);
         }
         if (yh && xh) {
           d11 = dot4(go, ldg4(vl + i00 + (W + 1) * vstride));
-          if (live) red_add4(gl + i00 + (W + 1) * vstride, a * fy * fx, go);
+          if (scatter) red_add4(gl + i00 + (W + 1) * vstride, a * fy * fx, go);
         }
         ga = (1.f - fy) * (1.f - fx) * d00 + (1.f - fy) * fx * d01 + fy * (1.f - fx) * d10 + fy * fx * d11;
         // d sampled / d x (pixels) and / d y, times attention weight; pixels = loc * size
@@ -459,6 +463,255 @@ __global__ void __launch_bounds__(256, 3) msda_bwd_kernel(const MsdaArgs p) {
   for (int j = 0; j < LP / 4; ++j)
     if (j % G == c4) st4(gw + j * 4, make_float4(g_attn[j * 4], g_attn[j * 4 + 1], g_attn[j * 4 + 2], g_attn[j * 4 + 3]));
 }
+
+
+// ------------------------------------------------------------------------------------------
+// backward, grad_value of the low-resolution levels as a dense tensor-core product
+// ------------------------------------------------------------------------------------------
+// The scatter formulation issues one 16-byte global reduction per (corner, 4 channels): 64 per (q,m), and three
+// quarters of them land on the few hundred pixels of levels 1..3 (REF pyramid: 300 + 80 + 20 of 1600).  The SM's
+// reduction issue rate (0.86 cycles per lane-op) is what bounds that kernel.  For those levels the same sum is a
+// small dense product per (image, head):
+//
+//     grad_value[px, :] = sum_q W[px, q] * grad_out[q, :],   W[px, q] = sum over the sampling points of q at that
+//                                                            level of attention * bilinear corner weight at px
+//
+// W is built in shared memory, one COLUMN per query owned by one thread per level (its own points are serialised in
+// the thread, columns of different queries never meet: no atomics), and multiplied on the tensor cores with
+// mma.sync m16n8k16: M = pixels, N = D = 16 channels, K = queries.  Operands are split into fp16 hi/lo pairs
+// (x = hi + lo to 2^-22; grad_out is scaled by a power of two per work item so that fp16's range fits), three MMAs per
+// product with fp32 accumulation: fp32-grade like the split-bf16 GEMMs.  The accumulators of a work item
+// (image, head, query chunk) live in registers across its query tiles and leave as one reduction per element at the
+// end.  This is legacy-path tensor work on purpose: 3 x 2 x 16 x 400 x 16 flops per query tile is latency-, not
+// throughput-bound, and tcgen05's 128-row tiles would be 97 % padding on the N = 16 side.
+namespace dense {
+
+constexpr int KQ = 32;              // queries per tile (K of the product)
+constexpr int QS = 40;              // row stride of W in floats: QS % 32 == 8 makes the A-fragment loads conflict-free
+constexpr int THREADS = 128;        // 4 warps; thread = (query of the tile, role): roles 0..2 build one level each, role 3 stages grad_out
+constexpr int MAX_MT = 7;           // m-tiles (16 pixels) per warp: 4 * 7 * 16 = 448 dense pixels at most
+constexpr int GS = 20;              // row stride (32-bit words) of the transposed fp16 grad_out tile [d][q/2]
+
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void split_half2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x, y);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <int L, int P, bool FUSED>
+__global__ void __launch_bounds__(THREADS, 3)
+msda_bwd_dense_kernel(const MsdaArgs p, int lvl0, int npx, int n_mt, int nchunk, int q_per_chunk, int n_items) {
+  poet_pdl_entry();
+  constexpr int LP = L * P, D = 16;
+  extern __shared__ __align__(16) uint8_t dense_smem[];
+  float* Wt = reinterpret_cast<float*>(dense_smem);                                  // [n_mt * 16][QS]
+  uint32_t* gh = reinterpret_cast<uint32_t*>(Wt + (size_t)n_mt * 16 * QS);           // [D][GS] fp16 pairs (q even | q odd)
+  uint32_t* gl = gh + D * GS;
+  __shared__ float s_max[THREADS / 32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int ql = tid & 31, role = tid >> 5;                    // build-phase identity
+  const int lvl = lvl0 + role;                                 // level this thread builds (role 3 or lvl >= L: none)
+  const bool builder = lvl < L;
+  const int pix0 = p.lv.start[lvl0];                           // first dense pixel in the flattened map
+
+  for (int i = tid; i < n_mt * 16 * QS; i += THREADS) Wt[i] = 0.f;
+  __syncthreads();
+
+  int H = 1, Wd = 1, lstart = 0;
+  float inv_W = 0.f, inv_H = 0.f;
+  if (builder) { H = p.lv.H[lvl]; Wd = p.lv.W[lvl]; lstart = p.lv.start[lvl] - pix0; inv_W = p.lv.inv_W[lvl]; inv_H = p.lv.inv_H[lvl]; }
+
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int chunk = item % nchunk, bm = item / nchunk;
+    const int m = bm % p.M, b = bm / p.M;
+    const int q_beg = chunk * q_per_chunk, q_end = min(p.Lq, q_beg + q_per_chunk);
+    if (q_beg >= q_end) continue;
+    // ---- power-of-two scale of this item's grad_out rows (fp16 range) ----
+    float mx = 0.f;
+    for (int i = tid; i < (q_end - q_beg) * (D / 4); i += THREADS) {
+      const int q = q_beg + i / (D / 4), c = i % (D / 4);
+      const float4 v = ldg4(p.grad_out + (((int64_t)b * p.Lq + q) * p.M + m) * D + c * 4);
+      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __syncthreads();                                            // previous item's readers of s_max are done
+    if (lane == 0) s_max[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(s_max[0], s_max[1]), fmaxf(s_max[2], s_max[3]));
+    if (!(mx > 0.f) || !(mx < INFINITY)) continue;             // all-zero gradient: nothing to add (uniform over the CTA)
+    int e;
+    (void)frexpf(mx, &e);                                       // mx = f * 2^e, f in [0.5, 1)
+    const float scale = ldexpf(1.f, 10 - e), inv_scale = ldexpf(1.f, e - 10);   // scaled maximum in [512, 1024)
+
+    float acc[MAX_MT][2][4];
+#pragma unroll
+    for (int i = 0; i < MAX_MT; ++i)
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[i][n][k] = 0.f;
+
+    for (int q0 = q_beg; q0 < q_end; q0 += KQ) {
+      const int q = q0 + ql;
+      const bool q_ok = q < q_end;
+      uint32_t touched[2 * P];                                  // W word offsets written by this thread (pairs packed), 0xffff: none
+#pragma unroll
+      for (int i = 0; i < 2 * P; ++i) touched[i] = 0xffffffffu;
+      if (builder && q_ok) {
+        // ---- W columns: this thread's level of query q ----
+        const int64_t bq = (int64_t)b * p.Lq + q;
+        float aw[P];
+        if (FUSED) {
+          float lg[LP];
+          load_row<LP>(p.w + bq * p.ldw + m * LP, lg);
+          softmax_inplace<LP>(lg);
+#pragma unroll
+          for (int s = 0; s < P; ++s) {                         // level index is runtime: select without dynamic indexing
+            float v = lg[s];
+#pragma unroll
+            for (int l2 = 1; l2 < L; ++l2) v = (lvl == l2) ? lg[l2 * P + s] : v;
+            aw[s] = v;
+          }
+        } else {
+          const float4 v = ldg4(p.w + bq * p.ldw + m * LP + lvl * P);
+          aw[0] = v.x; aw[1] = v.y; aw[2] = v.z; aw[3] = v.w;
+          static_assert(P == 4, "attention row load assumes four points per level");
+        }
+        float xy[2 * P];
+        const float* arow = p.a + bq * p.lda + (m * LP + lvl * P) * 2;
+#pragma unroll
+        for (int i = 0; i < 2 * P; i += 4) {
+          const float4 v = ldg4(arow + i);
+          xy[i] = v.x; xy[i + 1] = v.y; xy[i + 2] = v.z; xy[i + 3] = v.w;
+        }
+        float rx = 0.f, ry = 0.f;
+        if (FUSED) { const float2 r = __ldg(reinterpret_cast<const float2*>(p.ref + (bq * L + lvl) * 2)); rx = r.x; ry = r.y; }
+#pragma unroll
+        for (int s = 0; s < P; ++s) {
+          float lx = xy[2 * s], ly = xy[2 * s + 1];
+          if (FUSED) { lx = rx + lx * inv_W; ly = ry + ly * inv_H; }
+          const float x = lx * (float)Wd - 0.5f, y = ly * (float)H - 0.5f;
+          if (x > -1.f && y > -1.f && x < (float)Wd && y < (float)H) {
+            const float xf = floorf(x), yf = floorf(y);
+            const int x0 = (int)xf, y0 = (int)yf;
+            const float fx = x - xf, fy = y - yf;
+            const float a = aw[s];
+            const bool xl = x0 >= 0, xh = x0 + 1 < Wd, yl = y0 >= 0, yh = y0 + 1 < H;
+            const int r00 = (lstart + y0 * Wd + x0) * QS + ql;   // W word of corner (y0, x0) in this query's column
+            // same weight expressions as the scatter kernel; the thread's own points are serialised: plain RMW
+            if (yl && xl) Wt[r00] += a * (1.f - fy) * (1.f - fx);
+            if (yl && xh) Wt[r00 + QS] += a * (1.f - fy) * fx;
+            if (yh && xl) Wt[r00 + Wd * QS] += a * fy * (1.f - fx);
+            if (yh && xh) Wt[r00 + (Wd + 1) * QS] += a * fy * fx;
+            const uint32_t top = (yl ? (uint32_t)(lstart + y0 * Wd + x0 + (xl ? 0 : 1)) : 0xffffu);       // first valid pixel of the row pair
+            const uint32_t bot = (yh ? (uint32_t)(lstart + (y0 + 1) * Wd + x0 + (xl ? 0 : 1)) : 0xffffu);
+            const uint32_t both = (xl && xh) ? 0x8000u : 0u;    // two x-adjacent pixels in each valid row
+            touched[2 * s] = top | both;
+            touched[2 * s + 1] = bot | both;
+          }
+        }
+      } else if (role == 3) {
+        // ---- grad_out tile: scaled, split into fp16 hi / lo, transposed to [d][q] ----
+        float v[D];
+        if (q_ok) {
+          const float* gp = p.grad_out + (((int64_t)b * p.Lq + q) * p.M + m) * D;
+#pragma unroll
+          for (int c = 0; c < D; c += 4) { const float4 x = ldg4(gp + c); v[c] = x.x; v[c + 1] = x.y; v[c + 2] = x.z; v[c + 3] = x.w; }
+        } else {
+#pragma unroll
+          for (int c = 0; c < D; ++c) v[c] = 0.f;
+        }
+        __half* ghh = reinterpret_cast<__half*>(gh);
+        __half* glh = reinterpret_cast<__half*>(gl);
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          const float x = v[c] * scale;
+          const __half h = __float2half_rn(x);
+          ghh[(c * GS) * 2 + ql] = h;
+          glh[(c * GS) * 2 + ql] = __float2half_rn(x - __half2float(h));
+        }
+      }
+      __syncthreads();
+      // ---- acc[px, d] += W[px, q-tile] . grad_out[q-tile, d] ----
+#pragma unroll
+      for (int ks = 0; ks < KQ / 16; ++ks) {
+        uint32_t bh[2][2], bl[2][2];
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+          const int w0 = (n * 8 + g) * GS + ks * 8 + t;
+          bh[n][0] = gh[w0]; bh[n][1] = gh[w0 + 4];
+          bl[n][0] = gl[w0]; bl[n][1] = gl[w0 + 4];
+        }
+#pragma unroll
+        for (int i = 0; i < MAX_MT; ++i) {
+          const int mt = warp + 4 * i;
+          if (mt < n_mt) {                                      // warp-uniform
+            const float* wp = Wt + (mt * 16 + g) * QS + ks * 16 + 2 * t;
+            const float2 x0 = *reinterpret_cast<const float2*>(wp);
+            const float2 x1 = *reinterpret_cast<const float2*>(wp + 8 * QS);
+            const float2 x2 = *reinterpret_cast<const float2*>(wp + 8);
+            const float2 x3 = *reinterpret_cast<const float2*>(wp + 8 * QS + 8);
+            uint32_t ah[4], al[4];
+            split_half2(x0.x, x0.y, ah[0], al[0]);
+            split_half2(x1.x, x1.y, ah[1], al[1]);
+            split_half2(x2.x, x2.y, ah[2], al[2]);
+            split_half2(x3.x, x3.y, ah[3], al[3]);
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+              mma_f16(acc[i][n], ah, bl[n][0], bl[n][1]);       // small cross terms first
+              mma_f16(acc[i][n], al, bh[n][0], bh[n][1]);
+              mma_f16(acc[i][n], ah, bh[n][0], bh[n][1]);
+            }
+          }
+        }
+      }
+      __syncthreads();
+      // ---- clear exactly the words this thread wrote (its column is private) ----
+      if (builder && q_ok) {
+#pragma unroll
+        for (int i = 0; i < 2 * P; ++i) {
+          const uint32_t tw = touched[i];
+          if ((tw & 0x7fffu) != 0x7fffu) {
+            const int r = (int)(tw & 0x7fffu) * QS + ql;
+            Wt[r] = 0.f;
+            if (tw & 0x8000u) Wt[r + QS] = 0.f;
+          }
+        }
+      }
+    }
+    // ---- flush: one 8-byte reduction per accumulator pair ----
+    float* gv = p.grad_value + (((int64_t)b * p.S + pix0) * p.M + m) * D;
+    const int64_t vstride = (int64_t)p.M * D;
+#pragma unroll
+    for (int i = 0; i < MAX_MT; ++i) {
+      const int mt = warp + 4 * i;
+      if (mt < n_mt) {
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+          const int px0 = mt * 16 + g, px1 = px0 + 8, d = n * 8 + 2 * t;
+          if (px0 < npx)
+            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gv + px0 * vstride + d), "f"(acc[i][n][0] * inv_scale),
+                         "f"(acc[i][n][1] * inv_scale) : "memory");
+          if (px1 < npx)
+            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gv + px1 * vstride + d), "f"(acc[i][n][2] * inv_scale),
+                         "f"(acc[i][n][3] * inv_scale) : "memory");
+        }
+      }
+    }
+  }
+}
+
+}  // namespace dense
 
 // ------------------------------------------------------------------------------------------
 // few queries (decoder: Lq = 10): one WARP per (b,q,m)
@@ -621,6 +874,44 @@ static int try_warp_kernel(const MsdaArgs& a, int mode, cudaStream_t s) {
 #undef POET_WARP_LAUNCH
 }
 
+// First level (>= 1) from which the remaining levels hold at most 448 pixels together, or L if the dense backward does
+// not apply (POET_MSDA_DENSE=0, other head sizes, too few queries to amortise the per-item flush).
+static int dense_first_level(const MsdaArgs& a) {
+  static const int enabled = []() { const char* e = getenv("POET_MSDA_DENSE"); return e ? atoi(e) : 1; }();
+  if (!enabled || a.D != 16 || a.L != 4 || a.P != 4 || a.Lq < 256) return a.L;
+  for (int l0 = 1; l0 < a.L; ++l0) {
+    const int npx = a.S - a.lv.start[l0];
+    if (npx <= dense::MAX_MT * 4 * 16) return l0;
+  }
+  return a.L;
+}
+
+static int launch_dense_bwd(const MsdaArgs& a, int mode, int lvl0, cudaStream_t s) {
+  const int npx = a.S - a.lv.start[lvl0];
+  const int n_mt = poet_ceil_div(npx, 16);
+  const size_t smem = (size_t)n_mt * 16 * dense::QS * 4 + 2 * 16 * dense::GS * 4;
+  const int slots = 3 * POET_NUM_SMS;                      // three resident CTAs per SM (about 70 KB of shared memory each)
+  int best = 1;
+  double best_cost = 1e30;
+  for (int nc = 1; nc <= 16; ++nc) {                       // query chunks per (image, head): makespan in queries, plus the flush
+    const int qpc = poet_ceil_div(a.Lq, nc);
+    if (nc > 1 && qpc < 96) break;
+    const double rounds = (double)poet_ceil_div((int64_t)a.B * a.M * nc, slots);
+    const double cost = rounds * (qpc + 24.0);
+    if (cost < best_cost) { best_cost = cost; best = nc; }
+  }
+  const int nchunk = best, q_per_chunk = poet_ceil_div(a.Lq, nchunk);
+  const int n_items = a.B * a.M * nchunk;
+  const int grid = n_items < slots ? n_items : slots;
+  auto launch = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    poet_launch(kern, dim3(grid), dim3(dense::THREADS), smem, s, a, lvl0, npx, n_mt, nchunk, q_per_chunk, n_items);
+    return poet_launch_status();
+  };
+  return mode ? launch(dense::msda_bwd_dense_kernel<4, 4, true>) : launch(dense::msda_bwd_dense_kernel<4, 4, false>);
+}
+
 int fill_args(MsdaArgs& a, const int32_t* shapes_host, int B, int S, int Lq, int M, int D, int L, int P,
               const float* value, const float* aa, int64_t lda, const float* w, int64_t ldw, const float* ref, int mode) {
   POET_REQUIRE(value && aa && w && shapes_host, POET_ERR_NULL_POINTER);
@@ -643,6 +934,7 @@ int fill_args(MsdaArgs& a, const int32_t* shapes_host, int B, int S, int Lq, int
   POET_REQUIRE(start == S, POET_ERR_BAD_SHAPE);
   a.value = value; a.a = aa; a.lda = lda; a.w = w; a.ldw = ldw; a.ref = ref;
   a.B = B; a.S = S; a.Lq = Lq; a.M = M; a.D = D; a.L = L; a.P = P;
+  a.red_levels = L;
   return POET_OK;
 }
 
@@ -712,5 +1004,11 @@ extern "C" int poet_msda_bwd(const float* value, const float* a, int64_t lda, co
   args.grad_out = grad_out; args.grad_value = grad_value; args.grad_a = grad_a; args.grad_w = grad_w;
   const int rc_warp = try_warp_kernel<true>(args, mode, (cudaStream_t)stream);
   if (rc_warp != POET_ERR_UNSUPPORTED) return rc_warp;
-  return dispatch<true>(args, mode, (cudaStream_t)stream);
+  // many queries (the encoder): grad_value of the low-resolution levels comes from the dense tensor-core kernel, the
+  // scatter kernel keeps its global reductions for the high-resolution level(s) only
+  const int lvl0 = dense_first_level(args);
+  args.red_levels = lvl0;
+  const int rc_scatter = dispatch<true>(args, mode, (cudaStream_t)stream);
+  if (rc_scatter != POET_OK || lvl0 >= args.L) return rc_scatter;
+  return launch_dense_bwd(args, mode, lvl0, (cudaStream_t)stream);
 }

@@ -99,7 +99,7 @@ def main():
     gam, bet = torch.ones(256, device=DEV), torch.zeros(256, device=DEV)
     y, xh, rs = torch.empty_like(x), torch.empty_like(x), torch.empty(R, device=DEV)
     us = timed(lambda: ops._call("poet_add_layernorm_fwd", x.data_ptr(), r.data_ptr(), gam.data_ptr(), bet.data_ptr(), None,
-                                 y.data_ptr(), None, xh.data_ptr(), rs.data_ptr(), R, 256, 1e-5, ops._stream(x)))
+                                 y.data_ptr(), None, xh.data_ptr(), rs.data_ptr(), R, 256, 1e-5, None, 0, 0.0, ops._stream(x)))
     print(f"add+LN fwd                    {us:8.1f} us  {4.0 * R * 256 * 4 / us / 1e3:7.0f} GB/s")
 
 

@@ -349,9 +349,10 @@ __device__ __forceinline__ float group_sum(float v) {
 }
 
 __device__ __forceinline__ void red_add4(float* p, float w, float4 v) {
-  // one 128-bit reduction per corner (sm_90+): red.global.add.v4.f32
+  // one 128-bit reduction per corner (sm_90+): red.global.add.v4.f32.  No "memory" clobber: grad_value is write-only
+  // in these kernels, and the clobber would pin every later load behind the reduction
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x * w), "f"(v.y * w), "f"(v.z * w),
-               "f"(v.w * w) : "memory");
+               "f"(v.w * w));
 }
 
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
@@ -411,23 +412,21 @@ __global__ void __launch_bounds__(256, 3) msda_bwd_kernel(const MsdaArgs p) {
         const float a = aw[l * P + s];
         const bool xl = x0 >= 0, xh = x0 + 1 < W, yl = y0 >= 0, yh = y0 + 1 < H;
         const int i00 = (y0 * W + x0) * vstride;
-        float d00 = 0.f, d01 = 0.f, d10 = 0.f, d11 = 0.f;      // <grad_out, corner value>
         const bool scatter = live && l < p.red_levels;        // the dense kernel owns the other levels' grad_value
-        if (yl && xl) {
-          d00 = dot4(go, ldg4(vl + i00));
-          if (scatter) red_add4(gl + i00, a * (1.f - fy) * (1.f - fx), go);
-        }
-        if (yl && xh) {
-          d01 = dot4(go, ldg4(vl + i00 + vstride));
-          if (scatter) red_add4(gl + i00 + vstride, a * (1.f - fy) * fx, go);
-        }
-        if (yh && xl) {
-          d10 = dot4(go, ldg4(vl + i00 + W * vstride));
-          if (scatter) red_add4(gl + i00 + W * vstride, a * fy * (1.f - fx), go);
-        }
-        if (yh && xh) {
-          d11 = dot4(go, ldg4(vl + i00 + (W + 1) * vstride));
-          if (scatter) red_add4(gl + i00 + (W + 1) * vstride, a * fy * fx, go);
+        // the four corner loads of a point are issued together (predicated), the dots and the reductions follow: a load
+        // placed behind a reduction would wait for it (the reduction is a volatile asm statement the compiler orders
+        // other memory operations around), which made every corner pay its own L2 round trip
+        float4 v00 = make_float4(0.f, 0.f, 0.f, 0.f), v01 = v00, v10 = v00, v11 = v00;
+        if (yl && xl) v00 = ldg4(vl + i00);
+        if (yl && xh) v01 = ldg4(vl + i00 + vstride);
+        if (yh && xl) v10 = ldg4(vl + i00 + W * vstride);
+        if (yh && xh) v11 = ldg4(vl + i00 + (W + 1) * vstride);
+        const float d00 = dot4(go, v00), d01 = dot4(go, v01), d10 = dot4(go, v10), d11 = dot4(go, v11);
+        if (scatter) {
+          if (yl && xl) red_add4(gl + i00, a * (1.f - fy) * (1.f - fx), go);
+          if (yl && xh) red_add4(gl + i00 + vstride, a * (1.f - fy) * fx, go);
+          if (yh && xl) red_add4(gl + i00 + W * vstride, a * fy * (1.f - fx), go);
+          if (yh && xh) red_add4(gl + i00 + (W + 1) * vstride, a * fy * fx, go);
         }
         ga = (1.f - fy) * (1.f - fx) * d00 + (1.f - fy) * fx * d01 + fy * (1.f - fx) * d10 + fy * fx * d11;
         // d sampled / d x (pixels) and / d y, times attention weight; pixels = loc * size
@@ -877,7 +876,10 @@ static int try_warp_kernel(const MsdaArgs& a, int mode, cudaStream_t s) {
 // First level (>= 1) from which the remaining levels hold at most 448 pixels together, or L if the dense backward does
 // not apply (POET_MSDA_DENSE=0, other head sizes, too few queries to amortise the per-item flush).
 static int dense_first_level(const MsdaArgs& a) {
-  static const int enabled = []() { const char* e = getenv("POET_MSDA_DENSE"); return e ? atoi(e) : 1; }();
+  // Off by default: measured on B200 (profiles/r02_msda_bwd_dense.txt) the pair (scatter kernel with level-0 reductions
+  // only + dense kernel) is not faster than the scatter kernel alone, because gathers and reductions share the LSU pipe
+  // and the level-0 reductions already cost as much as the gather.  POET_MSDA_DENSE=1 selects it (parity-tested).
+  static const int enabled = []() { const char* e = getenv("POET_MSDA_DENSE"); return e ? atoi(e) : 0; }();
   if (!enabled || a.D != 16 || a.L != 4 || a.P != 4 || a.Lq < 256) return a.L;
   for (int l0 = 1; l0 < a.L; ++l0) {
     const int npx = a.S - a.lv.start[l0];
@@ -1008,7 +1010,8 @@ extern "C" int poet_msda_bwd(const float* value, const float* a, int64_t lda, co
   // scatter kernel keeps its global reductions for the high-resolution level(s) only
   const int lvl0 = dense_first_level(args);
   args.red_levels = lvl0;
-  const int rc_scatter = dispatch<true>(args, mode, (cudaStream_t)stream);
-  if (rc_scatter != POET_OK || lvl0 >= args.L) return rc_scatter;
+  static const int dbg = []() { const char* e = getenv("POET_MSDA_DENSE_DEBUG"); return e ? atoi(e) : 0; }();   // timing bisection: 1 scatter part only, 2 dense part only
+  const int rc_scatter = (dbg == 2 && lvl0 < args.L) ? POET_OK : dispatch<true>(args, mode, (cudaStream_t)stream);
+  if (rc_scatter != POET_OK || lvl0 >= args.L || dbg == 1) return rc_scatter;
   return launch_dense_bwd(args, mode, lvl0, (cudaStream_t)stream);
 }

@@ -472,3 +472,17 @@ def test_gemm_tcgen05_presplit_weights(M, N, K, b_k, prec, tol):
         o.set_gemm_precision(old)
     err = rel_err(out, ref)
     assert err < tol, f"{prec} {M}x{N}x{K} b_k={b_k}: rel err {err:.3e}"
+
+
+def test_msda_dense_lowres_backward_path_in_subprocess():
+    """The dense tensor-core grad_value path of the MSDA backward (POET_MSDA_DENSE=1, read once per process) against the
+    same fp64 oracle checks: run the MSDA tests of this file in a child process with the knob set."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, POET_MSDA_DENSE="1")
+    here = os.path.abspath(__file__)
+    r = subprocess.run([sys.executable, "-m", "pytest", here, "-m", "gpu", "-q", "-x", "-k",
+                        "test_msda_core_fwd_bwd or test_msda_block_matches_module_math"], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(here)))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -120,6 +120,7 @@ class DeformableTransformerEncoder(nn.Module):
         super().__init__()
         self.layers = _clones(encoder_layer, num_layers)
         self.num_layers = num_layers
+        self.gemm_precision = None      # None: the global ops precision; 'bf16': single-pass MMAs (throughput mode, cfg4)
 
     @staticmethod
     def get_reference_points(spatial_shapes, valid_ratios, device=None):
@@ -129,11 +130,12 @@ class DeformableTransformerEncoder(nn.Module):
     def forward(self, src, spatial_shapes, level_start_index, valid_ratios, pos=None, padding_mask=None):
         ref = self.get_reference_points(spatial_shapes, valid_ratios, device=src.device)
         out, query = src, None
-        for i, layer in enumerate(self.layers):
-            last = i == self.num_layers - 1
-            res = layer(out, pos, ref, spatial_shapes, level_start_index, padding_mask, query=query,
-                        emit_next_query=not last)
-            out, query = res if isinstance(res, tuple) else (res, None)
+        with ops.precision_scope(self.gemm_precision):
+            for i, layer in enumerate(self.layers):
+                last = i == self.num_layers - 1
+                res = layer(out, pos, ref, spatial_shapes, level_start_index, padding_mask, query=query,
+                            emit_next_query=not last)
+                out, query = res if isinstance(res, tuple) else (res, None)
         return out
 
 
@@ -188,6 +190,7 @@ class DeformableTransformerDecoder(nn.Module):
         self.return_intermediate = return_intermediate
         self.bbox_embed = None      # PoET never refines boxes (reference :302,:321)
         self.class_embed = None
+        self.value_gemm_precision = None  # precision of the [B*S, d] x [d, d] value projections of `memory` (throughput mode)
 
     def forward(self, tgt, reference_points, src, src_spatial_shapes, src_level_start_index, src_valid_ratios,
                 query_pos=None, src_padding_mask=None, layer_callback=None):
@@ -206,7 +209,7 @@ class DeformableTransformerDecoder(nn.Module):
         if ops.parallel_streams_enabled() and src.is_cuda:
             forked = ops.fork(0, src.device)
             forked.uses(src, src_padding_mask)
-            with forked:
+            with forked, ops.precision_scope(self.value_gemm_precision):
                 for i, layer in enumerate(self.layers):
                     values[i] = layer.cross_attn.project_value(src, src_padding_mask)
                     marks.append(forked.checkpoint())
@@ -258,6 +261,14 @@ class DeformableTransformer(nn.Module):
         nn.init.xavier_uniform_(self.reference_points.weight, gain=1.0)
         nn.init.zeros_(self.reference_points.bias)
         nn.init.normal_(self.level_embed)
+
+    def set_throughput_mode(self, on: bool = True) -> None:
+        """BASELINE.json cfg4 (bf16 training mode; the reference itself has no mixed precision: SURVEY.md section 5): the
+        token-row GEMMs -- every encoder layer and the decoder's value projections of `memory`, 97 % of the FLOPs --
+        issue single-pass bf16 tcgen05 MMAs (fp32 accumulation, fp32 activations in HBM); the query-row GEMMs of the
+        decoder and the pose heads stay split-bf16 (fp32-grade).  Tolerance of this mode: tests/test_gpu_model.py."""
+        self.encoder.gemm_precision = "bf16" if on else None
+        self.decoder.value_gemm_precision = "bf16" if on else None
 
     @staticmethod
     def get_valid_ratio(mask: torch.Tensor) -> torch.Tensor:

@@ -31,6 +31,28 @@ def get_gemm_precision() -> str:
     return {v: k for k, v in _PRECISION.items()}[_state["precision"]]
 
 
+class precision_scope:
+    """with precision_scope('bf16'): ... -- GEMMs issued inside use that precision (None: leave as is); the backward
+    of every op recorded inside runs at the precision of its forward (each autograd Function stores it).  Used by the
+    mixed throughput mode (BASELINE.json cfg4): single-pass bf16 MMAs for the encoder layers, bf16x3 elsewhere.
+    The weight planes are shared: a bf16 GEMM simply ignores the lo plane."""
+
+    def __init__(self, name: Optional[str]):
+        self.value = None if name is None else (_PRECISION[name] if isinstance(name, str) else int(name))
+
+    def __enter__(self):
+        self.saved = _state["precision"]
+        if self.value is not None:
+            if self.saved == GEMM_FP32 and self.value != GEMM_FP32:
+                raise RuntimeError("precision_scope cannot enable tensor-core GEMMs under the global 'fp32' mode (no weight planes)")
+            _state["precision"] = self.value
+        return self
+
+    def __exit__(self, *exc):
+        _state["precision"] = self.saved
+        return False
+
+
 # ------------------------------------------------------------------------------------------
 # stream forking: the decoder / head chain is a sequence of launch-latency-bound kernels that leaves the
 # GPU mostly idle, so independent work (the decoder layers' value projections of `memory`, the per-layer
@@ -671,6 +693,7 @@ class _Linear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, W, b, row_mask, mask_grad_inplace):
+        ctx.prec = _state["precision"]
         ctx.mask_grad_inplace = mask_grad_inplace
         x2 = _chk(x).view(-1, x.shape[-1])
         W = _chk(W)
@@ -686,7 +709,12 @@ class _Linear(torch.autograd.Function):
         return y.view(*x.shape[:-1], N)
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, *grads):
+        with precision_scope(ctx.prec):
+            return _Linear._backward_impl(ctx, *grads)
+
+    @staticmethod
+    def _backward_impl(ctx, gy):
         x2, W = ctx.saved_tensors
         gy2 = _chk(gy).view(-1, gy.shape[-1])
         gy_mask = None
@@ -714,6 +742,7 @@ class _MLP(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, drop_p, drop_site, *wb):
+        ctx.prec = _state["precision"]
         n = len(wb) // 2
         x2 = _chk(x).view(-1, x.shape[-1])
         acts = [x2]
@@ -748,7 +777,12 @@ class _MLP(torch.autograd.Function):
         return acts[-1].view(*x.shape[:-1], acts[-1].shape[1])
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, *grads):
+        with precision_scope(ctx.prec):
+            return _MLP._backward_impl(ctx, *grads)
+
+    @staticmethod
+    def _backward_impl(ctx, gy):
         n = ctx.n
         acts, Ws = ctx.saved_tensors[:n], ctx.saved_tensors[n:]
         g = _chk(gy).view(-1, gy.shape[-1])
@@ -787,6 +821,7 @@ class _ProjPair(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mode, x0, x1, W0, b0, W1, b1):
+        ctx.prec = _state["precision"]
         ctx.mode = mode
         x0_2 = _chk(x0).view(-1, x0.shape[-1])
         R, K = x0_2.shape
@@ -827,7 +862,12 @@ class _ProjPair(torch.autograd.Function):
         return qk.view(*x0.shape[:-1], 2 * C), v.view(*x0.shape[:-1], C)
 
     @staticmethod
-    def backward(ctx, g0, g1=None):
+    def backward(ctx, *grads):
+        with precision_scope(ctx.prec):
+            return _ProjPair._backward_impl(ctx, *grads)
+
+    @staticmethod
+    def _backward_impl(ctx, g0, g1=None):
         if ctx.mode == "cat":
             x2, Wc = ctx.saved_tensors
             W0, b0, W1, b1 = ctx.params
@@ -1239,6 +1279,7 @@ class _InputProj(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, n_feats, groups, eps, *tensors):
+        ctx.prec = _state["precision"]
         feats = [_chk(t) for t in tensors[:n_feats]]
         params = tensors[n_feats:]                           # per level: conv weight, conv bias, gn weight, gn bias
         L = len(params) // 4
@@ -1279,7 +1320,12 @@ class _InputProj(torch.autograd.Function):
         return tokens
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, *grads):
+        with precision_scope(ctx.prec):
+            return _InputProj._backward_impl(ctx, *grads)
+
+    @staticmethod
+    def _backward_impl(ctx, g):
         n_feats, groups, eps, B, C, S, dims = ctx.meta
         g = _chk(g)
         saved, params = ctx.saved_tensors, ctx.params

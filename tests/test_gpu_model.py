@@ -431,3 +431,45 @@ def test_backbone_mode_inference_vs_reference_golden():
     t, R = stack_outputs(out)
     assert float((t.cpu() - g["translation"]).abs().max()) < TOL_T
     assert float((R.cpu() - g["rotation"]).abs().max()) < TOL_R
+
+
+def test_throughput_mode_tolerance():
+    """BASELINE.json cfg4 (bf16 training mode; no reference counterpart): single-pass bf16 tensor-core
+    MMAs on the token-row GEMMs (encoder layers + decoder value projections), split-bf16 elsewhere.  ITS OWN tolerance,
+    measured on B200 (profiles/r02_grad_noise.txt: 6.7e-3 / 2.8e-2 forward, <= 0.16 relative L2 on any gradient):
+    |translation| <= 2e-2, |rotation| <= 5e-2 vs the fp32 oracle on every decoder layer, every gradient within 0.35
+    relative L2 and 90 % of them within 0.2; the default (parity) mode of the same model stays inside 1e-4 / 1e-3."""
+    from poet_b200 import ops
+    cfg = S.CONFIGS["cfg2_b2"]
+    P = S.make_params(cfg)
+    inp = S.make_inputs(cfg, pad_columns=True)
+    g_t, g_R = S.make_cotangents(cfg)
+    Pr = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    cap = {}
+    O.poet_path_forward(Pr, cfg, inp["srcs"], inp["masks"], inp["boxes"], inp["labels"], capture=cap)
+    O.synthetic_loss((cap["translation_all"], cap["rotation_all"]), g_t, g_R).backward()
+    old = ops.get_gemm_precision()
+    ops.set_gemm_precision("bf16x3")
+    try:
+        model = build_model(cfg, P)
+        srcs, masks = [s.to(DEV) for s in inp["srcs"]], [m.to(DEV) for m in inp["masks"]]
+        with torch.no_grad():
+            t0, R0 = stack_outputs(model.forward_pyramid(srcs, masks, inp["boxes"], inp["labels"])[0])
+        model.transformer.set_throughput_mode(True)
+        out, _ = model.forward_pyramid(srcs, masks, inp["boxes"], inp["labels"])
+        t, R = stack_outputs(out)
+        ((t * g_t.to(DEV)).sum() + (R * g_R.to(DEV)).sum()).backward()
+    finally:
+        ops.set_gemm_precision(old)
+    assert float((t0.cpu() - cap["translation_all"]).abs().max()) < TOL_T and float((R0.cpu() - cap["rotation_all"]).abs().max()) < TOL_R
+    dt = float((t.detach().cpu() - cap["translation_all"]).abs().max())
+    dR = float((R.detach().cpu() - cap["rotation_all"]).abs().max())
+    assert 1e-4 < dt < 2e-2 and dR < 5e-2, (dt, dR)                      # really a different (cheaper) arithmetic, inside its budget
+    errs = []
+    for k, p in model.named_parameters():
+        ref = Pr[k].grad
+        if ref is None:
+            continue
+        assert torch.isfinite(p.grad).all(), k
+        errs.append(float((p.grad.cpu().double() - ref.double()).norm() / (ref.double().norm() + 1e-12)))
+    assert max(errs) < 0.35 and sum(e < 0.2 for e in errs) >= 0.9 * len(errs), sorted(errs)[-5:]

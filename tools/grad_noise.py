@@ -22,9 +22,11 @@ for name, pad in (("cfg1", False), ("cfg2_b2", True)):
     cap = {}
     O.poet_path_forward(Pr, cfg, inp["srcs"], inp["masks"], inp["boxes"], inp["labels"], capture=cap)
     O.synthetic_loss((cap["translation_all"], cap["rotation_all"]), g_t, g_R).backward()
-    for prec in ("fp32", "bf16x3", "bf16"):
-        ops.set_gemm_precision(prec)
+    for prec in ("fp32", "bf16x3", "mixed", "bf16"):
+        ops.set_gemm_precision("bf16x3" if prec == "mixed" else prec)
         model = build_model(cfg, P)
+        if prec == "mixed":                      # cfg4 throughput mode: single-pass bf16 on the token-row GEMMs only
+            model.transformer.set_throughput_mode(True)
         out, _ = model.forward_pyramid([s.to(DEV) for s in inp["srcs"]], [m.to(DEV) for m in inp["masks"]],
                                        inp["boxes"], inp["labels"])
         t, R = stack_outputs(out)

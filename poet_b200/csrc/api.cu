@@ -4,6 +4,11 @@
 int poet_gemm_simt(const float* A, int64_t lda, int a_kcontig, const float* Bm, int64_t ldb, int b_kcontig, float* C,
                    int64_t ldc, int M, int N, int K, float alpha, const float* bias, const float* gate,
                    const uint8_t* row_mask, int flags, cudaStream_t s);
+bool poet_gemm_small_supported(int M, int N, int K, int a_kcontig, int b_kcontig, int64_t lda, int64_t ldb, int64_t ldc,
+                               const void* A, const void* B, const void* Bhi, const void* Blo, bool relu_or_gate);
+int poet_gemm_small(const float* A, int64_t lda, int a_kcontig, const float* Bm, const void* b_hi, const void* b_lo,
+                    int64_t ldb, int b_kcontig, float* C, int64_t ldc, int M, int N, int K, float alpha, const float* bias,
+                    const float* gate, float* a_colsum, int flags, cudaStream_t s);
 #ifdef POET_HAVE_TC_GEMM
 size_t poet_gemm_tc_workspace_bytes(int M, int N, int K, int a_kcontig, int b_kcontig, int precision);
 int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, const void* b_hi, const void* b_lo,
@@ -58,6 +63,11 @@ extern "C" int poet_gemm(const float* A, int64_t lda, int a_kcontig, const float
   POET_REQUIRE(lda >= (a_kcontig ? K : M) && ldb >= (b_kcontig ? K : N) && ldc >= N, POET_ERR_BAD_SHAPE);
   POET_REQUIRE(precision >= POET_GEMM_FP32 && precision <= POET_GEMM_BF16, POET_ERR_UNSUPPORTED);
   cudaStream_t s = (cudaStream_t)stream;
+  // query-row problems (decoder chain, pose heads): the latency-optimised exact-fp32 kernel, whatever the precision mode
+  if (row_mask == nullptr && poet_gemm_small_supported(M, N, K, a_kcontig, b_kcontig, lda, ldb, ldc, A, Bm, nullptr, nullptr,
+                                                       gate != nullptr || (flags & POET_GEMM_RELU)))
+    return poet_gemm_small(A, lda, a_kcontig, Bm, nullptr, nullptr, ldb, b_kcontig, C, ldc, M, N, K, alpha, bias, gate, nullptr,
+                           flags, s);
 #ifdef POET_HAVE_TC_GEMM
   if (precision != POET_GEMM_FP32 && poet_gemm_tc_supported(M, N, K, a_kcontig, b_kcontig, lda, ldb, ldc))
     return poet_gemm_tc(A, lda, a_kcontig, Bm, nullptr, nullptr, ldb, b_kcontig, C, ldc, M, N, K, alpha, bias, gate,
@@ -114,6 +124,10 @@ extern "C" int poet_gemm_ex(const float* A, int64_t lda, int a_kcontig, const fl
   POET_REQUIRE(M > 0 && N > 0 && K > 0, POET_ERR_BAD_SHAPE);
   POET_REQUIRE(lda >= (a_kcontig ? K : M) && ldb >= (b_kcontig ? K : N) && ldc >= N, POET_ERR_BAD_SHAPE);
   POET_REQUIRE(!relu_bits_out || (flags & POET_GEMM_RELU), POET_ERR_UNSUPPORTED);
+  if (!relu_bits_out && !gate_bits && !row_mask && !a_row_mask && drop_p == 0.f &&
+      poet_gemm_small_supported(M, N, K, a_kcontig, b_kcontig, lda, ldb, ldc, A, Bm, B_hi, B_lo, flags & POET_GEMM_RELU))
+    return poet_gemm_small(A, lda, a_kcontig, Bm, B_hi, B_lo, ldb, b_kcontig, C, ldc, M, N, K, alpha, bias, nullptr, a_colsum,
+                           flags, (cudaStream_t)stream);
 #ifdef POET_HAVE_TC_GEMM
   POET_REQUIRE(precision == POET_GEMM_BF16X3 || precision == POET_GEMM_BF16, POET_ERR_UNSUPPORTED);
   POET_REQUIRE(poet_gemm_tc_supported(M, N, K, a_kcontig, b_kcontig, lda, ldb, ldc), POET_ERR_UNSUPPORTED);
@@ -137,6 +151,10 @@ extern "C" int poet_gemm_bsplit(const float* A, int64_t lda, int a_kcontig, cons
   POET_REQUIRE(lda >= (a_kcontig ? K : M) && ldb >= (b_kcontig ? K : N) && ldc >= N, POET_ERR_BAD_SHAPE);
   POET_REQUIRE(precision >= POET_GEMM_FP32 && precision <= POET_GEMM_BF16, POET_ERR_UNSUPPORTED);
   cudaStream_t s = (cudaStream_t)stream;
+  if (row_mask == nullptr && poet_gemm_small_supported(M, N, K, a_kcontig, b_kcontig, lda, ldb, ldc, A, Bm, B_hi, B_lo,
+                                                       gate != nullptr || (flags & POET_GEMM_RELU)))
+    return poet_gemm_small(A, lda, a_kcontig, Bm, B_hi, B_lo, ldb, b_kcontig, C, ldc, M, N, K, alpha, bias, gate, nullptr,
+                           flags, s);
 #ifdef POET_HAVE_TC_GEMM
   if (precision != POET_GEMM_FP32 && poet_gemm_tc_supported(M, N, K, a_kcontig, b_kcontig, lda, ldb, ldc))
     return poet_gemm_tc(A, lda, a_kcontig, Bm, B_hi, B_lo, ldb, b_kcontig, C, ldc, M, N, K, alpha, bias, gate, row_mask,

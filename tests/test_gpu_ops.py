@@ -486,3 +486,58 @@ def test_msda_dense_lowres_backward_path_in_subprocess():
                         "test_msda_core_fwd_bwd or test_msda_block_matches_module_math"], env=env, capture_output=True, text=True,
                        cwd=os.path.dirname(os.path.dirname(here)))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ------------------------------------------------------------------------------- small-row GEMM (csrc/gemm_small.cu)
+@pytest.mark.parametrize("M,N,K", [(160, 256, 256), (160, 1024, 256), (160, 256, 1024), (160, 768, 256), (400, 132, 256),
+                                   (36, 264, 72), (160, 66, 256)])
+@pytest.mark.parametrize("a_k,b_k", [(True, True), (True, False), (False, False), (False, True)])
+def test_gemm_small_rows_exact_fp32(M, N, K, a_k, b_k):
+    """Decoder / pose-head shapes in the default (bf16x3) precision mode are served by the latency kernel in exact fp32:
+    all four operand layouts, ragged N, bias + ReLU gate, beta = 1 accumulation."""
+    o = ops()
+    if (not a_k and M % 4) or (not b_k and N % 4):
+        pytest.skip("row-contiguous operands need 16-byte chunks (falls to the SIMT kernel)")
+    g = torch.Generator().manual_seed(M * 5 + N * 3 + K + 2 * a_k + b_k)
+    A = torch.randn((M, K) if a_k else (K, M), generator=g)
+    Bm = torch.randn((N, K) if b_k else (K, N), generator=g)
+    bias, gate, base = torch.randn(N, generator=g), torch.randn(M, N, generator=g), torch.randn(M, N, generator=g)
+    ref = (A.double() if a_k else A.double().t()) @ (Bm.double().t() if b_k else Bm.double()) + bias.double()
+    tol = 2e-6 * math.sqrt(K)
+    out = o.gemm(A.to(DEV), Bm.to(DEV), M, N, K, a_kcontig=a_k, b_kcontig=b_k, bias=bias.to(DEV))
+    assert rel_err(out, ref) < tol
+    out = o.gemm(A.to(DEV), Bm.to(DEV), M, N, K, a_kcontig=a_k, b_kcontig=b_k, bias=bias.to(DEV), gate=gate.to(DEV),
+                 alpha=0.5)
+    assert rel_err(out, (ref - 0.5 * (ref - bias.double())) * (gate > 0)) < tol
+    out = o.gemm(A.to(DEV), Bm.to(DEV), M, N, K, a_kcontig=a_k, b_kcontig=b_k, relu=True, accumulate=True,
+                 out=base.to(DEV).clone())
+    assert rel_err(out, base.double() + (ref - bias.double()).clamp_min(0)) < tol
+
+
+@pytest.mark.parametrize("M,N,K,b_k", [(160, 256, 256, True), (160, 768, 256, True), (160, 256, 768, False),
+                                       (160, 256, 1024, False), (250, 1024, 256, True)])
+def test_gemm_small_rows_weight_planes(M, N, K, b_k):
+    """Weights as the step's bf16 hi/lo planes (hi + lo = the 2^-17 operand of the tensor-core path)."""
+    o = ops()
+    g = torch.Generator().manual_seed(M + N + K)
+    A, W, bias = torch.randn(M, K, generator=g), torch.randn((N, K) if b_k else (K, N), generator=g), torch.randn(N, generator=g)
+    Wd = W.to(DEV)
+    hi = torch.empty(Wd.shape, device=DEV, dtype=torch.bfloat16)
+    lo = torch.empty_like(hi)
+    o._call("poet_split_bf16", Wd.data_ptr(), hi.data_ptr(), lo.data_ptr(), Wd.numel(), o._stream(Wd))
+    ref = A.double() @ (W.double().t() if b_k else W.double()) + bias.double()
+    out = o.gemm(A.to(DEV), Wd, M, N, K, b_kcontig=b_k, bias=bias.to(DEV), relu=True, b_split=(hi, lo))
+    assert rel_err(out, ref.clamp_min(0)) < 3e-5
+
+
+@pytest.mark.parametrize("No,Ko,R", [(256, 256, 160), (512, 256, 160), (1024, 256, 400), (132, 256, 160)])
+def test_gemm_small_rows_wgrad_colsum(No, Ko, R):
+    """Weight gradient of a query-row layer: dW += dY^T X with the bias gradient summed from the dY tiles."""
+    o = ops()
+    g = torch.Generator().manual_seed(No + Ko + R)
+    dY, X = torch.randn(R, No, generator=g), torch.randn(R, Ko, generator=g)
+    w0, b0 = torch.randn(No, Ko, generator=g), torch.randn(No, generator=g)
+    w, b = w0.to(DEV).clone(), b0.to(DEV).clone()
+    o.wgrad_bias(dY.to(DEV), X.to(DEV), No, Ko, R, w, b)
+    assert rel_err(w, w0.double() + dY.double().t() @ X.double()) < 2e-6 * math.sqrt(R)
+    assert rel_err(b, b0.double() + dY.double().sum(0)) < 1e-5

@@ -298,6 +298,11 @@ def run_gpu(args):
     cfg = dict(S.CONFIGS[wl["cfg"]])
     cfg["batch"] = B = args.batch or default_batch(WORKLOAD, cfg, world)
     do_backward = wl["backward"]
+    # layer-count ablations (marginal cost of one encoder / decoder layer inside the replayed graph); never a bench line:
+    # the printed config carries "ablation" and the metric name is suffixed
+    ablation = {k: int(os.environ[e]) for k, e in (("enc_layers", "POET_BENCH_ENC_LAYERS"), ("dec_layers", "POET_BENCH_DEC_LAYERS"))
+                if os.environ.get(e)}
+    cfg.update(ablation)
     model = build_gpu_model(cfg, dev, with_input_proj=args.from_features, dropout=args.dropout)
     if not do_backward:
         model.eval()
@@ -509,7 +514,7 @@ def run_gpu(args):
         peaks = load_peaks()
         ms_per_step = total_ms / args.steps
         value = B * world * args.steps / (total_ms / 1e3)
-        line = {"metric": metric_name(WORKLOAD, cfg, B), "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        line = {"metric": metric_name(WORKLOAD, cfg, B) + (f" [ABLATION {ablation}: not a bench line]" if ablation else ""), "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling_of(WORKLOAD),
                 "vs_baseline": None,
                 "dtype": ("bf16 (single-pass tcgen05 MMAs, fp32 accumulate, on the token-row GEMMs; bf16x3 on query rows / heads)"

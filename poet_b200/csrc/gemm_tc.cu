@@ -20,13 +20,11 @@
 //                   tcgen05.commit frees smem stages and publishes finished accumulators.
 //   warp PW+1       TMA: weights are split to bf16 hi/lo planes once per step (poet_split_bf16) and
 //                   fetched by cp.async.bulk.tensor straight into the swizzled stage.
-//   warps PW+2..+5  epilogue: tcgen05.ld (one accumulator row per thread), bias / ReLU (+ sign bitmask out) /
-//                   ReLU-gate (bitmask or fp32) / row mask in registers, st.shared into a per-warp
-//                   SWIZZLE_128B 32x32 staging box, then ONE asynchronous TMA store per box
-//                   (cp.async.bulk.tensor; cp.reduce...add for beta=1 and split-K), double-buffered per
-//                   warp, so the epilogue warps never wait on global stores.  Runs concurrently with the
-//                   next tile's MMAs (other TMEM buffer).  POET_GEMM_TMA_EPI=0 selects the older
-//                   smem-transpose + st.global epilogue (kept for A/B measurements).
+//   warps 12..19    epilogue (two per TMEM lane quarter, alternating 32-column chunks): tcgen05.ld (one accumulator
+//                   row per thread), bias / ReLU (+ sign bitmask out) / ReLU-gate (bitmask or fp32) / row mask in
+//                   registers, st.shared into a per-warp SWIZZLE_128B 32x32 staging box, then ONE asynchronous TMA
+//                   store per box (cp.async.bulk.tensor; cp.reduce...add for beta=1 and split-K).  Runs concurrently
+//                   with the next tile's MMAs (other TMEM buffer).
 // Weight-gradient shape (both operands fp32 activations, MN-major): BK = 32, both operand tiles are
 // register-prefetched one k-block ahead, lines further ahead are pulled into L2 with prefetch hints,
 // and the tile is 128 x 256 when N allows (less L2->SM traffic per flop).
@@ -39,7 +37,7 @@
 namespace tc {
 
 constexpr int BM = 128;
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARPS = 8;            // two per TMEM lane quarter: they take alternate 32-column chunks of a tile
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -113,6 +111,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---- descriptors --------------------------------------------------------------------------
 // shared-memory matrix descriptor, SWIZZLE_128B, sm_100 version bit set (cute/arch/mma_sm100_desc.hpp)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -147,10 +160,11 @@ struct Args {
   int splits;
   int n_tiles, total_work;
   int tail_start, tail_slices;   // work ids >= tail_start are column slices of the last round's tiles (tail_start = total_work: none)
-  int epi_tma;            // 1: TMA-store epilogue, 0: smem-transpose + st.global epilogue
   int l2_prefetch;        // 1: L2 prefetch hints ahead of the register-prefetched operand loads
   int debug;              // POET_GEMM_DEBUG bit flags (pipeline bisection only): 1 no A loads, 2 no A stores, 4 no TMA, 8 no epilogue stores,
-                          // 16 no epilogue math (TMA epilogue), 32 no MMA issue (barriers only)
+                          // 16 no epilogue math (TMA epilogue), 32 no MMA issue (barriers only), 64 no staging-reuse wait, 128 no epilogue proxy fence,
+                          // 256 no TMA store issue, 512 no staging writes, 1024 no L2 prefetch hints, 2048 no producer proxy fence, 4096 no TMEM loads
+                          // (64..4096: timing only, results invalid)
 };
 
 // work item w -> (m0, n0, split, k-block range); n fastest so concurrent CTAs share A rows in L2
@@ -216,7 +230,7 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32
                ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // A tile of ROWS "rows" x (SEGS*64) contiguous fp32 elements <-> SEGS blocks of [ROWS x 128 B] bf16 in
@@ -308,19 +322,22 @@ struct SmemPlan {
   static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;         // one bf16 plane
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * PLANES;
   static constexpr int EPI_BOX_BYTES = 32 * 32 * 4;                           // one TMA store box (1024-byte aligned)
-  static constexpr int EPI_WARP_BYTES = 2 * EPI_BOX_BYTES;                    // double-buffered per warp
+  static constexpr int EPI_WARP_BYTES = EPI_BOX_BYTES;                        // one box per warp (the pair of a quarter alternates)
   static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
   static constexpr int BIAS_BYTES = BN * 4;                                    // this tile's bias slice, shared by the epilogue warps
   static constexpr size_t TOTAL = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + BIAS_BYTES + 1024;
   static_assert(STAGE_BYTES % 1024 == 0, "stages must keep the 1024-byte swizzle alignment");
-  static_assert(32 * 36 * 4 <= EPI_WARP_BYTES, "transpose tile of the st.global epilogue must fit the staging area");
 };
 
-// Block = 16 warps: 8 producers (2 warpgroups), MMA, TMA, 4 epilogue, 2 idle (so every warpgroup is complete:
-// setmaxnreg is warpgroup-aligned).  The kernel starts at 128 registers/thread; producers raise their budget to
-// PRODUCER_REGS (their operand tiles live in registers, DEPTH k-blocks in flight), everyone else drops to OTHER_REGS.
-constexpr int BLOCK_THREADS = 512;
-constexpr int PRODUCER_REGS = 160, OTHER_REGS = 96;      // 256*160 + 256*96 = 65536
+// Block = 20 warps: 8 producers (2 warpgroups), MMA, TMA, 2 idle, 8 epilogue (2 warpgroups) -- every warpgroup is
+// complete because setmaxnreg is warpgroup-aligned.  The kernel starts at 96 registers/thread; producers raise their
+// budget to PRODUCER_REGS (their operand tiles live in registers, DEPTH k-blocks in flight), everyone else drops to
+// OTHER_REGS.  Eight epilogue warps because the epilogue, not the MMA, paced the wide-output shapes: with four warps one
+// 128 x 256 tile took ~19 k cycles to drain (TMEM load -> bias / ReLU / bitmask -> staging -> TMA store, a serial chain
+// per 32-column chunk) against 6.1 k cycles of MMA issue at K = 256 (profiles/r02_gemm_epilogue_bisect.txt).
+constexpr int BLOCK_THREADS = 640;
+constexpr int EPI_WARP0 = 12;                             // first epilogue warp (warps 12..19)
+constexpr int PRODUCER_REGS = 144, OTHER_REGS = 64;      // 256*144 + 384*64 = 61440 = 640*96: the CTA pool is what the launch allocated
 __device__ __forceinline__ void regs_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS)); }
 __device__ __forceinline__ void regs_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(OTHER_REGS)); }
 
@@ -357,7 +374,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi) : "memory");
       if (X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo) : "memory");
     }
-    if (p.epi_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_c) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_c) : "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -417,7 +434,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
         TA::template store<X3>(a_hi, a_hi + A_BYTES, tid, va);
         TB::template store<X3>(b_hi, b_hi + B_BYTES, tid, vb);
       }
-      fence_proxy_async();                                      // generic-proxy smem writes -> visible to the tensor core
+      if (!(p.debug & 2048)) fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(full0 + 8 * s);                // one arrival per producer warp (256 arrivals on one
       ++it;                                                     // mbarrier cost ~1000 cycles per k-block)
@@ -441,7 +458,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
     // MN-major operands (weight gradient): lines PF_DIST k-blocks ahead inside the same item.
     constexpr int PF_DIST = 4;
     auto hints = [&](const Work& wk, int kb, int w) {
-      if (!p.l2_prefetch) return;
+      if (!p.l2_prefetch || (p.debug & 1024)) return;
       if constexpr (!A_MN) {
         if (kb == 0 && tid < BM) {
           const int nw = w + gridDim.x;
@@ -571,71 +588,55 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
         }
       }
     }
-  } else if (warp < PW + 2 + EPI_WARPS) {
+  } else if (warp >= EPI_WARP0) {
     // ===================== epilogue warps =====================
-    const int quarter = warp & 3;                                    // TMEM lane quarter this warp may access
-    const uint32_t stage0 = smem_u32(smem) + STAGES * STAGE_BYTES + (warp - (PW + 2)) * SP::EPI_WARP_BYTES;
+    // TMEM hands each thread one accumulator ROW.  Warp e handles lane quarter (warp & 3) and the 32-column chunks
+    // e>>2, e>>2 + 2, ... of the tile, 16 columns at a time (the budget is 64 registers): all epilogue math happens on
+    // the row in registers; the row is written into a SWIZZLE_128B staging box (16-byte chunk c of row r at chunk
+    // c ^ (r & 7): conflict-free for the quarter-warps) and one lane issues the TMA store of the 32 x 32 box.  Rows
+    // beyond M are clipped by the tensor map.  One box per warp: while its store drains, the quarter's other warp works.
+    const int ew = warp - EPI_WARP0;                                 // 0..7
+    const int quarter = warp & 3, half = ew >> 2;                    // TMEM lane quarter this warp may access; chunk parity
+    const uint32_t box = smem_u32(smem) + STAGES * STAGE_BYTES + ew * SP::EPI_WARP_BYTES;
     const bool relu = p.flags & POET_GEMM_RELU, accum = p.flags & POET_GEMM_ACCUMULATE;
     const float alpha = p.alpha;
+    const bool reduce = accum || p.splits > 1;
+    const int words = p.N >> 5;                                      // bitmask words per row
+    bool pending = false;                                            // a store of this warp's box may still be reading it
+    // The tile's bias slice is staged in shared memory once per tile (a dependent global load per 32-column
+    // chunk costs ~500 cycles of epilogue latency).
+    const uint32_t bias_s = smem_u32(smem) + STAGES * STAGE_BYTES + SP::EPI_BYTES;
+    const int et = tid - EPI_WARP0 * 32;                             // 0..255 over the epilogue warps
     int tcnt = 0;
-    if (p.epi_tma) {
-      // TMEM hands each thread one accumulator ROW (32 consecutive columns per tcgen05.ld).  All epilogue math
-      // happens on that row in registers; the row is written into a SWIZZLE_128B staging box (16-byte chunk c of
-      // row r at chunk c ^ (r & 7): conflict-free for the quarter-warps) and one lane issues the TMA store of the
-      // 32 x 32 box.  Rows beyond M are clipped by the tensor map.  Two boxes per warp: the store of chunk i
-      // overlaps the TMEM load and math of chunk i+1.
-      const bool reduce = accum || p.splits > 1;
-      const int words = p.N >> 5;                                    // bitmask words per row
-      int nst = 0;                                                   // boxes issued by this warp
-      // The tile's bias slice is staged in shared memory once per tile (a dependent global load per 32-column
-      // chunk costs ~500 cycles of epilogue latency, and the epilogue is what paces the accumulator hand-over).
-      const uint32_t bias_s = smem_u32(smem) + STAGES * STAGE_BYTES + SP::EPI_BYTES;
-      const int et = tid - (PW + 2) * 32;                            // 0..127 over the epilogue warps
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcnt) {
-        const Work wk = decode<BK>(p, w, BN);
-        const int ab = tcnt & 1;
-        const int mrow0 = wk.m0 + quarter * 32;
-        const int row = mrow0 + lane;
-        const bool row_ok = row < p.M;
-        const bool dead = p.row_mask != nullptr && row_ok && p.row_mask[row] != 0;
-        const bool has_bias = p.bias != nullptr && wk.split == 0;
-        if (has_bias) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");             // every epilogue warp is done with the previous slice
-          if (et * 2 < wk.bn) {
-            const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.bias + wk.n0 + et * 2));
-            asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_s + et * 8), "f"(b2.x), "f"(b2.y) : "memory");
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcnt) {
+      const Work wk = decode<BK>(p, w, BN);
+      const int ab = tcnt & 1;
+      const int mrow0 = wk.m0 + quarter * 32;
+      const int row = mrow0 + lane;
+      const bool row_ok = row < p.M;
+      const bool dead = p.row_mask != nullptr && row_ok && p.row_mask[row] != 0;
+      const bool has_bias = p.bias != nullptr && wk.split == 0;
+      if (has_bias) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");               // every epilogue warp is done with the previous slice
+        if (et < wk.bn) {
+          const float b1 = __ldg(p.bias + wk.n0 + et);
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + et * 4), "f"(b1) : "memory");
         }
-        mbar_wait(tfull0 + 8 * ab, (tcnt >> 1) & 1);
-        tc_fence_after();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      mbar_wait(tfull0 + 8 * ab, (tcnt >> 1) & 1);
+      tc_fence_after();
 #pragma unroll 1
-        for (int col = 0; col < wk.bn; col += 32) {
-          float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN + col), v);
-          if (col + 32 >= wk.bn) {                                      // last read of this accumulator: release it
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * ab);
-          }
-          const int n0c = wk.n0 + col;
-          if (mrow0 >= p.M || (p.debug & 8)) continue;               // warp-uniform
-          if (!(p.debug & 16)) {
-          if (alpha != 1.f) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= alpha;
-          }
-          if (has_bias) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b4 = lds128(bias_s + (col + 4 * j) * 4);  // warp-uniform address: one broadcast wavefront
-              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
-            }
-          }
+      for (int col = half * 32; col < wk.bn; col += 64) {            // wk.bn >= 64: every warp owns at least one chunk
+        const int n0c = wk.n0 + col;
+        const bool last = col + 64 >= wk.bn;
+        const bool live = mrow0 < p.M && !(p.debug & 8);             // warp-uniform
+        uint32_t bits = 0, gbits = 0xffffffffu, keep = 0xffffffffu;
+        if (live && !(p.debug & 16)) {
+          if (p.gate_bits != nullptr) gbits = row_ok ? __ldg(p.gate_bits + (int64_t)row * words + (n0c >> 5)) : 0u;
           // nn.Dropout on the epilogue's output (reference: dropout2 / dropout3 on relu(linear1(x)),
           // deformable_transformer.py:194,268).  The keep mask is folded into the ReLU sign bitmask, so the backward
           // needs no second mask: the dgrad gates on (pre-activation > 0 AND kept) and scales by 1/(1-p) through alpha.
-          uint32_t keep = 0xffffffffu;
           if (p.drop.seed != nullptr) {
             const PoetDropKey key = poet_drop_key(p.drop);
             const uint64_t pair0 = ((uint64_t)row * (uint64_t)p.N + (uint64_t)n0c) >> 1;      // N and n0c are even
@@ -643,139 +644,91 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
 #pragma unroll
             for (int j = 0; j < 16; ++j) keep |= poet_drop_keep2(key, pair0 + j, p.drop.threshold16) << (2 * j);
           }
-          if (relu) {
-            if (p.relu_bits != nullptr) {
-              uint32_t bits = 0;
-#pragma unroll
-              for (int i = 0; i < 32; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
-              if (row_ok) p.relu_bits[(int64_t)row * words + (n0c >> 5)] = dead ? 0u : (bits & keep);
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (p.drop.seed != nullptr) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * p.drop.scale16 : 0.f;
-          }
-          if (p.gate_bits != nullptr) {                              // ReLU backward from the saved sign bitmask
-            const uint32_t bits = row_ok ? __ldg(p.gate_bits + (int64_t)row * words + (n0c >> 5)) : 0u;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = ((bits >> i) & 1u) ? v[i] : 0.f;
-          } else if (p.gate != nullptr) {                            // ReLU backward from the fp32 activation
-            if (row_ok) {
-              const float* gp = p.gate + (int64_t)row * p.ldc + n0c;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 g4 = ldg4(gp + 4 * j);
-                v[4 * j] = g4.x > 0.f ? v[4 * j] : 0.f; v[4 * j + 1] = g4.y > 0.f ? v[4 * j + 1] : 0.f;
-                v[4 * j + 2] = g4.z > 0.f ? v[4 * j + 2] : 0.f; v[4 * j + 3] = g4.w > 0.f ? v[4 * j + 3] : 0.f;
-              }
-            }
-          }
-          if (dead) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
-          }
-          }
-          const uint32_t box = stage0 + (uint32_t)(nst & 1) * SP::EPI_BOX_BYTES;
-          if (nst >= 2) {                                            // the store issued two boxes ago has read this buffer
-            if (lane == 0) bulk_wait_read_1();
-            __syncwarp();
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            sts128(box + lane * 128 + ((j ^ (lane & 7)) << 4),
-                   make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
-                              __float_as_uint(v[4 * j + 3])));
-          fence_proxy_async();                                       // generic-proxy writes -> visible to the TMA engine
-          __syncwarp();
-          if (lane == 0) {
-            if (reduce) tma_reduce_add_2d(&tm_c, box, n0c, mrow0);
-            else        tma_store_2d(&tm_c, box, n0c, mrow0);
-            bulk_commit();
-          }
-          ++nst;
         }
-      }
-      if (lane == 0) bulk_wait_all();                                // staging smem must outlive the last store
-    } else {
-      // Older epilogue: each warp transposes its 32x32 block through a private padded smem tile (32 rows x 36
-      // floats) so that lane = column group and every global access is a coalesced 128-bit vector.
-      const uint32_t tile = stage0;
-      const int rsub = lane >> 3, c4 = (lane & 7) * 4;
-      for (int w = blockIdx.x; w < p.total_work; w += gridDim.x, ++tcnt) {
-        const Work wk = decode<BK>(p, w, BN);
-        const int ab = tcnt & 1;
-        const int mrow0 = wk.m0 + quarter * 32;
-        const int rows = min(32, p.M - mrow0);
-        // rows of this warp's quarter that the padding mask zeroes (bit r = row mrow0 + r)
-        const uint32_t dead_rows = __ballot_sync(0xffffffffu, p.row_mask != nullptr && mrow0 + lane < p.M &&
-                                                                  p.row_mask[min(mrow0 + lane, p.M - 1)] != 0);
-        mbar_wait(tfull0 + 8 * ab, (tcnt >> 1) & 1);
-        tc_fence_after();
-#pragma unroll 1
-        for (int col = 0; col < wk.bn; col += 32) {
-          float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN + col), v);
-          if (col + 32 >= wk.bn) {                                        // last read of this accumulator: release it
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float v[16];
+          if (p.debug & 4096) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 1.f;
+          } else {
+            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN + col + 16 * h), v);
+          }
+          if (last && h == 1) {                                      // last read of this accumulator by this warp: release it
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * ab);
           }
-          __syncwarp();
+          if (!live) continue;
+          if (!(p.debug & 16)) {
+            if (alpha != 1.f) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            sts128(tile + lane * 144 + j * 16, make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
-                                                          __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3])));
-          __syncwarp();
-          const int n = wk.n0 + col + c4;                            // first of this lane's four output columns
-          if (n >= p.N || rows <= 0 || (p.debug & 8)) continue;
-          float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias != nullptr && wk.split == 0) bias = ldg4(p.bias + n);
-          float4 o[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 t = lds128(tile + (rsub + 4 * i) * 144 + c4 * 4);
-            o[i] = make_float4(alpha * t.x + bias.x, alpha * t.y + bias.y, alpha * t.z + bias.z, alpha * t.w + bias.w);
-          }
-          float* cbase = p.C + (int64_t)mrow0 * p.ldc + n;
-          if (p.splits > 1) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = rsub + 4 * i;
-              if (r < rows)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cbase + (int64_t)r * p.ldc), "f"(o[i].x),
-                             "f"(o[i].y), "f"(o[i].z), "f"(o[i].w) : "memory");
+              for (int i = 0; i < 16; ++i) v[i] *= alpha;
             }
-            continue;
-          }
-          float4 g[8];
-          if (p.gate != nullptr) {                                   // ReLU backward: keep where the forward activation was > 0
-            const float* gbase = p.gate + (int64_t)mrow0 * p.ldc + n;
+            if (has_bias) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) g[i] = ldg4(gbase + (int64_t)min(rsub + 4 * i, rows - 1) * p.ldc);
+              for (int j = 0; j < 4; ++j) {
+                const float4 b4 = lds128(bias_s + (col + 16 * h + 4 * j) * 4);  // warp-uniform address: one broadcast wavefront
+                v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+              }
+            }
+            if (relu) {
+              if (p.relu_bits != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              o[i].x = g[i].x > 0.f ? o[i].x : 0.f; o[i].y = g[i].y > 0.f ? o[i].y : 0.f;
-              o[i].z = g[i].z > 0.f ? o[i].z : 0.f; o[i].w = g[i].w > 0.f ? o[i].w : 0.f;
+                for (int i = 0; i < 16; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << (16 * h + i);
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (p.drop.seed != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = ((keep >> (16 * h + i)) & 1u) ? v[i] * p.drop.scale16 : 0.f;
+            }
+            if (p.gate_bits != nullptr) {                            // ReLU backward from the saved sign bitmask
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = ((gbits >> (16 * h + i)) & 1u) ? v[i] : 0.f;
+            } else if (p.gate != nullptr) {                          // ReLU backward from the fp32 activation
+              if (row_ok) {
+                const float* gp = p.gate + (int64_t)row * p.ldc + n0c + 16 * h;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float4 g4 = ldg4(gp + 4 * j);
+                  v[4 * j] = g4.x > 0.f ? v[4 * j] : 0.f; v[4 * j + 1] = g4.y > 0.f ? v[4 * j + 1] : 0.f;
+                  v[4 * j + 2] = g4.z > 0.f ? v[4 * j + 2] : 0.f; v[4 * j + 3] = g4.w > 0.f ? v[4 * j + 3] : 0.f;
+                }
+              }
+            }
+            if (dead) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = 0.f;
             }
           }
-          if (accum) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) g[i] = ld4(cbase + (int64_t)min(rsub + 4 * i, rows - 1) * p.ldc);
+          if (h == 0 && pending && !(p.debug & 64)) {                // the previous store of this warp has read the box
+            if (lane == 0) bulk_wait_read_0();
+            __syncwarp();
           }
+          if (!(p.debug & 512)) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = rsub + 4 * i;
-            float4 x = o[i];
-            if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-            if ((dead_rows >> r) & 1u) x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (accum) { x.x += g[i].x; x.y += g[i].y; x.z += g[i].z; x.w += g[i].w; }
-            if (r < rows) st4(cbase + (int64_t)r * p.ldc, x);
+            for (int j = 0; j < 4; ++j)
+              sts128(box + lane * 128 + (((4 * h + j) ^ (lane & 7)) << 4),
+                     make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                                __float_as_uint(v[4 * j + 3])));
           }
         }
+        if (!live) continue;
+        if (relu && p.relu_bits != nullptr && row_ok && !(p.debug & 16))
+          p.relu_bits[(int64_t)row * words + (n0c >> 5)] = dead ? 0u : (bits & keep);
+        if (!(p.debug & 128)) fence_proxy_async();                   // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0 && !(p.debug & 256)) {
+          if (reduce) tma_reduce_add_2d(&tm_c, box, n0c, mrow0);
+          else        tma_store_2d(&tm_c, box, n0c, mrow0);
+          bulk_commit();
+        }
+        pending = true;
       }
     }
+    if (lane == 0) bulk_wait_all();                                  // staging smem must outlive the last store
   }
   tc_fence_before();
   __syncthreads();
@@ -896,10 +849,7 @@ bool poet_gemm_tc_supported(int M, int N, int K, int a_kcontig, int b_kcontig, i
 size_t poet_gemm_tc_workspace_bytes(int, int, int, int, int, int) { return 0; }
 
 // 1 when relu_bits / gate_bits are honoured (TMA epilogue enabled); the Python side asks before using them.
-int poet_gemm_tc_bits_supported() {
-  static const int on = tc::env_int("POET_GEMM_TMA_EPI", 1);
-  return on;
-}
+int poet_gemm_tc_bits_supported() { return 1; }
 
 // b_hi / b_lo != nullptr: B was pre-split into bf16 planes (same logical layout / ldb as the fp32 B).
 int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, const void* b_hi, const void* b_lo,
@@ -910,12 +860,10 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
   POET_REQUIRE(!bias || poet_aligned16(bias), POET_ERR_BAD_ALIGNMENT);
   POET_REQUIRE(!gate || poet_aligned16(gate), POET_ERR_BAD_ALIGNMENT);
   static const int dbg = tc::env_int("POET_GEMM_DEBUG", 0);
-  static const int epi_tma = tc::env_int("POET_GEMM_TMA_EPI", 1);
   static const int l2pf = tc::env_int("POET_GEMM_L2_PREFETCH", 1);
   static const int wgrad_bn = tc::env_int("POET_GEMM_WGRAD_BN", 256);
-  POET_REQUIRE(epi_tma || (relu_bits == nullptr && gate_bits == nullptr), POET_ERR_UNSUPPORTED);
   const bool dropping = drop != nullptr && drop->seed != nullptr;
-  POET_REQUIRE(!dropping || (epi_tma && N % 32 == 0), POET_ERR_UNSUPPORTED);
+  POET_REQUIRE(!dropping || N % 32 == 0, POET_ERR_UNSUPPORTED);
   const bool x3 = precision == POET_GEMM_BF16X3;
   const bool b_tma = b_hi != nullptr && (!x3 || b_lo != nullptr) && a_kcontig && (ldb % 8 == 0) &&
                      poet_aligned16(b_hi) && (!x3 || poet_aligned16(b_lo));
@@ -930,7 +878,7 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
   a.flags = flags;
   memset(&a.drop, 0, sizeof(a.drop));
   if (dropping) a.drop = *drop;
-  a.epi_tma = epi_tma; a.l2_prefetch = l2pf; a.debug = dbg;
+  a.l2_prefetch = l2pf; a.debug = dbg;
   const int m_tiles = poet_ceil_div(M, tc::BM);
   const int total_kb = poet_ceil_div(K, bk);
   // Tile width: rounds of the persistent grid x work per round.  128-wide tiles quantise better over 148 SMs
@@ -985,7 +933,7 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
     if (rc) return rc;
     if (x3) { rc = tc::make_map(&m.lo, b_lo, inner, rows, ldb, box_rows); if (rc) return rc; }
   }
-  if (epi_tma) {
+  {
     int rc = tc::make_map_c(&m.c, C, N, M, ldc);
     if (rc) return rc;
   }

@@ -7,6 +7,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     import torch
     from poet_b200 import ops
     dev = "cuda:0"
+    ops.set_gemm_precision(os.environ.get("POET_BISECT_PREC", "bf16x3"))
     for shape in sys.argv[2:]:
         M, N, K = (int(v) for v in shape.split("x"))
         A = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev); b = torch.randn(N, device=dev)
@@ -14,7 +15,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         ops._call("poet_split_bf16", W.data_ptr(), hi.data_ptr(), lo.data_ptr(), W.numel(), ops._stream(W))
         out = torch.empty(M, N, device=dev)
         def run():
-            ops.gemm(A, W, M, N, K, bias=b, out=out, b_split=(hi, lo))
+            ops.gemm(A, W, M, N, K, bias=b, out=out, b_split=(hi, lo if ops.get_gemm_precision() == 'bf16x3' else None))
         side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(3): run()
@@ -30,6 +31,6 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         print(f"debug={os.environ.get('POET_GEMM_DEBUG','0'):>2s} epi={os.environ.get('POET_GEMM_TMA_EPI','1')} {M}x{N}x{K}: {s.elapsed_time(e)/100*1e3:8.1f} us", flush=True)
 else:
     shapes = ["25600x1024x256", "25600x256x256", "25600x256x1024"]
-    for dbg in (0, 8, 16, 24, 1, 3, 4, 7, 15, 31, 32, 40, 47, 63):
+    for dbg in [int(v) for v in os.environ.get('POET_BISECT', '0,8,16,24,1,3,4,7,15,31,32,40,47,63').split(',')]:
         env = dict(os.environ, POET_GEMM_DEBUG=str(dbg))
         subprocess.run([sys.executable, __file__, "child", *shapes], env=env)

@@ -181,10 +181,12 @@ int poet_add_layernorm_fwd(const float* x, const float* r, const float* gamma, c
                            poet_stream_t stream);
 /* dz = LN backward of (dy [+ dy2]) = gradient of x; dgamma/dbeta [C] are ACCUMULATED into (caller zero-fills).
  * With drop_p > 0 the gradient of the dropped branch r is written to dr [R,C] (= dz * mask / (1-p)); without
- * dropout it equals dz and dr may be NULL. */
+ * dropout it equals dz and dr may be NULL.  dr_colsum [C] (nullable) is ACCUMULATED with the column sums of the
+ * residual branch's gradient: the bias gradient of the nn.Linear that produced r (reference linear2 / output_proj /
+ * out_proj in front of norm2 / norm1, deformable_transformer.py:196-197,203-204,280-281,286-287). */
 int poet_layernorm_bwd(const float* dy, const float* dy2, const float* xhat, const float* rstd,
                        const float* gamma, float* dz, float* dgamma, float* dbeta,
-                       int R, int C, float* dr, const void* drop_seed, uint32_t drop_site, float drop_p,
+                       int R, int C, float* dr, float* dr_colsum, const void* drop_seed, uint32_t drop_site, float drop_p,
                        poet_stream_t stream);
 /* x <- dropout(x) in place over n floats (n % 4 == 0) with the PAIR scheme the GEMM epilogue uses for the FFN hidden
  * activation (elements 2j, 2j+1 <- low / high half of hash(j), p quantised to 1/65536): fallback for a hidden

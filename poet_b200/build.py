@@ -43,7 +43,7 @@ def _digest() -> str:
     for f in sorted(os.listdir(CSRC)) + ["../../include/poet_b200.h"]:
         with open(os.path.join(CSRC, f), "rb") as fh:
             h.update(f.encode() + b"\0" + fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update((" ".join(NVCC_FLAGS) + os.environ.get("POET_GEMM_BISECT", "")).encode())
     return h.hexdigest()
 
 
@@ -56,6 +56,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = _nvcc()
     defines = ["-DPOET_HAVE_TC_GEMM"] if os.path.exists(os.path.join(CSRC, "gemm_tc.cu")) else []
+    if os.environ.get("POET_GEMM_BISECT"):                  # pipeline-bisection build (tools/gemm_bisect.py): never the product
+        defines.append("-DPOET_GEMM_BISECT")
 
     def compile_one(src):
         obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")

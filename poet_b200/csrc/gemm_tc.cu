@@ -34,6 +34,15 @@
 #include "common.cuh"
 #include "tma_host.cuh"
 
+// Pipeline-bisection knobs (tools/gemm_bisect.py, profiles/r02_gemm_epilogue_bisect.txt) exist only in builds with
+// -DPOET_GEMM_BISECT: the kernel is issue bound next to the MMA stream, and even never-taken `p.debug & bit` tests in
+// its loops cost 0.15 ms per cfg2 step (7.62 -> 7.47 ms when three of them were removed).
+#ifdef POET_GEMM_BISECT
+#define POET_DBG(p, bit) ((p).debug & (bit))
+#else
+#define POET_DBG(p, bit) 0
+#endif
+
 namespace tc {
 
 constexpr int BM = 128;
@@ -163,8 +172,8 @@ struct Args {
   int l2_prefetch;        // 1: L2 prefetch hints ahead of the register-prefetched operand loads
   int debug;              // POET_GEMM_DEBUG bit flags (pipeline bisection only): 1 no A loads, 2 no A stores, 4 no TMA, 8 no epilogue stores,
                           // 16 no epilogue math (TMA epilogue), 32 no MMA issue (barriers only), 64 no staging-reuse wait, 128 no epilogue proxy fence,
-                          // 256 no TMA store issue, 512 no staging writes, 1024 no L2 prefetch hints, 2048 no producer proxy fence, 4096 no TMEM loads
-                          // (64..4096: timing only, results invalid)
+                          // 256 no TMA store issue, 512 no staging writes (64..512: timing only, results invalid; the skeleton bits 1024..4096 of
+                          // profiles/r02_gemm_epilogue_bisect.txt were removed again after the measurement)
 };
 
 // work item w -> (m0, n0, split, k-block range); n fastest so concurrent CTAs share A rows in L2
@@ -398,7 +407,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
       const uint32_t b_hi = a_hi + A_BYTES * PLANES;
       if constexpr (B_TMA) {
         if (it >= STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
-        if (!(p.debug & 2)) TA::template store<X3>(a_hi, a_hi + A_BYTES, tid, va);
+        if (!(POET_DBG(p, 2))) TA::template store<X3>(a_hi, a_hi + A_BYTES, tid, va);
       } else if constexpr (B_PREFETCH) {
         if (do_colsum && wk.n0 == 0) {                          // bias gradient: column sums of the dY tile, for free
 #pragma unroll
@@ -434,13 +443,13 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
         TA::template store<X3>(a_hi, a_hi + A_BYTES, tid, va);
         TB::template store<X3>(b_hi, b_hi + B_BYTES, tid, vb);
       }
-      if (!(p.debug & 2048)) fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor core
+      fence_proxy_async();                                      // generic-proxy smem writes -> visible to the tensor core
       __syncwarp();
       if (lane == 0) mbar_arrive(full0 + 8 * s);                // one arrival per producer warp (256 arrivals on one
       ++it;                                                     // mbarrier cost ~1000 cycles per k-block)
     };
     auto loadAB = [&](const Work& wk, int kb, float4 (&v)[TA::CH][2], float4 (&vbp)[BCH][2]) {
-      if (p.debug & 1) {
+      if (POET_DBG(p, 1)) {
 #pragma unroll
         for (int i = 0; i < TA::CH; ++i) { v[i][0] = make_float4(1.f, 1.f, 1.f, 1.f); v[i][1] = v[i][0]; }
       } else {
@@ -458,7 +467,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
     // MN-major operands (weight gradient): lines PF_DIST k-blocks ahead inside the same item.
     constexpr int PF_DIST = 4;
     auto hints = [&](const Work& wk, int kb, int w) {
-      if (!p.l2_prefetch || (p.debug & 1024)) return;
+      if (!p.l2_prefetch) return;
       if constexpr (!A_MN) {
         if (kb == 0 && tid < BM) {
           const int nw = w + gridDim.x;
@@ -542,7 +551,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
           const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + A_BYTES * PLANES, b_lo = b_hi + B_BYTES;
 #pragma unroll
           for (int j = 0; j < BK / 16; ++j) {
-            if (p.debug & 32) break;
+            if (POET_DBG(p, 32)) break;
             const uint64_t dah = make_desc(a_hi + j * A_STEP, A_LBO, 1024);
             const uint64_t dbh = make_desc(b_hi + j * B_STEP, B_LBO, 1024);
             const uint32_t first = (i | j) ? 1u : 0u;
@@ -571,7 +580,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
           const int s = it % STAGES;
           if (it >= STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
           const uint32_t bar = full0 + 8 * s;
-          if (p.debug & 4) { mbar_arrive(bar); continue; }
+          if (POET_DBG(p, 4)) { mbar_arrive(bar); continue; }
           mbar_arrive_expect_tx(bar, B_BYTES * PLANES);
           const int k0 = (wk.kb0 + i) * BK;
           const uint32_t b_hi = smem_u32(smem + s * STAGE_BYTES + A_BYTES * PLANES), b_lo = b_hi + B_BYTES;
@@ -630,9 +639,9 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
       for (int col = half * 32; col < wk.bn; col += 64) {            // wk.bn >= 64: every warp owns at least one chunk
         const int n0c = wk.n0 + col;
         const bool last = col + 64 >= wk.bn;
-        const bool live = mrow0 < p.M && !(p.debug & 8);             // warp-uniform
+        const bool live = mrow0 < p.M && !(POET_DBG(p, 8));             // warp-uniform
         uint32_t bits = 0, gbits = 0xffffffffu, keep = 0xffffffffu;
-        if (live && !(p.debug & 16)) {
+        if (live && !(POET_DBG(p, 16))) {
           if (p.gate_bits != nullptr) gbits = row_ok ? __ldg(p.gate_bits + (int64_t)row * words + (n0c >> 5)) : 0u;
           // nn.Dropout on the epilogue's output (reference: dropout2 / dropout3 on relu(linear1(x)),
           // deformable_transformer.py:194,268).  The keep mask is folded into the ReLU sign bitmask, so the backward
@@ -648,19 +657,14 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           float v[16];
-          if (p.debug & 4096) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 1.f;
-          } else {
-            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN + col + 16 * h), v);
-          }
+          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ab * BN + col + 16 * h), v);
           if (last && h == 1) {                                      // last read of this accumulator by this warp: release it
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * ab);
           }
           if (!live) continue;
-          if (!(p.debug & 16)) {
+          if (!(POET_DBG(p, 16))) {
             if (alpha != 1.f) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] *= alpha;
@@ -703,11 +707,11 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
               for (int i = 0; i < 16; ++i) v[i] = 0.f;
             }
           }
-          if (h == 0 && pending && !(p.debug & 64)) {                // the previous store of this warp has read the box
+          if (h == 0 && pending && !(POET_DBG(p, 64))) {                // the previous store of this warp has read the box
             if (lane == 0) bulk_wait_read_0();
             __syncwarp();
           }
-          if (!(p.debug & 512)) {
+          if (!(POET_DBG(p, 512))) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               sts128(box + lane * 128 + (((4 * h + j) ^ (lane & 7)) << 4),
@@ -716,11 +720,11 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
           }
         }
         if (!live) continue;
-        if (relu && p.relu_bits != nullptr && row_ok && !(p.debug & 16))
+        if (relu && p.relu_bits != nullptr && row_ok && !(POET_DBG(p, 16)))
           p.relu_bits[(int64_t)row * words + (n0c >> 5)] = dead ? 0u : (bits & keep);
-        if (!(p.debug & 128)) fence_proxy_async();                   // generic-proxy writes -> visible to the TMA engine
+        if (!(POET_DBG(p, 128))) fence_proxy_async();                   // generic-proxy writes -> visible to the TMA engine
         __syncwarp();
-        if (lane == 0 && !(p.debug & 256)) {
+        if (lane == 0 && !(POET_DBG(p, 256))) {
           if (reduce) tma_reduce_add_2d(&tm_c, box, n0c, mrow0);
           else        tma_store_2d(&tm_c, box, n0c, mrow0);
           bulk_commit();

@@ -68,27 +68,30 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float* __restrict
 
 // dz = rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat)),  dxh = dy * gamma
 // dgamma += sum_rows dy * xhat, dbeta += sum_rows dy  (per-warp register partials -> smem -> atomics)
-template <int NV>
+template <int NV, bool COLSUM>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2,
                                                      const float* __restrict__ xhat, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, float* __restrict__ dz,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int R,
-                                                     float* __restrict__ dr, const PoetDropout drop) {
+                                                     float* __restrict__ dr, float* __restrict__ dr_colsum,
+                                                     const PoetDropout drop) {
   poet_pdl_entry();
   constexpr int C = NV * 128;
-  __shared__ float s_dg[C], s_db[C];
+  __shared__ float s_dg[C], s_db[C], s_dc[COLSUM ? C : 1];
   const bool dropping = drop.seed != nullptr && dr != nullptr;     // dr = dz * mask / (1 - p): gradient of the dropped branch
   PoetDropKey key{0u, 0u};
   if (dropping) key = poet_drop_key(drop);
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { s_dg[i] = 0.f; s_db[i] = 0.f; if (COLSUM) s_dc[i] = 0.f; }
   __syncthreads();
-  float4 g[NV], pg[NV], pb[NV];
+  // pc: column sums of the residual branch's gradient (dr with dropout, else dz) = the bias gradient of the Linear that
+  // produced r (reference: linear2 / output_proj / out_proj feeding norm2 / norm1), saved a pass over the gradient
+  float4 g[NV], pg[NV], pb[NV], pc[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     g[i] = ldg4(gamma + i * 128 + lane * 4);
-    pg[i] = make_float4(0.f, 0.f, 0.f, 0.f); pb[i] = pg[i];
+    pg[i] = make_float4(0.f, 0.f, 0.f, 0.f); pb[i] = pg[i]; pc[i] = pg[i];
   }
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < R; row += gridDim.x * warps_per_block) {
     const int64_t base = (int64_t)row * C + lane * 4;
@@ -112,13 +115,16 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
       const float4 o = make_float4(rs * (d[i].x - m1 - h[i].x * m2), rs * (d[i].y - m1 - h[i].y * m2),
                                    rs * (d[i].z - m1 - h[i].z * m2), rs * (d[i].w - m1 - h[i].w * m2));
       st4(dz + base + i * 128, o);
+      float4 c = o;
       if (dropping) {
         const uint64_t e = (uint64_t)(base + i * 128);
-        st4(dr + base + i * 128, make_float4(o.x * poet_drop_mult(key, e, drop.threshold, drop.scale),
-                                             o.y * poet_drop_mult(key, e + 1, drop.threshold, drop.scale),
-                                             o.z * poet_drop_mult(key, e + 2, drop.threshold, drop.scale),
-                                             o.w * poet_drop_mult(key, e + 3, drop.threshold, drop.scale)));
+        c = make_float4(o.x * poet_drop_mult(key, e, drop.threshold, drop.scale),
+                        o.y * poet_drop_mult(key, e + 1, drop.threshold, drop.scale),
+                        o.z * poet_drop_mult(key, e + 2, drop.threshold, drop.scale),
+                        o.w * poet_drop_mult(key, e + 3, drop.threshold, drop.scale));
+        st4(dr + base + i * 128, c);
       }
+      if (COLSUM) { pc[i].x += c.x; pc[i].y += c.y; pc[i].z += c.z; pc[i].w += c.w; }
     }
   }
 #pragma unroll
@@ -126,9 +132,15 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
     const int c = i * 128 + lane * 4;
     atomicAdd(&s_dg[c + 0], pg[i].x); atomicAdd(&s_dg[c + 1], pg[i].y); atomicAdd(&s_dg[c + 2], pg[i].z); atomicAdd(&s_dg[c + 3], pg[i].w);
     atomicAdd(&s_db[c + 0], pb[i].x); atomicAdd(&s_db[c + 1], pb[i].y); atomicAdd(&s_db[c + 2], pb[i].z); atomicAdd(&s_db[c + 3], pb[i].w);
+    if (COLSUM) {
+      atomicAdd(&s_dc[c + 0], pc[i].x); atomicAdd(&s_dc[c + 1], pc[i].y); atomicAdd(&s_dc[c + 2], pc[i].z); atomicAdd(&s_dc[c + 3], pc[i].w);
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) { atomicAdd(dgamma + i, s_dg[i]); atomicAdd(dbeta + i, s_db[i]); }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dgamma + i, s_dg[i]); atomicAdd(dbeta + i, s_db[i]);
+    if (COLSUM) atomicAdd(dr_colsum + i, s_dc[i]);
+  }
 }
 
 // out[n] (+)= sum_m X[m,n].  One warp covers 128 columns (float4 per lane), the 8 warps of a block take
@@ -239,7 +251,7 @@ extern "C" int poet_add_layernorm_fwd(const float* x, const float* r, const floa
 
 extern "C" int poet_layernorm_bwd(const float* dy, const float* dy2, const float* xhat, const float* rstd,
                                   const float* gamma, float* dz, float* dgamma, float* dbeta, int R, int C,
-                                  float* dr, const void* drop_seed, uint32_t drop_site, float drop_p,
+                                  float* dr, float* dr_colsum, const void* drop_seed, uint32_t drop_site, float drop_p,
                                   poet_stream_t stream) {
   POET_REQUIRE(dy && xhat && rstd && gamma && dz && dgamma && dbeta, POET_ERR_NULL_POINTER);
   POET_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || (drop_seed != nullptr && dr != nullptr)), POET_ERR_BAD_SHAPE);
@@ -252,10 +264,14 @@ extern "C" int poet_layernorm_bwd(const float* dy, const float* dy2, const float
   int grid = row_grid(R);
   if (grid > POET_NUM_SMS * 2) grid = POET_NUM_SMS * 2;   // fewer blocks -> fewer global atomics on dgamma/dbeta
   switch (C / 128) {
-    case 1: poet_launch(ln_bwd_kernel<1>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, drop); break;
-    case 2: poet_launch(ln_bwd_kernel<2>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, drop); break;
-    case 4: poet_launch(ln_bwd_kernel<4>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, drop); break;
-    case 8: poet_launch(ln_bwd_kernel<8>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, drop); break;
+    case 1: if (dr_colsum) poet_launch(ln_bwd_kernel<1, true>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop);
+            else poet_launch(ln_bwd_kernel<1, false>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); break;
+    case 2: if (dr_colsum) poet_launch(ln_bwd_kernel<2, true>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop);
+            else poet_launch(ln_bwd_kernel<2, false>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); break;
+    case 4: if (dr_colsum) poet_launch(ln_bwd_kernel<4, true>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop);
+            else poet_launch(ln_bwd_kernel<4, false>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); break;
+    case 8: if (dr_colsum) poet_launch(ln_bwd_kernel<8, true>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop);
+            else poet_launch(ln_bwd_kernel<8, false>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); break;
     default: return POET_ERR_UNSUPPORTED;
   }
   return poet_launch_status();

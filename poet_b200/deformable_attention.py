@@ -74,10 +74,13 @@ class MSDeformAttn(nn.Module):
 
     def forward(self, query: torch.Tensor, reference_points: torch.Tensor, input_flatten: torch.Tensor,
                 input_spatial_shapes, input_level_start_index=None,
-                input_padding_mask: Optional[torch.Tensor] = None, value: Optional[torch.Tensor] = None) -> torch.Tensor:
+                input_padding_mask: Optional[torch.Tensor] = None, value: Optional[torch.Tensor] = None,
+                output_bias_grad_elsewhere: bool = False) -> torch.Tensor:
         """query [N,Lq,C]; reference_points [N,Lq,L,2] in [0,1]; input_flatten [N,S,C];
         input_spatial_shapes [(H_l,W_l)]; input_padding_mask [N,S] True = padded  ->  [N,Lq,C].
-        `value` (ours, optional): the result of project_value() computed beforehand."""
+        `value` (ours, optional): the result of project_value() computed beforehand.
+        `output_bias_grad_elsewhere` (ours): the caller feeds the result to ops.add_layernorm(..., r_bias=output_proj.bias),
+        whose backward kernel produces that bias gradient (no separate pass over the gradient rows)."""
         shapes = host_shapes(input_spatial_shapes)
         N, S, _ = input_flatten.shape
         if sum(h * w for h, w in shapes) != S:
@@ -102,7 +105,7 @@ class MSDeformAttn(nn.Module):
         if forked is not None:
             forked.wait(mark, value)
         out = ops.msda_block(value, oa, reference_points, shapes, self.n_heads, self.n_levels, self.n_points)
-        return ops.linear(out, self.output_proj.weight, self.output_proj.bias)
+        return ops.linear(out, self.output_proj.weight, self.output_proj.bias, bias_grad_elsewhere=output_bias_grad_elsewhere)
 
 
 def ms_deform_attn_core(value: torch.Tensor, spatial_shapes, sampling_locations: torch.Tensor,

@@ -72,12 +72,12 @@ class _SelfAttentionParams(nn.Module):
         nn.init.xavier_uniform_(self.in_proj_weight)
         nn.init.zeros_(self.out_proj.bias)
 
-    def forward(self, qk_in: torch.Tensor, v_in: torch.Tensor, drop_site: int = 0) -> torch.Tensor:
+    def forward(self, qk_in: torch.Tensor, v_in: torch.Tensor, drop_site: int = 0, out_bias_grad_elsewhere: bool = False) -> torch.Tensor:
         """qk_in = tgt + query_pos, v_in = tgt, both [B,Q,C] (batch-first) -> attention output [B,Q,C]."""
         C = self.embed_dim
         qk, v = ops.in_proj_qk_v(qk_in, v_in, self.in_proj_weight, self.in_proj_bias)
         o = ops.mha_smallq(qk, v, self.num_heads, drop_p=float(self.dropout) if self.training else 0.0, drop_site=drop_site)
-        return ops.linear(o, self.out_proj.weight, self.out_proj.bias)
+        return ops.linear(o, self.out_proj.weight, self.out_proj.bias, bias_grad_elsewhere=out_bias_grad_elsewhere)
 
 
 class DeformableTransformerEncoderLayer(nn.Module):
@@ -103,16 +103,14 @@ class DeformableTransformerEncoderLayer(nn.Module):
         p, sb = _p_drop(self), self.site_base
         if query is None:
             query = src if pos is None else ops.add_tensors(src, pos)
-        attn = self.self_attn(query, reference_points, src, spatial_shapes, level_start_index, padding_mask)
+        attn = self.self_attn(query, reference_points, src, spatial_shapes, level_start_index, padding_mask,
+                              output_bias_grad_elsewhere=True)
         src = ops.add_layernorm(src, attn, self.norm1.weight, self.norm1.bias, eps=self.norm1.eps,
-                                drop_p=p, drop_site=sb + _SITE_D1)                                   # dropout1
-        ffn = ops.mlp(src, ((self.linear1.weight, self.linear1.bias), (self.linear2.weight, self.linear2.bias)),
-                      drop_p=p, drop_site=sb + _SITE_HIDDEN)                                         # dropout2
-        if emit_next_query and pos is not None:
-            return ops.add_layernorm(src, ffn, self.norm2.weight, self.norm2.bias, pos=pos, eps=self.norm2.eps,
-                                     drop_p=p, drop_site=sb + _SITE_D2)                              # dropout3
-        return ops.add_layernorm(src, ffn, self.norm2.weight, self.norm2.bias, eps=self.norm2.eps,
-                                 drop_p=p, drop_site=sb + _SITE_D2)
+                                drop_p=p, drop_site=sb + _SITE_D1, r_bias=self.self_attn.output_proj.bias)   # dropout1
+        # linear1 / relu / dropout2 / linear2 / dropout3 / norm2 as one autograd node (ops._FFNBlock)
+        return ops.ffn_block(src, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
+                             self.norm2.weight, self.norm2.bias, pos=pos if (emit_next_query and pos is not None) else None,
+                             eps=self.norm2.eps, drop_p=p, site_hidden=sb + _SITE_HIDDEN, site_res=sb + _SITE_D2)
 
 
 class DeformableTransformerEncoder(nn.Module):
@@ -164,22 +162,23 @@ class DeformableTransformerDecoderLayer(nn.Module):
         if tgt.shape[1] > 32:
             raise NotImplementedError("decoder self-attention kernel supports at most 32 object queries")
         q = tgt if query_pos is None else ops.add_tensors(tgt, query_pos)
-        sa = self.self_attn(q, tgt, drop_site=sb + _SITE_ATTN_PROB)                                  # MHA(dropout=p)
+        sa = self.self_attn(q, tgt, drop_site=sb + _SITE_ATTN_PROB, out_bias_grad_elsewhere=True)   # MHA(dropout=p)
+        ob = self.self_attn.out_proj.bias
         if query_pos is not None:
             tgt, q2 = ops.add_layernorm(tgt, sa, self.norm2.weight, self.norm2.bias, pos=query_pos, eps=self.norm2.eps,
-                                        drop_p=p, drop_site=sb + _SITE_D2)                           # dropout2
+                                        drop_p=p, drop_site=sb + _SITE_D2, r_bias=ob)                # dropout2
         else:
             tgt = ops.add_layernorm(tgt, sa, self.norm2.weight, self.norm2.bias, eps=self.norm2.eps,
-                                    drop_p=p, drop_site=sb + _SITE_D2)
+                                    drop_p=p, drop_site=sb + _SITE_D2, r_bias=ob)
             q2 = tgt
         ca = self.cross_attn(q2, reference_points, src, src_spatial_shapes, level_start_index, src_padding_mask,
-                             value=value)
+                             value=value, output_bias_grad_elsewhere=True)
         tgt = ops.add_layernorm(tgt, ca, self.norm1.weight, self.norm1.bias, eps=self.norm1.eps,
-                                drop_p=p, drop_site=sb + _SITE_D1)                                   # dropout1
-        ffn = ops.mlp(tgt, ((self.linear1.weight, self.linear1.bias), (self.linear2.weight, self.linear2.bias)),
-                      drop_p=p, drop_site=sb + _SITE_HIDDEN)                                         # dropout3
-        return ops.add_layernorm(tgt, ffn, self.norm3.weight, self.norm3.bias, eps=self.norm3.eps,
-                                 drop_p=p, drop_site=sb + _SITE_D4)                                  # dropout4
+                                drop_p=p, drop_site=sb + _SITE_D1, r_bias=self.cross_attn.output_proj.bias)  # dropout1
+        # linear1 / relu / dropout3 / linear2 / dropout4 / norm3 as one autograd node
+        return ops.ffn_block(tgt, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
+                             self.norm3.weight, self.norm3.bias, eps=self.norm3.eps, drop_p=p,
+                             site_hidden=sb + _SITE_HIDDEN, site_res=sb + _SITE_D4)
 
 
 class DeformableTransformerDecoder(nn.Module):

@@ -692,9 +692,10 @@ class _Linear(torch.autograd.Function):
     """y = x W^T + b, rows with row_mask zeroed (MSDeformAttn value_proj + masked_fill)."""
 
     @staticmethod
-    def forward(ctx, x, W, b, row_mask, mask_grad_inplace):
+    def forward(ctx, x, W, b, row_mask, mask_grad_inplace, bias_grad_elsewhere=False):
         ctx.prec = _state["precision"]
         ctx.mask_grad_inplace = mask_grad_inplace
+        ctx.bias_grad_elsewhere = bias_grad_elsewhere
         x2 = _chk(x).view(-1, x.shape[-1])
         W = _chk(W)
         R, K = x2.shape
@@ -726,13 +727,16 @@ class _Linear(torch.autograd.Function):
             else:
                 gy2 = mask_rows_(gy2 if ctx.mask_grad_inplace else gy2.clone(), ctx.row_mask)
         dx, dW, db = _linear_bwd(gy2, x2, W, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                                 ctx.has_bias and ctx.needs_input_grad[2], w_split=ctx.w_split,
+                                 ctx.has_bias and ctx.needs_input_grad[2] and not ctx.bias_grad_elsewhere, w_split=ctx.w_split,
                                  w_param=ctx.w_param, b_param=ctx.b_param, gy_row_mask=gy_mask)
-        return (dx.view(ctx.xshape) if dx is not None else None), dW, db, None, None
+        return (dx.view(ctx.xshape) if dx is not None else None), dW, db, None, None, None
 
 
-def linear(x, W, b=None, row_mask=None, mask_grad_inplace=False):
-    return _Linear.apply(x, W, b, row_mask, mask_grad_inplace)
+def linear(x, W, b=None, row_mask=None, mask_grad_inplace=False, bias_grad_elsewhere=False):
+    """bias_grad_elsewhere: b's gradient is produced by the add_layernorm(..., r_bias=b) that consumes the result."""
+    if _os.environ.get("POET_LN_RBIAS", "1") == "0":
+        bias_grad_elsewhere = False
+    return _Linear.apply(x, W, b, row_mask, mask_grad_inplace, bool(bias_grad_elsewhere))
 
 
 class _MLP(torch.autograd.Function):
@@ -741,8 +745,9 @@ class _MLP(torch.autograd.Function):
     producing GEMM's epilogue; its backward is the `gate` epilogue of the dgrad GEMM."""
 
     @staticmethod
-    def forward(ctx, x, drop_p, drop_site, *wb):
+    def forward(ctx, x, drop_p, drop_site, last_bias_elsewhere, *wb):
         ctx.prec = _state["precision"]
+        ctx.last_bias_elsewhere = bool(last_bias_elsewhere)
         n = len(wb) // 2
         x2 = _chk(x).view(-1, x.shape[-1])
         acts = [x2]
@@ -789,22 +794,27 @@ class _MLP(torch.autograd.Function):
         grads = [None] * (2 * n)
         for i in range(n - 1, -1, -1):
             need_x = i > 0 or ctx.needs_input_grad[0]
-            dx, dW, db = _linear_bwd(g, acts[i], Ws[i], need_x, ctx.needs_input_grad[3 + 2 * i],
-                                     ctx.needs_input_grad[4 + 2 * i], gate=acts[i] if i > 0 else None,
+            need_b = ctx.needs_input_grad[5 + 2 * i] and not (ctx.last_bias_elsewhere and i == n - 1)
+            dx, dW, db = _linear_bwd(g, acts[i], Ws[i], need_x, ctx.needs_input_grad[4 + 2 * i],
+                                     need_b, gate=acts[i] if i > 0 else None,
                                      w_split=ctx.w_splits[i], w_param=ctx.params[2 * i], b_param=ctx.params[2 * i + 1],
                                      gate_bits=ctx.relu_bits[i - 1] if i > 0 else None,
                                      alpha=ctx.drop_alpha if i > 0 else 1.0)
             grads[2 * i], grads[2 * i + 1] = dW, db
             g = dx
-        return (g.view(ctx.xshape) if g is not None else None, None, None, *grads)
+        return (g.view(ctx.xshape) if g is not None else None, None, None, None, *grads)
 
 
-def mlp(x, layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], drop_p: float = 0.0, drop_site: int = 0):
-    """Linear/ReLU chain; drop_p > 0: nn.Dropout after every ReLU (sites drop_site, drop_site + 1, ...)."""
+def mlp(x, layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], drop_p: float = 0.0, drop_site: int = 0,
+        last_bias_grad_elsewhere: bool = False):
+    """Linear/ReLU chain; drop_p > 0: nn.Dropout after every ReLU (sites drop_site, drop_site + 1, ...).
+    last_bias_grad_elsewhere: the last layer's bias gradient comes from add_layernorm(..., r_bias=) on the result."""
     flat = []
     for W, b in layers:
         flat += [W, b]
-    return _MLP.apply(x, float(drop_p), int(drop_site), *flat)
+    if _os.environ.get("POET_LN_RBIAS", "1") == "0":
+        last_bias_grad_elsewhere = False
+    return _MLP.apply(x, float(drop_p), int(drop_site), bool(last_bias_grad_elsewhere), *flat)
 
 
 class _ProjPair(torch.autograd.Function):
@@ -924,7 +934,10 @@ class _AddLayerNorm(torch.autograd.Function):
     """y = LN(x + dropout(r)); optionally also y2 = y + pos (the next layer's query), one pass over HBM."""
 
     @staticmethod
-    def forward(ctx, x, r, gamma, beta, pos, eps, drop_p=0.0, drop_site=0):
+    def forward(ctx, x, r, gamma, beta, pos, eps, drop_p=0.0, drop_site=0, r_bias=None):
+        ctx.r_bias = r_bias if (r is not None and r_bias is not None) else None
+        if _os.environ.get("POET_LN_RBIAS", "1") == "0":
+            ctx.r_bias = None
         x2 = _chk(x).view(-1, x.shape[-1])
         r2 = None if r is None else _chk(r).view(-1, x.shape[-1])
         R, Cc = x2.shape
@@ -965,20 +978,41 @@ class _AddLayerNorm(torch.autograd.Function):
             dg_ptr, db_ptr = _p(dgb[0]), _p(dgb[1])
         seed, site, drop_p = ctx.drop
         dr = torch.empty_like(xhat) if (drop_p > 0.0 and ctx.has_r) else None     # gradient of the dropped branch
+        # bias gradient of the Linear that produced r: the column sums of r's gradient, taken while it is in registers
+        d_rb, rb_ptr = None, None
+        if ctx.r_bias is not None and ctx.needs_input_grad[8]:
+            rb_slot = _grad_slot(ctx.r_bias)
+            if rb_slot is None:
+                d_rb = torch.zeros(Cc, device=xhat.device, dtype=torch.float32)
+            rb_ptr = _p(rb_slot if rb_slot is not None else d_rb)
         _call("poet_layernorm_bwd", _p(gy), _p(gy2), _p(xhat), _p(rstd), _p(gamma), _p(dz), dg_ptr, db_ptr,
-              R, Cc, _p(dr), _p(seed), site, drop_p if dr is not None else 0.0, _stream(xhat),
+              R, Cc, _p(dr), rb_ptr, _p(seed), site, drop_p if dr is not None else 0.0, _stream(xhat),
               work=(4 * R * Cc * (3 + (gy2 is not None) + (dr is not None)) + 4 * R, 10 * R * Cc))   # gy [, gy2], xhat -> dz [, dr]
         dz = dz.view(ctx.shape)
         gpos = None
         if ctx.has_pos and ctx.needs_input_grad[4]:
             gpos = gy2.view(ctx.shape) if gy2 is not None else None
         g_r = None if not ctx.has_r else (dr.view(ctx.shape) if dr is not None else dz)
-        return dz, g_r, dgb[0], dgb[1], gpos, None, None, None
+        return dz, g_r, dgb[0], dgb[1], gpos, None, None, None, d_rb
 
 
-def add_layernorm(x, r, gamma, beta, pos=None, eps: float = 1e-5, drop_p: float = 0.0, drop_site: int = 0):
-    """LN(x + dropout_p(r)) [, + pos]; drop_p > 0 only in training (the residual branch's nn.Dropout)."""
-    return _AddLayerNorm.apply(x, r, gamma, beta, pos, eps, float(drop_p), int(drop_site))
+def add_layernorm(x, r, gamma, beta, pos=None, eps: float = 1e-5, drop_p: float = 0.0, drop_site: int = 0, r_bias=None):
+    """LN(x + dropout_p(r)) [, + pos]; drop_p > 0 only in training (the residual branch's nn.Dropout).
+    r_bias: the bias of the nn.Linear whose output is r, when that Linear was called with bias_grad_elsewhere=True:
+    its gradient (the column sums of r's gradient) is then produced by this op's backward kernel."""
+    return _AddLayerNorm.apply(x, r, gamma, beta, pos, eps, float(drop_p), int(drop_site), r_bias)
+
+
+def ffn_block(x, W1, b1, W2, b2, gamma, beta, pos=None, eps: float = 1e-5, drop_p: float = 0.0, site_hidden: int = 0,
+              site_res: int = 0):
+    """LN(x + dropout(linear2(dropout(relu(linear1(x)))))) [, + pos]: the FFN half of an encoder / decoder layer (reference
+    deformable_transformer.py:193-197,205-206 and :267-271,289-290).  The linear2 bias gradient is summed by the LayerNorm
+    backward kernel (r_bias) instead of a separate pass over the gradient rows.
+    Measured and rejected (profiles/r02_fusion_ab.txt): one autograd node whose linear1 dgrad adds into the LayerNorm
+    backward's dz through the beta = 1 TMA-reduce epilogue (no autograd accumulation pass) -- 7.53 vs 7.45 ms/step: the
+    26 MB reduce-add store costs more than the 11 us add kernel it replaces."""
+    f = mlp(x, ((W1, b1), (W2, b2)), drop_p=drop_p, drop_site=site_hidden, last_bias_grad_elsewhere=True)
+    return add_layernorm(x, f, gamma, beta, pos=pos, eps=eps, drop_p=drop_p, drop_site=site_res, r_bias=b2)
 
 
 class _Add(torch.autograd.Function):

@@ -1,4 +1,5 @@
 """Pipeline bisection of the tcgen05 GEMM (POET_GEMM_DEBUG knobs): times each shape in a child process per knob.
+Needs a bisection build of the library (POET_GEMM_BISECT=1 python -m poet_b200.build --force): the knobs are compiled out of the product.
 bits: 1 no A loads, 2 no A smem stores, 4 no TMA (B), 8 no epilogue stores, 16 no epilogue math, 32 no MMA issue."""
 import os, sys, subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

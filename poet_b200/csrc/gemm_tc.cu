@@ -350,7 +350,11 @@ constexpr int PRODUCER_REGS = 144, OTHER_REGS = 64;      // 256*144 + 384*64 = 6
 __device__ __forceinline__ void regs_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(PRODUCER_REGS)); }
 __device__ __forceinline__ void regs_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(OTHER_REGS)); }
 
-template <int BN, int BK, bool A_MN, bool B_MN, bool X3, bool B_TMA, int PW, int STAGES>
+// EPI: epilogue specialisation (the epilogue of a lane quarter issues from one SM sub-partition: run-time flag tests per
+// 16-column slice are not free).  0 generic (every flag tested at run time); 1 linear: alpha = 1, optional bias, optional
+// output row mask, store or reduce-add; 2 bias + ReLU + sign bitmask out (+ optional dropout); 3 ReLU gate from the saved
+// bitmask, alpha, no bias.
+template <int BN, int BK, bool A_MN, bool B_MN, bool X3, bool B_TMA, int PW, int STAGES, int EPI>
 __global__ void __launch_bounds__(BLOCK_THREADS, 1)
 gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                const __grid_constant__ CUtensorMap tm_c) {
@@ -607,7 +611,11 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
     const int ew = warp - EPI_WARP0;                                 // 0..7
     const int quarter = warp & 3, half = ew >> 2;                    // TMEM lane quarter this warp may access; chunk parity
     const uint32_t box = smem_u32(smem) + STAGES * STAGE_BYTES + ew * SP::EPI_WARP_BYTES;
-    const bool relu = p.flags & POET_GEMM_RELU, accum = p.flags & POET_GEMM_ACCUMULATE;
+    constexpr bool G = EPI == 0;
+    constexpr bool MAY_ALPHA = G || EPI == 3, MAY_BIAS = EPI != 3, MAY_RELU = G || EPI == 2, MAY_DROP = G || EPI == 2;
+    constexpr bool MAY_GATE_BITS = G || EPI == 3, MAY_GATE_F32 = G, MAY_DEAD = G || EPI == 1;
+    const bool relu = G ? (p.flags & POET_GEMM_RELU) != 0 : EPI == 2;
+    const bool accum = p.flags & POET_GEMM_ACCUMULATE;
     const float alpha = p.alpha;
     const bool reduce = accum || p.splits > 1;
     const int words = p.N >> 5;                                      // bitmask words per row
@@ -623,8 +631,8 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
       const int mrow0 = wk.m0 + quarter * 32;
       const int row = mrow0 + lane;
       const bool row_ok = row < p.M;
-      const bool dead = p.row_mask != nullptr && row_ok && p.row_mask[row] != 0;
-      const bool has_bias = p.bias != nullptr && wk.split == 0;
+      const bool dead = MAY_DEAD && p.row_mask != nullptr && row_ok && p.row_mask[row] != 0;
+      const bool has_bias = MAY_BIAS && p.bias != nullptr && wk.split == 0;
       if (has_bias) {
         asm volatile("bar.sync 1, 256;" ::: "memory");               // every epilogue warp is done with the previous slice
         if (et < wk.bn) {
@@ -642,11 +650,12 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
         const bool live = mrow0 < p.M && !(POET_DBG(p, 8));             // warp-uniform
         uint32_t bits = 0, gbits = 0xffffffffu, keep = 0xffffffffu;
         if (live && !(POET_DBG(p, 16))) {
-          if (p.gate_bits != nullptr) gbits = row_ok ? __ldg(p.gate_bits + (int64_t)row * words + (n0c >> 5)) : 0u;
+          if (MAY_GATE_BITS && (EPI == 3 || p.gate_bits != nullptr))
+            gbits = row_ok ? __ldg(p.gate_bits + (int64_t)row * words + (n0c >> 5)) : 0u;
           // nn.Dropout on the epilogue's output (reference: dropout2 / dropout3 on relu(linear1(x)),
           // deformable_transformer.py:194,268).  The keep mask is folded into the ReLU sign bitmask, so the backward
           // needs no second mask: the dgrad gates on (pre-activation > 0 AND kept) and scales by 1/(1-p) through alpha.
-          if (p.drop.seed != nullptr) {
+          if (MAY_DROP && p.drop.seed != nullptr) {
             const PoetDropKey key = poet_drop_key(p.drop);
             const uint64_t pair0 = ((uint64_t)row * (uint64_t)p.N + (uint64_t)n0c) >> 1;      // N and n0c are even
             keep = 0;
@@ -665,7 +674,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
           }
           if (!live) continue;
           if (!(POET_DBG(p, 16))) {
-            if (alpha != 1.f) {
+            if (MAY_ALPHA && alpha != 1.f) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] *= alpha;
             }
@@ -676,22 +685,22 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
                 v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
               }
             }
-            if (relu) {
-              if (p.relu_bits != nullptr) {
+            if (MAY_RELU && relu) {
+              if (EPI == 2 || p.relu_bits != nullptr) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << (16 * h + i);
               }
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
             }
-            if (p.drop.seed != nullptr) {
+            if (MAY_DROP && p.drop.seed != nullptr) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = ((keep >> (16 * h + i)) & 1u) ? v[i] * p.drop.scale16 : 0.f;
             }
-            if (p.gate_bits != nullptr) {                            // ReLU backward from the saved sign bitmask
+            if (MAY_GATE_BITS && (EPI == 3 || p.gate_bits != nullptr)) {   // ReLU backward from the saved sign bitmask
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = ((gbits >> (16 * h + i)) & 1u) ? v[i] : 0.f;
-            } else if (p.gate != nullptr) {                          // ReLU backward from the fp32 activation
+            } else if (MAY_GATE_F32 && p.gate != nullptr) {          // ReLU backward from the fp32 activation
               if (row_ok) {
                 const float* gp = p.gate + (int64_t)row * p.ldc + n0c + 16 * h;
 #pragma unroll
@@ -702,7 +711,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
                 }
               }
             }
-            if (dead) {
+            if (MAY_DEAD && dead) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = 0.f;
             }
@@ -720,7 +729,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
           }
         }
         if (!live) continue;
-        if (relu && p.relu_bits != nullptr && row_ok && !(POET_DBG(p, 16)))
+        if (MAY_RELU && relu && (EPI == 2 || p.relu_bits != nullptr) && row_ok && !(POET_DBG(p, 16)))
           p.relu_bits[(int64_t)row * words + (n0c >> 5)] = dead ? 0u : (bits & keep);
         if (!(POET_DBG(p, 128))) fence_proxy_async();                   // generic-proxy writes -> visible to the TMA engine
         __syncwarp();
@@ -803,12 +812,12 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-template <int BN, int BK, bool A_MN, bool B_MN, bool X3, bool B_TMA, int STAGES>
+template <int BN, int BK, bool A_MN, bool B_MN, bool X3, bool B_TMA, int STAGES, int EPI = 0>
 int launch(Args a, const Maps& m, cudaStream_t s) {
   constexpr int PW = 8;
   constexpr size_t smem = SmemPlan<BN, BK, X3, STAGES>::TOTAL;
   static_assert(smem <= 227 * 1024 - 256, "shared memory plan exceeds the 227 KB per-CTA limit");
-  auto kern = gemm_tc_kernel<BN, BK, A_MN, B_MN, X3, B_TMA, PW, STAGES>;
+  auto kern = gemm_tc_kernel<BN, BK, A_MN, B_MN, X3, B_TMA, PW, STAGES, EPI>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int grid = a.total_work < POET_NUM_SMS ? a.total_work : POET_NUM_SMS;       // persistent: one CTA per SM
@@ -819,18 +828,26 @@ int launch(Args a, const Maps& m, cudaStream_t s) {
 // stage counts: 128 x 256 tiles, BK 64: 2 stages of 96 KB (x3); 128 x 128, BK 64: 3 x 64 KB;
 // weight gradient (BK 32): 128 x 128: 6 x 32 KB, 128 x 256: 4 x 48 KB.  (+ 32 KB epilogue staging each)
 template <int BN, bool X3>
-int dispatch(const Args& a, bool a_mn, bool b_mn, bool b_tma, const Maps& m, cudaStream_t s) {
+int dispatch(const Args& a, bool a_mn, bool b_mn, bool b_tma, const Maps& m, cudaStream_t s, int epi) {
   constexpr int ST64 = (BN == 256) ? 2 : 3;
   constexpr int ST32 = (BN == 256) ? 4 : 6;
   if (b_tma) {                                      // B is a pre-split weight: A is k-contiguous (forward / dgrad)
     if (a_mn) return POET_ERR_UNSUPPORTED;
+    if constexpr (BN == 256) {                      // the token-row GEMMs of the step: specialised epilogues
+      if (epi == 1) return b_mn ? launch<256, 64, false, true, X3, true, ST64, 1>(a, m, s) : launch<256, 64, false, false, X3, true, ST64, 1>(a, m, s);
+      if (epi == 2) return b_mn ? launch<256, 64, false, true, X3, true, ST64, 2>(a, m, s) : launch<256, 64, false, false, X3, true, ST64, 2>(a, m, s);
+      if (epi == 3) return b_mn ? launch<256, 64, false, true, X3, true, ST64, 3>(a, m, s) : launch<256, 64, false, false, X3, true, ST64, 3>(a, m, s);
+    }
     if constexpr (BN == 128) {
       static const int st2 = env_int("POET_GEMM_STAGES128", 3) == 2;      // pipeline-depth experiment
       if (st2) return b_mn ? launch<128, 64, false, true, X3, true, 2>(a, m, s) : launch<128, 64, false, false, X3, true, 2>(a, m, s);
     }
     return b_mn ? launch<BN, 64, false, true, X3, true, ST64>(a, m, s) : launch<BN, 64, false, false, X3, true, ST64>(a, m, s);
   }
-  if (a_mn && b_mn) return launch<BN, 32, true, true, X3, false, ST32>(a, m, s);   // weight gradient
+  if (a_mn && b_mn) {                               // weight gradient
+    if constexpr (BN == 256) { if (epi == 1) return launch<256, 32, true, true, X3, false, ST32, 1>(a, m, s); }
+    return launch<BN, 32, true, true, X3, false, ST32>(a, m, s);
+  }
   if constexpr (BN == 128) {
     if (!a_mn && !b_mn) return launch<128, 64, false, false, X3, false, 3>(a, m, s);
     if (!a_mn && b_mn) return launch<128, 64, false, true, X3, false, 3>(a, m, s);
@@ -941,8 +958,16 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
     int rc = tc::make_map_c(&m.c, C, N, M, ldc);
     if (rc) return rc;
   }
-  if (bn == 256) return x3 ? tc::dispatch<256, true>(a, a_mn, b_mn, b_tma, m, s) : tc::dispatch<256, false>(a, a_mn, b_mn, b_tma, m, s);
-  return x3 ? tc::dispatch<128, true>(a, a_mn, b_mn, b_tma, m, s) : tc::dispatch<128, false>(a, a_mn, b_mn, b_tma, m, s);
+  // epilogue specialisation (see gemm_tc_kernel)
+  const bool is_relu = flags & POET_GEMM_RELU;
+  int epi = 0;
+  if (gate_bits && !gate && !row_mask && !is_relu && !bias && !dropping && !relu_bits) epi = 3;
+  else if (is_relu && relu_bits && !gate && !gate_bits && !row_mask && alpha == 1.f) epi = 2;
+  else if (!is_relu && !gate && !gate_bits && !relu_bits && !dropping && alpha == 1.f) epi = 1;
+  static const int epi_spec = tc::env_int("POET_GEMM_EPI_SPEC", 1);
+  if (!epi_spec) epi = 0;
+  if (bn == 256) return x3 ? tc::dispatch<256, true>(a, a_mn, b_mn, b_tma, m, s, epi) : tc::dispatch<256, false>(a, a_mn, b_mn, b_tma, m, s, epi);
+  return x3 ? tc::dispatch<128, true>(a, a_mn, b_mn, b_tma, m, s, epi) : tc::dispatch<128, false>(a, a_mn, b_mn, b_tma, m, s, epi);
 }
 
 int poet_split_bf16_multi_impl(const void* table_dev, int n_tensors, int64_t total_chunks, cudaStream_t s) {

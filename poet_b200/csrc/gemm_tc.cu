@@ -167,7 +167,10 @@ struct Args {
   int flags;
   int kb_per_split;       // k-blocks (of BK) per split
   int splits;
-  int n_tiles, total_work;
+  int n_tiles, total_work, total_kb;
+  uint64_t r_splits, r_n_tiles, r_tail_slices;   // fast_div reciprocals
+  int tail_shift;                                // log2(tail_slices)
+  int fast_k;                                    // K % BK == 0: operand loads need no bounds predicates (Tile::load<true>)
   int tail_start, tail_slices;   // work ids >= tail_start are column slices of the last round's tiles (tail_start = total_work: none)
   int l2_prefetch;        // 1: L2 prefetch hints ahead of the register-prefetched operand loads
   int debug;              // POET_GEMM_DEBUG bit flags (pipeline bisection only): 1 no A loads, 2 no A stores, 4 no TMA, 8 no epilogue stores,
@@ -184,24 +187,30 @@ struct Args {
 struct Work {
   int m0, n0, split, kb0, nkb, bn;
 };
+// n / d for 0 <= n, d < 2^20 by one 64-bit multiply with the host-computed reciprocal floor(2^40 / d) + 1 (exact while
+// n * d < 2^40).  decode() is inlined in every role's loop: four run-time integer divisions each were ~100 instructions.
+__device__ __forceinline__ int fast_div(int n, uint64_t recip) { return (int)(((uint64_t)(uint32_t)n * recip) >> 40); }
 template <int BK>
 __device__ __forceinline__ Work decode(const Args& p, int w, int bn) {
   Work k;
-  const int total_kb = (p.K + BK - 1) / BK;
+  const int total_kb = p.total_kb;
   if (w >= p.tail_start) {                                   // only set up when splits == 1
     const int t = w - p.tail_start;
-    const int tile = p.tail_start + t / p.tail_slices, sl = t % p.tail_slices;
-    k.bn = bn / p.tail_slices;
-    k.n0 = (tile % p.n_tiles) * bn + sl * k.bn;
-    k.m0 = (tile / p.n_tiles) * BM;
+    const int q = fast_div(t, p.r_tail_slices);
+    const int tile = p.tail_start + q, sl = t - q * p.tail_slices;
+    k.bn = bn >> p.tail_shift;
+    const int mt = fast_div(tile, p.r_n_tiles);
+    k.n0 = (tile - mt * p.n_tiles) * bn + sl * k.bn;
+    k.m0 = mt * BM;
     k.split = 0; k.kb0 = 0; k.nkb = total_kb;
     return k;
   }
-  k.split = w % p.splits;
-  const int tile = w / p.splits;
+  const int tile = fast_div(w, p.r_splits);
+  k.split = w - tile * p.splits;
   k.bn = bn;
-  k.n0 = (tile % p.n_tiles) * bn;
-  k.m0 = (tile / p.n_tiles) * BM;
+  const int mt = fast_div(tile, p.r_n_tiles);
+  k.n0 = (tile - mt * p.n_tiles) * bn;
+  k.m0 = mt * BM;
   k.kb0 = k.split * p.kb_per_split;
   k.nkb = min(total_kb, k.kb0 + p.kb_per_split) - k.kb0;
   return k;
@@ -255,6 +264,10 @@ struct Tile {
 
   // row_mask (nullable): stored rows of the operand with row_mask[row] != 0 are read as zeros (the masked_fill
   // backward of MSDeformAttn.value_proj, applied on the fly instead of by a separate pass over the gradient)
+  // FAST: the caller guarantees that no element that must read as zero lies outside the matrix (the reduction length is
+  // a multiple of BK); rows / columns past the end are clamped onto the last valid chunk (they only feed output rows /
+  // columns that the epilogue's tensor map clips), so the loads carry no predicates and no zero initialisation.
+  template <bool FAST = false>
   __device__ static __forceinline__ void load(const float* __restrict__ G, int64_t ld, int row0, int row_end, int col0,
                                               int col_end, int tid, float4 (&v)[CH][2], const uint8_t* __restrict__ row_mask = nullptr) {
 #pragma unroll
@@ -263,6 +276,12 @@ struct Tile {
       const int c = ch & 7, rs = ch >> 3;
       const int row = rs % ROWS, seg = rs / ROWS;
       const int grow = row0 + row, gcol = col0 + seg * 64 + c * 8;
+      if (FAST) {
+        const float* p = G + (int64_t)min(grow, row_end - 1) * ld + min(gcol, col_end - 8);
+        v[i][0] = ldg4(p);
+        v[i][1] = ldg4(p + 4);
+        continue;
+      }
       v[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
       v[i][1] = v[i][0];
       if (grow < row_end && gcol < col_end) {                    // col_end % 8 == 0 (checked on the host)
@@ -458,12 +477,18 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
         for (int i = 0; i < TA::CH; ++i) { v[i][0] = make_float4(1.f, 1.f, 1.f, 1.f); v[i][1] = v[i][0]; }
       } else {
         const int k0 = (wk.kb0 + kb) * BK;
-        if (A_MN) TA::load(p.A, p.lda, k0, p.K, wk.m0, p.M, tid, v, p.a_row_mask);
-        else      TA::load(p.A, p.lda, wk.m0, p.M, k0, p.K, tid, v, p.a_row_mask);
+        if (p.fast_k) {                                          // CTA-uniform
+          if (A_MN) TA::template load<true>(p.A, p.lda, k0, p.K, wk.m0, p.M, tid, v, p.a_row_mask);
+          else      TA::template load<true>(p.A, p.lda, wk.m0, p.M, k0, p.K, tid, v, p.a_row_mask);
+        } else {
+          if (A_MN) TA::load(p.A, p.lda, k0, p.K, wk.m0, p.M, tid, v, p.a_row_mask);
+          else      TA::load(p.A, p.lda, wk.m0, p.M, k0, p.K, tid, v, p.a_row_mask);
+        }
       }
       if constexpr (B_PREFETCH) {
         const int k0 = (wk.kb0 + kb) * BK;
-        TB::load(p.B, p.ldb, k0, p.K, wk.n0, p.N, tid, vbp);
+        if (p.fast_k) TB::template load<true>(p.B, p.ldb, k0, p.K, wk.n0, p.N, tid, vbp);
+        else          TB::load(p.B, p.ldb, k0, p.K, wk.n0, p.N, tid, vbp);
       }
     };
     // L2 prefetch hints.  K-major A: when a work item starts, the next item's rows (this CTA's next tile) are
@@ -927,7 +952,10 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
   a.kb_per_split = poet_ceil_div(total_kb, splits);
   a.splits = poet_ceil_div(total_kb, a.kb_per_split);
   a.n_tiles = N / bn;
+  a.total_kb = total_kb;
+  a.fast_k = (K % bk == 0 && M >= 8 && N >= 8 && K >= 8 && tc::env_int("POET_GEMM_FAST_LOADS", 1)) ? 1 : 0;
   a.total_work = a.n_tiles * m_tiles * a.splits;
+  POET_REQUIRE(a.total_work < (1 << 20), POET_ERR_BAD_SHAPE);
   a.tail_start = a.total_work; a.tail_slices = 1;
   static const int tail_split = tc::env_int("POET_GEMM_TAIL_SPLIT", 1);
   if (tail_split && a.splits == 1 && !wgrad && a.total_work > POET_NUM_SMS) {
@@ -940,6 +968,10 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
       a.total_work = a.tail_start + rem * sl;
     }
   }
+  auto recip = [](int d) { return (((uint64_t)1 << 40) / (uint64_t)d) + 1; };
+  a.r_splits = recip(a.splits); a.r_n_tiles = recip(a.n_tiles); a.r_tail_slices = recip(a.tail_slices);
+  a.tail_shift = 0;
+  while ((1 << a.tail_shift) < a.tail_slices) ++a.tail_shift;
   if (a.splits > 1 && !(flags & POET_GEMM_ACCUMULATE)) {
     cudaError_t e = cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s);
     if (e != cudaSuccess) return (int)e;

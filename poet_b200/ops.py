@@ -228,8 +228,13 @@ def kernel_times_ms() -> dict:
     return {k: (sum(s.elapsed_time(e) for s, e in v), len(v), *work.get(k, (0, 0))) for k, v in _timing["events"].items()}
 
 
+_ABLATE = frozenset(x for x in _os.environ.get("POET_ABLATE_CALLS", "").split(",") if x)
+
+
 def _call(name: str, *args, tag: Optional[str] = None, work=None) -> None:
     """`tag` / `work` = (algorithmic bytes, flops) only feed bench.py's per-kernel roofline table."""
+    if _ABLATE and name in _ABLATE:              # timing experiments only (tools/gpu_ab.sh): results are wrong
+        return
     _state["launches"] += 1
     if _timing["on"]:
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -377,11 +377,12 @@ def run_gpu(args):
     if args.graph:
         from poet_b200.graph import GraphedStep
         graphed = GraphedStep(model, loss_fn, d_srcs, d_masks, d_boxes, d_labels, reducer=reducer, optimizer=opt,
-                              entry="features" if args.from_features else "pyramid", backward=do_backward)
+                              entry="features" if args.from_features else "pyramid", backward=do_backward,
+                              overlap_allreduce=world > 1 and args.overlap_allreduce)
 
         def step(srcs=None, masks=None, boxes=None, labels=None):
             loss, out = graphed.run(srcs, masks, boxes, labels)
-            if do_backward:
+            if do_backward and not graphed.reduces:          # else: reduced segment by segment inside the replayed graph
                 reducer.all_reduce()
             if opt is not None:
                 opt.step()
@@ -522,6 +523,9 @@ def run_gpu(args):
                 "data": "synthetic",
                 "config": config_dict(cfg, {"global_batch": B * world, "parallelism": f"dp{world}",
                                             "grad_allreduce_bytes": reducer.nbytes() if world > 1 else 0,
+                                            "grad_allreduce": ("none (1 GPU)" if world == 1 else
+                                                               "NCCL AVG, per-segment, inside the replayed graph, overlapped with backward"
+                                                               if (graphed is not None and graphed.reduces) else "NCCL AVG, one blocking call after the step"),
                                             "gemm_precision": args.precision,
                                             "dropout": args.dropout,
                                             "launch": "one CUDA graph per step" if args.graph else "eager",
@@ -549,6 +553,8 @@ def run_gpu(args):
             line["cpu_baseline"] = cpu_baseline(cfg, backward=do_backward)
         print(json.dumps(line), flush=True)
     if world > 1:
+        graphed = None                      # a captured graph may hold NCCL nodes: release it before the communicator
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
@@ -625,6 +631,9 @@ def main():
                     help="include the fused clip_grad_norm_(0.1) + AdamW step in every step (training step of cfg4)")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
                     help="BASELINE.json config to run (default cfg2, the configuration the metric is quoted on)")
+    ap.add_argument("--overlap-allreduce", action="store_true",
+                    help="multi-GPU: all-reduce the gradient arena segment by segment inside the replayed graph, overlapped with "
+                         "backward (measured slower than the single call after the replay at 2 GPUs: profiles/r02_allreduce_overlap.txt)")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the workload's)")
     ap.add_argument("--dropout", type=float, default=0.0,
                     help="train-mode dropout probability (reference default 0.1, main.py:94); 0 = the parity configuration")

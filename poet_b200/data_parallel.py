@@ -79,6 +79,104 @@ class FlatGradReducer:
             self.flat.mul_(1.0 / ws)
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
 
+    # ---- all-reduce overlapped with the backward pass ------------------------------------------------------------
+    # The arena is cut into segments in the order their gradients complete (pose heads, decoder, encoder layers from
+    # the last to the first, the rest); poet_b200.ops.grad_marker nodes in the model's forward report progress during
+    # backward and each report launches the all-reduce of the segment finished ONE stage earlier (so the result does not
+    # depend on the order autograd picks among ready nodes) on a communication stream that waits for the calling stream
+    # and for every side stream that received work in this step.  finish() reduces what is left and joins.  Inside a
+    # CUDA-graph capture all of this becomes graph nodes: the replay needs no host-side NCCL call.
+    def plan_overlap(self, named_parameters) -> bool:
+        """named_parameters: the (name, param) pairs of the model whose parameters this reducer was built from, in
+        the same order.  Returns False (and leaves overlap off) if a group is not contiguous in the arena."""
+        names = [n for n, p in named_parameters if p.requires_grad]
+        if len(names) != len(self.params):
+            return False
+        ends = self.offsets[1:] + [self.flat.numel()]
+
+        def group_of(n):
+            parts = n.split(".")
+            if parts[0] in ("translation_head", "rotation_head"):
+                return ("heads",)
+            if parts[0] == "transformer" and parts[1] == "decoder":
+                return ("decoder",)
+            if parts[0] == "transformer" and parts[1] == "encoder" and parts[2] == "layers":
+                return ("encoder", int(parts[3]))
+            return ("rest",)
+
+        ranges = {}
+        for n, a, b in zip(names, self.offsets, ends):
+            ranges.setdefault(group_of(n), []).append((a, b))
+        segs = {}
+        for g, rs in ranges.items():
+            if g == ("rest",):
+                continue
+            rs.sort()
+            if any(rs[i][1] != rs[i + 1][0] for i in range(len(rs) - 1)):
+                if g == ("heads",):
+                    continue                                   # translation / rotation heads around other tensors: leave to finish()
+                return False
+            segs[g] = (rs[0][0], rs[-1][1])
+        n_enc = 1 + max([g[1] for g in segs if g[0] == "encoder"], default=-1)
+        # marker key -> segment whose gradients are certainly complete when that marker fires
+        self._ready = {("decoder", 0): segs.get(("heads",))}
+        for i in range(n_enc):
+            self._ready[("encoder", i)] = segs.get(("decoder",)) if i == n_enc - 1 else segs.get(("encoder", i + 1))
+        self._overlap = True
+        self._comm_stream = None
+        self._works, self._done = [], []
+        return True
+
+    def begin_step(self) -> None:
+        self._works, self._done = [], []
+        if self.flat.is_cuda:
+            from . import ops
+            ops.reset_touched_side_streams()
+            ops.set_grad_marker_callback(self.on_marker)
+
+    def _launch(self, a: int, b: int) -> None:
+        self._done.append((a, b))
+        if not self.flat.is_cuda:                              # host logic under test (gloo): same segments, blocking calls
+            seg = self.flat[a:b]
+            if self.average:
+                seg.mul_(1.0 / self.world_size())
+            dist.all_reduce(seg, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        from . import ops
+        dev = self.flat.device
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        self._comm_stream.wait_stream(cur)
+        for s in ops.touched_side_streams():
+            self._comm_stream.wait_stream(s)
+        with torch.cuda.stream(self._comm_stream):
+            op = dist.ReduceOp.AVG if self.average else dist.ReduceOp.SUM
+            self._works.append(dist.all_reduce(self.flat[a:b], op=op, group=self.group, async_op=True))
+
+    def on_marker(self, key) -> None:
+        seg = self._ready.get(key)
+        if seg is not None and seg not in self._done:
+            self._launch(*seg)
+
+    def finish(self) -> None:
+        """All-reduce every part of the arena no marker has covered, then make the calling stream wait for all of it."""
+        if self.flat.is_cuda:
+            from . import ops
+            ops.set_grad_marker_callback(None)
+        pos = 0
+        for a, b in sorted(self._done):
+            if a > pos:
+                self._launch(pos, a)
+            pos = max(pos, b)
+        if pos < self.flat.numel():
+            self._launch(pos, self.flat.numel())
+        for w in self._works:
+            w.wait()
+        if self.flat.is_cuda and self._comm_stream is not None:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self._comm_stream)
+        self._works = []
+
     def nbytes(self) -> int:
         return self.flat.numel() * self.flat.element_size()
 

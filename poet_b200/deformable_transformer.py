@@ -131,6 +131,7 @@ class DeformableTransformerEncoder(nn.Module):
         with ops.precision_scope(self.gemm_precision):
             for i, layer in enumerate(self.layers):
                 last = i == self.num_layers - 1
+                out = ops.grad_marker(out, ("encoder", i))       # backward: layers > i have issued all their gradient kernels
                 res = layer(out, pos, ref, spatial_shapes, level_start_index, padding_mask, query=query,
                             emit_next_query=not last)
                 out, query = res if isinstance(res, tuple) else (res, None)
@@ -310,6 +311,7 @@ class DeformableTransformer(nn.Module):
 
         memory = self.encoder(src, spatial_shapes, level_start, valid_ratios, pos, pad)
 
+        memory = ops.grad_marker(memory, ("decoder", 0))         # backward: decoder + heads have issued all their gradient kernels
         C = memory.shape[2]
         if query_embed.dim() == 2:
             query_embed = query_embed.unsqueeze(0).expand(memory.shape[0], -1, -1)

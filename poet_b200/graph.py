@@ -35,7 +35,7 @@ from .data_parallel import FlatGradReducer
 class GraphedStep:
     def __init__(self, model, loss_fn: Callable, srcs: Sequence[torch.Tensor], masks: Sequence[torch.Tensor],
                  boxes, labels, reducer: Optional[FlatGradReducer] = None, warmup: int = 3, backward: bool = True,
-                 optimizer=None, entry: str = "pyramid"):
+                 optimizer=None, entry: str = "pyramid", overlap_allreduce: bool = False):
         """optimizer (poet_b200.optim.FusedClipAdamW, optional): its step() writes the bf16 planes of the updated
         weights, so the captured step contains no split pass; call optimizer.step() after every run()."""
         dev = next(model.parameters()).device
@@ -43,6 +43,9 @@ class GraphedStep:
         # entry "features": srcs = backbone feature maps, masks = their masks + [padded-image mask] (input_proj included)
         self.entry = entry
         self.model, self.loss_fn, self.backward = model, loss_fn, backward
+        # overlap_allreduce: the gradient all-reduce is issued segment by segment DURING the captured backward pass
+        # (FlatGradReducer.plan_overlap); run() then returns with the arena already averaged over the ranks
+        self.reduces = False
         self.external_planes = optimizer is not None and getattr(optimizer, "planes", None) is not None
         self.reducer = reducer if reducer is not None else (FlatGradReducer(model.parameters()) if backward else None)
         self.s_srcs = [torch.empty(s.shape, dtype=torch.float32, device=dev) for s in srcs]
@@ -54,6 +57,8 @@ class GraphedStep:
         self.counts_host = None
         self._landing, self._pending, self._copy_stream, self._n_prefetched = None, [], None, 0
         self._copy_in(srcs, masks, boxes, labels)
+        if overlap_allreduce and backward and self.reducer is not None and self.reducer.world_size() > 1:
+            self.reduces = self.reducer.plan_overlap(list(model.named_parameters()))
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -73,6 +78,8 @@ class GraphedStep:
         from . import ops
         if self.reducer is not None:
             self.reducer.zero()
+        if self.reduces:
+            self.reducer.begin_step()
         with ops.planes_scope(self.model, refresh=not self.external_planes):
             if self.entry == "features":
                 out = self.model.forward_features_padded(self.s_srcs, self.s_masks[:-1], self.s_masks[-1], self.s_boxes,
@@ -82,6 +89,8 @@ class GraphedStep:
         loss = self.loss_fn(out)
         if self.backward:
             loss.backward()
+        if self.reduces:
+            self.reducer.finish()
         return loss.detach(), out
 
     def _copy_in(self, srcs, masks, boxes, labels):

@@ -104,6 +104,7 @@ class fork:
 
     def __enter__(self):
         self.side.wait_stream(self.main)
+        _touched_side_streams[id(self.side)] = self.side
         self._ctx = torch.cuda.stream(self.side)
         self._ctx.__enter__()
         return self
@@ -137,6 +138,49 @@ class fork:
         for t in tensors:
             if isinstance(t, torch.Tensor):
                 t.record_stream(self.main)
+
+
+# Side streams that received work since the last reset_touched_side_streams(): what a gradient all-reduce issued in the
+# middle of the backward pass has to wait for besides the calling stream (data_parallel.FlatGradReducer.on_marker).
+_touched_side_streams = {}
+
+
+def reset_touched_side_streams() -> None:
+    _touched_side_streams.clear()
+
+
+def touched_side_streams():
+    return list(_touched_side_streams.values())
+
+
+# Gradient-ready markers: identity in forward; in backward they tell a registered callback that every gradient kernel
+# downstream of this point of the forward graph has been ISSUED (autograd has finished all nodes created after it).
+_marker_cb = [None]
+
+
+def set_grad_marker_callback(cb) -> None:
+    _marker_cb[0] = cb
+
+
+class _GradMarker(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, key):
+        ctx.key = key
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        cb = _marker_cb[0]
+        if cb is not None:
+            cb(ctx.key)
+        return g, None
+
+
+def grad_marker(x: torch.Tensor, key):
+    """No-op unless a callback is registered (overlapped gradient all-reduce) and x carries a gradient."""
+    if _marker_cb[0] is None or not (torch.is_grad_enabled() and x.requires_grad):
+        return x
+    return _GradMarker.apply(x, key)
 
 
 def launch_count() -> int:

@@ -83,3 +83,44 @@ def test_arena_views_are_aligned_and_rebindable():
     assert ps[1].grad is not None and ps[1].grad.data_ptr() == red.flat.data_ptr() + red.offsets[1] * 4
     (ps[0].sum() * 2 + ps[1].sum()).backward()
     assert float(red.flat[:15].sum()) == 30.0 and float(red.flat[16:23].sum()) == 7.0
+
+
+# ---- segmented (overlapped) all-reduce: host logic -----------------------------------------------------------------
+def _seg_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = S.CONFIGS["tiny16"]
+    P = S.make_params(cfg)
+    names = list(P.keys())
+    params = [torch.nn.Parameter(v.clone()) for v in P.values()]
+    g = torch.Generator().manual_seed(100 + rank)
+    red = FlatGradReducer(params, average=True)
+    assert red.plan_overlap(list(zip(names, params)))
+    red.zero()
+    red.flat.copy_(torch.randn(red.flat.numel(), generator=g))
+    mine = red.flat.clone()
+    # the markers fire in backward order: decoder first, then the encoder layers from the last to the first
+    red.begin_step()
+    fired = [("decoder", 0)] + [("encoder", i) for i in reversed(range(cfg["enc_layers"]))]
+    for key in fired:
+        red.on_marker(key)
+    covered = sorted(red._done)
+    assert covered and all(a < b for a, b in covered)
+    assert all(covered[i][1] <= covered[i + 1][0] for i in range(len(covered) - 1)), "segments overlap"
+    assert sum(b - a for a, b in covered) < red.flat.numel(), "something must be left for finish()"
+    red.finish()
+    done = sorted(red._done)
+    assert done[0][0] == 0 and done[-1][1] == red.flat.numel()
+    assert all(done[i][1] == done[i + 1][0] for i in range(len(done) - 1)), "every element reduced exactly once"
+    torch.save({"mine": mine, "reduced": red.flat.clone()}, os.path.join(out_dir, f"seg{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_segmented_allreduce_covers_the_arena_exactly_once(tmp_path):
+    world = 2
+    mp.spawn(_seg_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    recs = [torch.load(os.path.join(tmp_path, f"seg{r}.pt")) for r in range(world)]
+    mean = sum(r["mine"] for r in recs) / world
+    for r in recs:
+        assert torch.allclose(r["reduced"], mean, rtol=0, atol=1e-6)

@@ -1,8 +1,14 @@
 """SURVEY.md §4 'distributed' tier on real GPUs: N ranks (one per GPU, NCCL), each running the CUDA path on its image
-shard; after FlatGradReducer.all_reduce() the gradient arena of every rank must equal the single-process gradients of
-the concatenated batch (divided by N: the reducer averages, like DDP).  Needs >= 2 GPUs (gpurun --gpus 2); skipped on
-one GPU.  Also covers the whole-step CUDA graph with the all-reduce of the arena after the replay, the way bench.py
-runs it."""
+shard.  Two checks:
+  (1) exact: after the all-reduce (one call, the call after a graph replay, or the per-segment calls inside the captured
+      backward) every rank holds the MEAN of the ranks' local gradient arenas, to the run-to-run noise of the scatter
+      atomics (2e-5 of each tensor's largest entry);
+  (2) sharding: that mean agrees with the single-process gradients of the concatenated batch divided by N within the
+      kink-flip budget of DESIGN.md section 2 -- the forward of a shard is not bitwise the forward of the same images inside
+      a larger batch (kernel variants are chosen by problem size), the network is piecewise smooth, and a flipped ReLU /
+      bilinear cell moves single gradient entries by O(1); measured on one GPU, two half batches vs the whole batch:
+      up to 4.5e-2 of the largest entry (tools/shard_check.py) at a rerun noise of 4e-6.
+Needs >= 2 GPUs (gpurun --gpus 2); skipped on one GPU."""
 import os
 import socket
 
@@ -44,8 +50,12 @@ def _step(model, red, cfg, inp, g_t, g_R, lo, hi, dev, graphed):
         return (t * gt).sum() + (R * gR).sum()
 
     if graphed:
-        step = GraphedStep(model, loss_fn, srcs, masks, inp["boxes"][lo:hi], inp["labels"][lo:hi], reducer=red, warmup=1)
+        step = GraphedStep(model, loss_fn, srcs, masks, inp["boxes"][lo:hi], inp["labels"][lo:hi], reducer=red, warmup=1,
+                           overlap_allreduce=graphed == "overlap")
+        assert step.reduces == (graphed == "overlap" and red.world_size() > 1)
         step.run()
+        torch.cuda.synchronize(dev)
+        return step.reduces
     else:
         red.zero()
         out, _ = model.forward_pyramid(srcs, masks, inp["boxes"][lo:hi], inp["labels"][lo:hi])
@@ -68,8 +78,14 @@ def _worker(rank, world, port, out_dir, graphed):
     model = _build(cfg, P, dev)
     red = FlatGradReducer(model.parameters())
     lo, hi = shard_range(cfg["batch"], rank, world)
-    _step(model, red, cfg, inp, g_t, g_R, lo, hi, dev, graphed)
-    red.all_reduce()
+    _step(model, red, cfg, inp, g_t, g_R, lo, hi, dev, False)          # local gradients of this shard, not reduced
+    local = red.flat.detach().clone()
+    locals_ = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(locals_, local)
+    mean_local = torch.stack(locals_).sum(0) / world
+    reduced = _step(model, red, cfg, inp, g_t, g_R, lo, hi, dev, graphed)
+    if not reduced:
+        red.all_reduce()
     torch.cuda.synchronize(dev)
     mine = red.flat.detach().clone()
     # every rank holds the same reduced arena
@@ -77,6 +93,8 @@ def _worker(rank, world, port, out_dir, graphed):
     dist.all_gather(gathered, mine)
     for g in gathered:
         assert torch.equal(g, mine)
+    if rank == 0:
+        torch.save({"mean_local": mean_local.cpu()}, os.path.join(out_dir, "locals.pt"))
     if rank == 0:
         full = _build(cfg, P, dev)
         red_full = FlatGradReducer(full.parameters())
@@ -87,24 +105,31 @@ def _worker(rank, world, port, out_dir, graphed):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("graphed", [False, True])
+@pytest.mark.parametrize("graphed", [False, True, "overlap"])     # "overlap": all-reduce per arena segment inside the captured backward
 def test_nccl_allreduced_gradients_equal_single_process(tmp_path, graphed):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs at least two GPUs")
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), graphed), nprocs=world, join=True)
     rec = torch.load(os.path.join(tmp_path, "grads.pt"))
+    mean_local = torch.load(os.path.join(tmp_path, "locals.pt"))["mean_local"]
     reduced, ref = rec["reduced"], rec["full"] / rec["world"]
     bounds = list(rec["offsets"]) + [reduced.numel()]
-    worst = 0.0
+    worst, tight, n = 0.0, 0, 0
     for name, a, b in zip(rec["names"], bounds[:-1], bounds[1:]):
-        r, f = reduced[a:b], ref[a:b]
-        scale = float(f.abs().max())
+        r, f, m = reduced[a:b], ref[a:b], mean_local[a:b]
+        scale = float(m.abs().max())
         if scale == 0.0:
-            assert float(r.abs().max()) == 0.0, name
+            assert float(r.abs().max()) == 0.0 and float(f.abs().max()) == 0.0, name
             continue
-        err = float((r - f).abs().max()) / scale
+        # (1) the collective: the mean of the ranks' arenas (two runs of the same shard differ by the order of the scatter atomics)
+        err = float((r - m).abs().max()) / scale
         worst = max(worst, err)
-        # fp32 summation order differs (B*S rows reduced per rank, then across ranks): a few ulps of the largest entry
         assert err <= 2e-5, (name, err)
+        # (2) sharding vs the whole batch in one process: relative L2 per tensor, kink-flip budget
+        l2 = float((r - f).norm()) / max(float(f.norm()), 1e-30)
+        assert l2 <= 0.15, (name, l2)
+        tight += l2 <= 2e-2
+        n += 1
+    assert tight >= 0.85 * n, (tight, n)
     assert worst > 0.0 or world == 1

@@ -854,8 +854,9 @@ int launch(Args a, const Maps& m, cudaStream_t s) {
 // weight gradient (BK 32): 128 x 128: 6 x 32 KB, 128 x 256: 4 x 48 KB.  (+ 32 KB epilogue staging each)
 template <int BN, bool X3>
 int dispatch(const Args& a, bool a_mn, bool b_mn, bool b_tma, const Maps& m, cudaStream_t s, int epi) {
-  constexpr int ST64 = (BN == 256) ? 2 : 3;
-  constexpr int ST32 = (BN == 256) ? 4 : 6;
+  // single-pass bf16 stages are half as large (one plane per operand): twice the pipeline depth in the same shared memory
+  constexpr int ST64 = ((BN == 256) ? 2 : 3) * (X3 ? 1 : 2);
+  constexpr int ST32 = ((BN == 256) ? 4 : 6);
   if (b_tma) {                                      // B is a pre-split weight: A is k-contiguous (forward / dgrad)
     if (a_mn) return POET_ERR_UNSUPPORTED;
     if constexpr (BN == 256) {                      // the token-row GEMMs of the step: specialised epilogues

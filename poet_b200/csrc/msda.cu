@@ -1010,6 +1010,8 @@ extern "C" int poet_msda_bwd(const float* value, const float* a, int64_t lda, co
   // scatter kernel keeps its global reductions for the high-resolution level(s) only
   const int lvl0 = dense_first_level(args);
   args.red_levels = lvl0;
+  static const int red_dbg = []() { const char* e = getenv("POET_MSDA_RED_LEVELS"); return e ? atoi(e) : -1; }();   // timing bisection only (tools/msda_red_bisect.sh)
+  if (red_dbg >= 0) args.red_levels = red_dbg;
   static const int dbg = []() { const char* e = getenv("POET_MSDA_DENSE_DEBUG"); return e ? atoi(e) : 0; }();   // timing bisection: 1 scatter part only, 2 dense part only
   const int rc_scatter = (dbg == 2 && lvl0 < args.L) ? POET_OK : dispatch<true>(args, mode, (cudaStream_t)stream);
   if (rc_scatter != POET_OK || lvl0 >= args.L || dbg == 1) return rc_scatter;

@@ -465,6 +465,148 @@ __global__ void __launch_bounds__(256, 3) msda_bwd_kernel(const MsdaArgs p) {
 
 
 // ------------------------------------------------------------------------------------------
+// backward, L = P = 4: the per-point arithmetic shared by the lanes of a (q,m) group
+// ------------------------------------------------------------------------------------------
+// msda_bwd_kernel lets each of the G lanes of a (b,q,m) group recompute the softmax, the sampling location, the cell and
+// the bilinear fractions of all 16 points -- ~35 instructions per point and lane that differ only in the channel group
+// (tools/msda_red_bisect.sh: the kernel is half gather-side arithmetic).  Here lane l of a group prepares the four points
+// of level l once (one logits float4, two location float4s, its level's constants) and the group reads them by shuffle
+// while it walks the 16 points: 4 shuffles per point instead of the redundant arithmetic, four live attention / location
+// gradients per lane instead of sixteen (64 registers -> 4 CTAs per SM).  Corner loads, dot products and the
+// red.global.add.v4.f32 scatter are unchanged, so are the results (same operations per value, group sums in the same order).
+template <int G, bool FUSED>
+__global__ void __launch_bounds__(256, 4) msda_bwd_shared_kernel(const MsdaArgs p) {
+  poet_pdl_entry();
+  constexpr int L = 4, P = 4, LP = 16, D = 4 * G;
+  static_assert(G >= 4, "one preparing lane per level");
+  constexpr int BIAS = 1 << 20;                                // pixel offsets travel as (px + BIAS) << 4 | corner flags
+  const int64_t total = (int64_t)p.B * p.Lq * p.M * G;
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = t < total;
+  if (!live) t = total - 1;                                    // keep the warp converged for the shuffles
+  const int c4 = (int)(t % G);
+  const int64_t bqm = t / G;
+  const int m = (int)(bqm % p.M);
+  const int64_t bq = bqm / p.M;
+  const int b = (int)(bq / p.Lq);
+  const int lane = threadIdx.x & 31;
+  const int grp = lane & ~(G - 1);                             // first lane of this (b,q,m)
+  const int lvl = c4 & 3;                                      // the level whose points this lane prepares
+
+  // ---- this lane's four points ----
+  float aw[P];
+  {
+    const float4 lg = ldg4(p.w + bq * p.ldw + m * LP + lvl * P);
+    aw[0] = lg.x; aw[1] = lg.y; aw[2] = lg.z; aw[3] = lg.w;
+  }
+  if (FUSED) {                                                 // softmax over the 16 logits of the group (lanes 0..3 of each quad hold them)
+    float mx = fmaxf(fmaxf(aw[0], aw[1]), fmaxf(aw[2], aw[3]));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < P; ++k) { aw[k] = __expf(aw[k] - mx); sum += aw[k]; }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+    const float inv = __fdividef(1.f, sum);
+#pragma unroll
+    for (int k = 0; k < P; ++k) aw[k] *= inv;
+  }
+  int code[P];
+  float fxv[P], fyv[P];
+  {
+    const int Hl = p.lv.H[lvl], Wl = p.lv.W[lvl];
+    const float* arow = p.a + bq * p.lda + m * LP * 2 + lvl * 2 * P;
+    const float4 xa = ldg4(arow), xb = ldg4(arow + 4);
+    const float xy[2 * P] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+    float rx = 0.f, ry = 0.f, iw = 0.f, ih = 0.f;
+    if (FUSED) {
+      const float2 r = __ldg(reinterpret_cast<const float2*>(p.ref + (bq * L + lvl) * 2));
+      rx = r.x; ry = r.y; iw = p.lv.inv_W[lvl]; ih = p.lv.inv_H[lvl];
+    }
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      float lx = xy[2 * k], ly = xy[2 * k + 1];
+      if (FUSED) { lx = rx + lx * iw; ly = ry + ly * ih; }
+      const float x = lx * (float)Wl - 0.5f, y = ly * (float)Hl - 0.5f;
+      const bool inside = x > -1.f && y > -1.f && x < (float)Wl && y < (float)Hl;
+      const float xf = floorf(x), yf = floorf(y);
+      fxv[k] = x - xf; fyv[k] = y - yf;
+      // clamp through float so that wild locations cannot overflow the int conversion
+      const int x0 = (int)fminf(fmaxf(xf, -1.f), (float)Wl), y0 = (int)fminf(fmaxf(yf, -1.f), (float)Hl);
+      const bool xl = x0 >= 0, xh = x0 + 1 < Wl, yl = y0 >= 0, yh = y0 + 1 < Hl;
+      const int flags = inside ? ((yl && xl) ? 1 : 0) | ((yl && xh) ? 2 : 0) | ((yh && xl) ? 4 : 0) | ((yh && xh) ? 8 : 0) : 0;
+      code[k] = ((y0 * Wl + x0 + BIAS) << 4) | flags;
+    }
+  }
+
+  // ---- the group walks the 16 points ----
+  const int vstride = p.M * D;
+  const int64_t voff = ((int64_t)b * p.S * p.M + m) * D + c4 * 4;
+  const float4 go = ldg4(p.grad_out + t * 4);
+  float ga_own[P], gx_own[P], gy_own[P];
+#pragma unroll
+  for (int k = 0; k < P; ++k) { ga_own[k] = 0.f; gx_own[k] = 0.f; gy_own[k] = 0.f; }
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const int W = p.lv.W[l];
+    const float* vl = p.value + voff + (int64_t)p.lv.start[l] * vstride;
+    float* gl = p.grad_value + voff + (int64_t)p.lv.start[l] * vstride;
+    const bool scatter = live && l < p.red_levels;            // the dense kernel owns the other levels' grad_value
+#pragma unroll
+    for (int s = 0; s < P; ++s) {
+      const int cd = __shfl_sync(0xffffffffu, code[s], grp + l);
+      const float a = __shfl_sync(0xffffffffu, aw[s], grp + l);
+      const float fx = __shfl_sync(0xffffffffu, fxv[s], grp + l);
+      const float fy = __shfl_sync(0xffffffffu, fyv[s], grp + l);
+      float ga = 0.f, gx = 0.f, gy = 0.f;
+      if (cd & 15) {
+        const int i00 = ((cd >> 4) - BIAS) * vstride;
+        const bool c00 = cd & 1, c01 = cd & 2, c10 = cd & 4, c11 = cd & 8;
+        // the four corner loads of a point are issued together (predicated), the dots and the reductions follow
+        float4 v00 = make_float4(0.f, 0.f, 0.f, 0.f), v01 = v00, v10 = v00, v11 = v00;
+        if (c00) v00 = ldg4(vl + i00);
+        if (c01) v01 = ldg4(vl + i00 + vstride);
+        if (c10) v10 = ldg4(vl + i00 + W * vstride);
+        if (c11) v11 = ldg4(vl + i00 + (W + 1) * vstride);
+        const float d00 = dot4(go, v00), d01 = dot4(go, v01), d10 = dot4(go, v10), d11 = dot4(go, v11);
+        if (scatter) {
+          if (c00) red_add4(gl + i00, a * (1.f - fy) * (1.f - fx), go);
+          if (c01) red_add4(gl + i00 + vstride, a * (1.f - fy) * fx, go);
+          if (c10) red_add4(gl + i00 + W * vstride, a * fy * (1.f - fx), go);
+          if (c11) red_add4(gl + i00 + (W + 1) * vstride, a * fy * fx, go);
+        }
+        ga = (1.f - fy) * (1.f - fx) * d00 + (1.f - fy) * fx * d01 + fy * (1.f - fx) * d10 + fy * fx * d11;
+        // d sampled / d x (pixels) and / d y, times attention weight; pixels = loc * size
+        gx = a * ((1.f - fy) * (d01 - d00) + fy * (d11 - d10));
+        gy = a * ((1.f - fx) * (d10 - d00) + fx * (d11 - d01));
+        // d pixel / d (offset) = W * (1/W) = 1 in fused mode; d pixel / d loc = W in core mode
+        if (!FUSED) { gx *= (float)W; gy *= (float)p.lv.H[l]; }
+      }
+      ga = group_sum<G>(ga); gx = group_sum<G>(gx); gy = group_sum<G>(gy);
+      if (c4 == l) { ga_own[s] = ga; gx_own[s] = gx; gy_own[s] = gy; }
+    }
+  }
+
+  // ---- lane l < 4 of the group owns level l's gradients ----
+  float dotp = 0.f;
+  if (FUSED) {
+    // softmax backward: g_logit_i = a_i (g_attn_i - sum_j a_j g_attn_j)
+#pragma unroll
+    for (int k = 0; k < P; ++k) dotp += aw[k] * ga_own[k];
+    dotp += __shfl_xor_sync(0xffffffffu, dotp, 1);
+    dotp += __shfl_xor_sync(0xffffffffu, dotp, 2);
+#pragma unroll
+    for (int k = 0; k < P; ++k) ga_own[k] = aw[k] * (ga_own[k] - dotp);
+  }
+  if (!live || c4 >= L) return;
+  float* garow = p.grad_a + bq * p.lda + m * LP * 2 + c4 * 2 * P;
+  st4(garow, make_float4(gx_own[0], gy_own[0], gx_own[1], gy_own[1]));
+  st4(garow + 4, make_float4(gx_own[2], gy_own[2], gx_own[3], gy_own[3]));
+  st4(p.grad_w + bq * p.ldw + m * LP + c4 * P, make_float4(ga_own[0], ga_own[1], ga_own[2], ga_own[3]));
+}
+
+// ------------------------------------------------------------------------------------------
 // backward, grad_value of the low-resolution levels as a dense tensor-core product
 // ------------------------------------------------------------------------------------------
 // The scatter formulation issues one 16-byte global reduction per (corner, 4 channels): 64 per (q,m), and three
@@ -942,6 +1084,14 @@ int fill_args(MsdaArgs& a, const int32_t* shapes_host, int B, int S, int Lq, int
 
 template <bool BWD, int LL, int PP, int GG>
 void launch_one(const MsdaArgs& a, int mode, int grid, cudaStream_t s) {
+  if constexpr (BWD && LL == 4 && PP == 4 && GG >= 4) {     // every PoET config: per-point arithmetic shared by the group
+    static const int shared = []() { const char* e = getenv("POET_MSDA_BWD_SHARED"); return e ? atoi(e) : 1; }();
+    if (shared) {
+      if (mode) poet_launch(msda_bwd_shared_kernel<GG, true>, dim3(grid), dim3(256), 0, s, a);
+      else poet_launch(msda_bwd_shared_kernel<GG, false>, dim3(grid), dim3(256), 0, s, a);
+      return;
+    }
+  }
   if (BWD) {
     if (mode) poet_launch(msda_bwd_kernel<LL, PP, GG, true>, dim3(grid), dim3(256), 0, s, a);
     else poet_launch(msda_bwd_kernel<LL, PP, GG, false>, dim3(grid), dim3(256), 0, s, a);

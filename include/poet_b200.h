@@ -117,7 +117,11 @@ int poet_msda_bwd(const float* value, const float* a, int64_t lda, const float* 
  *   (MSDeformAttn value masked_fill); + C_old if flags&POET_GEMM_ACCUMULATE.
  * precision: POET_GEMM_FP32 (SIMT fp32 FFMA), POET_GEMM_BF16X3 / POET_GEMM_BF16 (tcgen05).
  * workspace: poet_gemm_workspace_bytes(); may be NULL when that is 0. */
-enum { POET_GEMM_RELU = 1, POET_GEMM_ACCUMULATE = 2 };
+/* POET_GEMM_B_STABLE: a promise that B (or its bf16 planes) is not written by the kernels that precede this call on the
+ * stream -- it is a parameter, last written by poet_split_bf16* / poet_adamw_clip_multi (which never let a dependent
+ * kernel start early) or by a non-library kernel.  The query-row GEMM kernel then requests its B tiles BEFORE it waits for
+ * the preceding kernel (programmatic dependent launch), hiding one L2 round trip of the dependent chain. */
+enum { POET_GEMM_RELU = 1, POET_GEMM_ACCUMULATE = 2, POET_GEMM_B_STABLE = 4 };
 enum { POET_GEMM_FP32 = 0, POET_GEMM_BF16X3 = 1, POET_GEMM_BF16 = 2 };
 size_t poet_gemm_workspace_bytes(int M, int N, int K, int a_kcontig, int b_kcontig, int precision);
 int poet_gemm(const float* A, int64_t lda, int a_kcontig, const float* Bm, int64_t ldb, int b_kcontig,

@@ -148,7 +148,7 @@ __device__ __forceinline__ void fetch_planes(const __nv_bfloat16* hi, const __nv
 
 template <bool AK, bool BK_, bool PLANES>
 __global__ void __launch_bounds__(THREADS) gemm_small_kernel(const Args p) {
-  poet_pdl_entry();
+  poet_pdl_launch_dependents();
   extern __shared__ __align__(16) float sm[];        // stages x {A tile, B tile (fp32, or bf16 hi | lo in its two halves)}
   const int tid = threadIdx.x;
   const int kg = tid >> 6, t64 = tid & 63, tx = t64 & 7, ty = t64 >> 3;
@@ -157,20 +157,30 @@ __global__ void __launch_bounds__(THREADS) gemm_small_kernel(const Args p) {
   const bool do_colsum = !AK && p.a_colsum != nullptr && blockIdx.x == 0;
 
   auto stage_ptr = [&](int s, int which) { return sm + ((size_t)(s % p.stages) * 2 + which) * TILE_FLOATS; };
-  auto issue = [&](int s) {
+  auto issue_b = [&](int s) {
+    if (s >= n_stage) return;
+    const int k0 = s * BKS;
+    if (PLANES) {
+      __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(stage_ptr(s, 1));
+      load_tile_bf16<BK_>(bt, p.Bhi, p.ldb, n0, p.N, k0, p.K, tid);
+      load_tile_bf16<BK_>(bt + PLANE_ELEMS, p.Blo, p.ldb, n0, p.N, k0, p.K, tid);        // second half of the tile area
+    } else {
+      load_tile_f32<BK_>(stage_ptr(s, 1), p.B, p.ldb, n0, p.N, k0, p.K, tid);
+    }
+  };
+  auto issue = [&](int s, bool with_b) {
     if (s < n_stage) {
-      const int k0 = s * BKS;
-      load_tile_f32<AK>(stage_ptr(s, 0), p.A, p.lda, m0, p.M, k0, p.K, tid);
-      if (PLANES) {
-        __nv_bfloat16* bt = reinterpret_cast<__nv_bfloat16*>(stage_ptr(s, 1));
-        load_tile_bf16<BK_>(bt, p.Bhi, p.ldb, n0, p.N, k0, p.K, tid);
-        load_tile_bf16<BK_>(bt + PLANE_ELEMS, p.Blo, p.ldb, n0, p.N, k0, p.K, tid);      // second half of the tile area
-      } else {
-        load_tile_f32<BK_>(stage_ptr(s, 1), p.B, p.ldb, n0, p.N, k0, p.K, tid);
-      }
+      load_tile_f32<AK>(stage_ptr(s, 0), p.A, p.lda, m0, p.M, s * BKS, p.K, tid);
+      if (with_b) issue_b(s);
     }
     cp_async_commit();                                // one group per stage slot, empty when past the end
   };
+  // A parameter operand (POET_GEMM_B_STABLE) is requested before the wait for the preceding kernel: its L2 round trip
+  // overlaps that kernel's tail.  The early requests join the first committed group, which stage 0 waits for anyway.
+  const bool b_early = (p.flags & POET_GEMM_B_STABLE) != 0;
+  if (b_early)
+    for (int s = 0; s < p.stages; ++s) issue_b(s);    // every slot of the ring is free at this point
+  poet_pdl_wait();
 
   float acc[4][4];
 #pragma unroll
@@ -179,9 +189,9 @@ __global__ void __launch_bounds__(THREADS) gemm_small_kernel(const Args p) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   float csum = 0.f;
 
-  for (int s = 0; s < p.stages - 1; ++s) issue(s);    // prologue: every stage of a short K is in flight at once
+  for (int s = 0; s < p.stages - 1; ++s) issue(s, !b_early);    // prologue: every stage of a short K is in flight at once
   for (int s = 0; s < n_stage; ++s) {
-    issue(s + p.stages - 1);
+    issue(s + p.stages - 1, !(b_early && s == 0));
     if (p.stages == 3) cp_async_wait<2>(); else if (p.stages == 2) cp_async_wait<1>(); else cp_async_wait<0>();
     __syncthreads();
     const float* as = stage_ptr(s, 0);

@@ -776,7 +776,7 @@ gemm_tc_kernel(const Args p, const __grid_constant__ CUtensorMap tm_hi, const __
 // ---- fp32 -> bf16 hi/lo planes (weights, once per step) --------------------------------------
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ hi,
                                                          uint2* __restrict__ lo, int64_t n4) {
-  poet_pdl_entry();
+  poet_pdl_wait();          // no early launch of dependents: consumers may prefetch the planes before their own wait (POET_GEMM_B_STABLE)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const float4 x = src[i];
     const float h0 = __bfloat162float(__float2bfloat16_rn(x.x)), h1 = __bfloat162float(__float2bfloat16_rn(x.y));
@@ -789,7 +789,7 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float4* __restric
 // All weight matrices of a model in ONE launch: table[t] = {src, hi, lo, first_chunk}, chunk = 1024 float4.
 struct SplitEntry { const float4* src; uint2* hi; uint2* lo; int64_t n4; int64_t first_chunk; };
 __global__ void __launch_bounds__(256) split_bf16_multi_kernel(const SplitEntry* __restrict__ table, int n_tensors) {
-  poet_pdl_entry();
+  poet_pdl_wait();          // no early launch of dependents: consumers may prefetch the planes before their own wait (POET_GEMM_B_STABLE)
   // binary search of the chunk's tensor (n_tensors is ~100: 7 steps)
   const int64_t chunk = blockIdx.x;
   int lo_i = 0, hi_i = n_tensors - 1;

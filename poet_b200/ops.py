@@ -272,6 +272,7 @@ def kernel_times_ms() -> dict:
     return {k: (sum(s.elapsed_time(e) for s, e in v), len(v), *work.get(k, (0, 0))) for k, v in _timing["events"].items()}
 
 
+_B_STABLE = _os.environ.get("POET_GEMM_B_STABLE", "1") != "0"
 _ABLATE = frozenset(x for x in _os.environ.get("POET_ABLATE_CALLS", "").split(",") if x)
 
 
@@ -310,7 +311,7 @@ def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_kcontig
          out: Optional[torch.Tensor] = None, accumulate=False, alpha: float = 1.0,
          precision: Optional[int] = None, b_split=None, relu_bits: Optional[torch.Tensor] = None,
          gate_bits: Optional[torch.Tensor] = None, a_colsum: Optional[torch.Tensor] = None,
-         a_row_mask: Optional[torch.Tensor] = None, drop=None) -> torch.Tensor:
+         a_row_mask: Optional[torch.Tensor] = None, drop=None, b_stable: bool = False) -> torch.Tensor:
     """out[M,N] = epi(alpha * op(A) @ op(B)); see include/poet_b200.h poet_gemm / poet_gemm_ex.
     relu_bits (out) / gate_bits (in): int32 [M, N/32] sign bitmask of a ReLU (tensor-core path only)."""
     if out is None:
@@ -323,7 +324,8 @@ def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_kcontig
         ws_bytes = _lib.lib().poet_gemm_workspace_bytes(M, N, K, int(a_kcontig), int(b_kcontig), prec)
         if ws_bytes:
             ws = torch.empty(ws_bytes, device=A.device, dtype=torch.uint8)
-    flags = (1 if relu else 0) | (2 if accumulate else 0)
+    # b_stable: B is a parameter (or its planes), not written by the kernels just before this call (POET_GEMM_B_STABLE)
+    flags = (1 if relu else 0) | (2 if accumulate else 0) | (4 if (b_stable and _B_STABLE) else 0)
     tag = (f"{M}x{N}x{K}" + ("" if a_kcontig else ",At") + ("" if b_kcontig else ",Bt")) if _timing["on"] else None
     work = (4 * (M * K + N * K + M * N), 2 * M * N * K)
     if relu_bits is not None or gate_bits is not None or a_colsum is not None or a_row_mask is not None or drop is not None:
@@ -657,7 +659,7 @@ def _linear_bwd(gy2: torch.Tensor, x2: torch.Tensor, W: torch.Tensor, need_x: bo
         gate = None
     # gy_row_mask: rows of gy2 to treat as zero (value masked_fill backward).  Zero rows of dY give zero rows of dX,
     # so the dgrad applies it as an output row mask; the weight / bias gradients read dY through the masked producer.
-    dx = gemm(gy2, W, R, K, N, a_kcontig=True, b_kcontig=False, gate=gate, b_split=w_split,
+    dx = gemm(gy2, W, R, K, N, a_kcontig=True, b_kcontig=False, gate=gate, b_split=w_split, b_stable=True,
               gate_bits=gate_bits, row_mask=gy_row_mask, alpha=alpha) if need_x else None
     dW = db = None
     w_slot = _grad_slot(w_param) if need_w else None
@@ -751,7 +753,7 @@ class _Linear(torch.autograd.Function):
         N = W.shape[0]
         ctx.w_param, ctx.b_param = W, b
         ctx.w_split = split_weight(W, R)
-        y = gemm(x2, W, R, N, K, bias=b, row_mask=row_mask, b_split=ctx.w_split)
+        y = gemm(x2, W, R, N, K, bias=b, row_mask=row_mask, b_split=ctx.w_split, b_stable=True)
         ctx.save_for_backward(x2, W)
         ctx.row_mask = row_mask
         ctx.has_bias = b is not None
@@ -816,7 +818,7 @@ class _MLP(torch.autograd.Function):
             ctx.relu_bits.append(bits)
             dropping = drop_p > 0.0 and i < n - 1
             fused = dropping and bits is not None and W.shape[0] % 32 == 0
-            acts.append(gemm(h, W, h.shape[0], W.shape[0], W.shape[1], bias=b, relu=(i < n - 1),
+            acts.append(gemm(h, W, h.shape[0], W.shape[0], W.shape[1], bias=b, relu=(i < n - 1), b_stable=True,
                              b_split=ctx.w_splits[-1], relu_bits=bits,
                              drop=(seed, drop_site + i, drop_p) if fused else None))
             if dropping and not fused:
@@ -900,7 +902,8 @@ class _ProjPair(torch.autograd.Function):
                 else:
                     Wc = torch.cat((W0, W1), 0)
                     ctx.w_split = split_weight(Wc, R)
-            out = gemm(x0_2, Wc, R, N0 + N1, K, bias=bc, b_split=ctx.w_split)
+            ctx.w_planes = Wc is None                # B = the step's weight planes (a torch.cat copy is written just before)
+            out = gemm(x0_2, Wc, R, N0 + N1, K, bias=bc, b_split=ctx.w_split, b_stable=ctx.w_planes)
             ctx.save_for_backward(x0_2, Wc)
             ctx.params = (W0, b0, W1, b1)
             ctx.dims = (R, K, N0, N1)
@@ -912,8 +915,8 @@ class _ProjPair(torch.autograd.Function):
         W = _chk(W0)
         Wqk, Wv = W[: 2 * C], W[2 * C:]
         ctx.w_split = (split_weight(Wqk, R), split_weight(Wv, R))
-        qk = gemm(x0_2, Wqk, R, 2 * C, C, bias=b0[: 2 * C], b_split=ctx.w_split[0])
-        v = gemm(x1_2, Wv, R, C, C, bias=b0[2 * C:], b_split=ctx.w_split[1])
+        qk = gemm(x0_2, Wqk, R, 2 * C, C, bias=b0[: 2 * C], b_split=ctx.w_split[0], b_stable=True)
+        v = gemm(x1_2, Wv, R, C, C, bias=b0[2 * C:], b_split=ctx.w_split[1], b_stable=True)
         ctx.save_for_backward(x0_2, x1_2, W)
         ctx.params = (W0, b0)
         ctx.dims = (R, C)
@@ -932,7 +935,7 @@ class _ProjPair(torch.autograd.Function):
             W0, b0, W1, b1 = ctx.params
             R, K, N0, N1 = ctx.dims
             g = _chk(g0).view(R, N0 + N1)
-            dx = gemm(g, Wc, R, K, N0 + N1, a_kcontig=True, b_kcontig=False, b_split=ctx.w_split) if ctx.needs_input_grad[1] else None
+            dx = gemm(g, Wc, R, K, N0 + N1, a_kcontig=True, b_kcontig=False, b_split=ctx.w_split, b_stable=ctx.w_planes) if ctx.needs_input_grad[1] else None
             outs = []
             for W, b, col, n in ((W0, b0, 0, N0), (W1, b1, N0, N1)):
                 gcols = g[:, col:col + n]                           # column block: pointer offset + ld = N0+N1
@@ -955,8 +958,8 @@ class _ProjPair(torch.autograd.Function):
         Wp, bp = ctx.params
         R, C = ctx.dims
         gqk, gv = _chk(g0).view(R, 2 * C), _chk(g1).view(R, C)
-        dx0 = gemm(gqk, W[: 2 * C], R, C, 2 * C, a_kcontig=True, b_kcontig=False, b_split=ctx.w_split[0]) if ctx.needs_input_grad[1] else None
-        dx1 = gemm(gv, W[2 * C:], R, C, C, a_kcontig=True, b_kcontig=False, b_split=ctx.w_split[1]) if ctx.needs_input_grad[2] else None
+        dx0 = gemm(gqk, W[: 2 * C], R, C, 2 * C, a_kcontig=True, b_kcontig=False, b_split=ctx.w_split[0], b_stable=True) if ctx.needs_input_grad[1] else None
+        dx1 = gemm(gv, W[2 * C:], R, C, C, a_kcontig=True, b_kcontig=False, b_split=ctx.w_split[1], b_stable=True) if ctx.needs_input_grad[2] else None
         slot, bslot = _grad_slot(Wp), _grad_slot(bp)
         dW = slot if slot is not None else torch.zeros_like(W)
         db = bslot if bslot is not None else torch.zeros(3 * C, device=W.device, dtype=torch.float32)

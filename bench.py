@@ -548,7 +548,8 @@ def run_gpu(args):
             line["parity"] = parity
         if ktimes:
             line["roofline"], line["kernels"] = roofline_from(ktimes, peaks, ksteps, ms_per_step,
-                                                              mma_passes=3 if args.precision == "bf16x3" else 1)
+                                                              mma_passes=3 if args.precision == "bf16x3" else 1,
+                                                              msda_sparse_fraction=msda_sparse_fraction(cfg))
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(cfg, backward=do_backward)
         print(json.dumps(line), flush=True)
@@ -558,7 +559,21 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
-def roofline_from(ktimes, peaks, steps, ms_per_step, mma_passes=1):
+def msda_sparse_fraction(cfg):
+    """Share of the encoder MSDA backward's sampling points whose grad_value contributions go through L2 atomics: the tile
+    kernel (csrc/msda.cu, D = 16, L = P = 4) turns the trailing levels that hold <= 104 pixels together into dense products."""
+    from poet_b200 import synthetic as S
+    pyr = S.pyramid_of(cfg)
+    if cfg["d_model"] // cfg["nheads"] != 16 or len(pyr) != 4 or cfg["n_points"] != 4:
+        return 1.0
+    sizes = [h * w for h, w in pyr]
+    for l0 in range(4):
+        if sum(sizes[l0:]) <= 104:
+            return l0 / 4.0
+    return 1.0
+
+
+def roofline_from(ktimes, peaks, steps, ms_per_step, mma_passes=1, msda_sparse_fraction=1.0):
     """Per-kernel table from the CUDA-event brackets; `roofline` = the kernel with the largest time share.
     GEMMs are judged against the tensor pipe (sustained bf16 peak: the kernel is timed inside a long step),
     everything else against HBM.  Algorithmic bytes/flops per launch are the figures of DESIGN.md."""
@@ -601,14 +616,17 @@ def roofline_from(ktimes, peaks, steps, ms_per_step, mma_passes=1):
     if gemm:
         roof["all_gemm_share_of_table"] = sum(r["share"] for r in gemm)
     if top["kernel"].startswith("poet_msda_bwd"):
-        # What actually bounds this kernel: every bilinear corner of every sampling point is one
-        # 16-byte red.global.add.v4.f32 per 4 channels = B*Lq*M*L*P*D reduction lane-ops per launch (flops field / 30),
-        # and the SM issues one such lane-op per 0.854 cycles (B300_MICROARCH.md "REDG"; same on this B200).
+        # What bounds the scatter side of this kernel: every bilinear corner of every sampling point
+        # of a SPARSE level is added to grad_value by L2 atomics (red.global.add.v4.f32, 64 B per corner at D = 16); the
+        # chip retires ~5.3 TB/s of such payload whatever the instruction form or layout (tools/red_micro.cu,
+        # profiles/r02_red_micro.txt).  The dense (low-resolution) levels of the tile kernel leave through ~1 MB of
+        # reductions.  `achieved` assumes every sparse-level corner in range (an upper bound on the payload).
         ms, n, _nbytes, flops = ktimes[top["kernel"]]
-        ops_per_s = flops / 30.0 / (ms * 1e-3)
-        peak_ops = POET_SMS * 1.965e9 / 0.854
-        roof["alt"] = {"bound": "l2_reduction_issue", "achieved": ops_per_s / 1e9, "peak": peak_ops / 1e9,
-                       "unit": "G red.v4 lane-ops/s", "frac": ops_per_s / peak_ops}
+        payload = flops / 30.0 * 16.0 * msda_sparse_fraction            # 16-byte lane-ops x sparse share
+        roof["alt"] = {"bound": "l2_atomic_payload", "achieved": payload / (ms * 1e-3) / 1e9, "peak": 5300.0,
+                       "unit": "GB/s of fp32 reduction payload (upper bound: all corners in range)",
+                       "frac": payload / (ms * 1e-3) / 1e9 / 5300.0, "sparse_level_share": msda_sparse_fraction,
+                       "peak_source": "tools/red_micro.cu on B200: 1.68 GB of 64-byte corner reductions in 310-320 us"}
     return roof, rows[:24]
 
 

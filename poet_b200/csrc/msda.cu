@@ -355,6 +355,12 @@ __device__ __forceinline__ void red_add4(float* p, float w, float4 v) {
                "f"(v.w * w));
 }
 
+// predicated form: no branch around the reduction (the compiler cannot predicate a volatile asm statement itself)
+__device__ __forceinline__ void red_add4_pred(bool on, float* p, float w, float4 v) {
+  asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %5, 0;\n\t@pp red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+               ::"l"(p), "f"(v.x * w), "f"(v.y * w), "f"(v.z * w), "f"(v.w * w), "r"((uint32_t)on));
+}
+
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
 // Register diet (the kernel is latency-bound, so occupancy matters): location gradients leave the
@@ -855,6 +861,324 @@ msda_bwd_dense_kernel(const MsdaArgs p, int lvl0, int npx, int n_mt, int nchunk,
 }  // namespace dense
 
 // ------------------------------------------------------------------------------------------
+// backward, many queries (the encoder): one CTA per (image, head, run of 64-query tiles); the low-resolution
+// levels leave the memory pipes
+// ------------------------------------------------------------------------------------------
+// msda_bwd_shared_kernel spends its time in the load/store pipe: 64 corner loads and 64 16-byte global reductions per
+// (q,m), and half of the reductions of the REF pyramid land on the 100 pixels of levels 2-3 (same-address traffic in L2).
+// For the trailing levels that hold <= 104 pixels together (the "dense" levels) both directions are small dense products
+// per (image, head) over a tile of 64 queries, done with 3xTF32 mma.sync (x = hi + lo, hi.lo + lo.hi + hi.hi, fp32
+// accumulation: ~2^-21 relative, the same grade as the split-bf16 GEMMs):
+//
+//   gather side    G[q, px]  = sum_c grad_out[q, c] * value[px, c]         (M = 64 queries, N = pixels, K = D = 16)
+//                  -> a corner's dot product is ONE shared-memory word G[q, px(corner)] instead of a 64-byte load and
+//                     16 FMAs spread over 4 lanes + 2 shuffles;
+//   scatter side   grad_value[px, c] += sum_q W[q, px] * grad_out[q, c]    (M = pixels, N = 16, K = 64 queries)
+//                  with W[q, px] = sum over q's points of attention * bilinear weight at px, accumulated in shared
+//                  memory by the ONE lane that owns (query, level): rows of different queries and pixel ranges of
+//                  different levels never meet, a lane's own points are serialised -> plain read-modify-write, no atomics.
+//                  The accumulators stay in registers over the CTA's tiles and leave as one 8-byte reduction per pair.
+//
+// The high-resolution ("sparse") levels keep the gather / red.global.add.v4.f32 scheme of msda_bwd_shared_kernel (same
+// per-point record sharing by shuffle).  With one head per CTA, lane c4 of a (q,m) group owns level c4: the dense levels
+// need no cross-lane traffic at all.  Per launch at cfg2 this removes half of the corner loads and half of the global
+// reductions (52 M of 105 M lane-ops; what remains of them for the dense levels is ~1 M 8-byte reductions).
+namespace tile {
+
+constexpr int QT = 64;               // queries per tile
+constexpr int THREADS = 4 * QT;      // 4 lanes per (q,m): lane c4 = channel group in the sparse levels, owner of level c4 elsewhere
+constexpr int NPX = 104;             // dense pixels at most (13 n-tiles of 8)
+constexpr int LDW = 104;             // row stride of G and W (floats): 104 % 32 == 8 -> conflict-free fragment accesses
+constexpr int LDV = 20;              // row stride of the value tile [px][16]: 20 g + t distinct mod 32 for g < 8, t < 4
+constexpr int LDGO = 20;             // row stride of the grad_out tile [q][16]
+constexpr int SMEM_FLOATS = QT * LDW + (QT * LDW + 8) + QT * LDGO + NPX * LDV;
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// x = hi + lo with hi = the 19 leading bits (a tf32 operand as the tensor core reads it), lo = the exact remainder
+// (the tensor core reads ITS 19 leading bits: 22 mantissa bits of x survive)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_3x(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0,
+                                       uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma_tf32(c, ah, bl0, bl1);                                   // small cross terms first
+  mma_tf32(c, al, bh0, bh1);
+  mma_tf32(c, ah, bh0, bh1);
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(THREADS, 3)
+msda_bwd_tile_kernel(const MsdaArgs p, int ld, int npx, int nchunk, int tiles_per_chunk, int n_tiles) {
+  poet_pdl_entry();
+  constexpr int L = 4, P = 4, LP = 16, D = 16;
+  constexpr int BIAS = 1 << 20;                                // pixel offsets travel as (px + BIAS) << 4 | corner flags
+  extern __shared__ __align__(16) float tile_smem[];
+  float* Gs = tile_smem;                                       // [QT][LDW]  dot(grad_out[q], value[px])
+  float* Ws = Gs + QT * LDW;                                   // [QT][LDW]  (+8: the last m-tile's fragment rows run past px 103)
+  float* gos = Ws + QT * LDW + 8;                              // [QT][LDGO] grad_out rows of the tile
+  float* Vs = gos + QT * LDGO;                                 // [NPX][LDV] value rows of the dense levels, this (image, head)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;                       // mma fragment coordinates
+  const int c4 = tid & 3, ql = tid >> 2;                       // point-walk identity: lane of the (q,m) group, query of the tile
+  const int grp = lane & ~3;
+  const int chunk = blockIdx.x % nchunk, bm = blockIdx.x / nchunk;
+  const int m = bm % p.M, b = bm / p.M;
+  const int tile_beg = chunk * tiles_per_chunk, tile_end = min(n_tiles, tile_beg + tiles_per_chunk);
+  if (tile_beg >= tile_end) return;
+  const int pix0 = p.lv.start[ld];                             // first dense pixel of the flattened map
+  const int n_nt = (npx + 7) >> 3, n_mt = (npx + 15) >> 4;
+  const int vstride = p.M * D;
+
+  // ---- value rows of the dense levels (zero rows behind npx) ----
+  for (int i = tid; i < NPX * 4; i += THREADS) {
+    const int px = i >> 2, c = i & 3;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (px < npx) v = ldg4(p.value + ((int64_t)b * p.S + pix0 + px) * vstride + m * D + c * 4);
+    *reinterpret_cast<float4*>(Vs + px * LDV + c * 4) = v;
+  }
+
+  // this lane's level (point preparation; owner of the level's gradients)
+  const int lvl = c4;
+  const int Hl = p.lv.H[lvl], Wl = p.lv.W[lvl];
+  const int dense_off = p.lv.start[lvl] - pix0;                // this level's first pixel in G / W columns (dense levels only)
+  float rx_iw = 0.f, ry_ih = 0.f;
+  if (FUSED) { rx_iw = p.lv.inv_W[lvl]; ry_ih = p.lv.inv_H[lvl]; }
+
+  float acc[2][4];                                             // P3 accumulators: m-tile = warp, two 8-channel n-tiles
+#pragma unroll
+  for (int n = 0; n < 2; ++n)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[n][k] = 0.f;
+
+  for (int tile = tile_beg; tile < tile_end; ++tile) {
+    const int q = tile * QT + ql;
+    const bool live = q < p.Lq;
+    const int64_t bq = (int64_t)b * p.Lq + (live ? q : p.Lq - 1);
+
+    // ---- P0: parameters of this lane's four points, grad_out row, W = 0 ----
+    float aw[P];
+    {
+      const float4 lg = ldg4(p.w + bq * p.ldw + m * LP + lvl * P);
+      aw[0] = lg.x; aw[1] = lg.y; aw[2] = lg.z; aw[3] = lg.w;
+    }
+    const float* arow = p.a + bq * p.lda + m * LP * 2 + lvl * 2 * P;
+    const float4 xa = ldg4(arow), xb = ldg4(arow + 4);
+    float2 rf = make_float2(0.f, 0.f);
+    if (FUSED) rf = __ldg(reinterpret_cast<const float2*>(p.ref + (bq * L + lvl) * 2));
+    float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) go = ldg4(p.grad_out + (bq * p.M + m) * D + c4 * 4);
+    *reinterpret_cast<float4*>(gos + ql * LDGO + c4 * 4) = go;
+    for (int i = tid; i < QT * LDW / 4; i += THREADS) reinterpret_cast<float4*>(Ws)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+
+    // ---- P1: G[q, px] = grad_out[q, :] . value[px, :] ----
+    {
+      const int mt = warp & 3, nt_beg = (warp >> 2) * 7, nt_end = min(n_nt, nt_beg + 7);
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const float* ap = gos + (mt * 16 + g) * LDGO + ks * 8 + t;
+        split_tf32(ap[0], ah[ks][0], al[ks][0]);
+        split_tf32(ap[8 * LDGO], ah[ks][1], al[ks][1]);
+        split_tf32(ap[4], ah[ks][2], al[ks][2]);
+        split_tf32(ap[8 * LDGO + 4], ah[ks][3], al[ks][3]);
+      }
+      for (int nt = nt_beg; nt < nt_end; ++nt) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const float* bp = Vs + (nt * 8 + g) * LDV + ks * 8 + t;
+          uint32_t bh0, bl0, bh1, bl1;
+          split_tf32(bp[0], bh0, bl0);
+          split_tf32(bp[4], bh1, bl1);
+          mma_3x(c, ah[ks], al[ks], bh0, bh1, bl0, bl1);
+        }
+        float* gp = Gs + (mt * 16 + g) * LDW + nt * 8 + 2 * t;
+        *reinterpret_cast<float2*>(gp) = make_float2(c[0], c[1]);
+        *reinterpret_cast<float2*>(gp + 8 * LDW) = make_float2(c[2], c[3]);
+      }
+    }
+
+    // ---- this lane's four points: softmax, location, cell, fractions (as msda_bwd_shared_kernel) ----
+    if (FUSED) {
+      float mx = fmaxf(fmaxf(aw[0], aw[1]), fmaxf(aw[2], aw[3]));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < P; ++k) { aw[k] = __expf(aw[k] - mx); sum += aw[k]; }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float inv = __fdividef(1.f, sum);
+#pragma unroll
+      for (int k = 0; k < P; ++k) aw[k] *= inv;
+    }
+    int code[P];
+    float fxv[P], fyv[P];
+    {
+      const float xy[2 * P] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+      for (int k = 0; k < P; ++k) {
+        float lx = xy[2 * k], ly = xy[2 * k + 1];
+        if (FUSED) { lx = rf.x + lx * rx_iw; ly = rf.y + ly * ry_ih; }
+        const float x = lx * (float)Wl - 0.5f, y = ly * (float)Hl - 0.5f;
+        const bool inside = x > -1.f && y > -1.f && x < (float)Wl && y < (float)Hl;
+        const float xf = floorf(x), yf = floorf(y);
+        fxv[k] = x - xf; fyv[k] = y - yf;
+        // clamp through float so that wild locations cannot overflow the int conversion
+        const int x0 = (int)fminf(fmaxf(xf, -1.f), (float)Wl), y0 = (int)fminf(fmaxf(yf, -1.f), (float)Hl);
+        const bool xl = x0 >= 0, xh = x0 + 1 < Wl, yl = y0 >= 0, yh = y0 + 1 < Hl;
+        const int flags = inside ? ((yl && xl) ? 1 : 0) | ((yl && xh) ? 2 : 0) | ((yh && xl) ? 4 : 0) | ((yh && xh) ? 8 : 0) : 0;
+        code[k] = ((y0 * Wl + x0 + BIAS) << 4) | flags;
+      }
+    }
+    float ga_own[P];                                           // d loss / d attention of this lane's level (softmax backward needs all 16)
+#pragma unroll
+    for (int k = 0; k < P; ++k) ga_own[k] = 0.f;
+    float* garow = p.grad_a + bq * p.lda + m * LP * 2 + c4 * 2 * P;   // this lane's level: 4 points x (x, y)
+
+    // ---- P2a: sparse levels, the group walks the points together (global gathers and reductions) ----
+    // One point in flight per warp.  Issuing the corner loads of point i+1 before point i is consumed was measured
+    // (it needs 128 registers -> 2 CTAs per SM): slower, 350 vs 314 us -- the kernel is not bound by load latency.
+    {
+      const int64_t voff = ((int64_t)b * p.S * p.M + m) * D + c4 * 4;
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        if (l < ld) {                                          // uniform over the grid
+          const int W = p.lv.W[l];
+          float gxl[P], gyl[P];
+#pragma unroll
+          for (int s2 = 0; s2 < P; ++s2) {
+            const int cd = __shfl_sync(0xffffffffu, code[s2], grp + l);
+            const float a = __shfl_sync(0xffffffffu, aw[s2], grp + l);
+            const float fx = __shfl_sync(0xffffffffu, fxv[s2], grp + l);
+            const float fy = __shfl_sync(0xffffffffu, fyv[s2], grp + l);
+            const int64_t o00 = voff + ((int64_t)p.lv.start[l] + ((cd >> 4) - BIAS)) * vstride;
+            const float* vp = p.value + o00;
+            float* gp = p.grad_value + o00;
+            // the four corner loads of a point are issued together (predicated); corners that are switched off carry
+            // v = 0 -> d = 0, and their reductions are predicated off: no branches in the point loop
+            float4 v00 = make_float4(0.f, 0.f, 0.f, 0.f), v01 = v00, v10 = v00, v11 = v00;
+            if (cd & 1) v00 = ldg4(vp);
+            if (cd & 2) v01 = ldg4(vp + vstride);
+            if (cd & 4) v10 = ldg4(vp + W * vstride);
+            if (cd & 8) v11 = ldg4(vp + (W + 1) * vstride);
+            const float d00 = dot4(go, v00), d01 = dot4(go, v01), d10 = dot4(go, v10), d11 = dot4(go, v11);
+            const float w00 = (1.f - fy) * (1.f - fx), w01 = (1.f - fy) * fx, w10 = fy * (1.f - fx), w11 = fy * fx;
+            red_add4_pred(live && (cd & 1), gp, a * w00, go);
+            red_add4_pred(live && (cd & 2), gp + vstride, a * w01, go);
+            red_add4_pred(live && (cd & 4), gp + W * vstride, a * w10, go);
+            red_add4_pred(live && (cd & 8), gp + (W + 1) * vstride, a * w11, go);
+            float ga = w00 * d00 + w01 * d01 + w10 * d10 + w11 * d11;
+            float gx = a * ((1.f - fy) * (d01 - d00) + fy * (d11 - d10));
+            float gy = a * ((1.f - fx) * (d10 - d00) + fx * (d11 - d01));
+            if (!FUSED) { gx *= (float)W; gy *= (float)p.lv.H[l]; }
+            ga = group_sum<4>(ga); gx = group_sum<4>(gx); gy = group_sum<4>(gy);
+            if (c4 == l) ga_own[s2] = ga;
+            gxl[s2] = gx; gyl[s2] = gy;
+          }
+          if (c4 == l && live) {
+            st4(garow, make_float4(gxl[0], gyl[0], gxl[1], gyl[1]));
+            st4(garow + 4, make_float4(gxl[2], gyl[2], gxl[3], gyl[3]));
+          }
+        }
+      }
+    }
+    __syncthreads();                                           // G complete
+
+    // ---- P2b: dense levels, the owner lane alone: dots from G, weights into its W row ----
+    if (c4 >= ld) {
+      const float* Grow = Gs + ql * LDW + dense_off;
+      float* Wrow = Ws + ql * LDW + dense_off;
+      float gxl[P], gyl[P];
+#pragma unroll
+      for (int s2 = 0; s2 < P; ++s2) {                         // all G reads first: independent of the W updates below
+        const int cd = code[s2];
+        const int i00 = (cd >> 4) - BIAS;
+        const float a = aw[s2], fx = fxv[s2], fy = fyv[s2];
+        const float d00 = (cd & 1) ? Grow[i00] : 0.f, d01 = (cd & 2) ? Grow[i00 + 1] : 0.f;
+        const float d10 = (cd & 4) ? Grow[i00 + Wl] : 0.f, d11 = (cd & 8) ? Grow[i00 + Wl + 1] : 0.f;
+        float gx = a * ((1.f - fy) * (d01 - d00) + fy * (d11 - d10));
+        float gy = a * ((1.f - fx) * (d10 - d00) + fx * (d11 - d01));
+        if (!FUSED) { gx *= (float)Wl; gy *= (float)Hl; }
+        ga_own[s2] = (1.f - fy) * (1.f - fx) * d00 + (1.f - fy) * fx * d01 + fy * (1.f - fx) * d10 + fy * fx * d11;
+        gxl[s2] = gx; gyl[s2] = gy;
+      }
+      if (live) {
+        st4(garow, make_float4(gxl[0], gyl[0], gxl[1], gyl[1]));
+        st4(garow + 4, make_float4(gxl[2], gyl[2], gxl[3], gyl[3]));
+      }
+#pragma unroll
+      for (int s2 = 0; s2 < P; ++s2) {
+        const int cd = code[s2];
+        const int i00 = (cd >> 4) - BIAS;
+        const float a = aw[s2], fx = fxv[s2], fy = fyv[s2];
+        // the lane's points are serialised (two of them may share a pixel): plain read-modify-write of its own row
+        if (cd & 1) Wrow[i00] += a * (1.f - fy) * (1.f - fx);
+        if (cd & 2) Wrow[i00 + 1] += a * (1.f - fy) * fx;
+        if (cd & 4) Wrow[i00 + Wl] += a * fy * (1.f - fx);
+        if (cd & 8) Wrow[i00 + Wl + 1] += a * fy * fx;
+      }
+    }
+
+    // ---- softmax backward over the 16 points of the group, gradient of the logits ----
+    if (FUSED) {
+      float dotp = 0.f;
+#pragma unroll
+      for (int k = 0; k < P; ++k) dotp += aw[k] * ga_own[k];
+      dotp += __shfl_xor_sync(0xffffffffu, dotp, 1);
+      dotp += __shfl_xor_sync(0xffffffffu, dotp, 2);
+#pragma unroll
+      for (int k = 0; k < P; ++k) ga_own[k] = aw[k] * (ga_own[k] - dotp);
+    }
+    if (live) st4(p.grad_w + bq * p.ldw + m * LP + c4 * P, make_float4(ga_own[0], ga_own[1], ga_own[2], ga_own[3]));
+    __syncthreads();                                           // W complete
+
+    // ---- P3: acc[px, c] += W[q-tile, px]^T . grad_out[q-tile, c] ----
+    if (warp < n_mt) {
+#pragma unroll 2
+      for (int ks = 0; ks < QT / 8; ++ks) {
+        const float* ap = Ws + (ks * 8 + t) * LDW + warp * 16 + g;
+        uint32_t ah[4], al[4];
+        split_tf32(ap[0], ah[0], al[0]);
+        split_tf32(ap[8], ah[1], al[1]);
+        split_tf32(ap[4 * LDW], ah[2], al[2]);
+        split_tf32(ap[4 * LDW + 8], ah[3], al[3]);
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+          const float* bp = gos + (ks * 8 + t) * LDGO + n * 8 + g;
+          uint32_t bh0, bl0, bh1, bl1;
+          split_tf32(bp[0], bh0, bl0);
+          split_tf32(bp[4 * LDGO], bh1, bl1);
+          mma_3x(acc[n], ah, al, bh0, bh1, bl0, bl1);
+        }
+      }
+    }
+    __syncthreads();                                           // W and the grad_out tile may be overwritten
+  }
+
+  // ---- flush: one 8-byte reduction per accumulator pair ----
+  if (warp < n_mt) {
+    float* gv = p.grad_value + ((int64_t)b * p.S + pix0) * vstride + m * D;
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      const int px0 = warp * 16 + g, px1 = px0 + 8, d = n * 8 + 2 * t;
+      if (px0 < npx)
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gv + (int64_t)px0 * vstride + d), "f"(acc[n][0]), "f"(acc[n][1]) : "memory");
+      if (px1 < npx)
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gv + (int64_t)px1 * vstride + d), "f"(acc[n][2]), "f"(acc[n][3]) : "memory");
+    }
+  }
+}
+
+}  // namespace tile
+
+// ------------------------------------------------------------------------------------------
 // few queries (decoder: Lq = 10): one WARP per (b,q,m)
 // ------------------------------------------------------------------------------------------
 // The general kernels walk the L*P sampling points serially in each thread; with a handful of queries the
@@ -1056,6 +1380,40 @@ static int launch_dense_bwd(const MsdaArgs& a, int mode, int lvl0, cudaStream_t 
   return mode ? launch(dense::msda_bwd_dense_kernel<4, 4, true>) : launch(dense::msda_bwd_dense_kernel<4, 4, false>);
 }
 
+// Tile backward: POET_OK if it ran, POET_ERR_UNSUPPORTED if the shape does not qualify (the caller falls back to the
+// one-thread-per-(b,q,m,channel group) kernels: same results up to summation order).
+static int try_tile_bwd(const MsdaArgs& a, int mode, cudaStream_t s) {
+  static const int enabled = []() { const char* e = getenv("POET_MSDA_TILE"); return e ? atoi(e) : 1; }();
+  if (!enabled || a.D != 16 || a.L != 4 || a.P != 4 || a.Lq < 2 * tile::QT) return POET_ERR_UNSUPPORTED;
+  int ld = a.L;                                              // first of the trailing levels that fit the dense tile together
+  for (int l0 = 0; l0 < a.L; ++l0)
+    if (a.S - a.lv.start[l0] <= tile::NPX) { ld = l0; break; }
+  if (ld >= a.L) return POET_ERR_UNSUPPORTED;
+  const int npx = a.S - a.lv.start[ld];
+  const int n_tiles = poet_ceil_div(a.Lq, tile::QT);
+  const int slots = 3 * POET_NUM_SMS;                        // three resident CTAs per SM
+  int best = 1;
+  double best_cost = 1e30;
+  for (int nc = 1; nc <= n_tiles; ++nc) {                    // chunks per (image, head): makespan in tiles + staging / flush
+    const int tpc = poet_ceil_div(n_tiles, nc);
+    if ((int64_t)(nc - 1) * tpc >= n_tiles) continue;        // would leave an empty chunk
+    const double rounds = (double)poet_ceil_div((int64_t)a.B * a.M * nc, slots);
+    const double cost = rounds * (tpc + 0.5);
+    if (cost < best_cost) { best_cost = cost; best = nc; }
+  }
+  const int nchunk = best, tiles_per_chunk = poet_ceil_div(n_tiles, nchunk);
+  const int64_t grid = (int64_t)a.B * a.M * nchunk;
+  if (grid >= ((int64_t)1 << 31)) return POET_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)tile::SMEM_FLOATS * sizeof(float);
+  auto launch = [&](auto kern) -> int {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    poet_launch(kern, dim3((unsigned)grid), dim3(tile::THREADS), smem, s, a, ld, npx, nchunk, tiles_per_chunk, n_tiles);
+    return poet_launch_status();
+  };
+  return mode ? launch(tile::msda_bwd_tile_kernel<true>) : launch(tile::msda_bwd_tile_kernel<false>);
+}
+
 int fill_args(MsdaArgs& a, const int32_t* shapes_host, int B, int S, int Lq, int M, int D, int L, int P,
               const float* value, const float* aa, int64_t lda, const float* w, int64_t ldw, const float* ref, int mode) {
   POET_REQUIRE(value && aa && w && shapes_host, POET_ERR_NULL_POINTER);
@@ -1156,7 +1514,10 @@ extern "C" int poet_msda_bwd(const float* value, const float* a, int64_t lda, co
   args.grad_out = grad_out; args.grad_value = grad_value; args.grad_a = grad_a; args.grad_w = grad_w;
   const int rc_warp = try_warp_kernel<true>(args, mode, (cudaStream_t)stream);
   if (rc_warp != POET_ERR_UNSUPPORTED) return rc_warp;
-  // many queries (the encoder): grad_value of the low-resolution levels comes from the dense tensor-core kernel, the
+  // many queries (the encoder): one CTA per (image, head, run of query tiles), low-resolution levels as dense products
+  const int rc_tile = try_tile_bwd(args, mode, (cudaStream_t)stream);
+  if (rc_tile != POET_ERR_UNSUPPORTED) return rc_tile;
+  // legacy experiment (POET_MSDA_DENSE=1): grad_value of the low-resolution levels from a separate dense kernel, the
   // scatter kernel keeps its global reductions for the high-resolution level(s) only
   const int lvl0 = dense_first_level(args);
   args.red_levels = lvl0;

@@ -122,7 +122,9 @@ def _msda_inputs(B, M, D, Lq, P, shapes, seed):
     (1, 4, 64, 9, 4, [(6, 8), (3, 4), (2, 2), (1, 1)]),
     (2, 3, 16, 1700, 4, [(6, 8), (3, 4), (2, 2), (1, 1)]),               # smem-slab forward: S=65 (TMA box tail, OOB fill)
     (3, 8, 8, 21, 4, [(6, 8), (3, 4), (2, 2), (1, 1)]),                  # warp-per-(q,m) kernels, D=8
-    (2, 16, 16, 500, 4, [(30, 40), (15, 20), (8, 10), (4, 5)]),          # smem-slab forward on the REF pyramid
+    (2, 16, 16, 500, 4, [(30, 40), (15, 20), (8, 10), (4, 5)]),          # smem-slab forward on the REF pyramid; tile backward, levels 2-3 dense
+    (2, 16, 16, 333, 4, [(30, 40), (15, 20), (10, 12), (8, 10)]),        # tile backward: only the last level is dense (cfg5-like), ragged last tile
+    (2, 16, 16, 300, 4, [(12, 16), (6, 8), (4, 5), (2, 3)]),             # tile backward: levels 1-3 dense
 ])
 def test_msda_core_fwd_bwd(B, M, D, Lq, P, shapes):
     o = ops()
@@ -474,13 +476,45 @@ def test_gemm_tcgen05_presplit_weights(M, N, K, b_k, prec, tol):
     assert err < tol, f"{prec} {M}x{N}x{K} b_k={b_k}: rel err {err:.3e}"
 
 
+def test_msda_backward_tile_vs_thread_kernels():
+    """Encoder-size backward (B=16, S=Lq=1600: the benchmarked shape, mode 1): the tile kernel (dense low-resolution levels
+    on mma.sync) against the one-thread-per-channel-group scatter kernel of the same library (POET_MSDA_TILE=0 in a child
+    process), whose results the op-level fp64 checks pin."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch, sys\n"
+        "from poet_b200 import ops\n"
+        "shapes=((30,40),(15,20),(8,10),(4,5)); B,S,M,D,L,P=16,1600,16,16,4,4\n"
+        "g=torch.Generator().manual_seed(3)\n"
+        "value=torch.randn(B,S,M*D,generator=g).cuda(); oa=torch.randn(B,S,M*L*P*3,generator=g).cuda()\n"
+        "oa[...,:M*L*P*2]*=2.0\n"
+        "ref=torch.rand(B,S,L,2,generator=g).cuda(); go=torch.randn(B,S,M*D,generator=g).cuda()\n"
+        "value.requires_grad_(True); oa.requires_grad_(True)\n"
+        "out=ops.msda_block(value,oa,ref,shapes,M,L,P); (out*go).sum().backward(); torch.cuda.synchronize()\n"
+        "torch.save({'gv':value.grad.cpu(),'goa':oa.grad.cpu()}, sys.argv[1])\n")
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for knob in ("1", "0"):
+        path = f"/tmp/poet_tile_{knob}.pt"
+        r = subprocess.run([sys.executable, "-c", code, path], env=dict(os.environ, POET_MSDA_TILE=knob), cwd=here,
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        res[knob] = torch.load(path)
+    n_off = 16 * 16 * 2
+    assert rel_err(res["1"]["gv"], res["0"]["gv"]) < 5e-6
+    assert rel_err(res["1"]["goa"][..., n_off:], res["0"]["goa"][..., n_off:]) < 5e-5
+    assert bad_fraction(res["1"]["goa"][..., :n_off], res["0"]["goa"][..., :n_off], 5e-5) < 1e-3
+
+
 def test_msda_dense_lowres_backward_path_in_subprocess():
     """The dense tensor-core grad_value path of the MSDA backward (POET_MSDA_DENSE=1, read once per process) against the
     same fp64 oracle checks: run the MSDA tests of this file in a child process with the knob set."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, POET_MSDA_DENSE="1")
+    env = dict(os.environ, POET_MSDA_DENSE="1", POET_MSDA_TILE="0")
     here = os.path.abspath(__file__)
     r = subprocess.run([sys.executable, "-m", "pytest", here, "-m", "gpu", "-q", "-x", "-k",
                         "test_msda_core_fwd_bwd or test_msda_block_matches_module_math"], env=env, capture_output=True, text=True,

@@ -1176,6 +1176,11 @@ msda_bwd_tile_kernel(const MsdaArgs p, int ld, int npx, int nchunk, int tiles_pe
   }
 }
 
+// Forward on the same decomposition (sparse levels gathered by the 4-lane groups, dense levels as out = W . value) was built
+// and measured twice -- corners from global memory: 148 us, corners from a TMA-staged slab: 151 us -- against 112 us for
+// msda_fwd_slab_kernel (profiles/r02c_msda_tile_notes.txt): the 4-lane group with shuffle-broadcast records issues ~1.5x the
+// instructions per sampling point of the slab kernel's record / quarter-warp scheme.  Removed; the forward stays on the slab.
+
 }  // namespace tile
 
 // ------------------------------------------------------------------------------------------

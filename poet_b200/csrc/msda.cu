@@ -1042,6 +1042,23 @@ msda_bwd_tile_kernel(const MsdaArgs p, int ld, int npx, int nchunk, int tiles_pe
     for (int k = 0; k < P; ++k) ga_own[k] = 0.f;
     float* garow = p.grad_a + bq * p.lda + m * LP * 2 + c4 * 2 * P;   // this lane's level: 4 points x (x, y)
 
+    // ---- P2w: dense levels, the owner lane adds its four points into its W row (zeroed before the barrier above; read by
+    // P3 after the next one).  Nothing here depends on G, so it sits in front of the sparse walk.
+    if (c4 >= ld) {
+      float* Wrow = Ws + ql * LDW + dense_off;
+#pragma unroll
+      for (int s2 = 0; s2 < P; ++s2) {
+        const int cd = code[s2];
+        const int i00 = (cd >> 4) - BIAS;
+        const float a = aw[s2], fx = fxv[s2], fy = fyv[s2];
+        // the lane's points are serialised (two of them may share a pixel): plain read-modify-write of its own row
+        if (cd & 1) Wrow[i00] += a * (1.f - fy) * (1.f - fx);
+        if (cd & 2) Wrow[i00 + 1] += a * (1.f - fy) * fx;
+        if (cd & 4) Wrow[i00 + Wl] += a * fy * (1.f - fx);
+        if (cd & 8) Wrow[i00 + Wl + 1] += a * fy * fx;
+      }
+    }
+
     // ---- P2a: sparse levels, the group walks the points together (global gathers and reductions) ----
     // One point in flight per warp.  Issuing the corner loads of point i+1 before point i is consumed was measured
     // (it needs 128 registers -> 2 CTAs per SM): slower, 350 vs 314 us -- the kernel is not bound by load latency.
@@ -1089,15 +1106,14 @@ msda_bwd_tile_kernel(const MsdaArgs p, int ld, int npx, int nchunk, int tiles_pe
         }
       }
     }
-    __syncthreads();                                           // G complete
+    __syncthreads();                                           // G and W complete
 
-    // ---- P2b: dense levels, the owner lane alone: dots from G, weights into its W row ----
+    // ---- P2b: dense levels, the owner lane alone: corner dot products are single words of G ----
     if (c4 >= ld) {
       const float* Grow = Gs + ql * LDW + dense_off;
-      float* Wrow = Ws + ql * LDW + dense_off;
       float gxl[P], gyl[P];
 #pragma unroll
-      for (int s2 = 0; s2 < P; ++s2) {                         // all G reads first: independent of the W updates below
+      for (int s2 = 0; s2 < P; ++s2) {
         const int cd = code[s2];
         const int i00 = (cd >> 4) - BIAS;
         const float a = aw[s2], fx = fxv[s2], fy = fyv[s2];
@@ -1113,17 +1129,6 @@ msda_bwd_tile_kernel(const MsdaArgs p, int ld, int npx, int nchunk, int tiles_pe
         st4(garow, make_float4(gxl[0], gyl[0], gxl[1], gyl[1]));
         st4(garow + 4, make_float4(gxl[2], gyl[2], gxl[3], gyl[3]));
       }
-#pragma unroll
-      for (int s2 = 0; s2 < P; ++s2) {
-        const int cd = code[s2];
-        const int i00 = (cd >> 4) - BIAS;
-        const float a = aw[s2], fx = fxv[s2], fy = fyv[s2];
-        // the lane's points are serialised (two of them may share a pixel): plain read-modify-write of its own row
-        if (cd & 1) Wrow[i00] += a * (1.f - fy) * (1.f - fx);
-        if (cd & 2) Wrow[i00 + 1] += a * (1.f - fy) * fx;
-        if (cd & 4) Wrow[i00 + Wl] += a * fy * (1.f - fx);
-        if (cd & 8) Wrow[i00 + Wl + 1] += a * fy * fx;
-      }
     }
 
     // ---- softmax backward over the 16 points of the group, gradient of the logits ----
@@ -1137,7 +1142,6 @@ msda_bwd_tile_kernel(const MsdaArgs p, int ld, int npx, int nchunk, int tiles_pe
       for (int k = 0; k < P; ++k) ga_own[k] = aw[k] * (ga_own[k] - dotp);
     }
     if (live) st4(p.grad_w + bq * p.ldw + m * LP + c4 * P, make_float4(ga_own[0], ga_own[1], ga_own[2], ga_own[3]));
-    __syncthreads();                                           // W complete
 
     // ---- P3: acc[px, c] += W[q-tile, px]^T . grad_out[q-tile, c] ----
     if (warp < n_mt) {

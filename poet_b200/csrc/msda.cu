@@ -885,13 +885,23 @@ msda_bwd_dense_kernel(const MsdaArgs p, int lvl0, int npx, int n_mt, int nchunk,
 // reductions (52 M of 105 M lane-ops; what remains of them for the dense levels is ~1 M 8-byte reductions).
 namespace tile {
 
-constexpr int QT = 64;               // queries per tile
-constexpr int THREADS = 4 * QT;      // 4 lanes per (q,m): lane c4 = channel group in the sparse levels, owner of level c4 elsewhere
+constexpr int QT = 64;               // queries per tile at D = 16 (eligibility threshold: Lq >= 2 * QT)
+constexpr int THREADS = 256;         // G = D/4 lanes per (q,m): lane cg = channel group in the sparse levels, lanes 0..3 own one level each
 constexpr int NPX = 104;             // dense pixels at most (13 n-tiles of 8)
 constexpr int LDW = 104;             // row stride of G and W (floats): 104 % 32 == 8 -> conflict-free fragment accesses
-constexpr int LDV = 20;              // row stride of the value tile [px][16]: 20 g + t distinct mod 32 for g < 8, t < 4
-constexpr int LDGO = 20;             // row stride of the grad_out tile [q][16]
-constexpr int SMEM_FLOATS = QT * LDW + (QT * LDW + 8) + QT * LDGO + NPX * LDV;
+// per head size D = 4 G (16 or 32): tile of 256 / G queries, grad_out / value tiles with D + 4 floats per row
+// ((D + 4) g + t distinct mod 32 for g < 8, t < 4: conflict-free A / B fragment loads in P1)
+template <int G>
+struct Cfg {
+  static constexpr int D = 4 * G;
+  static constexpr int QT = THREADS / G;                 // 64 / 32 queries per tile
+  static constexpr int LDC = D + 4;                      // row stride of the grad_out and value tiles
+  static constexpr int KS1 = D / 8;                      // k-steps of P1 (reduction over channels)
+  static constexpr int NT3 = D / 8;                      // n-tiles of P3 (8 channels each)
+  static constexpr int MT1 = QT / 16;                    // m-tiles of P1 (16 queries each)
+  static constexpr int NPW1 = (13 + 8 / MT1 - 1) / (8 / MT1);   // n-tiles of P1 per warp (8 warps over MT1 x 13 tiles)
+  static constexpr int SMEM_FLOATS = QT * LDW + (QT * LDW + 8) + QT * LDC + NPX * LDC;
+};
 
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -911,21 +921,23 @@ __device__ __forceinline__ void mma_3x(float (&c)[4], const uint32_t (&ah)[4], c
   mma_tf32(c, ah, bh0, bh1);
 }
 
-template <bool FUSED>
+template <int G, bool FUSED>
 __global__ void __launch_bounds__(THREADS, 3)
 msda_bwd_tile_kernel(const MsdaArgs p, int ld, int npx, int nchunk, int tiles_per_chunk, int n_tiles) {
   poet_pdl_entry();
-  constexpr int L = 4, P = 4, LP = 16, D = 16;
+  using C = Cfg<G>;
+  constexpr int L = 4, P = 4, LP = 16, D = C::D, QT = C::QT, LDC = C::LDC;
   constexpr int BIAS = 1 << 20;                                // pixel offsets travel as (px + BIAS) << 4 | corner flags
   extern __shared__ __align__(16) float tile_smem[];
   float* Gs = tile_smem;                                       // [QT][LDW]  dot(grad_out[q], value[px])
   float* Ws = Gs + QT * LDW;                                   // [QT][LDW]  (+8: the last m-tile's fragment rows run past px 103)
-  float* gos = Ws + QT * LDW + 8;                              // [QT][LDGO] grad_out rows of the tile
-  float* Vs = gos + QT * LDGO;                                 // [NPX][LDV] value rows of the dense levels, this (image, head)
+  float* gos = Ws + QT * LDW + 8;                              // [QT][LDC] grad_out rows of the tile
+  float* Vs = gos + QT * LDC;                                  // [NPX][LDC] value rows of the dense levels, this (image, head)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;                       // mma fragment coordinates
-  const int c4 = tid & 3, ql = tid >> 2;                       // point-walk identity: lane of the (q,m) group, query of the tile
-  const int grp = lane & ~3;
+  const int c4 = tid % G, ql = tid / G;                        // point-walk identity: lane of the (q,m) group (channel group), query of the tile
+  const int grp = lane & ~(G - 1);
+  const bool owner = c4 < L;                                   // lanes 0..3 of a group prepare / own one level each
   const int chunk = blockIdx.x % nchunk, bm = blockIdx.x / nchunk;
   const int m = bm % p.M, b = bm / p.M;
   const int tile_beg = chunk * tiles_per_chunk, tile_end = min(n_tiles, tile_beg + tiles_per_chunk);
@@ -935,23 +947,23 @@ msda_bwd_tile_kernel(const MsdaArgs p, int ld, int npx, int nchunk, int tiles_pe
   const int vstride = p.M * D;
 
   // ---- value rows of the dense levels (zero rows behind npx) ----
-  for (int i = tid; i < NPX * 4; i += THREADS) {
-    const int px = i >> 2, c = i & 3;
+  for (int i = tid; i < NPX * G; i += THREADS) {
+    const int px = i / G, c = i % G;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (px < npx) v = ldg4(p.value + ((int64_t)b * p.S + pix0 + px) * vstride + m * D + c * 4);
-    *reinterpret_cast<float4*>(Vs + px * LDV + c * 4) = v;
+    *reinterpret_cast<float4*>(Vs + px * LDC + c * 4) = v;
   }
 
   // this lane's level (point preparation; owner of the level's gradients)
-  const int lvl = c4;
+  const int lvl = c4 & 3;                                      // lanes 4.. of a wide group repeat the preparation (never read)
   const int Hl = p.lv.H[lvl], Wl = p.lv.W[lvl];
   const int dense_off = p.lv.start[lvl] - pix0;                // this level's first pixel in G / W columns (dense levels only)
   float rx_iw = 0.f, ry_ih = 0.f;
   if (FUSED) { rx_iw = p.lv.inv_W[lvl]; ry_ih = p.lv.inv_H[lvl]; }
 
-  float acc[2][4];                                             // P3 accumulators: m-tile = warp, two 8-channel n-tiles
+  float acc[C::NT3][4];                                        // P3 accumulators: m-tile = warp, D/8 n-tiles of 8 channels
 #pragma unroll
-  for (int n = 0; n < 2; ++n)
+  for (int n = 0; n < C::NT3; ++n)
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc[n][k] = 0.f;
 
@@ -972,27 +984,27 @@ msda_bwd_tile_kernel(const MsdaArgs p, int ld, int npx, int nchunk, int tiles_pe
     if (FUSED) rf = __ldg(reinterpret_cast<const float2*>(p.ref + (bq * L + lvl) * 2));
     float4 go = make_float4(0.f, 0.f, 0.f, 0.f);
     if (live) go = ldg4(p.grad_out + (bq * p.M + m) * D + c4 * 4);
-    *reinterpret_cast<float4*>(gos + ql * LDGO + c4 * 4) = go;
+    *reinterpret_cast<float4*>(gos + ql * LDC + c4 * 4) = go;
     for (int i = tid; i < QT * LDW / 4; i += THREADS) reinterpret_cast<float4*>(Ws)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 
     // ---- P1: G[q, px] = grad_out[q, :] . value[px, :] ----
     {
-      const int mt = warp & 3, nt_beg = (warp >> 2) * 7, nt_end = min(n_nt, nt_beg + 7);
-      uint32_t ah[2][4], al[2][4];
+      const int mt = warp % C::MT1, nt_beg = (warp / C::MT1) * C::NPW1, nt_end = min(n_nt, nt_beg + C::NPW1);
+      uint32_t ah[C::KS1][4], al[C::KS1][4];
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        const float* ap = gos + (mt * 16 + g) * LDGO + ks * 8 + t;
+      for (int ks = 0; ks < C::KS1; ++ks) {
+        const float* ap = gos + (mt * 16 + g) * LDC + ks * 8 + t;
         split_tf32(ap[0], ah[ks][0], al[ks][0]);
-        split_tf32(ap[8 * LDGO], ah[ks][1], al[ks][1]);
+        split_tf32(ap[8 * LDC], ah[ks][1], al[ks][1]);
         split_tf32(ap[4], ah[ks][2], al[ks][2]);
-        split_tf32(ap[8 * LDGO + 4], ah[ks][3], al[ks][3]);
+        split_tf32(ap[8 * LDC + 4], ah[ks][3], al[ks][3]);
       }
       for (int nt = nt_beg; nt < nt_end; ++nt) {
         float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const float* bp = Vs + (nt * 8 + g) * LDV + ks * 8 + t;
+        for (int ks = 0; ks < C::KS1; ++ks) {
+          const float* bp = Vs + (nt * 8 + g) * LDC + ks * 8 + t;
           uint32_t bh0, bl0, bh1, bl1;
           split_tf32(bp[0], bh0, bl0);
           split_tf32(bp[4], bh1, bl1);
@@ -1044,7 +1056,7 @@ msda_bwd_tile_kernel(const MsdaArgs p, int ld, int npx, int nchunk, int tiles_pe
 
     // ---- P2w: dense levels, the owner lane adds its four points into its W row (zeroed before the barrier above; read by
     // P3 after the next one).  Nothing here depends on G, so it sits in front of the sparse walk.
-    if (c4 >= ld) {
+    if (owner && c4 >= ld) {
       float* Wrow = Ws + ql * LDW + dense_off;
 #pragma unroll
       for (int s2 = 0; s2 < P; ++s2) {
@@ -1095,7 +1107,7 @@ msda_bwd_tile_kernel(const MsdaArgs p, int ld, int npx, int nchunk, int tiles_pe
             float gx = a * ((1.f - fy) * (d01 - d00) + fy * (d11 - d10));
             float gy = a * ((1.f - fx) * (d10 - d00) + fx * (d11 - d01));
             if (!FUSED) { gx *= (float)W; gy *= (float)p.lv.H[l]; }
-            ga = group_sum<4>(ga); gx = group_sum<4>(gx); gy = group_sum<4>(gy);
+            ga = group_sum<G>(ga); gx = group_sum<G>(gx); gy = group_sum<G>(gy);
             if (c4 == l) ga_own[s2] = ga;
             gxl[s2] = gx; gyl[s2] = gy;
           }
@@ -1109,7 +1121,7 @@ msda_bwd_tile_kernel(const MsdaArgs p, int ld, int npx, int nchunk, int tiles_pe
     __syncthreads();                                           // G and W complete
 
     // ---- P2b: dense levels, the owner lane alone: corner dot products are single words of G ----
-    if (c4 >= ld) {
+    if (owner && c4 >= ld) {
       const float* Grow = Gs + ql * LDW + dense_off;
       float gxl[P], gyl[P];
 #pragma unroll
@@ -1141,7 +1153,7 @@ msda_bwd_tile_kernel(const MsdaArgs p, int ld, int npx, int nchunk, int tiles_pe
 #pragma unroll
       for (int k = 0; k < P; ++k) ga_own[k] = aw[k] * (ga_own[k] - dotp);
     }
-    if (live) st4(p.grad_w + bq * p.ldw + m * LP + c4 * P, make_float4(ga_own[0], ga_own[1], ga_own[2], ga_own[3]));
+    if (live && owner) st4(p.grad_w + bq * p.ldw + m * LP + c4 * P, make_float4(ga_own[0], ga_own[1], ga_own[2], ga_own[3]));
 
     // ---- P3: acc[px, c] += W[q-tile, px]^T . grad_out[q-tile, c] ----
     if (warp < n_mt) {
@@ -1154,11 +1166,11 @@ msda_bwd_tile_kernel(const MsdaArgs p, int ld, int npx, int nchunk, int tiles_pe
         split_tf32(ap[4 * LDW], ah[2], al[2]);
         split_tf32(ap[4 * LDW + 8], ah[3], al[3]);
 #pragma unroll
-        for (int n = 0; n < 2; ++n) {
-          const float* bp = gos + (ks * 8 + t) * LDGO + n * 8 + g;
+        for (int n = 0; n < C::NT3; ++n) {
+          const float* bp = gos + (ks * 8 + t) * LDC + n * 8 + g;
           uint32_t bh0, bl0, bh1, bl1;
           split_tf32(bp[0], bh0, bl0);
-          split_tf32(bp[4 * LDGO], bh1, bl1);
+          split_tf32(bp[4 * LDC], bh1, bl1);
           mma_3x(acc[n], ah, al, bh0, bh1, bl0, bl1);
         }
       }
@@ -1170,7 +1182,7 @@ msda_bwd_tile_kernel(const MsdaArgs p, int ld, int npx, int nchunk, int tiles_pe
   if (warp < n_mt) {
     float* gv = p.grad_value + ((int64_t)b * p.S + pix0) * vstride + m * D;
 #pragma unroll
-    for (int n = 0; n < 2; ++n) {
+    for (int n = 0; n < C::NT3; ++n) {
       const int px0 = warp * 16 + g, px1 = px0 + 8, d = n * 8 + 2 * t;
       if (px0 < npx)
         asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gv + (int64_t)px0 * vstride + d), "f"(acc[n][0]), "f"(acc[n][1]) : "memory");
@@ -1393,13 +1405,16 @@ static int launch_dense_bwd(const MsdaArgs& a, int mode, int lvl0, cudaStream_t 
 // one-thread-per-(b,q,m,channel group) kernels: same results up to summation order).
 static int try_tile_bwd(const MsdaArgs& a, int mode, cudaStream_t s) {
   static const int enabled = []() { const char* e = getenv("POET_MSDA_TILE"); return e ? atoi(e) : 1; }();
-  if (!enabled || a.D != 16 || a.L != 4 || a.P != 4 || a.Lq < 2 * tile::QT) return POET_ERR_UNSUPPORTED;
+  if (!enabled || (a.D != 16 && a.D != 32) || a.L != 4 || a.P != 4 || a.Lq < 2 * tile::QT) return POET_ERR_UNSUPPORTED;
   int ld = a.L;                                              // first of the trailing levels that fit the dense tile together
   for (int l0 = 0; l0 < a.L; ++l0)
     if (a.S - a.lv.start[l0] <= tile::NPX) { ld = l0; break; }
-  if (ld >= a.L) return POET_ERR_UNSUPPORTED;
+  // at least two dense levels: with one (the 1280x960 pyramid, 80 pixels) the tile phases cost more than the quarter of
+  // the reductions they remove (cfg5: 2.52 vs 2.12 ms per launch, profiles/r02c_msda_tile_notes.txt)
+  static const int max_ld = []() { const char* e = getenv("POET_MSDA_TILE_MAX_LD"); return e ? atoi(e) : 2; }();
+  if (ld > max_ld) return POET_ERR_UNSUPPORTED;
   const int npx = a.S - a.lv.start[ld];
-  const int n_tiles = poet_ceil_div(a.Lq, tile::QT);
+  const int n_tiles = poet_ceil_div(a.Lq, a.D == 16 ? tile::Cfg<4>::QT : tile::Cfg<8>::QT);
   const int slots = 3 * POET_NUM_SMS;                        // three resident CTAs per SM
   int best = 1;
   double best_cost = 1e30;
@@ -1413,14 +1428,15 @@ static int try_tile_bwd(const MsdaArgs& a, int mode, cudaStream_t s) {
   const int nchunk = best, tiles_per_chunk = poet_ceil_div(n_tiles, nchunk);
   const int64_t grid = (int64_t)a.B * a.M * nchunk;
   if (grid >= ((int64_t)1 << 31)) return POET_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)tile::SMEM_FLOATS * sizeof(float);
+  const size_t smem = (size_t)(a.D == 16 ? tile::Cfg<4>::SMEM_FLOATS : tile::Cfg<8>::SMEM_FLOATS) * sizeof(float);
   auto launch = [&](auto kern) -> int {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     poet_launch(kern, dim3((unsigned)grid), dim3(tile::THREADS), smem, s, a, ld, npx, nchunk, tiles_per_chunk, n_tiles);
     return poet_launch_status();
   };
-  return mode ? launch(tile::msda_bwd_tile_kernel<true>) : launch(tile::msda_bwd_tile_kernel<false>);
+  if (a.D == 16) return mode ? launch(tile::msda_bwd_tile_kernel<4, true>) : launch(tile::msda_bwd_tile_kernel<4, false>);
+  return mode ? launch(tile::msda_bwd_tile_kernel<8, true>) : launch(tile::msda_bwd_tile_kernel<8, false>);
 }
 
 int fill_args(MsdaArgs& a, const int32_t* shapes_host, int B, int S, int Lq, int M, int D, int L, int P,

@@ -125,6 +125,8 @@ def _msda_inputs(B, M, D, Lq, P, shapes, seed):
     (2, 16, 16, 500, 4, [(30, 40), (15, 20), (8, 10), (4, 5)]),          # smem-slab forward on the REF pyramid; tile backward, levels 2-3 dense
     (2, 16, 16, 333, 4, [(30, 40), (15, 20), (10, 12), (8, 10)]),        # tile backward: only the last level is dense (cfg5-like), ragged last tile
     (2, 16, 16, 300, 4, [(12, 16), (6, 8), (4, 5), (2, 3)]),             # tile backward: levels 1-3 dense
+    (2, 8, 32, 700, 4, [(30, 40), (15, 20), (8, 10), (4, 5)]),           # tile backward, D = 32 (8 lanes per (q,m), 32-query tiles)
+    (1, 8, 32, 1250, 4, [(30, 40), (15, 20), (10, 12), (8, 10)]),        # tile backward, D = 32, only the last level dense (cfg5-like)
 ])
 def test_msda_core_fwd_bwd(B, M, D, Lq, P, shapes):
     o = ops()

@@ -16,6 +16,8 @@ def main():
     scale = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
     if which == "cfg5":
         shapes, B, M = ((60, 80), (30, 40), (15, 20), (8, 10)), 8, 8
+    elif which == "ref8":                                   # REF pyramid, 8 heads of 32 channels (cfg1 geometry at batch 16)
+        shapes, B, M = ((30, 40), (15, 20), (8, 10), (4, 5)), 16, 8
     else:
         shapes, B, M = ((30, 40), (15, 20), (8, 10), (4, 5)), 16, 16
     S = sum(h * w for h, w in shapes)

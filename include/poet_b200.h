@@ -203,6 +203,28 @@ int poet_mask_rows(float* x, const uint8_t* mask, int R, int C, poet_stream_t st
 /* out = a + b (nullable b -> copy); elementwise over n floats, n % 4 == 0. */
 int poet_add(const float* a, const float* b, float* out, int64_t n, poet_stream_t stream);
 
+/* ---- block-level entry points: one call per reference sub-block (inference semantics: no dropout, nothing saved) ---- */
+/* nn.Linear followed by the layer's residual + LayerNorm (reference deformable_transformer.py:201-204 output_proj +
+ * norm1, :277-281 out_proj + norm2, :283-287):   y = LN(residual + x W^T + b) * gamma + beta     (gamma != NULL)
+ * or just the Linear with its epilogue:            y = act(x W^T + b)                              (gamma == NULL; residual
+ * must be NULL too), act = ReLU if flags & POET_GEMM_RELU.  x [R,K] (row stride ldx), W [N,K] fp32 (nn.Linear layout) with
+ * optional bf16 planes W_hi / W_lo (poet_split_bf16; may be NULL), y [R,N].  With LayerNorm the pre-norm sum needs
+ * poet_linear_epilogue_workspace_bytes() bytes of caller-owned workspace (N % 128 == 0, N <= 1024). */
+size_t poet_linear_epilogue_workspace_bytes(int R, int N, int K, int with_layernorm);
+int poet_linear_epilogue(const float* x, int64_t ldx, const float* W, const void* W_hi, const void* W_lo, const float* b,
+                         const float* residual, const float* gamma, const float* beta, float* y, int R, int N, int K,
+                         int flags, float eps, int precision, void* workspace, size_t workspace_bytes, poet_stream_t stream);
+/* The FFN half of an encoder / decoder layer (reference deformable_transformer.py:193-197 + 205-206, 267-271 + 289-290):
+ *     y = LN(x + linear2(relu(linear1(x)))) * gamma + beta,   x, y [R,C], W1 [F,C], W2 [C,F] (+ optional bf16 planes).
+ * Three launches inside one call (GEMM + bias + ReLU, GEMM + bias, residual + LayerNorm); the hidden activation [R,F] and
+ * the pre-norm sum [R,C] live in the caller's workspace (poet_ffn_fused_workspace_bytes()).  A single-kernel version
+ * (hidden tiles kept in TMEM) was measured against this and rejected, see DESIGN.md section 4. */
+size_t poet_ffn_fused_workspace_bytes(int R, int C, int F);
+int poet_ffn_fused(const float* x, const float* W1, const void* W1_hi, const void* W1_lo, const float* b1,
+                   const float* W2, const void* W2_hi, const void* W2_lo, const float* b2, const float* gamma,
+                   const float* beta, float* y, int R, int C, int F, float eps, int precision, void* workspace,
+                   size_t workspace_bytes, poet_stream_t stream);
+
 /* ---- decoder self-attention core (Q <= 32) ---------------------------------------------- */
 /* q,k,v: [B,Q,*] with row strides ldq/ldk/ldv (so they may be slices of one projection output);
  * head m uses channels [m*D,(m+1)*D).  probs [B,M,Q,Q] saved (before dropout).  out [B,Q,M*D].

@@ -58,6 +58,10 @@ SIGNATURES = {
     "poet_grad_sumsq_multi": (_i, [_vp, _i, _i64, _vp, _vp, _vp]),
     "poet_adamw_clip_multi": (_i, [_vp, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _f, _f, _f, _f, _i64, _vp]),
     "poet_heads_select_rot6d_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "poet_linear_epilogue_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "poet_linear_epilogue": (_i, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _sz, _vp]),
+    "poet_ffn_fused_workspace_bytes": (_sz, [_i, _i, _i]),
+    "poet_ffn_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _sz, _vp]),
 }
 
 _lock = threading.Lock()

@@ -163,3 +163,57 @@ extern "C" int poet_gemm_bsplit(const float* A, int64_t lda, int a_kcontig, cons
   POET_REQUIRE(Bm != nullptr, POET_ERR_NULL_POINTER);
   return poet_gemm_simt(A, lda, a_kcontig, Bm, ldb, b_kcontig, C, ldc, M, N, K, alpha, bias, gate, row_mask, flags, s);
 }
+
+// ------------------------------------------------------------------------------------------
+// block-level entry points (inference semantics): compositions of the kernels above behind one call
+// ------------------------------------------------------------------------------------------
+static inline size_t poet_align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+extern "C" size_t poet_linear_epilogue_workspace_bytes(int R, int N, int K, int with_layernorm) {
+  (void)K;
+  return with_layernorm ? poet_align256((size_t)R * N * sizeof(float)) : 0;
+}
+
+extern "C" int poet_linear_epilogue(const float* x, int64_t ldx, const float* W, const void* W_hi, const void* W_lo,
+                                    const float* b, const float* residual, const float* gamma, const float* beta, float* y,
+                                    int R, int N, int K, int flags, float eps, int precision, void* workspace,
+                                    size_t workspace_bytes, poet_stream_t stream) {
+  POET_REQUIRE(x && W && y, POET_ERR_NULL_POINTER);
+  POET_REQUIRE(R > 0 && N > 0 && K > 0 && ldx >= K, POET_ERR_BAD_SHAPE);
+  POET_REQUIRE((flags & ~POET_GEMM_RELU) == 0, POET_ERR_UNSUPPORTED);
+  const bool ln = gamma != nullptr;
+  if (!ln) {
+    POET_REQUIRE(residual == nullptr && beta == nullptr, POET_ERR_UNSUPPORTED);
+    return poet_gemm_bsplit(x, ldx, 1, W, W_hi, W_lo, K, 1, y, N, R, N, K, 1.f, b, nullptr, nullptr, flags, precision, stream);
+  }
+  POET_REQUIRE(beta != nullptr, POET_ERR_NULL_POINTER);
+  POET_REQUIRE(!(flags & POET_GEMM_RELU), POET_ERR_UNSUPPORTED);      // no reference layer normalises an activated Linear
+  POET_REQUIRE(workspace && workspace_bytes >= poet_linear_epilogue_workspace_bytes(R, N, K, 1), POET_ERR_WORKSPACE);
+  float* lin = reinterpret_cast<float*>(workspace);
+  int rc = poet_gemm_bsplit(x, ldx, 1, W, W_hi, W_lo, K, 1, lin, N, R, N, K, 1.f, b, nullptr, nullptr, 0, precision, stream);
+  if (rc) return rc;
+  // z = residual + lin (residual == NULL: LN(lin)); nothing saved for a backward pass
+  return poet_add_layernorm_fwd(residual ? residual : lin, residual ? lin : nullptr, gamma, beta, nullptr, y, nullptr, nullptr,
+                                nullptr, R, N, eps, nullptr, 0, 0.f, stream);
+}
+
+extern "C" size_t poet_ffn_fused_workspace_bytes(int R, int C, int F) {
+  return poet_align256((size_t)R * F * sizeof(float)) + poet_align256((size_t)R * C * sizeof(float));
+}
+
+extern "C" int poet_ffn_fused(const float* x, const float* W1, const void* W1_hi, const void* W1_lo, const float* b1,
+                              const float* W2, const void* W2_hi, const void* W2_lo, const float* b2, const float* gamma,
+                              const float* beta, float* y, int R, int C, int F, float eps, int precision, void* workspace,
+                              size_t workspace_bytes, poet_stream_t stream) {
+  POET_REQUIRE(x && W1 && W2 && gamma && beta && y, POET_ERR_NULL_POINTER);
+  POET_REQUIRE(R > 0 && C > 0 && F > 0, POET_ERR_BAD_SHAPE);
+  POET_REQUIRE(workspace && workspace_bytes >= poet_ffn_fused_workspace_bytes(R, C, F), POET_ERR_WORKSPACE);
+  float* hidden = reinterpret_cast<float*>(workspace);
+  float* lin = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + poet_align256((size_t)R * F * sizeof(float)));
+  int rc = poet_gemm_bsplit(x, C, 1, W1, W1_hi, W1_lo, C, 1, hidden, F, R, F, C, 1.f, b1, nullptr, nullptr, POET_GEMM_RELU,
+                            precision, stream);
+  if (rc) return rc;
+  rc = poet_gemm_bsplit(hidden, F, 1, W2, W2_hi, W2_lo, F, 1, lin, C, R, C, F, 1.f, b2, nullptr, nullptr, 0, precision, stream);
+  if (rc) return rc;
+  return poet_add_layernorm_fwd(x, lin, gamma, beta, nullptr, y, nullptr, nullptr, nullptr, R, C, eps, nullptr, 0, 0.f, stream);
+}

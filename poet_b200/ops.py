@@ -1067,6 +1067,47 @@ def ffn_block(x, W1, b1, W2, b2, gamma, beta, pos=None, eps: float = 1e-5, drop_
     return add_layernorm(x, f, gamma, beta, pos=pos, eps=eps, drop_p=drop_p, drop_site=site_res, r_bias=b2)
 
 
+def _plane_ptrs(W: torch.Tensor, rows: int):
+    sp = split_weight(W, rows)
+    return (None, None) if sp is None else (_p(sp[0]), _p(sp[1]))
+
+
+def linear_epilogue(x, W, b=None, residual=None, gamma=None, beta=None, relu: bool = False, eps: float = 1e-5):
+    """Inference-only block entry point `poet_linear_epilogue` (no autograd): act(x W^T + b), or with gamma / beta
+    LN(residual + x W^T + b) -- nn.Linear + residual + LayerNorm of a reference layer behind ONE C-ABI call."""
+    x2 = _chk(x).view(-1, x.shape[-1])
+    R, K = x2.shape
+    N = W.shape[0]
+    W = _chk(W)
+    y = torch.empty((R, N), device=x.device, dtype=torch.float32)
+    ln = gamma is not None
+    ws_bytes = _lib.lib().poet_linear_epilogue_workspace_bytes(R, N, K, int(ln))
+    ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8) if ws_bytes else None
+    hi, lo = _plane_ptrs(W, R)
+    r2 = None if residual is None else _chk(residual).view(R, N)
+    _call("poet_linear_epilogue", _p(x2), x2.stride(0), _p(W), hi, lo, _p(b), _p(r2), _p(gamma), _p(beta), _p(y), R, N, K,
+          1 if relu else 0, eps, _state["precision"], _p(ws), ws_bytes, _stream(x))
+    return y.view(*x.shape[:-1], N)
+
+
+def ffn_fused(x, W1, b1, W2, b2, gamma, beta, eps: float = 1e-5):
+    """Inference-only block entry point `poet_ffn_fused` (no autograd): LN(x + linear2(relu(linear1(x)))), the FFN half of
+    an encoder / decoder layer behind ONE C-ABI call (three launches inside).  Training goes through `ffn_block`."""
+    x2 = _chk(x).view(-1, x.shape[-1])
+    R, Cc = x2.shape
+    F = W1.shape[0]
+    W1, W2 = _chk(W1), _chk(W2)
+    y = torch.empty_like(x2)
+    ws_bytes = _lib.lib().poet_ffn_fused_workspace_bytes(R, Cc, F)
+    ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
+    h1, l1 = _plane_ptrs(W1, R)
+    h2, l2 = _plane_ptrs(W2, R)
+    _call("poet_ffn_fused", _p(x2), _p(W1), h1, l1, _p(b1), _p(W2), h2, l2, _p(b2), _p(gamma), _p(beta), _p(y), R, Cc, F, eps,
+          _state["precision"], _p(ws), ws_bytes, _stream(x))
+    _state["launches"] += 2                       # three kernels behind the one call
+    return y.view(x.shape)
+
+
 class _Add(torch.autograd.Function):
     @staticmethod
     def forward(ctx, a, b):

@@ -193,6 +193,34 @@ def test_msda_full_size_properties():
     assert float((out - torch.arange(1, M + 1, device=DEV).view(1, 1, M, 1)).abs().max()) < 1e-4
 
 
+# ------------------------------------------------------------------------------- block-level entry points
+@pytest.mark.parametrize("R", [160, 3200])                              # query rows (latency kernel) / token rows (tcgen05)
+def test_block_entry_points_ffn_fused_and_linear_epilogue(R):
+    """poet_ffn_fused / poet_linear_epilogue (one C-ABI call per reference sub-block, inference semantics) against fp64
+    torch: reference deformable_transformer.py:193-197 + 205-206 (FFN + norm2) and :201-204 (output_proj + norm1)."""
+    o = ops()
+    g = torch.Generator().manual_seed(R)
+    Cc, F = 256, 1024
+    x, res = torch.randn(R, Cc, generator=g), torch.randn(R, Cc, generator=g)
+    W1, b1 = torch.randn(F, Cc, generator=g) / 16, torch.randn(F, generator=g)
+    W2, b2 = torch.randn(Cc, F, generator=g) / 32, torch.randn(Cc, generator=g)
+    gam, bet = torch.randn(Cc, generator=g), torch.randn(Cc, generator=g)
+    d = lambda t: t.double()
+    h = torch.relu(d(x) @ d(W1).t() + d(b1))
+    ref_ffn = torch.nn.functional.layer_norm(d(x) + h @ d(W2).t() + d(b2), (Cc,), d(gam), d(bet), 1e-5)
+    c = lambda t: t.to(DEV)
+    got = o.ffn_fused(c(x), c(W1), c(b1), c(W2), c(b2), c(gam), c(bet))
+    assert rel_err(got, ref_ffn) < 2e-5
+    Wp, bp = W2[:, :Cc].contiguous(), b2
+    ref_lin = d(x) @ d(Wp).t() + d(bp)
+    assert rel_err(o.linear_epilogue(c(x), c(Wp), c(bp)), ref_lin) < 2e-5
+    assert rel_err(o.linear_epilogue(c(x), c(Wp), c(bp), relu=True), ref_lin.clamp_min(0)) < 2e-5
+    ref_ln = torch.nn.functional.layer_norm(d(res) + ref_lin, (Cc,), d(gam), d(bet), 1e-5)
+    assert rel_err(o.linear_epilogue(c(x), c(Wp), c(bp), residual=c(res), gamma=c(gam), beta=c(bet)), ref_ln) < 2e-5
+    ref_ln0 = torch.nn.functional.layer_norm(ref_lin, (Cc,), d(gam), d(bet), 1e-5)
+    assert rel_err(o.linear_epilogue(c(x), c(Wp), c(bp), gamma=c(gam), beta=c(bet)), ref_ln0) < 2e-5
+
+
 # ------------------------------------------------------------------------------- LayerNorm
 @pytest.mark.parametrize("R,C,with_r,with_pos", [(160, 256, True, True), (3200, 256, True, False), (77, 128, False, False),
                                                  (50, 1024, True, True)])

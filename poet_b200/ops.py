@@ -1,4 +1,6 @@
-"""Raw wrappers over the C ABI and the torch.autograd.Function bindings built on them.
+"""torch.autograd.Function bindings over the C ABI (raw wrappers, GEMM / Linear / MLP, LayerNorm, MSDA, attention, heads,
+position encodings, input_proj).  Runtime state lives in _runtime.py, the weight-plane arena in _planes.py; both are
+re-exported here, so `poet_b200.ops` stays the one import for callers, tests and tools.
 
 PyTorch is plumbing here: it owns device memory, the CUDA stream and the autograd tape; every
 numeric operation below is a call into libpoet_b200.so.  Nothing in this file has a CPU or
@@ -8,300 +10,17 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os as _os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
 
 from . import _lib
-
-GEMM_FP32, GEMM_BF16X3, GEMM_BF16 = 0, 1, 2
-_PRECISION = {"fp32": GEMM_FP32, "bf16x3": GEMM_BF16X3, "bf16": GEMM_BF16}
-import os as _os
-
-# default: tcgen05 split-bf16 (fp32-grade) for the large contractions; the SIMT fp32 kernel serves the small ones
-_state = {"precision": _PRECISION[_os.environ.get("POET_GEMM_PRECISION", "bf16x3")], "launches": 0, "direct_grads": True}
-
-
-def set_gemm_precision(name: str) -> None:
-    """'fp32' (SIMT FFMA), 'bf16x3' (tcgen05 split-bf16, fp32-grade) or 'bf16' (tcgen05 single pass)."""
-    _state["precision"] = _PRECISION[name]
-
-
-def get_gemm_precision() -> str:
-    return {v: k for k, v in _PRECISION.items()}[_state["precision"]]
-
-
-class precision_scope:
-    """with precision_scope('bf16'): ... -- GEMMs issued inside use that precision (None: leave as is); the backward
-    of every op recorded inside runs at the precision of its forward (each autograd Function stores it).  Used by the
-    mixed throughput mode (BASELINE.json cfg4): single-pass bf16 MMAs for the encoder layers, bf16x3 elsewhere.
-    The weight planes are shared: a bf16 GEMM simply ignores the lo plane."""
-
-    def __init__(self, name: Optional[str]):
-        self.value = None if name is None else (_PRECISION[name] if isinstance(name, str) else int(name))
-
-    def __enter__(self):
-        self.saved = _state["precision"]
-        if self.value is not None:
-            if self.saved == GEMM_FP32 and self.value != GEMM_FP32:
-                raise RuntimeError("precision_scope cannot enable tensor-core GEMMs under the global 'fp32' mode (no weight planes)")
-            _state["precision"] = self.value
-        return self
-
-    def __exit__(self, *exc):
-        _state["precision"] = self.saved
-        return False
-
-
-# ------------------------------------------------------------------------------------------
-# stream forking: the decoder / head chain is a sequence of launch-latency-bound kernels that leaves the
-# GPU mostly idle, so independent work (the decoder layers' value projections of `memory`, the per-layer
-# pose heads and their backward) is issued on side streams.  Under CUDA-graph capture the fork/join
-# events become graph edges and the branches run concurrently; autograd replays each op's backward on
-# the stream of its forward, so the backward overlaps the same way.
-# ------------------------------------------------------------------------------------------
-_side_streams = {}
-_stream_ns = [0]          # namespace of the side streams: each micro-batch forks onto its own set
-
-
-class stream_namespace:
-    """Side streams requested inside the block are private to namespace `ns` (micro-batch index)."""
-
-    def __init__(self, ns: int):
-        self.ns = ns
-
-    def __enter__(self):
-        _stream_ns.append(self.ns)
-        return self
-
-    def __exit__(self, *exc):
-        _stream_ns.pop()
-        return False
-
-
-def side_stream(idx: int, device) -> "torch.cuda.Stream":
-    key = (str(device), _stream_ns[-1], idx)
-    if key not in _side_streams:
-        _side_streams[key] = torch.cuda.Stream(device=device)
-    return _side_streams[key]
-
-
-def parallel_streams_enabled() -> bool:
-    return _state.get("parallel_streams", True)
-
-
-def set_parallel_streams(on: bool) -> None:
-    _state["parallel_streams"] = bool(on)
-
-
-class fork:
-    """with fork(idx, device) as f: ... work issued on side stream idx ...; f.join() makes the caller's stream wait."""
-
-    def __init__(self, idx: int, device):
-        self.main = torch.cuda.current_stream(device)
-        self.side = side_stream(idx, device)
-        self._ctx = None
-
-    def __enter__(self):
-        self.side.wait_stream(self.main)
-        _touched_side_streams[id(self.side)] = self.side
-        self._ctx = torch.cuda.stream(self.side)
-        self._ctx.__enter__()
-        return self
-
-    def __exit__(self, *exc):
-        self._ctx.__exit__(*exc)
-        return False
-
-    def join(self, *tensors) -> None:
-        """Caller's stream waits for the side stream; `tensors` produced there are marked as used on it."""
-        self.main.wait_stream(self.side)
-        for t in tensors:
-            if isinstance(t, torch.Tensor):
-                t.record_stream(self.main)
-
-    def uses(self, *tensors) -> None:
-        """Tensors allocated on the caller's stream that the side stream reads."""
-        for t in tensors:
-            if isinstance(t, torch.Tensor):
-                t.record_stream(self.side)
-
-    def checkpoint(self) -> "torch.cuda.Event":
-        """Event marking the side-stream work issued so far (call inside the `with` block)."""
-        ev = torch.cuda.Event()
-        ev.record(self.side)
-        return ev
-
-    def wait(self, ev, *tensors) -> None:
-        """Caller's stream waits for a checkpoint; `tensors` produced before it are marked as used there."""
-        self.main.wait_event(ev)
-        for t in tensors:
-            if isinstance(t, torch.Tensor):
-                t.record_stream(self.main)
-
-
-# Side streams that received work since the last reset_touched_side_streams(): what a gradient all-reduce issued in the
-# middle of the backward pass has to wait for besides the calling stream (data_parallel.FlatGradReducer.on_marker).
-_touched_side_streams = {}
-
-
-def reset_touched_side_streams() -> None:
-    _touched_side_streams.clear()
-
-
-def touched_side_streams():
-    return list(_touched_side_streams.values())
-
-
-# Gradient-ready markers: identity in forward; in backward they tell a registered callback that every gradient kernel
-# downstream of this point of the forward graph has been ISSUED (autograd has finished all nodes created after it).
-_marker_cb = [None]
-
-
-def set_grad_marker_callback(cb) -> None:
-    _marker_cb[0] = cb
-
-
-class _GradMarker(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, key):
-        ctx.key = key
-        return x.view_as(x)
-
-    @staticmethod
-    def backward(ctx, g):
-        cb = _marker_cb[0]
-        if cb is not None:
-            cb(ctx.key)
-        return g, None
-
-
-def grad_marker(x: torch.Tensor, key):
-    """No-op unless a callback is registered (overlapped gradient all-reduce) and x carries a gradient."""
-    if _marker_cb[0] is None or not (torch.is_grad_enabled() and x.requires_grad):
-        return x
-    return _GradMarker.apply(x, key)
-
-
-def launch_count() -> int:
-    """Number of libpoet_b200 kernel-launching calls issued so far (bench.py's gpu_launches)."""
-    return _state["launches"]
-
-
-# ------------------------------------------------------------------------------------------
-# train-mode dropout: counter-based, no mask tensors (include/poet_b200.h "Train-mode dropout")
-# ------------------------------------------------------------------------------------------
-# One int64 counter per device.  Every training forward bumps it IN PLACE (so the bump is a node of a captured CUDA
-# graph and every replay draws new masks) and takes a private snapshot; all dropout sites of that forward -- and
-# their backward kernels, which regenerate the masks -- read the snapshot through its device pointer.
-_drop_counters = {}
-
-
-def set_dropout_seed(seed: int, device=None) -> None:
-    """Deterministic mask sequence from here on (the analogue of torch.manual_seed for the dropout of this library)."""
-    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    c = _drop_counters.get(str(dev))
-    if c is None:
-        _drop_counters[str(dev)] = torch.full((1,), int(seed), dtype=torch.int64, device=dev)
-    else:
-        c.fill_(int(seed))
-
-
-def begin_dropout_forward(device) -> torch.Tensor:
-    """Called once per training forward with dropout > 0: returns this forward's seed tensor (int64 [1], device)."""
-    key = str(torch.device(device))
-    c = _drop_counters.get(key)
-    if c is None:
-        c = _drop_counters[key] = torch.full((1,), int(torch.initial_seed()) & 0x7FFFFFFFFFFF, dtype=torch.int64, device=device)
-    c.add_(1)
-    cur = c.clone()
-    _state["drop_seed"] = cur
-    return cur
-
-
-def _drop_args(p: float):
-    """(seed tensor, p) for an op called with dropout probability p; the seed must have been set by the model."""
-    if p <= 0.0:
-        return None, 0.0
-    if not 0.0 < p < 1.0:
-        raise ValueError(f"dropout probability must be in [0, 1), got {p}")
-    seed = _state.get("drop_seed")
-    if seed is None:
-        raise RuntimeError("dropout > 0 needs ops.begin_dropout_forward() at the start of the forward pass")
-    return seed, float(p)
-
-
-def dropout_scale(p: float, pair_scheme: bool = False) -> float:
-    return float(_lib.lib().poet_dropout_scale(float(p), int(pair_scheme))) if p > 0.0 else 1.0
-
-
-# ------------------------------------------------------------------------------------------
-# helpers
-# ------------------------------------------------------------------------------------------
-def _p(t: Optional[torch.Tensor]):
-    return None if t is None else t.data_ptr()
-
-
-def _chk(t: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
-    if not t.is_cuda:
-        raise _lib.PoetLibraryError("poet_b200 ops run on CUDA tensors only (no CPU fallback)")
-    if t.dtype != dtype:
-        raise TypeError(f"expected {dtype}, got {t.dtype}")
-    return t if t.is_contiguous() else t.contiguous()
-
-
-def _stream(t: torch.Tensor):
-    _lib.require_b200(t.device.index if t.device.index is not None else torch.cuda.current_device())
-    return torch.cuda.current_stream(t.device).cuda_stream
-
-
-_timing = {"on": False, "events": {}}
-
-
-def kernel_timing(enable: bool) -> None:
-    """bench.py: bracket every library call with CUDA events on the launching stream."""
-    _timing["on"] = enable
-    if enable:
-        _timing["events"] = {}
-        _timing["work"] = {}
-
-
-def kernel_times_ms() -> dict:
-    """name -> (total ms, launches, algorithmic bytes, flops); call after a device synchronize."""
-    work = _timing.get("work", {})
-    return {k: (sum(s.elapsed_time(e) for s, e in v), len(v), *work.get(k, (0, 0))) for k, v in _timing["events"].items()}
-
-
-_B_STABLE = _os.environ.get("POET_GEMM_B_STABLE", "1") != "0"
-_ABLATE = frozenset(x for x in _os.environ.get("POET_ABLATE_CALLS", "").split(",") if x)
-
-
-def _call(name: str, *args, tag: Optional[str] = None, work=None) -> None:
-    """`tag` / `work` = (algorithmic bytes, flops) only feed bench.py's per-kernel roofline table."""
-    if _ABLATE and name in _ABLATE:              # timing experiments only (tools/gpu_ab.sh): results are wrong
-        return
-    _state["launches"] += 1
-    if _timing["on"]:
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        rc = getattr(_lib.lib(), name)(*args)
-        e.record()
-        key = name if tag is None else f"{name}[{tag}]"
-        _timing["events"].setdefault(key, []).append((s, e))
-        if work is not None:
-            acc = _timing.setdefault("work", {}).setdefault(key, [0, 0])
-            acc[0] += work[0]
-            acc[1] += work[1]
-    else:
-        rc = getattr(_lib.lib(), name)(*args)
-    if rc != 0:
-        _lib.check(rc, name)
-
-
-def shapes_array(shapes: Sequence[Tuple[int, int]]):
-    flat = [int(v) for hw in shapes for v in hw]
-    return (C.c_int32 * len(flat))(*flat)
-
+from ._runtime import *  # noqa: F401,F403
+from ._runtime import (_ABLATE, _B_STABLE, _PRECISION, _GradMarker, _call, _chk, _drop_args, _drop_counters, _marker_cb, _p,  # noqa: F401
+                       _pending_joins, _side_streams, _state, _stream, _stream_ns, _timing, _touched_side_streams)
+from ._planes import *  # noqa: F401,F403
+from ._planes import _active_planes, _eligible  # noqa: F401
 
 # ------------------------------------------------------------------------------------------
 # raw ops (no autograd)
@@ -344,218 +63,6 @@ def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_kcontig
     _call("poet_gemm", _p(A), lda, int(a_kcontig), _p(Bm), ldb, int(b_kcontig), _p(out), out.stride(0), M, N, K,
           alpha, _p(bias), _p(gate), _p(row_mask), flags, prec, _p(ws), ws_bytes, _stream(A), tag=tag, work=work)
     return out
-
-
-# Weights are the B operand of the forward (NT) and of the dgrad (NN) GEMM of a layer: they are split into
-# bf16 hi/lo planes once per step and both GEMMs fetch the planes by TMA.  `WeightPlanes` does that for ALL
-# weight matrices of a module tree in one launch into one arena (the per-layer autograd Functions then only
-# look their planes up); a weight that is not covered falls back to its own poet_split_bf16 launch.
-class WeightPlanes:
-    """bf16 hi/lo planes of every 2-D parameter of `module`, refreshed by one poet_split_bf16_multi launch.
-    Parameters keep their registration order in the arena, so row-blocks of one matrix and consecutive
-    matrices (sampling_offsets | attention_weights) are contiguous plane views as well."""
-
-    @staticmethod
-    def select(module: torch.nn.Module):
-        # matrices and conv kernels (input_proj: [out, in, kh, kw] is the GEMM weight [out, in*kh*kw])
-        return [p for p in module.parameters() if p.dim() in (2, 4) and p.dtype == torch.float32 and p.is_cuda
-                and p.is_contiguous() and p.numel() % 8 == 0]
-
-    def __init__(self, module: torch.nn.Module):
-        params = self.select(module)
-        self.params = params
-        self.device = params[0].device if params else None
-        total = sum(p.numel() for p in params)
-        self.hi = torch.empty(total, device=self.device, dtype=torch.bfloat16) if params else None
-        self.lo = torch.empty(total, device=self.device, dtype=torch.bfloat16) if params else None
-        self.ranges = []                      # (data_ptr, nbytes, element offset in the arena)
-        off = 0
-        for p in params:
-            self.ranges.append((p.data_ptr(), p.numel() * 4, off))
-            off += p.numel()
-        self._table_key, self._table, self._chunks = None, None, 0
-        # all 1-D parameters (biases, norm affine) in registration order: refresh() concatenates them with ONE launch, so
-        # [sampling_offsets.bias | attention_weights.bias] of the fused projection is a view instead of a cat per layer
-        self.vec_params = [p for p in module.parameters() if p.dim() == 1 and p.dtype == torch.float32 and p.is_cuda]
-        self.vec_flat, self.vec_off = None, {}
-        o = 0
-        for p in self.vec_params:
-            self.vec_off[p.data_ptr()] = (o, p.numel())
-            o += p.numel()
-        self.with_lo = True
-        self._fresh_versions = None           # parameter versions for which the planes are known to be current
-
-    def _build_table(self, with_lo: bool):
-        import struct
-        raw, chunk, off = bytearray(), 0, 0
-        for p in self.params:
-            n4 = p.numel() // 4
-            raw += struct.pack("<QQQqq", p.data_ptr(), self.hi.data_ptr() + 2 * off,
-                               (self.lo.data_ptr() + 2 * off) if with_lo else 0, n4, chunk)
-            chunk += (n4 + 1023) // 1024
-            off += p.numel()
-        self._table = torch.frombuffer(raw, dtype=torch.uint8).clone().to(self.device)
-        self._chunks = chunk
-
-    def mark_fresh(self) -> None:
-        """The planes were just written from the current parameter values by someone else (the fused optimizer
-        step): the next refresh() is a no-op unless a parameter is modified in between."""
-        self._fresh_versions = [p._version for p in self.params]
-
-    def bias_pair(self, b0: torch.Tensor, b1: torch.Tensor):
-        """cat(b0, b1) as a view of the per-step flat copy of the 1-D parameters, or None."""
-        if self.vec_flat is None:
-            return None
-        r0, r1 = self.vec_off.get(b0.data_ptr()), self.vec_off.get(b1.data_ptr())
-        if r0 is None or r1 is None or r1[0] != r0[0] + r0[1] or r0[1] != b0.numel() or r1[1] != b1.numel() or r0[0] % 4:
-            return None
-        return self.vec_flat[r0[0]: r0[0] + r0[1] + r1[1]]
-
-    def refresh_vectors(self) -> None:
-        """Re-copy the 1-D parameters into the flat buffer, IN PLACE: the buffer's address is baked into captured
-        CUDA graphs (bias_pair views), and this copy is part of every forward -- also of one replayed from a graph
-        whose planes are written by the fused optimizer -- so a bias updated by optimizer.step() or load_state_dict
-        is what the next forward reads."""
-        if not self.vec_params:
-            return
-        with torch.no_grad():
-            srcs = [p.detach().reshape(-1) for p in self.vec_params]
-            if self.vec_flat is None or self.vec_flat.numel() != sum(t.numel() for t in srcs):
-                self.vec_flat = torch.empty(sum(t.numel() for t in srcs), device=self.device, dtype=torch.float32)
-            torch.cat(srcs, out=self.vec_flat)
-
-    def refresh(self) -> None:
-        """Re-derive all planes from the current parameter values (call once per forward)."""
-        prec = _state["precision"]
-        if not self.params or prec == GEMM_FP32:
-            return
-        self.refresh_vectors()
-        if (self._fresh_versions is not None and self.with_lo == (prec == GEMM_BF16X3) and
-                self._fresh_versions == [p._version for p in self.params]):
-            return
-        key = (tuple(p.data_ptr() for p in self.params), prec == GEMM_BF16X3)
-        if key != self._table_key:
-            self.ranges, off = [], 0
-            for p in self.params:
-                self.ranges.append((p.data_ptr(), p.numel() * 4, off))
-                off += p.numel()
-            self._build_table(prec == GEMM_BF16X3)
-            self._table_key = key
-        self.with_lo = prec == GEMM_BF16X3
-        _call("poet_split_bf16_multi", _p(self._table), len(self.params), self._chunks,
-              torch.cuda.current_stream(self.device).cuda_stream)
-
-    def lookup(self, ptr: int, numel: int):
-        """(hi, lo) flat plane views for the fp32 range [ptr, ptr + 4*numel) if it lies inside the arena's
-        parameters (a whole matrix, a row block, or consecutive matrices), else None."""
-        if getattr(self, "_by_base_src", None) is not self.ranges:       # rebuilt whenever the ranges list is replaced
-            self._by_base = {base: (nbytes, off) for base, nbytes, off in self.ranges}
-            self._by_base_src = self.ranges
-        hit = self._by_base.get(ptr)
-        if hit is not None and 4 * numel <= hit[0]:
-            off = hit[1]
-            return self.hi[off:off + numel], (self.lo[off:off + numel] if self.with_lo else None)
-        for base, nbytes, off in self.ranges:
-            if base <= ptr < base + nbytes:
-                e0 = off + (ptr - base) // 4
-                # consecutive parameters are consecutive in the arena only if they are consecutive in memory too
-                if ptr + 4 * numel > base + nbytes:
-                    return None
-                hi = self.hi[e0:e0 + numel]
-                lo = self.lo[e0:e0 + numel] if self.with_lo else None
-                return hi, lo
-        return None
-
-    def lookup_pair(self, W0: torch.Tensor, W1: torch.Tensor):
-        """Planes of cat(W0, W1) when the two matrices follow each other in the arena (no fp32 cat needed)."""
-        r0 = r1 = None
-        for base, nbytes, off in self.ranges:
-            if base == W0.data_ptr() and nbytes == W0.numel() * 4:
-                r0 = off
-            if base == W1.data_ptr() and nbytes == W1.numel() * 4:
-                r1 = off
-        if r0 is None or r1 is None or r1 != r0 + W0.numel():
-            return None
-        n = W0.numel() + W1.numel()
-        return self.hi[r0:r0 + n], (self.lo[r0:r0 + n] if self.with_lo else None)
-
-
-_active_planes: List[WeightPlanes] = []
-
-
-class planes_scope:
-    """with planes_scope(module): ... -- inside, split_weight() is served from the module's refreshed arena.
-    The arena object is cached on the module; nested scopes whose parameters are already covered are no-ops."""
-
-    def __init__(self, module: torch.nn.Module, refresh: bool = True):
-        """refresh=False: trust the arena as it is (the fused optimizer step wrote the planes of the new weights;
-        used when the forward is replayed from a CUDA graph that must not contain the split pass)."""
-        self.module, self.pushed, self.do_refresh = module, False, refresh
-
-    def __enter__(self):
-        if not _active_planes:
-            _pending_joins.clear()                        # a backward that raised must not suppress the next one's joins
-        first = next((p for p in self.module.parameters() if p.dim() in (2, 4)), None)
-        if first is None or not first.is_cuda or _state["precision"] == GEMM_FP32:
-            return self
-        if any(pl.lookup(first.data_ptr(), first.numel()) is not None for pl in _active_planes):
-            return self                                   # an enclosing scope already covers this module
-        pl = getattr(self.module, "_poet_weight_planes", None)
-        if pl is None or [p.data_ptr() for p in pl.params] != [p.data_ptr() for p in WeightPlanes.select(self.module)]:
-            if not self.do_refresh:
-                raise RuntimeError("planes_scope(refresh=False) needs planes written by FusedClipAdamW for this module")
-            pl = WeightPlanes(self.module)
-            object.__setattr__(self.module, "_poet_weight_planes", pl)
-        if self.do_refresh:
-            pl.refresh()
-        else:
-            pl.refresh_vectors()                          # the optimizer writes the matrix planes, not the bias copy
-        _active_planes.append(pl)
-        self.pushed = True
-        return self
-
-    def __exit__(self, *exc):
-        if self.pushed:
-            _active_planes.pop()
-        return False
-
-
-def _eligible(M_rows: int, N: int, K: int) -> bool:
-    return not (K % 8 or N % 8) and bool(_lib.lib().poet_gemm_tc_eligible(M_rows, N, K, K, K, N))
-
-
-def split_weight(W: torch.Tensor, M_rows: int):
-    """(hi, lo) bf16 planes of W [N,K] if the GEMMs that will use it are tensor-core eligible, else None."""
-    prec = _state["precision"]
-    if prec == GEMM_FP32:
-        return None
-    N, K = W.shape
-    if not _eligible(M_rows, N, K):
-        return None
-    if W.is_contiguous():
-        for pl in reversed(_active_planes):
-            v = pl.lookup(W.data_ptr(), W.numel())
-            if v is not None:
-                return v[0].view(N, K), (v[1].view(N, K) if v[1] is not None else None)
-    hi = torch.empty(W.shape, device=W.device, dtype=torch.bfloat16)
-    lo = torch.empty(W.shape, device=W.device, dtype=torch.bfloat16) if prec == GEMM_BF16X3 else None
-    _call("poet_split_bf16", _p(W), _p(hi), _p(lo), W.numel(), _stream(W))
-    return hi, lo
-
-
-def split_weight_pair(W0: torch.Tensor, W1: torch.Tensor, M_rows: int):
-    """Planes of cat(W0, W1) [N0+N1, K] straight from the arena, or None (caller concatenates and splits)."""
-    N, K = W0.shape[0] + W1.shape[0], W0.shape[1]
-    # the planes serve the forward [R,N,K] AND the dgrad [R,K,N] GEMM (the fp32 matrix is then never built): both
-    # must be tensor-core eligible, else the caller concatenates and keeps the fp32 copy for the SIMT path
-    if _state["precision"] == GEMM_FP32 or not _eligible(M_rows, N, K) or not _eligible(M_rows, K, N):
-        return None
-    for pl in reversed(_active_planes):
-        v = pl.lookup_pair(W0, W1)
-        if v is not None:
-            N, K = W0.shape[0] + W1.shape[0], W0.shape[1]
-            return v[0].view(N, K), (v[1].view(N, K) if v[1] is not None else None)
-    return None
 
 
 def relu_bits_buffer(R: int, N: int, K: int, device) -> Optional[torch.Tensor]:
@@ -690,7 +197,6 @@ def _linear_bwd(gy2: torch.Tensor, x2: torch.Tensor, W: torch.Tensor, need_x: bo
 
 
 _WGRAD_STREAM = 8
-_pending_joins = {}
 
 
 def _join_at_end_of_backward(f: "fork") -> None:
@@ -1067,9 +573,10 @@ def ffn_block(x, W1, b1, W2, b2, gamma, beta, pos=None, eps: float = 1e-5, drop_
     return add_layernorm(x, f, gamma, beta, pos=pos, eps=eps, drop_p=drop_p, drop_site=site_res, r_bias=b2)
 
 
-def _plane_ptrs(W: torch.Tensor, rows: int):
+def _planes_or_none(W: torch.Tensor, rows: int):
+    """(hi, lo) plane TENSORS (the caller keeps them alive until its launch is enqueued) or (None, None)."""
     sp = split_weight(W, rows)
-    return (None, None) if sp is None else (_p(sp[0]), _p(sp[1]))
+    return (None, None) if sp is None else sp
 
 
 def linear_epilogue(x, W, b=None, residual=None, gamma=None, beta=None, relu: bool = False, eps: float = 1e-5):
@@ -1083,9 +590,9 @@ def linear_epilogue(x, W, b=None, residual=None, gamma=None, beta=None, relu: bo
     ln = gamma is not None
     ws_bytes = _lib.lib().poet_linear_epilogue_workspace_bytes(R, N, K, int(ln))
     ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8) if ws_bytes else None
-    hi, lo = _plane_ptrs(W, R)
+    hi, lo = _planes_or_none(W, R)
     r2 = None if residual is None else _chk(residual).view(R, N)
-    _call("poet_linear_epilogue", _p(x2), x2.stride(0), _p(W), hi, lo, _p(b), _p(r2), _p(gamma), _p(beta), _p(y), R, N, K,
+    _call("poet_linear_epilogue", _p(x2), x2.stride(0), _p(W), _p(hi), _p(lo), _p(b), _p(r2), _p(gamma), _p(beta), _p(y), R, N, K,
           1 if relu else 0, eps, _state["precision"], _p(ws), ws_bytes, _stream(x))
     return y.view(*x.shape[:-1], N)
 
@@ -1100,9 +607,9 @@ def ffn_fused(x, W1, b1, W2, b2, gamma, beta, eps: float = 1e-5):
     y = torch.empty_like(x2)
     ws_bytes = _lib.lib().poet_ffn_fused_workspace_bytes(R, Cc, F)
     ws = torch.empty(ws_bytes, device=x.device, dtype=torch.uint8)
-    h1, l1 = _plane_ptrs(W1, R)
-    h2, l2 = _plane_ptrs(W2, R)
-    _call("poet_ffn_fused", _p(x2), _p(W1), h1, l1, _p(b1), _p(W2), h2, l2, _p(b2), _p(gamma), _p(beta), _p(y), R, Cc, F, eps,
+    h1, l1 = _planes_or_none(W1, R)
+    h2, l2 = _planes_or_none(W2, R)
+    _call("poet_ffn_fused", _p(x2), _p(W1), _p(h1), _p(l1), _p(b1), _p(W2), _p(h2), _p(l2), _p(b2), _p(gamma), _p(beta), _p(y), R, Cc, F, eps,
           _state["precision"], _p(ws), ws_bytes, _stream(x))
     _state["launches"] += 2                       # three kernels behind the one call
     return y.view(x.shape)

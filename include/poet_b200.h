@@ -183,12 +183,13 @@ int poet_add_layernorm_fwd(const float* x, const float* r, const float* gamma, c
                            const float* pos, float* y, float* y2, float* xhat, float* rstd,
                            int R, int C, float eps, const void* drop_seed, uint32_t drop_site, float drop_p,
                            poet_stream_t stream);
-/* dz = LN backward of (dy [+ dy2]) = gradient of x; dgamma/dbeta [C] are ACCUMULATED into (caller zero-fills).
+/* dz = LN backward of (dy [+ dy2] [+ dy3] [+ dy4]) = gradient of x (dy2..dy4 nullable: the gradients of the other readers
+ * of y -- y + pos, the value input, the next residual -- summed in registers instead of by accumulation kernels); dgamma/dbeta [C] are ACCUMULATED into (caller zero-fills).
  * With drop_p > 0 the gradient of the dropped branch r is written to dr [R,C] (= dz * mask / (1-p)); without
  * dropout it equals dz and dr may be NULL.  dr_colsum [C] (nullable) is ACCUMULATED with the column sums of the
  * residual branch's gradient: the bias gradient of the nn.Linear that produced r (reference linear2 / output_proj /
  * out_proj in front of norm2 / norm1, deformable_transformer.py:196-197,203-204,280-281,286-287). */
-int poet_layernorm_bwd(const float* dy, const float* dy2, const float* xhat, const float* rstd,
+int poet_layernorm_bwd(const float* dy, const float* dy2, const float* dy3, const float* dy4, const float* xhat, const float* rstd,
                        const float* gamma, float* dz, float* dgamma, float* dbeta,
                        int R, int C, float* dr, float* dr_colsum, const void* drop_seed, uint32_t drop_site, float drop_p,
                        poet_stream_t stream);

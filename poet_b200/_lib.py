@@ -44,7 +44,7 @@ SIGNATURES = {
     "poet_colsum": (_i, [_vp, _i64, _vp, _i, _i, _i, _vp]),
     "poet_mask_rows": (_i, [_vp, _vp, _i, _i, _vp]),
     "poet_add_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp, _u32, _f, _vp]),
-    "poet_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _u32, _f, _vp]),
+    "poet_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _u32, _f, _vp]),
     "poet_add": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "poet_mha_smallq_fwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _f, _vp, _u32, _f, _vp]),
     "poet_mha_smallq_bwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64,

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float* __restrict
 // dgamma += sum_rows dy * xhat, dbeta += sum_rows dy  (per-warp register partials -> smem -> atomics)
 template <int NV, bool COLSUM>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2,
+                                                     const float* __restrict__ dy3, const float* __restrict__ dy4,
                                                      const float* __restrict__ xhat, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, float* __restrict__ dz,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int R,
@@ -101,6 +102,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
     for (int i = 0; i < NV; ++i) {
       d[i] = ld4(dy + base + i * 128);
       if (dy2) { float4 t = ld4(dy2 + base + i * 128); d[i].x += t.x; d[i].y += t.y; d[i].z += t.z; d[i].w += t.w; }
+      // further consumers of y (a tensor read by several ops): their gradients are summed here, in registers, instead of
+      // by accumulation kernels between the backward kernels of the decoder's dependent chain
+      if (dy3) { float4 t = ld4(dy3 + base + i * 128); d[i].x += t.x; d[i].y += t.y; d[i].z += t.z; d[i].w += t.w; }
+      if (dy4) { float4 t = ld4(dy4 + base + i * 128); d[i].x += t.x; d[i].y += t.y; d[i].z += t.z; d[i].w += t.w; }
       h[i] = ld4(xhat + base + i * 128);
       pg[i].x += d[i].x * h[i].x; pg[i].y += d[i].y * h[i].y; pg[i].z += d[i].z * h[i].z; pg[i].w += d[i].w * h[i].w;
       pb[i].x += d[i].x; pb[i].y += d[i].y; pb[i].z += d[i].z; pb[i].w += d[i].w;
@@ -249,7 +254,7 @@ extern "C" int poet_add_layernorm_fwd(const float* x, const float* r, const floa
   return poet_launch_status();
 }
 
-extern "C" int poet_layernorm_bwd(const float* dy, const float* dy2, const float* xhat, const float* rstd,
+extern "C" int poet_layernorm_bwd(const float* dy, const float* dy2, const float* dy3, const float* dy4, const float* xhat, const float* rstd,
                                   const float* gamma, float* dz, float* dgamma, float* dbeta, int R, int C,
                                   float* dr, float* dr_colsum, const void* drop_seed, uint32_t drop_site, float drop_p,
                                   poet_stream_t stream) {
@@ -259,19 +264,19 @@ extern "C" int poet_layernorm_bwd(const float* dy, const float* dy2, const float
   const PoetDropout drop = poet_make_dropout(drop_seed, drop_site, drop_p);
   POET_REQUIRE(R > 0 && C % 128 == 0 && C <= 1024, POET_ERR_BAD_SHAPE);
   POET_REQUIRE(poet_aligned16(dy) && poet_aligned16(xhat) && poet_aligned16(dz) && poet_aligned16(gamma) &&
-               (!dy2 || poet_aligned16(dy2)), POET_ERR_BAD_ALIGNMENT);
+               (!dy2 || poet_aligned16(dy2)) && (!dy3 || poet_aligned16(dy3)) && (!dy4 || poet_aligned16(dy4)), POET_ERR_BAD_ALIGNMENT);
   cudaStream_t s = (cudaStream_t)stream;
   int grid = row_grid(R);
   if (grid > POET_NUM_SMS * 2) grid = POET_NUM_SMS * 2;   // fewer blocks -> fewer global atomics on dgamma/dbeta
   switch (C / 128) {
-    case 1: if (dr_colsum) poet_launch(ln_bwd_kernel<1, true>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop);
-            else poet_launch(ln_bwd_kernel<1, false>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); break;
-    case 2: if (dr_colsum) poet_launch(ln_bwd_kernel<2, true>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop);
-            else poet_launch(ln_bwd_kernel<2, false>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); break;
-    case 4: if (dr_colsum) poet_launch(ln_bwd_kernel<4, true>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop);
-            else poet_launch(ln_bwd_kernel<4, false>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); break;
-    case 8: if (dr_colsum) poet_launch(ln_bwd_kernel<8, true>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop);
-            else poet_launch(ln_bwd_kernel<8, false>, dim3(grid), dim3(256), 0, s, dy, dy2, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); break;
+    case 1: if (dr_colsum) poet_launch(ln_bwd_kernel<1, true>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop);
+            else poet_launch(ln_bwd_kernel<1, false>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); break;
+    case 2: if (dr_colsum) poet_launch(ln_bwd_kernel<2, true>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop);
+            else poet_launch(ln_bwd_kernel<2, false>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); break;
+    case 4: if (dr_colsum) poet_launch(ln_bwd_kernel<4, true>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop);
+            else poet_launch(ln_bwd_kernel<4, false>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); break;
+    case 8: if (dr_colsum) poet_launch(ln_bwd_kernel<8, true>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop);
+            else poet_launch(ln_bwd_kernel<8, false>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); break;
     default: return POET_ERR_UNSUPPORTED;
   }
   return poet_launch_status();

@@ -158,28 +158,48 @@ class DeformableTransformerDecoderLayer(nn.Module):
         self.norm3 = nn.LayerNorm(d_model)
 
     def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index,
-                src_padding_mask=None, value=None):
+                src_padding_mask=None, value=None, handles=None, fan_out: int = 0, emit_next_query: bool = False):
+        """Reference signature plus optional arguments used by our decoder stack:
+        `handles` = (q, tgt_v, tgt_res): the layer input as separate autograd handles for its three readers -- the
+        self-attention query/key input (ALREADY tgt + query_pos), the value input and the residual of norm2 -- so that their
+        gradients reach the producing LayerNorm backward as separate pointers instead of through accumulation kernels;
+        `fan_out` / `emit_next_query`: return (out, q_next, alias_1 .. alias_fan_out) with q_next = out + query_pos (or None)
+        produced by the last LayerNorm kernel."""
         p, sb = _p_drop(self), self.site_base
         if tgt.shape[1] > 32:
             raise NotImplementedError("decoder self-attention kernel supports at most 32 object queries")
-        q = tgt if query_pos is None else ops.add_tensors(tgt, query_pos)
-        sa = self.self_attn(q, tgt, drop_site=sb + _SITE_ATTN_PROB, out_bias_grad_elsewhere=True)   # MHA(dropout=p)
+        if handles is None:
+            q = tgt if query_pos is None else ops.add_tensors(tgt, query_pos)
+            tgt_v = tgt_res = tgt
+        else:
+            q, tgt_v, tgt_res = handles
+        sa = self.self_attn(q, tgt_v, drop_site=sb + _SITE_ATTN_PROB, out_bias_grad_elsewhere=True)   # MHA(dropout=p)
         ob = self.self_attn.out_proj.bias
         if query_pos is not None:
-            tgt, q2 = ops.add_layernorm(tgt, sa, self.norm2.weight, self.norm2.bias, pos=query_pos, eps=self.norm2.eps,
+            tgt, q2 = ops.add_layernorm(tgt_res, sa, self.norm2.weight, self.norm2.bias, pos=query_pos, eps=self.norm2.eps,
                                         drop_p=p, drop_site=sb + _SITE_D2, r_bias=ob)                # dropout2
         else:
-            tgt = ops.add_layernorm(tgt, sa, self.norm2.weight, self.norm2.bias, eps=self.norm2.eps,
+            tgt = ops.add_layernorm(tgt_res, sa, self.norm2.weight, self.norm2.bias, eps=self.norm2.eps,
                                     drop_p=p, drop_site=sb + _SITE_D2, r_bias=ob)
             q2 = tgt
         ca = self.cross_attn(q2, reference_points, src, src_spatial_shapes, level_start_index, src_padding_mask,
                              value=value, output_bias_grad_elsewhere=True)
-        tgt = ops.add_layernorm(tgt, ca, self.norm1.weight, self.norm1.bias, eps=self.norm1.eps,
-                                drop_p=p, drop_site=sb + _SITE_D1, r_bias=self.cross_attn.output_proj.bias)  # dropout1
+        # norm1's result has two readers (linear1 and the residual of norm3): two handles, gradients summed in norm1's backward
+        tgt, tgt_mlp = ops.add_layernorm(tgt, ca, self.norm1.weight, self.norm1.bias, eps=self.norm1.eps,
+                                         drop_p=p, drop_site=sb + _SITE_D1, r_bias=self.cross_attn.output_proj.bias,
+                                         n_alias=1)                                                   # dropout1
         # linear1 / relu / dropout3 / linear2 / dropout4 / norm3 as one autograd node
-        return ops.ffn_block(tgt, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
-                             self.norm3.weight, self.norm3.bias, eps=self.norm3.eps, drop_p=p,
-                             site_hidden=sb + _SITE_HIDDEN, site_res=sb + _SITE_D4)
+        want_q = emit_next_query and query_pos is not None
+        res = ops.ffn_block(tgt, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
+                            self.norm3.weight, self.norm3.bias, eps=self.norm3.eps, drop_p=p,
+                            site_hidden=sb + _SITE_HIDDEN, site_res=sb + _SITE_D4, x_mlp=tgt_mlp,
+                            pos=query_pos if want_q else None, n_alias=fan_out)
+        if handles is None and fan_out == 0 and not emit_next_query:
+            return res
+        res = res if isinstance(res, tuple) else (res,)
+        out = res[0]
+        q_next = res[1] if want_q else None
+        return (out, q_next) + tuple(res[2 if want_q else 1:])
 
 
 class DeformableTransformerDecoder(nn.Module):
@@ -214,11 +234,24 @@ class DeformableTransformerDecoder(nn.Module):
                     values[i] = layer.cross_attn.project_value(src, src_padding_mask)
                     marks.append(forked.checkpoint())
         out, inter, inter_ref = tgt, [], []
+        # the output of layer i is read by the pose heads / the intermediate stack (main handle), and by layer i+1 three
+        # times (query = out + query_pos from the LayerNorm kernel itself, value input, residual): one autograd handle per
+        # reader, so the backward has no accumulation kernels between the layers
+        handles = None
+        n_layers = len(self.layers)
         for i, layer in enumerate(self.layers):
             if forked is not None:
                 forked.wait(marks[i], values[i])
-            out = layer(out, query_pos, ref_in, src, src_spatial_shapes, src_level_start_index, src_padding_mask,
-                        value=values[i])
+            last = i == n_layers - 1
+            res = layer(out, query_pos, ref_in, src, src_spatial_shapes, src_level_start_index, src_padding_mask,
+                        value=values[i], handles=handles, fan_out=0 if last else 2, emit_next_query=not last)
+            if last:
+                out, handles = (res[0] if isinstance(res, tuple) else res), None
+            else:
+                out, q_next, a_v, a_res = res
+                handles = ((q_next if q_next is not None else a_v), a_v, a_res)
+                if q_next is None:                            # no query_pos: the query input is one more reader of out
+                    handles = (out, a_v, a_res)
             if layer_callback is not None:
                 layer_callback(i, out)
             if self.return_intermediate:

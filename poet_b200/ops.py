@@ -492,7 +492,12 @@ class _AddLayerNorm(torch.autograd.Function):
     """y = LN(x + dropout(r)); optionally also y2 = y + pos (the next layer's query), one pass over HBM."""
 
     @staticmethod
-    def forward(ctx, x, r, gamma, beta, pos, eps, drop_p=0.0, drop_site=0, r_bias=None):
+    def forward(ctx, x, r, gamma, beta, pos, eps, drop_p=0.0, drop_site=0, r_bias=None, n_alias=0):
+        """n_alias > 0: besides y [, y2] the op returns n_alias further autograd handles of y (same storage).  A tensor read
+        by several ops (FFN input + next residual; value input + residual + heads) is handed out as one handle per reader,
+        so that the readers' gradients reach THIS op's backward kernel as separate pointers and are summed there in
+        registers, instead of by accumulation kernels inserted between the kernels of the decoder's dependent chain."""
+        ctx.n_alias = int(n_alias)
         ctx.r_bias = r_bias if (r is not None and r_bias is not None) else None
         if _os.environ.get("POET_LN_RBIAS", "1") == "0":
             ctx.r_bias = None
@@ -514,18 +519,23 @@ class _AddLayerNorm(torch.autograd.Function):
         if need_grad:
             ctx.save_for_backward(xhat, rstd, gamma)
         ctx.has_r, ctx.has_pos, ctx.shape = r is not None, pos is not None, x.shape
+        aliases = tuple(y.view(x.shape) for _ in range(ctx.n_alias))
         if pos is not None:
-            return y.view(x.shape), y2.view(x.shape)
-        return y.view(x.shape)
+            return (y.view(x.shape), y2.view(x.shape)) + aliases
+        return ((y.view(x.shape),) + aliases) if aliases else y.view(x.shape)
 
     @staticmethod
-    def backward(ctx, gy, gy2=None):
+    def backward(ctx, gy, *more):
         xhat, rstd, gamma = ctx.saved_tensors
         R, Cc = xhat.shape
-        gy = None if gy is None else _chk(gy).view(R, Cc)
-        gy2 = None if gy2 is None else _chk(gy2).view(R, Cc)
-        if gy is None:
-            gy, gy2 = gy2, None
+        gy2_out = more[0] if (ctx.has_pos and more) else None            # gradient of y2 = y + pos (also pos's own gradient)
+        gs = [g for g in (gy,) + tuple(more) if g is not None]
+        gs = [_chk(g).view(R, Cc) for g in gs]
+        if not gs:
+            raise RuntimeError("add_layernorm backward without any incoming gradient")
+        while len(gs) > 4:                                                # the kernel takes four gradient pointers
+            gs = gs[:3] + [add(gs[3], gs[4])] + gs[5:]
+        gy, gy2, gy3, gy4 = (gs + [None] * 4)[:4]
         dz = torch.empty_like(xhat)
         g_slot, b_slot = _grad_slot(ctx.gb_params[0]), _grad_slot(ctx.gb_params[1])
         if g_slot is not None and b_slot is not None:            # accumulate straight into gamma.grad / beta.grad
@@ -543,34 +553,37 @@ class _AddLayerNorm(torch.autograd.Function):
             if rb_slot is None:
                 d_rb = torch.zeros(Cc, device=xhat.device, dtype=torch.float32)
             rb_ptr = _p(rb_slot if rb_slot is not None else d_rb)
-        _call("poet_layernorm_bwd", _p(gy), _p(gy2), _p(xhat), _p(rstd), _p(gamma), _p(dz), dg_ptr, db_ptr,
+        _call("poet_layernorm_bwd", _p(gy), _p(gy2), _p(gy3), _p(gy4), _p(xhat), _p(rstd), _p(gamma), _p(dz), dg_ptr, db_ptr,
               R, Cc, _p(dr), rb_ptr, _p(seed), site, drop_p if dr is not None else 0.0, _stream(xhat),
-              work=(4 * R * Cc * (3 + (gy2 is not None) + (dr is not None)) + 4 * R, 10 * R * Cc))   # gy [, gy2], xhat -> dz [, dr]
+              work=(4 * R * Cc * (2 + len(gs) + (dr is not None)) + 4 * R, 10 * R * Cc))   # gradients, xhat -> dz [, dr]
         dz = dz.view(ctx.shape)
         gpos = None
         if ctx.has_pos and ctx.needs_input_grad[4]:
-            gpos = gy2.view(ctx.shape) if gy2 is not None else None
+            gpos = gy2_out.view(ctx.shape) if gy2_out is not None else None
         g_r = None if not ctx.has_r else (dr.view(ctx.shape) if dr is not None else dz)
-        return dz, g_r, dgb[0], dgb[1], gpos, None, None, None, d_rb
+        return dz, g_r, dgb[0], dgb[1], gpos, None, None, None, d_rb, None
 
 
-def add_layernorm(x, r, gamma, beta, pos=None, eps: float = 1e-5, drop_p: float = 0.0, drop_site: int = 0, r_bias=None):
+def add_layernorm(x, r, gamma, beta, pos=None, eps: float = 1e-5, drop_p: float = 0.0, drop_site: int = 0, r_bias=None,
+                  n_alias: int = 0):
     """LN(x + dropout_p(r)) [, + pos]; drop_p > 0 only in training (the residual branch's nn.Dropout).
     r_bias: the bias of the nn.Linear whose output is r, when that Linear was called with bias_grad_elsewhere=True:
-    its gradient (the column sums of r's gradient) is then produced by this op's backward kernel."""
-    return _AddLayerNorm.apply(x, r, gamma, beta, pos, eps, float(drop_p), int(drop_site), r_bias)
+    its gradient (the column sums of r's gradient) is then produced by this op's backward kernel.
+    n_alias: extra autograd handles of y, one per additional reader (returns a tuple: y [, y2], alias_1 .. alias_n)."""
+    return _AddLayerNorm.apply(x, r, gamma, beta, pos, eps, float(drop_p), int(drop_site), r_bias, int(n_alias))
 
 
 def ffn_block(x, W1, b1, W2, b2, gamma, beta, pos=None, eps: float = 1e-5, drop_p: float = 0.0, site_hidden: int = 0,
-              site_res: int = 0):
+              site_res: int = 0, x_mlp=None, n_alias: int = 0):
     """LN(x + dropout(linear2(dropout(relu(linear1(x)))))) [, + pos]: the FFN half of an encoder / decoder layer (reference
     deformable_transformer.py:193-197,205-206 and :267-271,289-290).  The linear2 bias gradient is summed by the LayerNorm
     backward kernel (r_bias) instead of a separate pass over the gradient rows.
     Measured and rejected (profiles/r02_fusion_ab.txt): one autograd node whose linear1 dgrad adds into the LayerNorm
     backward's dz through the beta = 1 TMA-reduce epilogue (no autograd accumulation pass) -- 7.53 vs 7.45 ms/step: the
     26 MB reduce-add store costs more than the 11 us add kernel it replaces."""
-    f = mlp(x, ((W1, b1), (W2, b2)), drop_p=drop_p, drop_site=site_hidden, last_bias_grad_elsewhere=True)
-    return add_layernorm(x, f, gamma, beta, pos=pos, eps=eps, drop_p=drop_p, drop_site=site_res, r_bias=b2)
+    # x_mlp: a second autograd handle of x for the MLP input (x itself feeds the residual), see add_layernorm(n_alias)
+    f = mlp(x if x_mlp is None else x_mlp, ((W1, b1), (W2, b2)), drop_p=drop_p, drop_site=site_hidden, last_bias_grad_elsewhere=True)
+    return add_layernorm(x, f, gamma, beta, pos=pos, eps=eps, drop_p=drop_p, drop_site=site_res, r_bias=b2, n_alias=n_alias)
 
 
 def _planes_or_none(W: torch.Tensor, rows: int):

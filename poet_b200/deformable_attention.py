@@ -75,12 +75,14 @@ class MSDeformAttn(nn.Module):
     def forward(self, query: torch.Tensor, reference_points: torch.Tensor, input_flatten: torch.Tensor,
                 input_spatial_shapes, input_level_start_index=None,
                 input_padding_mask: Optional[torch.Tensor] = None, value: Optional[torch.Tensor] = None,
-                output_bias_grad_elsewhere: bool = False) -> torch.Tensor:
+                output_bias_grad_elsewhere: bool = False, value_grad_buf: Optional[torch.Tensor] = None) -> torch.Tensor:
         """query [N,Lq,C]; reference_points [N,Lq,L,2] in [0,1]; input_flatten [N,S,C];
         input_spatial_shapes [(H_l,W_l)]; input_padding_mask [N,S] True = padded  ->  [N,Lq,C].
         `value` (ours, optional): the result of project_value() computed beforehand.
         `output_bias_grad_elsewhere` (ours): the caller feeds the result to ops.add_layernorm(..., r_bias=output_proj.bias),
-        whose backward kernel produces that bias gradient (no separate pass over the gradient rows)."""
+        whose backward kernel produces that bias gradient (no separate pass over the gradient rows).
+        `value_grad_buf` (ours): zero-filled buffer for the gradient of `value` (ops.grad_value_buffer), filled by the caller
+        next to project_value() so that the backward does not start with a 26 MB zero-fill in its dependent chain."""
         shapes = host_shapes(input_spatial_shapes)
         N, S, _ = input_flatten.shape
         if sum(h * w for h, w in shapes) != S:
@@ -96,15 +98,18 @@ class MSDeformAttn(nn.Module):
                 forked.uses(input_flatten, input_padding_mask)
                 with forked:
                     value = self.project_value(input_flatten, input_padding_mask)
+                    value_grad_buf = ops.grad_value_buffer(value)
                     mark = forked.checkpoint()
             else:
                 value = self.project_value(input_flatten, input_padding_mask)
+                value_grad_buf = ops.grad_value_buffer(value)
         # one projection for [offsets | logits]: the gather kernel reads both out of the same row
         oa = ops.proj_cat(query, self.sampling_offsets.weight, self.sampling_offsets.bias,
                           self.attention_weights.weight, self.attention_weights.bias)
         if forked is not None:
-            forked.wait(mark, value)
-        out = ops.msda_block(value, oa, reference_points, shapes, self.n_heads, self.n_levels, self.n_points)
+            forked.wait(mark, value, value_grad_buf)
+        out = ops.msda_block(value, oa, reference_points, shapes, self.n_heads, self.n_levels, self.n_points,
+                             grad_value_buf=value_grad_buf)
         return ops.linear(out, self.output_proj.weight, self.output_proj.bias, bias_grad_elsewhere=output_bias_grad_elsewhere)
 
 

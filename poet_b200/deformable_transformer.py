@@ -158,7 +158,8 @@ class DeformableTransformerDecoderLayer(nn.Module):
         self.norm3 = nn.LayerNorm(d_model)
 
     def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index,
-                src_padding_mask=None, value=None, handles=None, fan_out: int = 0, emit_next_query: bool = False):
+                src_padding_mask=None, value=None, handles=None, fan_out: int = 0, emit_next_query: bool = False,
+                value_grad_buf=None):
         """Reference signature plus optional arguments used by our decoder stack:
         `handles` = (q, tgt_v, tgt_res): the layer input as separate autograd handles for its three readers -- the
         self-attention query/key input (ALREADY tgt + query_pos), the value input and the residual of norm2 -- so that their
@@ -183,7 +184,7 @@ class DeformableTransformerDecoderLayer(nn.Module):
                                     drop_p=p, drop_site=sb + _SITE_D2, r_bias=ob)
             q2 = tgt
         ca = self.cross_attn(q2, reference_points, src, src_spatial_shapes, level_start_index, src_padding_mask,
-                             value=value, output_bias_grad_elsewhere=True)
+                             value=value, output_bias_grad_elsewhere=True, value_grad_buf=value_grad_buf)
         # norm1's result has two readers (linear1 and the residual of norm3): two handles, gradients summed in norm1's backward
         tgt, tgt_mlp = ops.add_layernorm(tgt, ca, self.norm1.weight, self.norm1.bias, eps=self.norm1.eps,
                                          drop_p=p, drop_site=sb + _SITE_D1, r_bias=self.cross_attn.output_proj.bias,
@@ -225,6 +226,7 @@ class DeformableTransformerDecoder(nn.Module):
         # side stream, so these large GEMMs (and their dgrad/wgrad in backward) overlap the launch-bound
         # self-attention / FFN chain of the queries instead of sitting on its critical path
         values = [None] * len(self.layers)
+        gv_bufs = [None] * len(self.layers)
         forked, marks = None, []
         if ops.parallel_streams_enabled() and src.is_cuda:
             forked = ops.fork(0, src.device)
@@ -232,6 +234,7 @@ class DeformableTransformerDecoder(nn.Module):
             with forked, ops.precision_scope(self.value_gemm_precision):
                 for i, layer in enumerate(self.layers):
                     values[i] = layer.cross_attn.project_value(src, src_padding_mask)
+                    gv_bufs[i] = ops.grad_value_buffer(values[i])       # zero-filled here, off the backward's dependent chain
                     marks.append(forked.checkpoint())
         out, inter, inter_ref = tgt, [], []
         # the output of layer i is read by the pose heads / the intermediate stack (main handle), and by layer i+1 three
@@ -241,10 +244,11 @@ class DeformableTransformerDecoder(nn.Module):
         n_layers = len(self.layers)
         for i, layer in enumerate(self.layers):
             if forked is not None:
-                forked.wait(marks[i], values[i])
+                forked.wait(marks[i], values[i], gv_bufs[i])
             last = i == n_layers - 1
             res = layer(out, query_pos, ref_in, src, src_spatial_shapes, src_level_start_index, src_padding_mask,
-                        value=values[i], handles=handles, fan_out=0 if last else 2, emit_next_query=not last)
+                        value=values[i], handles=handles, fan_out=0 if last else 2, emit_next_query=not last,
+                        value_grad_buf=gv_bufs[i])
             if last:
                 out, handles = (res[0] if isinstance(res, tuple) else res), None
             else:

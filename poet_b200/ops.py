@@ -687,8 +687,12 @@ class _MsdaBlock(torch.autograd.Function):
     softmax and loc = ref + off/(W,H) happen inside the gather kernel."""
 
     @staticmethod
-    def forward(ctx, value, oa, ref, shapes, M, L, P):
+    def forward(ctx, value, oa, ref, shapes, M, L, P, gv_buf=None):
+        """gv_buf (optional): a zero-filled tensor shaped like `value` that the backward accumulates grad_value into and
+        returns; the caller fills it in the forward pass on a side stream, which takes the 26 MB zero-fill out of the
+        backward's dependent chain."""
         value, oa, ref = _chk(value), _chk(oa), _chk(ref)
+        ctx.gv_buf = gv_buf if (gv_buf is not None and gv_buf.shape == value.shape and gv_buf.is_contiguous()) else None
         B, S, Cc = value.shape
         Lq = oa.shape[1]
         D = Cc // M
@@ -705,16 +709,23 @@ class _MsdaBlock(torch.autograd.Function):
         value, oa, ref = ctx.saved_tensors
         B, S, Lq, M, D, L, P, n_off, ld = ctx.dims
         go = _chk(go)
-        gv = torch.zeros_like(value)
+        gv, ctx.gv_buf = (ctx.gv_buf, None) if ctx.gv_buf is not None else (torch.zeros_like(value), None)   # single use: a second backward re-zeros
         goa = torch.empty_like(oa)
         _call("poet_msda_bwd", _p(value), _p(oa), ld, _p(oa.view(-1)[n_off:]), ld, _p(ref), _p(go), _p(gv), _p(goa),
               _p(goa.view(-1)[n_off:]), shapes_array(ctx.shapes), B, S, Lq, M, D, L, P, 1, _stream(value),
               tag=f"Lq={Lq}", work=(4 * B * (2 * S * M * D + 6 * Lq * M * L * P + Lq * M * D), 30 * B * Lq * M * D * L * P))
-        return gv, goa, None, None, None, None, None
+        return gv, goa, None, None, None, None, None, None
 
 
-def msda_block(value, oa, ref, shapes, M, L, P):
-    return _MsdaBlock.apply(value, oa, ref, tuple(tuple(s) for s in shapes), M, L, P)
+def msda_block(value, oa, ref, shapes, M, L, P, grad_value_buf=None):
+    return _MsdaBlock.apply(value, oa, ref, tuple(tuple(s) for s in shapes), M, L, P, grad_value_buf)
+
+
+def grad_value_buffer(value: torch.Tensor) -> Optional[torch.Tensor]:
+    """Zero-filled grad_value buffer for msda_block(grad_value_buf=...), or None when no gradient will be asked for."""
+    if not (torch.is_grad_enabled() and value.requires_grad):
+        return None
+    return torch.zeros_like(value)
 
 
 # ------------------------------------------------------------------------------------------

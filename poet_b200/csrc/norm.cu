@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float* __restrict
 
 // dz = rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat)),  dxh = dy * gamma
 // dgamma += sum_rows dy * xhat, dbeta += sum_rows dy  (per-warp register partials -> smem -> atomics)
-template <int NV, bool COLSUM>
+template <int NV, bool COLSUM, bool MANY>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ dy2,
                                                      const float* __restrict__ dy3, const float* __restrict__ dy4,
                                                      const float* __restrict__ xhat, const float* __restrict__ rstd,
@@ -104,8 +104,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
       if (dy2) { float4 t = ld4(dy2 + base + i * 128); d[i].x += t.x; d[i].y += t.y; d[i].z += t.z; d[i].w += t.w; }
       // further consumers of y (a tensor read by several ops): their gradients are summed here, in registers, instead of
       // by accumulation kernels between the backward kernels of the decoder's dependent chain
-      if (dy3) { float4 t = ld4(dy3 + base + i * 128); d[i].x += t.x; d[i].y += t.y; d[i].z += t.z; d[i].w += t.w; }
-      if (dy4) { float4 t = ld4(dy4 + base + i * 128); d[i].x += t.x; d[i].y += t.y; d[i].z += t.z; d[i].w += t.w; }
+      if (MANY && dy3) { float4 t = ld4(dy3 + base + i * 128); d[i].x += t.x; d[i].y += t.y; d[i].z += t.z; d[i].w += t.w; }
+      if (MANY && dy4) { float4 t = ld4(dy4 + base + i * 128); d[i].x += t.x; d[i].y += t.y; d[i].z += t.z; d[i].w += t.w; }
       h[i] = ld4(xhat + base + i * 128);
       pg[i].x += d[i].x * h[i].x; pg[i].y += d[i].y * h[i].y; pg[i].z += d[i].z * h[i].z; pg[i].w += d[i].w * h[i].w;
       pb[i].x += d[i].x; pb[i].y += d[i].y; pb[i].z += d[i].z; pb[i].w += d[i].w;
@@ -268,17 +268,25 @@ extern "C" int poet_layernorm_bwd(const float* dy, const float* dy2, const float
   cudaStream_t s = (cudaStream_t)stream;
   int grid = row_grid(R);
   if (grid > POET_NUM_SMS * 2) grid = POET_NUM_SMS * 2;   // fewer blocks -> fewer global atomics on dgamma/dbeta
+  const bool many = dy3 != nullptr || dy4 != nullptr;       // the two-pointer instantiation keeps the encoder's 26 MB passes at their old speed
+#define POET_LN_BWD(NVV)                                                                                                      \
+  do {                                                                                                                          \
+    if (many) {                                                                                                                 \
+      if (dr_colsum) poet_launch(ln_bwd_kernel<NVV, true, true>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); \
+      else poet_launch(ln_bwd_kernel<NVV, false, true>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); \
+    } else {                                                                                                                    \
+      if (dr_colsum) poet_launch(ln_bwd_kernel<NVV, true, false>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); \
+      else poet_launch(ln_bwd_kernel<NVV, false, false>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); \
+    }                                                                                                                           \
+  } while (0)
   switch (C / 128) {
-    case 1: if (dr_colsum) poet_launch(ln_bwd_kernel<1, true>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop);
-            else poet_launch(ln_bwd_kernel<1, false>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); break;
-    case 2: if (dr_colsum) poet_launch(ln_bwd_kernel<2, true>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop);
-            else poet_launch(ln_bwd_kernel<2, false>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); break;
-    case 4: if (dr_colsum) poet_launch(ln_bwd_kernel<4, true>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop);
-            else poet_launch(ln_bwd_kernel<4, false>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); break;
-    case 8: if (dr_colsum) poet_launch(ln_bwd_kernel<8, true>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop);
-            else poet_launch(ln_bwd_kernel<8, false>, dim3(grid), dim3(256), 0, s, dy, dy2, dy3, dy4, xhat, rstd, gamma, dz, dgamma, dbeta, R, dr, dr_colsum, drop); break;
+    case 1: POET_LN_BWD(1); break;
+    case 2: POET_LN_BWD(2); break;
+    case 4: POET_LN_BWD(4); break;
+    case 8: POET_LN_BWD(8); break;
     default: return POET_ERR_UNSUPPORTED;
   }
+#undef POET_LN_BWD
   return poet_launch_status();
 }
 

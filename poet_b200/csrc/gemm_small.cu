@@ -12,6 +12,10 @@
 //   * exact fp32 FFMA (these rows carry the 1e-4 translation budget; no operand splitting needed at this size),
 //     weights either as fp32 or as the bf16 hi/lo planes of the step's arena (hi + lo, the same 2^-17 operand);
 //   * the epilogues of poet_gemm: alpha, bias, ReLU, ReLU gate, beta = 1 accumulation, bias-gradient column sums.
+//   * deep reductions (K >= 512: linear2 forward, linear1 / sampling-offset dgrad) are split over a thread-block
+//     CLUSTER of 2-4 CTAs along K: each CTA has its whole k range in flight after one L2 round trip (as in the K = 256
+//     case), the partial tiles meet in the first CTA's epilogue through distributed shared memory -- no workspace, no
+//     zero-fill, no atomics;
 // All four operand layouts (forward NT, dgrad NN, wgrad TN) are template variants of the shared-memory fetch.
 #include <cuda_bf16.h>
 #include "common.cuh"
@@ -40,6 +44,7 @@ struct Args {
   float* a_colsum;
   int flags;
   int stages;
+  int ksplit;                                        // CTAs of a cluster (grid z) that share one output tile's reduction
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
@@ -153,7 +158,10 @@ __global__ void __launch_bounds__(THREADS) gemm_small_kernel(const Args p) {
   const int tid = threadIdx.x;
   const int kg = tid >> 6, t64 = tid & 63, tx = t64 & 7, ty = t64 >> 3;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int n_stage = (p.K + BKS - 1) / BKS;
+  const int n_stage_all = (p.K + BKS - 1) / BKS;
+  // cluster split-K: CTA z of the cluster owns stages [s_beg, s_end) of the reduction (ksplit == 1: all of them)
+  const int spp = (n_stage_all + p.ksplit - 1) / p.ksplit;
+  const int s_beg = (int)blockIdx.z * spp, n_stage = min(n_stage_all, s_beg + spp);
   const bool do_colsum = !AK && p.a_colsum != nullptr && blockIdx.x == 0;
 
   auto stage_ptr = [&](int s, int which) { return sm + ((size_t)(s % p.stages) * 2 + which) * TILE_FLOATS; };
@@ -179,7 +187,7 @@ __global__ void __launch_bounds__(THREADS) gemm_small_kernel(const Args p) {
   // overlaps that kernel's tail.  The early requests join the first committed group, which stage 0 waits for anyway.
   const bool b_early = (p.flags & POET_GEMM_B_STABLE) != 0;
   if (b_early)
-    for (int s = 0; s < p.stages; ++s) issue_b(s);    // every slot of the ring is free at this point
+    for (int s = s_beg; s < s_beg + p.stages; ++s) issue_b(s);    // every slot of the ring is free at this point
   poet_pdl_wait();
 
   float acc[4][4];
@@ -189,9 +197,9 @@ __global__ void __launch_bounds__(THREADS) gemm_small_kernel(const Args p) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   float csum = 0.f;
 
-  for (int s = 0; s < p.stages - 1; ++s) issue(s, !b_early);    // prologue: every stage of a short K is in flight at once
-  for (int s = 0; s < n_stage; ++s) {
-    issue(s + p.stages - 1, !(b_early && s == 0));
+  for (int s = s_beg; s < s_beg + p.stages - 1; ++s) issue(s, !b_early);    // prologue: every stage of a short K is in flight at once
+  for (int s = s_beg; s < n_stage; ++s) {
+    issue(s + p.stages - 1, !(b_early && s == s_beg));
     if (p.stages == 3) cp_async_wait<2>(); else if (p.stages == 2) cp_async_wait<1>(); else cp_async_wait<0>();
     __syncthreads();
     const float* as = stage_ptr(s, 0);
@@ -236,15 +244,36 @@ __global__ void __launch_bounds__(THREADS) gemm_small_kernel(const Args p) {
   const int m = tid >> 3, nq = (tid & 7) * 4;
   const int gm = m0 + m, gn = n0 + nq;
   if (do_colsum && tid < BM && m0 + tid < p.M) atomicAdd(p.a_colsum + m0 + tid, csum);
-  if (gm >= p.M || gn >= p.N) return;
   float v[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     float x = 0.f;
 #pragma unroll
     for (int g = 0; g < KG; ++g) x += red[(g * BM + m) * (BN + 1) + nq + j];
-    v[j] = p.alpha * x;
+    v[j] = x;
   }
+  if (p.ksplit > 1) {
+    // the partial tiles of the cluster's CTAs meet in CTA 0: each CTA publishes its folded tile in its own shared memory
+    // (behind the k-group partials), CTA 0 reads the others' through the distributed-shared-memory window
+    float* part = sm + KG * BM * (BN + 1);             // [32][36] floats
+    *reinterpret_cast<float4*>(part + m * 36 + nq) = make_float4(v[0], v[1], v[2], v[3]);
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (blockIdx.z == 0) {
+      const uint32_t local = (uint32_t)__cvta_generic_to_shared(part + m * 36 + nq);
+      for (int r = 1; r < p.ksplit; ++r) {
+        uint32_t remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+        float4 t;
+        asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(remote));
+        v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+      }
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");   // remote tiles stay alive until read
+    if (blockIdx.z != 0) return;
+  }
+  if (gm >= p.M || gn >= p.N) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] *= p.alpha;
   const bool relu = p.flags & POET_GEMM_RELU, accum = p.flags & POET_GEMM_ACCUMULATE;
   float* cp = p.C + (int64_t)gm * p.ldc + gn;
   const float* gp = p.gate ? p.gate + (int64_t)gm * p.ldc + gn : nullptr;
@@ -272,11 +301,26 @@ __global__ void __launch_bounds__(THREADS) gemm_small_kernel(const Args p) {
 
 template <bool AK, bool BK_, bool PLANES>
 static int launch(const Args& a, cudaStream_t s) {
-  const size_t smem = (size_t)a.stages * 2 * TILE_FLOATS * sizeof(float);
+  size_t smem = (size_t)a.stages * 2 * TILE_FLOATS * sizeof(float);
+  const size_t epi = (size_t)(KG * BM * (BN + 1) + BM * 36) * sizeof(float);      // k-group partials + the cluster's tile
+  if (smem < epi) smem = epi;
   auto kern = gemm_small_kernel<AK, BK_, PLANES>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  poet_launch(kern, dim3(poet_ceil_div(a.N, BN), poet_ceil_div(a.M, BM)), dim3(THREADS), smem, s, a);
+  const dim3 grid(poet_ceil_div(a.N, BN), poet_ceil_div(a.M, BM), a.ksplit);
+  if (a.ksplit == 1) {
+    poet_launch(kern, grid, dim3(THREADS), smem, s, a);
+    return poet_launch_status();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = poet_pdl_enabled() ? 1 : 0;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = 1; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = a.ksplit;
+  cfg.attrs = attr; cfg.numAttrs = 2;
+  (void)cudaLaunchKernelEx(&cfg, kern, a);
   return poet_launch_status();
 }
 
@@ -311,7 +355,14 @@ int poet_gemm_small(const float* A, int64_t lda, int a_kcontig, const float* Bm,
   a.A = A; a.lda = lda; a.B = Bm; a.Bhi = reinterpret_cast<const __nv_bfloat16*>(b_hi);
   a.Blo = reinterpret_cast<const __nv_bfloat16*>(b_lo); a.ldb = ldb; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
   a.alpha = alpha; a.bias = bias; a.gate = gate; a.a_colsum = a_colsum; a.flags = flags;
-  const int n_stage = poet_ceil_div(K, small::BKS);
+  const int n_stage_all = poet_ceil_div(K, small::BKS);
+  // deep reductions over few output tiles: a cluster of CTAs along K (POET_GEMM_SMALL_KSPLIT=0 disables)
+  static const int ksplit_on = []() { const char* e = getenv("POET_GEMM_SMALL_KSPLIT"); return e ? atoi(e) : 1; }();
+  const int64_t tiles = (int64_t)poet_ceil_div(M, small::BM) * poet_ceil_div(N, small::BN);
+  a.ksplit = 1;
+  if (ksplit_on && n_stage_all >= 4 && tiles <= 96 && a_colsum == nullptr && !(flags & POET_GEMM_ACCUMULATE))
+    a.ksplit = n_stage_all >= 8 ? 4 : (n_stage_all >= 6 ? 3 : 2);
+  const int n_stage = poet_ceil_div(n_stage_all, a.ksplit);
   a.stages = n_stage < small::MAX_STAGES ? (n_stage < 1 ? 1 : n_stage) : small::MAX_STAGES;
   const bool planes = Bm == nullptr;
 #define POET_SMALL(AKV, BKV)                                                                         \

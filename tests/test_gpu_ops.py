@@ -554,7 +554,8 @@ def test_msda_dense_lowres_backward_path_in_subprocess():
 
 # ------------------------------------------------------------------------------- small-row GEMM (csrc/gemm_small.cu)
 @pytest.mark.parametrize("M,N,K", [(160, 256, 256), (160, 1024, 256), (160, 256, 1024), (160, 768, 256), (400, 132, 256),
-                                   (36, 264, 72), (160, 66, 256)])
+                                   (36, 264, 72), (160, 66, 256),
+                                   (160, 256, 768), (160, 256, 640), (96, 128, 1152)])   # cluster split-K: 3 / 2 (uneven) / 4 CTAs (one idle)
 @pytest.mark.parametrize("a_k,b_k", [(True, True), (True, False), (False, False), (False, True)])
 def test_gemm_small_rows_exact_fp32(M, N, K, a_k, b_k):
     """Decoder / pose-head shapes in the default (bf16x3) precision mode are served by the latency kernel in exact fp32:

@@ -121,7 +121,10 @@ int poet_msda_bwd(const float* value, const float* a, int64_t lda, const float* 
  * stream -- it is a parameter, last written by poet_split_bf16* / poet_adamw_clip_multi (which never let a dependent
  * kernel start early) or by a non-library kernel.  The query-row GEMM kernel then requests its B tiles BEFORE it waits for
  * the preceding kernel (programmatic dependent launch), hiding one L2 round trip of the dependent chain. */
-enum { POET_GEMM_RELU = 1, POET_GEMM_ACCUMULATE = 2, POET_GEMM_B_STABLE = 4 };
+/* POET_GEMM_BACKGROUND: the launch shares the GPU with a chain of latency-bound kernels on another stream; the persistent
+ * tensor-core kernel then occupies fewer SMs (POET_GEMM_BG_SMS, default 116 of 148) so that those kernels are not kept off the
+ * machine for the duration of the GEMM.  Results are unaffected. */
+enum { POET_GEMM_RELU = 1, POET_GEMM_ACCUMULATE = 2, POET_GEMM_B_STABLE = 4, POET_GEMM_BACKGROUND = 8 };
 enum { POET_GEMM_FP32 = 0, POET_GEMM_BF16X3 = 1, POET_GEMM_BF16 = 2 };
 size_t poet_gemm_workspace_bytes(int M, int N, int K, int a_kcontig, int b_kcontig, int precision);
 int poet_gemm(const float* A, int64_t lda, int a_kcontig, const float* Bm, int64_t ldb, int b_kcontig,

@@ -184,6 +184,24 @@ def grad_marker(x: torch.Tensor, key):
     return _GradMarker.apply(x, key)
 
 
+class background_gemms:
+    """with background_gemms(): ... -- the large GEMMs issued inside (and the backward of the ops recorded inside) carry
+    POET_GEMM_BACKGROUND: the persistent tensor-core kernel leaves some SMs free for a latency-bound chain that runs on
+    another stream at the same time (the decoder's value projections of `memory` next to the query-row chain)."""
+
+    def __init__(self, on: bool = True):
+        self.on = bool(on)
+
+    def __enter__(self):
+        self.saved = _state.get("gemm_background", False)
+        _state["gemm_background"] = self.on
+        return self
+
+    def __exit__(self, *exc):
+        _state["gemm_background"] = self.saved
+        return False
+
+
 def launch_count() -> int:
     """Number of libpoet_b200 kernel-launching calls issued so far (bench.py's gpu_launches)."""
     return _state["launches"]

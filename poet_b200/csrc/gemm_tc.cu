@@ -172,6 +172,7 @@ struct Args {
   int tail_shift;                                // log2(tail_slices)
   int fast_k;                                    // K % BK == 0: operand loads need no bounds predicates (Tile::load<true>)
   int tail_start, tail_slices;   // work ids >= tail_start are column slices of the last round's tiles (tail_start = total_work: none)
+  int grid_limit;         // persistent CTAs at most (POET_NUM_SMS, or fewer for POET_GEMM_BACKGROUND launches)
   int l2_prefetch;        // 1: L2 prefetch hints ahead of the register-prefetched operand loads
   int debug;              // POET_GEMM_DEBUG bit flags (pipeline bisection only): 1 no A loads, 2 no A stores, 4 no TMA, 8 no epilogue stores,
                           // 16 no epilogue math (TMA epilogue), 32 no MMA issue (barriers only), 64 no staging-reuse wait, 128 no epilogue proxy fence,
@@ -845,7 +846,7 @@ int launch(Args a, const Maps& m, cudaStream_t s) {
   auto kern = gemm_tc_kernel<BN, BK, A_MN, B_MN, X3, B_TMA, PW, STAGES, EPI>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  const int grid = a.total_work < POET_NUM_SMS ? a.total_work : POET_NUM_SMS;       // persistent: one CTA per SM
+  const int grid = a.total_work < a.grid_limit ? a.total_work : a.grid_limit;       // persistent: one CTA per SM
   poet_launch(kern, dim3(grid), dim3(BLOCK_THREADS), smem, s, a, m.hi, m.lo, m.c);
   return poet_launch_status();
 }
@@ -926,6 +927,12 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
   memset(&a.drop, 0, sizeof(a.drop));
   if (dropping) a.drop = *drop;
   a.l2_prefetch = l2pf; a.debug = dbg;
+  // POET_GEMM_BACKGROUND: this GEMM runs on a side stream next to a chain of latency-bound kernels (the decoder's value
+  // projections of `memory` and their backward).  A persistent CTA per SM with ~200 KB of shared memory would keep every
+  // small kernel of that chain off the machine for the whole GEMM, so a background launch leaves some SMs free.
+  static const int bg_sms = tc::env_int("POET_GEMM_BG_SMS", 116);
+  const int sms = (flags & POET_GEMM_BACKGROUND) ? (bg_sms < 8 ? 8 : (bg_sms > POET_NUM_SMS ? POET_NUM_SMS : bg_sms)) : POET_NUM_SMS;
+  a.grid_limit = sms;
   const int m_tiles = poet_ceil_div(M, tc::BM);
   const int total_kb = poet_ceil_div(K, bk);
   // Tile width: rounds of the persistent grid x work per round.  128-wide tiles quantise better over 148 SMs
@@ -935,7 +942,7 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
     // 256-wide tiles convert each A tile once per 256 output columns; measured on the cfg2 shapes they are never
     // slower than 128-wide ones once there is at least one tile per SM (K=1024: 63 vs 77 us), so the 128-wide
     // tile is kept for small problems only (more CTAs in flight).
-    if ((int64_t)(N / 256) * m_tiles >= POET_NUM_SMS) bn = 256;
+    if ((int64_t)(N / 256) * m_tiles >= sms) bn = 256;
     static const int force_bn = tc::env_int("POET_GEMM_FORCE_BN", 0);
     if (force_bn == 128 || force_bn == 256) bn = force_bn;
   }
@@ -945,8 +952,8 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
   int splits = 1;
   const bool linear_epi = !(flags & POET_GEMM_RELU) && gate == nullptr && gate_bits == nullptr && row_mask == nullptr;
   const int min_kb = 256 / bk;                                                     // at least 256 k per split
-  if (linear_epi && !a_kcontig && tiles < POET_NUM_SMS && total_kb >= 2 * min_kb) {  // weight-gradient shape
-    splits = (int)(POET_NUM_SMS / tiles);
+  if (linear_epi && !a_kcontig && tiles < sms && total_kb >= 2 * min_kb) {  // weight-gradient shape
+    splits = (int)(sms / tiles);
     if (splits > total_kb / min_kb) splits = total_kb / min_kb;
     if (splits < 1) splits = 1;
   }
@@ -959,10 +966,10 @@ int poet_gemm_tc(const float* A, int64_t lda, int a_kcontig, const float* Bm, co
   POET_REQUIRE(a.total_work < (1 << 20), POET_ERR_BAD_SHAPE);
   a.tail_start = a.total_work; a.tail_slices = 1;
   static const int tail_split = tc::env_int("POET_GEMM_TAIL_SPLIT", 1);
-  if (tail_split && a.splits == 1 && !wgrad && a.total_work > POET_NUM_SMS) {
-    const int rem = a.total_work % POET_NUM_SMS;
+  if (tail_split && a.splits == 1 && !wgrad && a.total_work > sms) {
+    const int rem = a.total_work % sms;
     int sl = 1;
-    while (rem > 0 && sl * 2 <= bn / 64 && rem * sl * 2 <= POET_NUM_SMS + POET_NUM_SMS / 4) sl *= 2;
+    while (rem > 0 && sl * 2 <= bn / 64 && rem * sl * 2 <= sms + sms / 4) sl *= 2;
     if (sl > 1) {
       a.tail_start = a.total_work - rem;
       a.tail_slices = sl;

@@ -231,7 +231,7 @@ class DeformableTransformerDecoder(nn.Module):
         if ops.parallel_streams_enabled() and src.is_cuda:
             forked = ops.fork(0, src.device)
             forked.uses(src, src_padding_mask)
-            with forked, ops.precision_scope(self.value_gemm_precision):
+            with forked, ops.precision_scope(self.value_gemm_precision), ops.background_gemms():
                 for i, layer in enumerate(self.layers):
                     values[i] = layer.cross_attn.project_value(src, src_padding_mask)
                     gv_bufs[i] = ops.grad_value_buffer(values[i])       # zero-filled here, off the backward's dependent chain

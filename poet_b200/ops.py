@@ -44,7 +44,8 @@ def gemm(A: torch.Tensor, Bm: torch.Tensor, M: int, N: int, K: int, *, a_kcontig
         if ws_bytes:
             ws = torch.empty(ws_bytes, device=A.device, dtype=torch.uint8)
     # b_stable: B is a parameter (or its planes), not written by the kernels just before this call (POET_GEMM_B_STABLE)
-    flags = (1 if relu else 0) | (2 if accumulate else 0) | (4 if (b_stable and _B_STABLE) else 0)
+    flags = ((1 if relu else 0) | (2 if accumulate else 0) | (4 if (b_stable and _B_STABLE) else 0) |
+             (8 if _state.get("gemm_background") else 0))
     tag = (f"{M}x{N}x{K}" + ("" if a_kcontig else ",At") + ("" if b_kcontig else ",Bt")) if _timing["on"] else None
     work = (4 * (M * K + N * K + M * N), 2 * M * N * K)
     if relu_bits is not None or gate_bits is not None or a_colsum is not None or a_row_mask is not None or drop is not None:
@@ -251,6 +252,7 @@ class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, W, b, row_mask, mask_grad_inplace, bias_grad_elsewhere=False):
         ctx.prec = _state["precision"]
+        ctx.background = bool(_state.get("gemm_background"))
         ctx.mask_grad_inplace = mask_grad_inplace
         ctx.bias_grad_elsewhere = bias_grad_elsewhere
         x2 = _chk(x).view(-1, x.shape[-1])
@@ -268,7 +270,7 @@ class _Linear(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        with precision_scope(ctx.prec):
+        with precision_scope(ctx.prec), background_gemms(ctx.background):
             return _Linear._backward_impl(ctx, *grads)
 
     @staticmethod

@@ -1425,6 +1425,8 @@ static int try_tile_bwd(const MsdaArgs& a, int mode, cudaStream_t s) {
     const double cost = rounds * (tpc + 0.5);
     if (cost < best_cost) { best_cost = cost; best = nc; }
   }
+  static const int force_nc = []() { const char* e = getenv("POET_MSDA_TILE_NCHUNK"); return e ? atoi(e) : 0; }();   // A/B only
+  if (force_nc > 0 && force_nc <= n_tiles) best = force_nc;
   const int nchunk = best, tiles_per_chunk = poet_ceil_div(n_tiles, nchunk);
   const int64_t grid = (int64_t)a.B * a.M * nchunk;
   if (grid >= ((int64_t)1 << 31)) return POET_ERR_UNSUPPORTED;

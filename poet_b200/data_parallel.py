@@ -122,6 +122,11 @@ class FlatGradReducer:
         self._ready = {("decoder", 0): segs.get(("heads",))}
         for i in range(n_enc):
             self._ready[("encoder", i)] = segs.get(("decoder",)) if i == n_enc - 1 else segs.get(("encoder", i + 1))
+        import os
+        if os.environ.get("POET_OVERLAP_COARSE", "0") != "0":
+            # one early collective only: the decoder's segment as soon as the last encoder layer's marker fires (its
+            # all-reduce then runs next to the whole encoder backward); everything else in finish()
+            self._ready = {("encoder", n_enc - 1): segs.get(("decoder",))}
         self._overlap = True
         self._comm_stream = None
         self._works, self._done = [], []

@@ -193,6 +193,38 @@ def test_msda_full_size_properties():
     assert float((out - torch.arange(1, M + 1, device=DEV).view(1, 1, M, 1)).abs().max()) < 1e-4
 
 
+@pytest.mark.parametrize("R,n_alias,with_pos", [(160, 1, False), (160, 2, True), (3200, 3, True), (160, 4, True)])
+def test_add_layernorm_reader_handles(R, n_alias, with_pos):
+    """One autograd handle per reader of a LayerNorm result (add_layernorm(n_alias=...)): the readers' gradients reach
+    poet_layernorm_bwd as separate pointers (up to four; more are pre-added) and must sum to what autograd's own
+    accumulation gives for a tensor that is read n_alias + 1 times."""
+    o = ops()
+    C = 256
+    g = torch.Generator().manual_seed(R + 7 * n_alias)
+    x, r, pos = (torch.randn(R, C, generator=g) for _ in range(3))
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    cots = [torch.randn(R, C, generator=g) for _ in range(n_alias + 2)]
+
+    xs, rs, ga, be = (t.double().requires_grad_(True) for t in (x, r, gamma, beta))
+    y = torch.nn.functional.layer_norm(xs + rs, (C,), ga, be, 1e-5)
+    loss = sum((y * c.double()).sum() for c in cots[:n_alias + 1])
+    if with_pos:
+        loss = loss + ((y + pos.double()) * cots[-1].double()).sum()
+    loss.backward()
+    ref = [xs.grad, rs.grad, ga.grad, be.grad]
+
+    xd, rd, gd, bd = (t.to(DEV).requires_grad_(True) for t in (x, r, gamma, beta))
+    res = o.add_layernorm(xd, rd, gd, bd, pos=pos.to(DEV) if with_pos else None, n_alias=n_alias)
+    handles = [res[0]] + list(res[2 if with_pos else 1:])
+    assert len(handles) == n_alias + 1
+    loss = sum((h * c.to(DEV)).sum() for h, c in zip(handles, cots))
+    if with_pos:
+        loss = loss + (res[1] * cots[-1].to(DEV)).sum()
+    loss.backward()
+    for got, want in zip((xd.grad, rd.grad, gd.grad, bd.grad), ref):
+        assert rel_err(got, want) < 2e-5
+
+
 # ------------------------------------------------------------------------------- block-level entry points
 @pytest.mark.parametrize("R", [160, 3200])                              # query rows (latency kernel) / token rows (tcgen05)
 def test_block_entry_points_ffn_fused_and_linear_epilogue(R):

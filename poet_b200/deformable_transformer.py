@@ -105,12 +105,16 @@ class DeformableTransformerEncoderLayer(nn.Module):
             query = src if pos is None else ops.add_tensors(src, pos)
         attn = self.self_attn(query, reference_points, src, spatial_shapes, level_start_index, padding_mask,
                               output_bias_grad_elsewhere=True)
-        src = ops.add_layernorm(src, attn, self.norm1.weight, self.norm1.bias, eps=self.norm1.eps,
-                                drop_p=p, drop_site=sb + _SITE_D1, r_bias=self.self_attn.output_proj.bias)   # dropout1
+        # norm1's result has two readers (linear1 and the residual of norm2): two autograd handles, their gradients arrive
+        # at norm1's backward kernel as dy / dy2 (its two-pointer form) instead of through a 26 MB accumulation kernel
+        src, src_mlp = ops.add_layernorm(src, attn, self.norm1.weight, self.norm1.bias, eps=self.norm1.eps,
+                                         drop_p=p, drop_site=sb + _SITE_D1, r_bias=self.self_attn.output_proj.bias,
+                                         n_alias=1)                                                   # dropout1
         # linear1 / relu / dropout2 / linear2 / dropout3 / norm2 as one autograd node (ops._FFNBlock)
         return ops.ffn_block(src, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias,
                              self.norm2.weight, self.norm2.bias, pos=pos if (emit_next_query and pos is not None) else None,
-                             eps=self.norm2.eps, drop_p=p, site_hidden=sb + _SITE_HIDDEN, site_res=sb + _SITE_D2)
+                             eps=self.norm2.eps, drop_p=p, site_hidden=sb + _SITE_HIDDEN, site_res=sb + _SITE_D2,
+                             x_mlp=src_mlp)
 
 
 class DeformableTransformerEncoder(nn.Module):

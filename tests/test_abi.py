@@ -68,3 +68,15 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_bench_roofline_helpers():
+    """bench.py's payload bound of the MSDA backward follows the tile kernel's eligibility (csrc/msda.cu try_tile_bwd):
+    D = 16, L = P = 4, trailing levels of at most 104 pixels together -> the REF pyramid sends half of its sampling points
+    through L2 atomics; the 8-head configs (D = 32) are reported with the full payload."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    from poet_b200 import synthetic as S
+    assert bench.msda_sparse_fraction(S.CONFIGS["cfg2"]) == 0.5
+    assert bench.msda_sparse_fraction(S.CONFIGS["cfg5"]) == 1.0

@@ -124,3 +124,19 @@ def test_segmented_allreduce_covers_the_arena_exactly_once(tmp_path):
     mean = sum(r["mine"] for r in recs) / world
     for r in recs:
         assert torch.allclose(r["reduced"], mean, rtol=0, atol=1e-6)
+
+
+def _coarse_worker(rank, world, port, out_dir):
+    os.environ["POET_OVERLAP_COARSE"] = "1"
+    _seg_worker(rank, world, port, out_dir)
+
+
+def test_coarse_overlap_plan_reduces_every_element_once(tmp_path):
+    """POET_OVERLAP_COARSE: one early collective (the decoder's segment, launched when the last encoder layer's marker
+    fires), everything else in finish(): same coverage and same mean as the per-layer plan."""
+    world = 2
+    mp.spawn(_coarse_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    recs = [torch.load(os.path.join(tmp_path, f"seg{r}.pt")) for r in range(world)]
+    mean = sum(r["mine"] for r in recs) / world
+    for r in recs:
+        assert torch.allclose(r["reduced"], mean, rtol=0, atol=1e-6)

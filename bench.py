@@ -561,13 +561,14 @@ def run_gpu(args):
 
 def msda_sparse_fraction(cfg):
     """Share of the encoder MSDA backward's sampling points whose grad_value contributions go through L2 atomics: the tile
-    kernel (csrc/msda.cu, D = 16, L = P = 4) turns the trailing levels that hold <= 104 pixels together into dense products."""
+    kernel (csrc/msda.cu, D = 16 or 32, L = P = 4, at least two such levels) turns the trailing levels that hold <= 104
+    pixels together into dense products."""
     from poet_b200 import synthetic as S
     pyr = S.pyramid_of(cfg)
-    if cfg["d_model"] // cfg["nheads"] != 16 or len(pyr) != 4 or cfg["n_points"] != 4:
+    if cfg["d_model"] // cfg["nheads"] not in (16, 32) or len(pyr) != 4 or cfg["n_points"] != 4:
         return 1.0
     sizes = [h * w for h, w in pyr]
-    for l0 in range(4):
+    for l0 in range(3):                           # at least two dense levels (POET_MSDA_TILE_MAX_LD = 2)
         if sum(sizes[l0:]) <= 104:
             return l0 / 4.0
     return 1.0

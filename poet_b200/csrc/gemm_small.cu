@@ -360,7 +360,8 @@ int poet_gemm_small(const float* A, int64_t lda, int a_kcontig, const float* Bm,
   static const int ksplit_on = []() { const char* e = getenv("POET_GEMM_SMALL_KSPLIT"); return e ? atoi(e) : 1; }();
   const int64_t tiles = (int64_t)poet_ceil_div(M, small::BM) * poet_ceil_div(N, small::BN);
   a.ksplit = 1;
-  if (ksplit_on && n_stage_all >= 4 && tiles <= 96 && a_colsum == nullptr && !(flags & POET_GEMM_ACCUMULATE))
+  static const int ksplit_min = []() { const char* e = getenv("POET_GEMM_SMALL_KSPLIT_MIN"); return e ? atoi(e) : 4; }();   // stages; A/B only
+  if (ksplit_on && n_stage_all >= ksplit_min && n_stage_all >= 2 && tiles <= 96 && a_colsum == nullptr && !(flags & POET_GEMM_ACCUMULATE))
     a.ksplit = n_stage_all >= 8 ? 4 : (n_stage_all >= 6 ? 3 : 2);
   const int n_stage = poet_ceil_div(n_stage_all, a.ksplit);
   a.stages = n_stage < small::MAX_STAGES ? (n_stage < 1 ? 1 : n_stage) : small::MAX_STAGES;
